@@ -1,0 +1,195 @@
+/*
+ * dmpc_b200.h -- C-ABI of libdmpc_b200.so: the B200-native DMPC per-agent QP hot path.
+ *
+ * Drop-in boundary for carlosluis/multiagent_planning (reference paths relative to the
+ * reference repository root).  The reference has no FFI for this path: the path sits behind
+ * plain MATLAB function signatures (and the C++ class DMPC).  Each entry point below cites the
+ * reference interface it replaces.  Plain pointers and sizes only; all arrays are caller-owned,
+ * column-major fp64 exactly like MATLAB mxArray real data: a horizon buffer `l` is 3 x K x N,
+ * element (d,k,n) at l[d + 3*(k + K*n)] (0-based), identical to the C++ reference's
+ * std::vector<MatrixXd(3,K)> blocks (dmpc/cpp/dmpc.cpp:1630-1631).
+ *
+ * Return value: 0 = ok, <0 = API / CUDA error (text via dmpcb200_last_error).  Solver outcomes
+ * are NOT errors (the reference returns flags and empty arrays, solveSoftDMPCbound.m:26-31,
+ * 136-139); they are reported in the per-agent status word.
+ *
+ * There is no CPU fallback: every compute entry point needs a CUDA device and fails loudly
+ * (DMPCB200_ERR_CUDA) without one.
+ */
+#ifndef DMPC_B200_H
+#define DMPC_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DMPCB200_ABI_VERSION 1
+
+/* solver variants (which reference function the step reproduces) */
+enum {
+    DMPCB200_SOFT_BOUND = 0,    /* dmpc/matlab/solveSoftDMPCbound.m   (k_ctr = k,   slack >= -0.05) */
+    DMPCB200_SOFT_BOUND2 = 1,   /* dmpc/matlab/solveSoftDMPCbound2.m  (k_ctr = k-1, slack >= -0.01) */
+    DMPCB200_HARD = 2,          /* dmpc/matlab/solveHardDMPC.m         (all k, dist < 1, no slack)  */
+    DMPCB200_HARD_ONDEMAND = 3  /* dmpc/matlab/solveHardDMPCOnDemand.m (first violating k, no slack)*/
+};
+
+/* per-agent status word: low byte = flags, bits 8..15 = number of infeasible-retries taken */
+enum {
+    DMPCB200_ST_SOLVED = 1,      /* p, v, a valid                                                  */
+    DMPCB200_ST_COLL = 2,        /* k==1 violation deeper than coll_tol: reference returns coll=1   */
+    DMPCB200_ST_INFEASIBLE = 4,  /* QP infeasible after all retries: reference returns feasible=0   */
+    DMPCB200_ST_OUTBOUND = 8,    /* first predicted position outside workspace (is_inbounds.m)      */
+    DMPCB200_ST_QPFAIL = 16,     /* internal: iteration cap                                         */
+    DMPCB200_ST_OVERFLOW = 32    /* internal: constraint-row or active-set capacity exceeded        */
+};
+
+enum {
+    DMPCB200_OK = 0,
+    DMPCB200_ERR_ARG = -1,
+    DMPCB200_ERR_CUDA = -2,
+    DMPCB200_ERR_STATE = -3
+};
+
+/* Parameters.  Mirrors `struct Params` of dmpc/cpp/dmpc.h:50-63 plus the constants the MATLAB
+ * scripts hard-code (solveSoftDMPCbound.m:25,43-52,78; CheckCollSoftDMPC.m:12; is_inbounds.m:2;
+ * initDMPC.m:7; CollConstrHardDMPC.m:19; test/failure_rate.m:7-27).  dmpcb200_default_params
+ * fills the reference's values. */
+typedef struct dmpcb200_params {
+    int32_t K;            /* k_hor, horizon length (<= 32)                                  */
+    int32_t variant;      /* DMPCB200_SOFT_BOUND ...                                        */
+    int32_t max_tries;    /* 30 (solveSoftDMPCbound.m:102)                                  */
+    int32_t neigh_mode;   /* 0: dist < neigh_factor*rmin (MATLAB); 1: rmin*(1+k/K) (C++)    */
+    double h;             /* time step                                                      */
+    double rmin;          /* protection radius                                              */
+    double c;             /* ellipsoid z scaling, E = diag(1,1,c)                           */
+    double alim;          /* |a| bound                                                      */
+    double Q1, S1;        /* weights when a collision constraint was added                  */
+    double term;          /* linear slack penalty (negative)                                */
+    double Q_far, Q_near; /* 1000 / 10000                                                   */
+    double S_free;        /* 10                                                             */
+    double near_radius;   /* 1.0                                                            */
+    double slack_lb;      /* -0.05 (bound) / -0.01 (bound2)                                 */
+    double neigh_factor;  /* 3.0                                                            */
+    double coll_tol;      /* 0.05                                                           */
+    double inb_tol;       /* 0.05                                                           */
+    double hard_radius;   /* 1.0                                                            */
+    double init_div;      /* 10                                                             */
+    double goal_tol;      /* 0.01 (error_tol, test/failure_rate.m:24; ReachedGoal.m)        */
+} dmpcb200_params;
+
+typedef struct dmpcb200_handle dmpcb200_t;
+
+/* per-agent diagnostics written by the QP kernel (optional output) */
+typedef struct dmpcb200_diag {
+    int32_t kstar;    /* 1-based first violating horizon step, 0 = none      */
+    int32_t nv;       /* collision rows handed to the QP                     */
+    int32_t iters;    /* dual active-set iterations (all tries)              */
+    int32_t nact;     /* active-set size at the optimum                      */
+} dmpcb200_diag;
+
+int dmpcb200_abi_version(void);
+const char* dmpcb200_last_error(void);
+int dmpcb200_device_count(void);
+
+/* defaults = the reference scripts' values for the given variant */
+void dmpcb200_default_params(dmpcb200_params* p, int variant);
+
+/* getPosMat.m:1-23, getDeltaMat.m:1-9, precompute dmpc_soft_bound.m:81-108
+ * (C++: get_lambda_A_v_mat dmpc.cpp:83-108, get_delta_mat :110-134, get_A0_mat :136-155).
+ * Host computation (runs once per scenario in the reference too). Any output may be NULL.
+ * A_p, A_v, Delta: 3K x 3K; A_initp: 3K x 6; column-major. */
+int dmpcb200_model_mats(double h, int K, double* A_p, double* A_v, double* A_initp, double* Delta);
+
+/* Create a solver for N agents (whole swarm) of which this handle solves agents [n0, n1)
+ * on CUDA device `device` (one handle per GPU/process; dmpc.cpp:1600-1625 clusters).
+ * max_rows: capacity of the per-agent constraint-row buffer, 0 = automatic. */
+int dmpcb200_create(const dmpcb200_params* p, int N, int n0, int n1, int device, int max_rows,
+                    dmpcb200_t** out);
+void dmpcb200_destroy(dmpcb200_t* h);
+
+/* workspace box (set_boundaries dmpc.h:126) and goals (set_final_pts dmpc.h:130); pf is 3 x N */
+int dmpcb200_set_bounds(dmpcb200_t* h, const double* pmin, const double* pmax);
+int dmpcb200_set_goals(dmpcb200_t* h, const double* pf);
+
+/* initDMPC.m:1-13 for all N agents on the device: l (3 x K x N), p1,v1,a1 (3 x N) host outputs
+ * (any may be NULL); also seeds the device-resident state for dmpcb200_run. po is 3 x N. */
+int dmpcb200_init_horizons(dmpcb200_t* h, const double* po, double* l, double* p1, double* v1,
+                           double* a1);
+
+/* One Jacobi MPC step for agents [n0,n1): the body of `for n = 1:N` in test/failure_rate.m:100-119
+ * / dmpc_soft_bound.m:116-135 (C++ cluster_solvev2 dmpc.cpp:1792-1841), HOST buffers.
+ * Inputs: pk,vk,ak 3 x N current states (only columns n0..n1-1 are read), l_prev 3 x K x N.
+ * Outputs (rows of agents n0..n1-1 written, others untouched; any may be NULL):
+ *   l_new 3 x K x N, p1,v1,a1 3 x N (first columns), v_hor,a_hor 3 x K x N (full v,a horizons),
+ *   status[N], diag[N].  Agents that are not SOLVED keep l_new(:,:,n) = l_prev(:,:,n).
+ * first_fail: lowest agent index without SOLVED or with OUTBOUND, -1 if none. */
+int dmpcb200_step(dmpcb200_t* h, const double* pk, const double* vk, const double* ak,
+                  const double* l_prev, double* l_new, double* p1, double* v1, double* a1,
+                  double* v_hor, double* a_hor, int32_t* status, dmpcb200_diag* diag,
+                  int32_t* first_fail);
+
+/* Same step on DEVICE pointers, asynchronous on `stream` (a cudaStream_t passed as void*).
+ * State arrays are 3 x N, horizons 3 x K x N, on the handle's device.  No host sync. */
+int dmpcb200_step_dev(dmpcb200_t* h, const double* d_pk, const double* d_vk, const double* d_ak,
+                      const double* d_l_prev, double* d_l_new, double* d_p1, double* d_v1,
+                      double* d_a1, double* d_v_hor, double* d_a_hor, int32_t* d_status,
+                      dmpcb200_diag* d_diag, void* stream);
+
+/* ReachedGoal.m:1-11 / reached_goalv2 dmpc.cpp:1868-1882 on device pointers:
+ * d_out[0] = max_n ||p(:,n)-pf(:,n)||, d_out[1] = (that < goal_tol). */
+int dmpcb200_goal_dev(dmpcb200_t* h, const double* d_p, double* d_out, void* stream);
+
+/* Device-resident closed loop for single-GPU handles (n0 = 0, n1 = N): the
+ * `while ~reached_goal && k < max_K` loop of test/failure_rate.m:99-127 after
+ * dmpcb200_init_horizons.  Runs at most max_steps further MPC steps; agents that fail keep their
+ * state (the caller decides whether to abort like the reference does).
+ * traj_p/v/a: optional host outputs 3 x (max_steps+1) x N (column 0 = initial state).
+ * status_hist: optional max_steps x N.  *steps_done, *reached, *first_fail_step (-1 none). */
+int dmpcb200_run(dmpcb200_t* h, int max_steps, int stop_on_fail, double* traj_p, double* traj_v,
+                 double* traj_a, int32_t* status_hist, int32_t* steps_done, int32_t* reached,
+                 int32_t* first_fail_step, int32_t* first_fail_agent);
+
+/* ---- per-agent drop-ins (batch of one; keep the reference's helper semantics) ------------- */
+
+/* solveSoftDMPCbound.m / solveSoftDMPCbound2.m / solveHardDMPC.m / solveHardDMPCOnDemand.m
+ * (selected by params.variant at create): po,pf,vo,ao 3-vectors, n 0-based agent index,
+ * l 3 x K x N.  p,v,a: 3 x K outputs.  *status as above. */
+int dmpcb200_solve_agent(dmpcb200_t* h, const double* po, const double* pf, const double* vo,
+                         const double* ao, int n, const double* l, double* p, double* v,
+                         double* a, int32_t* status, dmpcb200_diag* diag);
+
+/* CheckCollSoftDMPC.m:1-17 (C++ check_collisionsv2 dmpc.cpp:395-448): p3 = own predicted
+ * position at horizon step k (1-based), l 3 x K x N.  violation/viol_constr: N bytes. */
+int dmpcb200_check_coll(dmpcb200_t* h, const double* p3, const double* l, int n, int k,
+                        uint8_t* violation, uint8_t* viol_constr, double* min_dist,
+                        int32_t* any_violation);
+
+/* CollConstrSoftDMPC.m / CollConstrSoftDMPC2.m / CollConstrHardDMPC.m / ...OnDemand.m
+ * (C++ build_collconstraintv2 dmpc.cpp:496-546): dense rows like the reference.
+ * Ain: cap x 3K column-major (leading dimension cap), bin, prev_dist: cap.  mask = viol_constr
+ * (N bytes; ignored for the HARD variant).  *nrows rows written, neighbour order ascending. */
+int dmpcb200_coll_constr(dmpcb200_t* h, const double* p3, const double* po, const double* vo,
+                         int n, int k, const double* l, const uint8_t* mask, int cap, double* Ain,
+                         double* bin, double* prev_dist, int32_t* nrows);
+
+/* propStatedmpc.m:1-8 for a batch of B agents on the device: a 3K x B -> p, v 3K x B */
+int dmpcb200_prop_state(dmpcb200_t* h, int B, const double* po, const double* vo, const double* a,
+                        double* p, double* v);
+
+/* timing of the last dmpcb200_step / dmpcb200_run, CUDA events on the launch stream:
+ * ms[0] = neighbour-scan kernel, ms[1] = QP kernel, ms[2] = whole step (device), averaged over
+ * the steps of the call; launches[0] = number of kernels launched. */
+int dmpcb200_last_timing(dmpcb200_t* h, double* ms, int64_t* launches);
+
+/* raw device pointers of the handle's resident state (for host frameworks that own streams):
+ * which: 0 l_cur, 1 l_next, 2 pk, 3 vk, 4 ak, 5 pf, 6 status, 7 goal_out(2 doubles) */
+void* dmpcb200_device_ptr(dmpcb200_t* h, int which);
+/* swap l_cur/l_next after a step + exchange (Jacobi `l = new_l`, failure_rate.m:124) */
+int dmpcb200_swap_horizons(dmpcb200_t* h);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

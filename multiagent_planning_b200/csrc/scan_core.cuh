@@ -1,0 +1,169 @@
+// scan_core.cuh -- per-agent neighbour scan and collision-row construction (warp-cooperative).
+//
+// Reference: the horizon scan of solveSoftDMPCbound.m:21-38 (solveSoftDMPCbound2.m:18-36,
+// solveHardDMPCOnDemand.m:18-27, solveHardDMPC.m:18-22) with CheckCollSoftDMPC.m:1-17 and
+// CollConstrSoftDMPC.m:1-32 / CollConstrSoftDMPC2.m / CollConstrHardDMPC.m /
+// CollConstrHardDMPCOnDemand.m.  The reference calls CheckColl once per horizon step (an O(N)
+// interpreted loop each) and then re-walks all agents to build dense 3K-wide rows.  Here one pass
+// over the neighbour horizons computes, for every neighbour, a K-bit "violates at step k" mask and
+// a K-bit "near at step k" mask; the first violating step is a warp OR-reduction, and the rows
+// are emitted from the near masks as the rank-1 data (d_j, dist_j, rhs_j, kc_j) only:
+//     dense reference row  =  -(Lam[kc,:] (x) d_j'),   slack column dist_j,   b = -r_j
+//     here                    d_j . P[kc] - dist_j eps_j >= rhs_j ,  rhs_j = r_j + d_j . p0[kc]
+//                                                              = dist_j (rmin - dist_j) + d_j . p
+// Distances use separately rounded multiply/add (no FMA) and IEEE sqrt/div so that the discrete
+// decisions (dist < rmin, first violating k, neighbour set) are bit-identical to a plain C
+// evaluation of the reference's formula.
+#pragma once
+#include "agent_solve.cuh"
+
+namespace dmpc {
+
+#if defined(__CUDA_ARCH__)
+DMPC_D double mul_rn(double a, double b) { return __dmul_rn(a, b); }
+DMPC_D double add_rn(double a, double b) { return __dadd_rn(a, b); }
+DMPC_D unsigned wor(unsigned v) { return __reduce_or_sync(0xffffffffu, v); }
+DMPC_D double wmin(double v) {
+#pragma unroll
+    for (int o = 16; o; o >>= 1) v = fmin(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+#else
+// host emulation: compiled with -ffp-contract=off
+inline double mul_rn(double a, double b) { volatile double r = a * b; return r; }
+inline double add_rn(double a, double b) { volatile double r = a + b; return r; }
+inline unsigned wor(unsigned v) { return v; }
+inline double wmin(double v) { return v; }
+#endif
+
+// norm(E1*(p-pj),2), E1 = diag(1,1,1/c)   (CheckCollSoftDMPC.m:10)
+DMPC_D double ell_dist(double dx, double dy, double dz, double c) {
+    const double ez = dz / c;
+    return sqrt(add_rn(add_rn(mul_rn(dx, dx), mul_rn(dy, dy)), mul_rn(ez, ez)));
+}
+
+// neighbour threshold at 1-based step k (CheckCollSoftDMPC.m:12 ; C++ dmpc.cpp:418)
+DMPC_D double neigh_thr(const DevParams& P, int k1) {
+    if (P.variant == VAR_HARD) return P.hard_radius;  // CollConstrHardDMPC.m:19
+    if (P.neigh_mode == 1) return P.rmin * (1.0 + (double)(k1 - 1) / P.K);
+    return P.rmin * P.neigh_factor;
+}
+
+struct ScanAcc {
+    unsigned vmask;  // per lane: bit k set if some neighbour of this lane violates at step k
+    double md0;      // per lane: min distance at step 1
+};
+
+// Accumulate `cnt` neighbours starting at global index ibase whose horizons lie at tile
+// (cnt x K x 3 doubles, same layout as l).  own = this agent's previous horizon (3K doubles).
+// nearmask[i] (i global) receives the K-bit near mask.
+DMPC_D void scan_tile(const DevParams& P, const double* __restrict__ own, int n,
+                      const double* __restrict__ tile, int ibase, int cnt, unsigned* nearmask,
+                      ScanAcc& acc) {
+    const int K = P.K;
+    for (int m = lane_id(); m < cnt; m += kLanes) {
+        const int i = ibase + m;
+        unsigned nm = 0;
+        if (i != n) {
+            const double* pj = tile + (size_t)m * 3 * K;
+            unsigned vm = 0;
+            for (int k = 0; k < K; ++k) {
+                const double dx = own[3 * k] - pj[3 * k];
+                const double dy = own[3 * k + 1] - pj[3 * k + 1];
+                const double dz = own[3 * k + 2] - pj[3 * k + 2];
+                const double dist = ell_dist(dx, dy, dz, P.c);
+                if (dist < P.rmin) vm |= 1u << k;
+                if (dist < neigh_thr(P, k + 1)) nm |= 1u << k;
+                if (k == 0) acc.md0 = fmin(acc.md0, dist);
+            }
+            acc.vmask |= vm;
+        }
+        nearmask[i] = nm;
+    }
+}
+
+struct ScanOut {
+    int kstar;     // 1-based, 0 = none
+    int nv;        // rows written
+    int flag;      // 0 / ST_COLL / ST_OVERFLOW
+    double md0;
+};
+
+// Decide the first violating step and emit rows.  l = full horizon buffer (global).
+// grow: d0[RMAX] d1[RMAX] d2[RMAX] dist[RMAX] rhs[RMAX]; gkc, gidx: RMAX ints.
+DMPC_D ScanOut scan_finish(const DevParams& P, const double* __restrict__ own, int n,
+                           const double* __restrict__ l, const unsigned* nearmask, ScanAcc acc,
+                           int RMAX, double* grow, int* gkc, int* gidx) {
+    const int K = P.K, N = P.N;
+    ScanOut o;
+    o.kstar = 0;
+    o.nv = 0;
+    o.flag = 0;
+    const unsigned vm = wor(acc.vmask);
+    o.md0 = wmin(acc.md0);
+    const bool soft = (P.variant == VAR_SOFT_BOUND || P.variant == VAR_SOFT_BOUND2);
+    const double c2 = P.c * P.c;
+    int kfirst = 0, klast = -1, kshift = 0;
+    if (P.variant == VAR_HARD) {
+        // solveHardDMPC.m:18-22: rows for every horizon step, k-major
+        kfirst = 0;
+        klast = K - 1;
+        o.kstar = 0;
+    } else {
+        unsigned m = vm;
+        if (soft && (m & 1u) && o.md0 < P.rmin - P.coll_tol) {
+            // solveSoftDMPCbound.m:25-32: predicted collision at the very next step
+            o.kstar = 1;
+            o.flag = ST_COLL;
+            return o;
+        }
+        if (P.variant == VAR_SOFT_BOUND2) {
+            m &= ~1u;  // solveSoftDMPCbound2.m:29-31: k == 1 is skipped
+            kshift = 1;  // CollConstrSoftDMPC2.m:8: k_ctr = k - 1
+        }
+        if (m == 0) return o;
+        int ks = 0;
+        while (!((m >> ks) & 1u)) ++ks;
+        o.kstar = ks + 1;
+        kfirst = klast = ks;
+    }
+    int nv = 0;
+    bool ovf = false;
+    for (int k = kfirst; k <= klast; ++k) {
+        const double px = own[3 * k], py = own[3 * k + 1], pz = own[3 * k + 2];
+        for (int base = 0; base < N; base += kLanes) {
+            const int i = base + lane_id();
+            const bool hit = (i < N) && ((nearmask[i] >> k) & 1u);
+            const unsigned bal = wballot(hit);
+            if (hit) {
+                const int slot = nv + popc_below(bal);
+                if (slot < RMAX) {
+                    const double* pj = l + 3 * ((size_t)k + (size_t)K * i);
+                    const double dx = px - pj[0], dy = py - pj[1], dz = pz - pj[2];
+                    const double dist = ell_dist(dx, dy, dz, P.c);
+                    const double d0 = dx, d1 = dy, d2 = dz / c2;  // diff = E2 (p - pj)
+                    const double dp = d0 * px + d1 * py + d2 * pz;
+                    grow[slot] = d0;
+                    grow[(size_t)RMAX + slot] = d1;
+                    grow[2 * (size_t)RMAX + slot] = d2;
+                    grow[3 * (size_t)RMAX + slot] = dist;
+                    grow[4 * (size_t)RMAX + slot] = dist * ((P.rmin - dist) + dp / dist);
+                    gkc[slot] = k - kshift;
+                    if (gidx) gidx[slot] = i;
+                } else {
+                    ovf = true;
+                }
+            }
+            nv += popc_all(bal);
+        }
+    }
+    if (wballot(ovf) || nv > RMAX) {
+        o.flag = ST_QPFAIL | ST_OVERFLOW;
+        nv = RMAX;
+    }
+    o.nv = nv;
+    if (P.variant == VAR_HARD) o.kstar = nv ? 1 : 0;
+    return o;
+}
+
+}  // namespace dmpc
