@@ -138,18 +138,35 @@ int dmpcb200_step_dev(dmpcb200_t* h, const double* d_pk, const double* d_vk, con
                       dmpcb200_diag* d_diag, void* stream);
 
 /* ReachedGoal.m:1-11 / reached_goalv2 dmpc.cpp:1868-1882 on device pointers:
- * d_out[0] = max_n ||p(:,n)-pf(:,n)||, d_out[1] = (that < goal_tol). */
-int dmpcb200_goal_dev(dmpcb200_t* h, const double* d_p, double* d_out, void* stream);
+ * d_out[0] = max_n ||p(:,n)-pf(:,n)||, d_out[1] = (that < goal_tol).  Agent n's position is at
+ * d_p + ld*n: ld = 3 for a packed 3 x N array, ld = 3K to read the first column of every horizon
+ * of an l buffer (after the all-gather every rank holds all of them). */
+int dmpcb200_goal_dev(dmpcb200_t* h, const double* d_p, int ld, double* d_out, void* stream);
+
+/* ReachedGoal.m:1-11 on HOST arrays: p, pf 3 x N; *pass = (max_n ||p-pf|| < tol). */
+int dmpcb200_reached_goal(dmpcb200_t* h, const double* p, const double* pf, double tol,
+                          double* max_dist, int32_t* pass);
 
 /* Device-resident closed loop for single-GPU handles (n0 = 0, n1 = N): the
  * `while ~reached_goal && k < max_K` loop of test/failure_rate.m:99-127 after
- * dmpcb200_init_horizons.  Runs at most max_steps further MPC steps; agents that fail keep their
- * state (the caller decides whether to abort like the reference does).
+ * dmpcb200_init_horizons (or dmpcb200_set_state).  Runs at most max_steps further MPC steps with
+ * no host synchronisation inside the loop (CUDA graph + device control word); stops at the goal
+ * (ReachedGoal.m) and, if stop_on_fail, at the first step in which an agent fails; otherwise
+ * agents that fail keep their state.
+ * mode: 0 = CUDA graph; bit 0 = per-kernel CUDA-event timing (plain launches);
+ *       bit 1 = plain launches without per-kernel events.
  * traj_p/v/a: optional host outputs 3 x (max_steps+1) x N (column 0 = initial state).
  * status_hist: optional max_steps x N.  *steps_done, *reached, *first_fail_step (-1 none). */
-int dmpcb200_run(dmpcb200_t* h, int max_steps, int stop_on_fail, double* traj_p, double* traj_v,
-                 double* traj_a, int32_t* status_hist, int32_t* steps_done, int32_t* reached,
-                 int32_t* first_fail_step, int32_t* first_fail_agent);
+int dmpcb200_run(dmpcb200_t* h, int max_steps, int stop_on_fail, int mode, double* traj_p,
+                 double* traj_v, double* traj_a, int32_t* status_hist, int32_t* steps_done,
+                 int32_t* reached, int32_t* first_fail_step, int32_t* first_fail_agent);
+
+/* read / overwrite the device-resident loop state (any output may be NULL):
+ * l 3 x K x N, pk,vk,ak 3 x N, status / diag of the last step. */
+int dmpcb200_get_state(dmpcb200_t* h, double* l, double* pk, double* vk, double* ak,
+                       int32_t* status, dmpcb200_diag* diag);
+int dmpcb200_set_state(dmpcb200_t* h, const double* l, const double* pk, const double* vk,
+                       const double* ak);
 
 /* ---- per-agent drop-ins (batch of one; keep the reference's helper semantics) ------------- */
 
@@ -184,10 +201,16 @@ int dmpcb200_prop_state(dmpcb200_t* h, int B, const double* po, const double* vo
 int dmpcb200_last_timing(dmpcb200_t* h, double* ms, int64_t* launches);
 
 /* raw device pointers of the handle's resident state (for host frameworks that own streams):
- * which: 0 l_cur, 1 l_next, 2 pk, 3 vk, 4 ak, 5 pf, 6 status, 7 goal_out(2 doubles) */
+ * which: 0 l_cur, 1 l_next, 2 pk, 3 vk, 4 ak, 5 pf, 6 status, 7 goal_out(2 doubles),
+ *        8 pk_next, 9 vk_next, 10 ak_next, 11 diag */
 void* dmpcb200_device_ptr(dmpcb200_t* h, int which);
 /* swap l_cur/l_next after a step + exchange (Jacobi `l = new_l`, failure_rate.m:124) */
 int dmpcb200_swap_horizons(dmpcb200_t* h);
+
+/* launch configuration chosen at create: out8 = {agents (warps) per QP block, QMAX (on-chip
+ * active-set capacity), RCAP (rows held on chip), RMAX (row capacity), QBIG (rescue capacity),
+ * rescue slots, QP kernel dynamic shared memory bytes, scan kernel shared memory bytes} */
+int dmpcb200_config(dmpcb200_t* h, int32_t* out8);
 
 #ifdef __cplusplus
 }

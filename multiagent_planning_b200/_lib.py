@@ -1,0 +1,136 @@
+"""Loader / builder of libdmpc_b200.so (the C-ABI of include/dmpc_b200.h) and its ctypes prototypes.
+
+The library is hand-written CUDA for sm_100a (multiagent_planning_b200/csrc).  It is built IN-TREE
+with nvcc (``build()``), never JIT-compiled, and there is no fallback: if it is missing or no B200
+is present, compute calls raise.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import shutil
+import subprocess
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_CSRC = os.path.join(_HERE, "csrc")
+LIB_PATH = os.path.join(_HERE, "libdmpc_b200.so")
+SOURCES = ["dmpc_b200.cu", "model_tables.cpp"]
+HEADERS = ["dmpc_kernels.cuh", "scan_core.cuh", "agent_solve.cuh", "qp_core.cuh", "model_tables.h",
+           os.path.join("..", "..", "include", "dmpc_b200.h")]
+NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
+              "-Xcompiler", "-fPIC", "-shared", "-diag-suppress", "177"]
+
+_LIB = None
+
+
+class DmpcError(RuntimeError):
+    """API / CUDA error reported by libdmpc_b200 (negative return code)."""
+
+
+class Params(C.Structure):
+    """dmpcb200_params (include/dmpc_b200.h) -- mirrors `struct Params` of dmpc/cpp/dmpc.h:50-63 plus
+    the constants the MATLAB scripts hard-code."""
+    _fields_ = [
+        ("K", C.c_int32), ("variant", C.c_int32), ("max_tries", C.c_int32), ("neigh_mode", C.c_int32),
+        ("h", C.c_double), ("rmin", C.c_double), ("c", C.c_double), ("alim", C.c_double),
+        ("Q1", C.c_double), ("S1", C.c_double), ("term", C.c_double),
+        ("Q_far", C.c_double), ("Q_near", C.c_double), ("S_free", C.c_double),
+        ("near_radius", C.c_double), ("slack_lb", C.c_double), ("neigh_factor", C.c_double),
+        ("coll_tol", C.c_double), ("inb_tol", C.c_double), ("hard_radius", C.c_double),
+        ("init_div", C.c_double), ("goal_tol", C.c_double),
+    ]
+
+    def as_dict(self):
+        return {n: getattr(self, n) for n, _ in self._fields_}
+
+
+class Diag(C.Structure):
+    _fields_ = [("kstar", C.c_int32), ("nv", C.c_int32), ("iters", C.c_int32), ("nact", C.c_int32)]
+
+
+def _nvcc():
+    for cand in (os.environ.get("NVCC"), shutil.which("nvcc"), "/usr/local/cuda/bin/nvcc"):
+        if cand and os.path.exists(cand):
+            return cand
+    raise DmpcError("nvcc not found: cannot build libdmpc_b200.so")
+
+
+def is_stale() -> bool:
+    if not os.path.exists(LIB_PATH):
+        return True
+    t = os.path.getmtime(LIB_PATH)
+    deps = [os.path.join(_CSRC, s) for s in SOURCES + HEADERS]
+    return any(os.path.exists(d) and os.path.getmtime(d) > t for d in deps)
+
+
+def build(force: bool = False, verbose: bool = False) -> str:
+    """nvcc -gencode arch=compute_100a,code=sm_100a -lineinfo ... -> multiagent_planning_b200/libdmpc_b200.so"""
+    if not force and not is_stale():
+        return LIB_PATH
+    cmd = [_nvcc()] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB_PATH] + SOURCES
+    subprocess.check_call(cmd, cwd=_CSRC)
+    return LIB_PATH
+
+
+def lib():
+    """The loaded library with prototypes set.  Raises DmpcError when it has not been built."""
+    global _LIB
+    if _LIB is not None:
+        return _LIB
+    if not os.path.exists(LIB_PATH):
+        raise DmpcError(f"{LIB_PATH} is missing: run `python -c 'import __graft_entry__ as g; g.build()'` "
+                        "(there is no CPU fallback)")
+    L = C.CDLL(LIB_PATH)
+    dp, ip, u8p, vp = C.POINTER(C.c_double), C.POINTER(C.c_int32), C.POINTER(C.c_uint8), C.c_void_p
+    PP, DP = C.POINTER(Params), C.POINTER(Diag)
+    I, D = C.c_int, C.c_double
+    protos = {
+        "dmpcb200_abi_version": ([], I),
+        "dmpcb200_last_error": ([], C.c_char_p),
+        "dmpcb200_device_count": ([], I),
+        "dmpcb200_default_params": ([PP, I], None),
+        "dmpcb200_model_mats": ([D, I, dp, dp, dp, dp], I),
+        "dmpcb200_create": ([PP, I, I, I, I, I, C.POINTER(vp)], I),
+        "dmpcb200_destroy": ([vp], None),
+        "dmpcb200_set_bounds": ([vp, dp, dp], I),
+        "dmpcb200_set_goals": ([vp, dp], I),
+        "dmpcb200_init_horizons": ([vp, dp, dp, dp, dp, dp], I),
+        "dmpcb200_step": ([vp, dp, dp, dp, dp, dp, dp, dp, dp, dp, dp, ip, DP, ip], I),
+        "dmpcb200_step_dev": ([vp] + [vp] * 12 + [vp], I),
+        "dmpcb200_goal_dev": ([vp, vp, I, vp, vp], I),
+        "dmpcb200_reached_goal": ([vp, dp, dp, D, dp, ip], I),
+        "dmpcb200_run": ([vp, I, I, I, dp, dp, dp, ip, ip, ip, ip, ip], I),
+        "dmpcb200_get_state": ([vp, dp, dp, dp, dp, ip, DP], I),
+        "dmpcb200_set_state": ([vp, dp, dp, dp, dp], I),
+        "dmpcb200_solve_agent": ([vp, dp, dp, dp, dp, I, dp, dp, dp, dp, ip, DP], I),
+        "dmpcb200_check_coll": ([vp, dp, dp, I, I, u8p, u8p, dp, ip], I),
+        "dmpcb200_coll_constr": ([vp, dp, dp, dp, I, I, dp, u8p, I, dp, dp, dp, ip], I),
+        "dmpcb200_prop_state": ([vp, I, dp, dp, dp, dp, dp], I),
+        "dmpcb200_last_timing": ([vp, dp, C.POINTER(C.c_int64)], I),
+        "dmpcb200_device_ptr": ([vp, I], vp),
+        "dmpcb200_swap_horizons": ([vp], I),
+        "dmpcb200_config": ([vp, ip], I),
+    }
+    for name, (args, res) in protos.items():
+        fn = getattr(L, name)
+        fn.argtypes = args
+        fn.restype = res
+    L._protos = protos
+    _LIB = L
+    return L
+
+
+EXPORTS = [
+    "dmpcb200_abi_version", "dmpcb200_last_error", "dmpcb200_device_count", "dmpcb200_default_params",
+    "dmpcb200_model_mats", "dmpcb200_create", "dmpcb200_destroy", "dmpcb200_set_bounds", "dmpcb200_set_goals",
+    "dmpcb200_init_horizons", "dmpcb200_step", "dmpcb200_step_dev", "dmpcb200_goal_dev", "dmpcb200_reached_goal", "dmpcb200_run",
+    "dmpcb200_get_state", "dmpcb200_set_state", "dmpcb200_solve_agent", "dmpcb200_check_coll",
+    "dmpcb200_coll_constr", "dmpcb200_prop_state", "dmpcb200_last_timing", "dmpcb200_device_ptr",
+    "dmpcb200_swap_horizons", "dmpcb200_config",
+]
+
+
+def check(rc: int, what: str = ""):
+    if rc != 0:
+        msg = lib().dmpcb200_last_error()
+        raise DmpcError(f"{what}: rc={rc}: {msg.decode() if msg else ''}")

@@ -28,13 +28,13 @@ struct AgentDiag {
 DMPC_HD int round_up(int v, int m) { return (v + m - 1) / m * m; }
 
 // bytes of per-agent scratch ("shared memory") for horizon K, active-set capacity QMAX and RCAP
-// rows held on chip
+// rows held on chip.  The constant tables are NOT part of it: they are staged once per thread
+// block (all three weight sets, model_tables.h layout) and shared by the block's agents.
 DMPC_HD size_t agent_smem_bytes(int K, int QMAX, int RCAP) {
     const int n3p = round_up(3 * K, 2);
-    size_t nd = (size_t)4 * K * K + 2 * K + 7 * (size_t)n3p + 3 * (size_t)QMAX + (size_t)QMAX * QMAX +
-                8 * (size_t)RCAP;
+    size_t nd = 7 * (size_t)n3p + 3 * (size_t)QMAX + (size_t)QMAX * QMAX + 8 * (size_t)RCAP;
     size_t ni = 2 * (size_t)QMAX + 2 * (size_t)n3p + 5 * (size_t)RCAP;
-    return nd * sizeof(double) + round_up((int)ni, 2) * sizeof(int);
+    return nd * sizeof(double) + round_up((int)ni, 4) * sizeof(int);  // multiple of 16 bytes
 }
 
 // layout of the table blob in global memory: see model_tables.h
@@ -58,7 +58,8 @@ struct AgentIO {
 };
 
 // All lanes of the warp call this with identical arguments.  Returns the status word.
-DMPC_D int agent_solve(const DevParams& P, const double* __restrict__ gtab, unsigned char* smem,
+// tab: the whole table blob (model_tables.h layout), normally resident in shared memory.
+DMPC_D int agent_solve(const DevParams& P, const double* __restrict__ tab, unsigned char* smem,
                        int QMAX, int RCAP, const AgentIO& io, AgentDiag* diag_out) {
     const int K = P.K, n3 = 3 * K, n3p = round_up(n3, 2);
     const int lane = lane_id();
@@ -74,12 +75,6 @@ DMPC_D int agent_solve(const DevParams& P, const double* __restrict__ gtab, unsi
     } else {
         // ---- carve the scratch ---------------------------------------------------------------
         double* dptr = reinterpret_cast<double*>(smem);
-        double* t_lam = dptr; dptr += K * K;
-        double* t_lnorm = dptr; dptr += K;
-        double* t_tt = dptr; dptr += K;
-        double* t_G = dptr; dptr += K * K;
-        double* t_B = dptr; dptr += K * K;
-        double* t_C = dptr; dptr += K * K;
         double* s_p0 = dptr; dptr += n3p;
         double* s_aunc = dptr; dptr += n3p;
         double* s_a = dptr; dptr += n3p;
@@ -118,20 +113,13 @@ DMPC_D int agent_solve(const DevParams& P, const double* __restrict__ gtab, unsi
         else if (!any_violation) { wset = 1; qw = P.Q_near; sw = P.S_free; }
         else { wset = 2; qw = P.Q1; sw = P.S1; }
 
-        // ---- stage the tables -----------------------------------------------------------------
-        {
-            const int nhead = K * K + 2 * K;  // lam, tt, lnorm are contiguous in the blob
-            // blob order: lam, tt, lnorm ; scratch order: lam, lnorm, tt
-            for (int i = lane; i < K * K; i += kLanes) t_lam[i] = gtab[i];
-            for (int i = lane; i < K; i += kLanes) {
-                t_tt[i] = gtab[K * K + i];
-                t_lnorm[i] = gtab[K * K + K + i];
-            }
-            const double* gset = gtab + tab_set_offset(K, wset);
-            for (int i = lane; i < 3 * K * K; i += kLanes) t_G[i] = gset[i];  // G,B,C contiguous
-            (void)nhead;
-        }
-        wsync();
+        // ---- tables of this agent's weight set (blob: lam, tt, lnorm, then G,B,C per set) --------
+        const double* t_lam = tab;
+        const double* t_tt = tab + K * K;
+        const double* t_lnorm = tab + K * K + K;
+        const double* t_G = tab + tab_set_offset(K, wset);
+        const double* t_B = t_G + K * K;
+        const double* t_C = t_B + K * K;
 
         // ---- rows: on chip when they fit, else in place in global memory --------------------
         const int nv = io.nv;

@@ -1,0 +1,917 @@
+// dmpc_b200.cu -- libdmpc_b200.so: handle, launches and the C-ABI of include/dmpc_b200.h.
+//
+// Built for sm_100a only.  There is no CPU path: every compute entry point needs a CUDA device.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/dmpc_b200.h"
+#include "dmpc_kernels.cuh"
+#include "model_tables.h"
+
+using namespace dmpc;
+
+static_assert(sizeof(AgentDiag) == sizeof(dmpcb200_diag), "diag layout");
+
+namespace {
+
+thread_local std::string g_err;
+
+int fail(int code, const std::string& msg) {
+    g_err = msg;
+    return code;
+}
+
+#define CK(call)                                                                                   \
+    do {                                                                                           \
+        cudaError_t e_ = (call);                                                                   \
+        if (e_ != cudaSuccess)                                                                     \
+            return fail(DMPCB200_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e_));    \
+    } while (0)
+
+template <typename T>
+cudaError_t dalloc(T** p, size_t n) {
+    cudaError_t e = cudaMalloc((void**)p, std::max<size_t>(n, 1) * sizeof(T));
+    if (e == cudaSuccess) e = cudaMemset(*p, 0, std::max<size_t>(n, 1) * sizeof(T));
+    return e;
+}
+
+}  // namespace
+
+struct dmpcb200_handle {
+    dmpcb200_params prm;
+    DevParams dp;
+    int N = 0, n0 = 0, n1 = 0, NL = 0, Npad = 0, K = 0, device = 0;
+    int RMAX = 0, QMAX = 0, RCAP = 0, QBIG = 0, W = 4, n_rescue = 0;
+    size_t rescue_bytes = 0;
+    cudaStream_t stream = nullptr;
+    // resident state
+    double* d_tab = nullptr;
+    double* d_l[2] = {nullptr, nullptr};
+    double* d_st[2][3] = {{nullptr, nullptr, nullptr}, {nullptr, nullptr, nullptr}};  // pk, vk, ak ping-pong
+    double* d_pf = nullptr;
+    double *d_vhor = nullptr, *d_ahor = nullptr;
+    int* d_status = nullptr;
+    AgentDiag* d_diag = nullptr;
+    int cur = 0;  // index of the current l / state
+    // scratch
+    unsigned* d_nearmask = nullptr;
+    ScanRec* d_scan = nullptr;
+    double *d_grow = nullptr, *d_gscr_d = nullptr;
+    int *d_gkc = nullptr, *d_gidx = nullptr, *d_gscr_i = nullptr;
+    unsigned char* d_rescue = nullptr;
+    int* d_rescue_next = nullptr;
+    Ctrl* d_ctrl = nullptr;
+    double* d_goal = nullptr;  // 2 doubles
+    int* d_fail = nullptr;
+    // helper scratch
+    unsigned char* d_u8 = nullptr;  // 2N
+    double* d_small = nullptr;      // misc
+    int* d_ismall = nullptr;
+    // trajectory record of dmpcb200_run
+    double *d_traj[3] = {nullptr, nullptr, nullptr};
+    int* d_hist = nullptr;
+    int traj_S = 0;
+    bool hist_on = false;
+    // closed-loop graph (two steps: even -> odd -> even)
+    cudaGraphExec_t graph = nullptr;
+    bool graph_record = false;
+    // pinned host staging
+    double* h_pin = nullptr;
+    size_t h_pin_n = 0;
+    // timing
+    std::vector<cudaEvent_t> ev;
+    double t_ms[3] = {0, 0, 0};
+    int64_t launches = 0;
+    bool have_bounds = false, have_goals = false, have_init = false;
+};
+
+namespace {
+
+int ensure_device(dmpcb200_t* h) {
+    CK(cudaSetDevice(h->device));
+    return 0;
+}
+
+StepArgs make_args(dmpcb200_t* h, int n0, int n1, const double* pk, const double* vk, const double* ak,
+                   const double* l_prev, double* l_new, double* p1, double* v1, double* a1, double* v_hor,
+                   double* a_hor, int* status, AgentDiag* diag, bool padded, Ctrl* ctrl) {
+    StepArgs A;
+    A.P = h->dp;
+    A.n0 = n0;
+    A.n1 = n1;
+    A.RMAX = h->RMAX;
+    A.QMAX = h->QMAX;
+    A.RCAP = h->RCAP;
+    A.QBIG = h->QBIG;
+    A.n_rescue = h->n_rescue;
+    A.tile_padded = padded ? 1 : 0;
+    A.l_prev = l_prev;
+    A.l_new = l_new;
+    A.pk = pk;
+    A.vk = vk;
+    A.ak = ak;
+    A.pf = h->d_pf;
+    A.p1 = p1;
+    A.v1 = v1;
+    A.a1 = a1;
+    A.v_hor = v_hor;
+    A.a_hor = a_hor;
+    A.status = status;
+    A.diag = diag;
+    A.tab = h->d_tab;
+    A.nearmask = h->d_nearmask;
+    A.nm_stride = (size_t)h->Npad;
+    A.scan = h->d_scan;
+    A.grow = h->d_grow;
+    A.gkc = h->d_gkc;
+    A.gidx = h->d_gidx;
+    A.gscr_d = h->d_gscr_d;
+    A.gscr_i = h->d_gscr_i;
+    A.rescue = h->d_rescue;
+    A.rescue_bytes = h->rescue_bytes;
+    A.rescue_next = h->d_rescue_next;
+    A.ctrl = ctrl;
+    return A;
+}
+
+template <int W>
+cudaError_t launch_scan_w(const StepArgs& A, int nl, size_t smem, cudaStream_t s) {
+    static bool attr_done = false;
+    if (!attr_done) {
+        cudaError_t e = cudaFuncSetAttribute(scan_kernel<W>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        if (e != cudaSuccess) return e;
+        attr_done = true;
+    }
+    scan_kernel<W><<<(nl + W - 1) / W, W * 32, smem, s>>>(A);
+    return cudaGetLastError();
+}
+template <int W>
+cudaError_t launch_qp_w(const StepArgs& A, int nl, size_t smem, cudaStream_t s) {
+    static bool attr_done = false;
+    if (!attr_done) {
+        cudaError_t e = cudaFuncSetAttribute(qp_kernel<W>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        if (e != cudaSuccess) return e;
+        attr_done = true;
+    }
+    qp_kernel<W><<<(nl + W - 1) / W, W * 32, smem, s>>>(A);
+    return cudaGetLastError();
+}
+
+constexpr int kScanW = 4;
+
+cudaError_t launch_scan(dmpcb200_t* h, const StepArgs& A, cudaStream_t s) {
+    return launch_scan_w<kScanW>(A, A.n1 - A.n0, scan_smem_bytes(h->K, kScanW), s);
+}
+cudaError_t launch_qp(dmpcb200_t* h, const StepArgs& A, cudaStream_t s) {
+    const int nl = A.n1 - A.n0;
+    const size_t smem = qp_smem_bytes(h->K, h->W, h->QMAX, h->RCAP);
+    switch (h->W) {
+        case 4: return launch_qp_w<4>(A, nl, smem, s);
+        case 3: return launch_qp_w<3>(A, nl, smem, s);
+        case 2: return launch_qp_w<2>(A, nl, smem, s);
+        default: return launch_qp_w<1>(A, nl, smem, s);
+    }
+}
+
+TailArgs make_tail(dmpcb200_t* h, const double* p, int ld, const int* status, const double* p1, const double* v1,
+                   const double* a1, bool record, Ctrl* ctrl) {
+    TailArgs T;
+    T.N = h->N;
+    T.n0 = h->n0;
+    T.n1 = h->n1;
+    T.ld = ld;
+    T.goal_tol = h->prm.goal_tol;
+    T.p = p;
+    T.pf = h->d_pf;
+    T.status = status;
+    T.p1 = p1;
+    T.v1 = v1;
+    T.a1 = a1;
+    T.traj_p = record ? h->d_traj[0] : nullptr;
+    T.traj_v = record ? h->d_traj[1] : nullptr;
+    T.traj_a = record ? h->d_traj[2] : nullptr;
+    T.status_hist = (record && h->hist_on) ? h->d_hist : nullptr;
+    T.S = h->traj_S;
+    T.goal_out = h->d_goal;
+    T.fail_out = h->d_fail;
+    T.rescue_next = h->d_rescue_next;
+    T.ctrl = ctrl;
+    return T;
+}
+
+// one full resident step: state[cur] -> state[cur^1]
+int launch_resident_step(dmpcb200_t* h, int cur, bool record, Ctrl* ctrl, cudaStream_t s, cudaEvent_t* evs) {
+    const int nx = cur ^ 1;
+    StepArgs A = make_args(h, h->n0, h->n1, h->d_st[cur][0], h->d_st[cur][1], h->d_st[cur][2], h->d_l[cur],
+                           h->d_l[nx], h->d_st[nx][0], h->d_st[nx][1], h->d_st[nx][2], nullptr, nullptr,
+                           h->d_status, h->d_diag, true, ctrl);
+    if (evs) CK(cudaEventRecord(evs[0], s));
+    CK(launch_scan(h, A, s));
+    if (evs) CK(cudaEventRecord(evs[1], s));
+    CK(launch_qp(h, A, s));
+    if (evs) CK(cudaEventRecord(evs[2], s));
+    TailArgs T = make_tail(h, h->d_st[nx][0], 3, h->d_status, h->d_st[nx][0], h->d_st[nx][1], h->d_st[nx][2],
+                           record, ctrl);
+    tail_kernel<<<1, 256, 0, s>>>(T);
+    CK(cudaGetLastError());
+    if (evs) CK(cudaEventRecord(evs[3], s));
+    return 0;
+}
+
+int ensure_events(dmpcb200_t* h, size_t n) {
+    while (h->ev.size() < n) {
+        cudaEvent_t e;
+        CK(cudaEventCreate(&e));
+        h->ev.push_back(e);
+    }
+    return 0;
+}
+
+int ensure_pin(dmpcb200_t* h, size_t n) {
+    if (h->h_pin_n >= n) return 0;
+    if (h->h_pin) cudaFreeHost(h->h_pin);
+    h->h_pin = nullptr;
+    h->h_pin_n = 0;
+    CK(cudaMallocHost((void**)&h->h_pin, n * sizeof(double)));
+    h->h_pin_n = n;
+    return 0;
+}
+
+void drop_graph(dmpcb200_t* h) {
+    if (h->graph) cudaGraphExecDestroy(h->graph);
+    h->graph = nullptr;
+}
+
+int check_arch(int device) {
+    cudaDeviceProp prop;
+    CK(cudaGetDeviceProperties(&prop, device));
+    if (prop.major != 10)
+        return fail(DMPCB200_ERR_CUDA, std::string("device ") + prop.name +
+                                           " is not sm_100: libdmpc_b200 is built for B200 (sm_100a) only");
+    return 0;
+}
+
+}  // namespace
+
+extern "C" {
+
+int dmpcb200_abi_version(void) { return DMPCB200_ABI_VERSION; }
+const char* dmpcb200_last_error(void) { return g_err.c_str(); }
+int dmpcb200_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) {
+        cudaGetLastError();
+        return 0;
+    }
+    return n;
+}
+
+void dmpcb200_default_params(dmpcb200_params* p, int variant) {
+    // test/failure_rate.m:7-27, dmpc_soft_bound.m:7-30, solveSoftDMPCbound.m, dmpc/cpp/dmpc.h:50-67
+    std::memset(p, 0, sizeof(*p));
+    p->K = 15;
+    p->variant = variant;
+    p->max_tries = 30;
+    p->neigh_mode = 0;
+    p->h = 0.2;
+    p->rmin = 0.35;
+    p->c = 2.0;
+    p->alim = 1.0;
+    p->Q1 = 1000.0;
+    p->S1 = (variant == DMPCB200_HARD || variant == DMPCB200_HARD_ONDEMAND) ? 10.0 : 100.0;  // dmpc_hard.m
+    p->term = -5e4;
+    p->Q_far = 1000.0;
+    p->Q_near = 10000.0;
+    p->S_free = 10.0;
+    p->near_radius = 1.0;
+    p->slack_lb = (variant == DMPCB200_SOFT_BOUND2) ? -0.01 : -0.05;
+    p->neigh_factor = 3.0;
+    p->coll_tol = 0.05;
+    p->inb_tol = 0.05;
+    p->hard_radius = 1.0;
+    p->init_div = 10.0;
+    p->goal_tol = 0.01;
+}
+
+int dmpcb200_model_mats(double h, int K, double* A_p, double* A_v, double* A_initp, double* Delta) {
+    if (K < 1 || K > 32 || !(h > 0)) return fail(DMPCB200_ERR_ARG, "model_mats: need 1 <= K <= 32, h > 0");
+    model_mats(h, K, A_p, A_v, A_initp, Delta);
+    return 0;
+}
+
+int dmpcb200_create(const dmpcb200_params* p, int N, int n0, int n1, int device, int max_rows, dmpcb200_t** out) {
+    if (!p || !out) return fail(DMPCB200_ERR_ARG, "create: null argument");
+    *out = nullptr;
+    if (p->K < 1 || p->K > 32) return fail(DMPCB200_ERR_ARG, "create: horizon K must be in 1..32");
+    if (N < 1 || n0 < 0 || n1 > N || n0 >= n1) return fail(DMPCB200_ERR_ARG, "create: bad agent range");
+    if (p->variant < 0 || p->variant > 3) return fail(DMPCB200_ERR_ARG, "create: unknown variant");
+    if (!(p->h > 0) || !(p->rmin > 0) || !(p->c > 0) || !(p->alim > 0))
+        return fail(DMPCB200_ERR_ARG, "create: h, rmin, c, alim must be positive");
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+        cudaGetLastError();
+        return fail(DMPCB200_ERR_CUDA, "create: no CUDA device (libdmpc_b200 has no CPU path)");
+    }
+    if (device < 0 || device >= ndev) return fail(DMPCB200_ERR_ARG, "create: bad device index");
+    if (int rc = check_arch(device)) return rc;
+    CK(cudaSetDevice(device));
+
+    dmpcb200_t* h = new dmpcb200_handle();
+    h->prm = *p;
+    h->N = N;
+    h->n0 = n0;
+    h->n1 = n1;
+    h->NL = n1 - n0;
+    h->K = p->K;
+    h->device = device;
+    h->Npad = round_up(N, kTile);
+    DevParams& D = h->dp;
+    D.K = p->K; D.variant = p->variant; D.max_tries = p->max_tries; D.neigh_mode = p->neigh_mode; D.N = N;
+    D.h = p->h; D.rmin = p->rmin; D.c = p->c; D.alim = p->alim; D.Q1 = p->Q1; D.S1 = p->S1; D.term = p->term;
+    D.Q_far = p->Q_far; D.Q_near = p->Q_near; D.S_free = p->S_free; D.near_radius = p->near_radius;
+    D.slack_lb = p->slack_lb; D.neigh_factor = p->neigh_factor; D.coll_tol = p->coll_tol;
+    D.inb_tol = p->inb_tol; D.hard_radius = p->hard_radius;
+    for (int x = 0; x < 3; ++x) { D.pmin[x] = -1e30; D.pmax[x] = 1e30; }
+
+    const int K = p->K, n3 = 3 * K;
+    // capacities
+    if (max_rows > 0) h->RMAX = max_rows;
+    else if (p->variant == DMPCB200_HARD) h->RMAX = std::min(K * std::max(N - 1, 1), 1024);
+    else h->RMAX = std::min(std::max(N - 1, 1), 256);
+    h->RMAX = round_up(h->RMAX, 2);
+    h->RCAP = 64;
+    const int qwant = round_up(n3 + 16, 8);
+    const size_t smem_max = 227 * 1024;
+    h->W = 0;
+    for (int w : {4, 3, 2, 1})
+        if (qp_smem_bytes(K, w, qwant, h->RCAP) <= smem_max) {
+            h->W = w;
+            break;
+        }
+    if (!h->W) {
+        delete h;
+        return fail(DMPCB200_ERR_ARG, "create: horizon too long for the on-chip QP workspace");
+    }
+    h->QMAX = qwant;
+    h->QBIG = round_up(n3 + 2 * std::min(h->RMAX, 256) + 8, 8);
+    h->n_rescue = 64;
+    h->rescue_bytes = align_up(agent_smem_bytes(K, h->QBIG, h->RCAP), 256);
+
+    auto bail = [&](cudaError_t e, const char* what) {
+        std::string m = std::string("create: ") + what + ": " + cudaGetErrorString(e);
+        dmpcb200_destroy(h);
+        return fail(DMPCB200_ERR_CUDA, m);
+    };
+    cudaError_t e;
+    if ((e = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking)) != cudaSuccess) return bail(e, "stream");
+    // tables
+    std::vector<double> tab;
+    const double qs[3][2] = {{p->Q_far, p->S_free}, {p->Q_near, p->S_free}, {p->Q1, p->S1}};
+    build_tables(p->h, K, qs, tab);
+    if ((e = dalloc(&h->d_tab, tab.size())) != cudaSuccess) return bail(e, "tables");
+    if ((e = cudaMemcpy(h->d_tab, tab.data(), tab.size() * sizeof(double), cudaMemcpyHostToDevice)) != cudaSuccess)
+        return bail(e, "tables copy");
+    const size_t lN = (size_t)h->Npad * n3;
+    for (int b = 0; b < 2; ++b) {
+        if ((e = dalloc(&h->d_l[b], lN)) != cudaSuccess) return bail(e, "horizons");
+        for (int s = 0; s < 3; ++s)
+            if ((e = dalloc(&h->d_st[b][s], 3 * (size_t)N)) != cudaSuccess) return bail(e, "state");
+    }
+    if ((e = dalloc(&h->d_pf, 3 * (size_t)N)) != cudaSuccess) return bail(e, "goals");
+    if ((e = dalloc(&h->d_vhor, (size_t)N * n3)) != cudaSuccess) return bail(e, "v_hor");
+    if ((e = dalloc(&h->d_ahor, (size_t)N * n3)) != cudaSuccess) return bail(e, "a_hor");
+    if ((e = dalloc(&h->d_status, (size_t)N)) != cudaSuccess) return bail(e, "status");
+    if ((e = dalloc(&h->d_diag, (size_t)N)) != cudaSuccess) return bail(e, "diag");
+    const size_t NL = h->NL;
+    if ((e = dalloc(&h->d_nearmask, NL * h->Npad)) != cudaSuccess) return bail(e, "nearmask");
+    if ((e = dalloc(&h->d_scan, NL)) != cudaSuccess) return bail(e, "scan");
+    if ((e = dalloc(&h->d_grow, NL * 5 * h->RMAX)) != cudaSuccess) return bail(e, "rows");
+    if ((e = dalloc(&h->d_gkc, NL * h->RMAX)) != cudaSuccess) return bail(e, "rows kc");
+    if ((e = dalloc(&h->d_gidx, NL * h->RMAX)) != cudaSuccess) return bail(e, "rows idx");
+    if ((e = dalloc(&h->d_gscr_d, NL * 3 * h->RMAX)) != cudaSuccess) return bail(e, "row scratch");
+    if ((e = dalloc(&h->d_gscr_i, NL * 4 * h->RMAX)) != cudaSuccess) return bail(e, "row scratch");
+    if ((e = dalloc(&h->d_rescue, h->rescue_bytes * h->n_rescue)) != cudaSuccess) return bail(e, "rescue");
+    if ((e = dalloc(&h->d_rescue_next, 1)) != cudaSuccess) return bail(e, "rescue counter");
+    if ((e = dalloc(&h->d_ctrl, 1)) != cudaSuccess) return bail(e, "ctrl");
+    if ((e = dalloc(&h->d_goal, 2)) != cudaSuccess) return bail(e, "goal");
+    if ((e = dalloc(&h->d_fail, 1)) != cudaSuccess) return bail(e, "fail");
+    if ((e = dalloc(&h->d_u8, 2 * (size_t)N)) != cudaSuccess) return bail(e, "u8");
+    if ((e = dalloc(&h->d_small, 64)) != cudaSuccess) return bail(e, "small");
+    if ((e = dalloc(&h->d_ismall, 16)) != cudaSuccess) return bail(e, "ismall");
+    *out = h;
+    return 0;
+}
+
+void dmpcb200_destroy(dmpcb200_t* h) {
+    if (!h) return;
+    cudaSetDevice(h->device);
+    if (h->stream) cudaStreamSynchronize(h->stream);
+    drop_graph(h);
+    for (auto e : h->ev) cudaEventDestroy(e);
+    cudaFree(h->d_tab);
+    for (int b = 0; b < 2; ++b) {
+        cudaFree(h->d_l[b]);
+        for (int s = 0; s < 3; ++s) cudaFree(h->d_st[b][s]);
+    }
+    cudaFree(h->d_pf); cudaFree(h->d_vhor); cudaFree(h->d_ahor); cudaFree(h->d_status); cudaFree(h->d_diag);
+    cudaFree(h->d_nearmask); cudaFree(h->d_scan); cudaFree(h->d_grow); cudaFree(h->d_gkc); cudaFree(h->d_gidx);
+    cudaFree(h->d_gscr_d); cudaFree(h->d_gscr_i); cudaFree(h->d_rescue); cudaFree(h->d_rescue_next);
+    cudaFree(h->d_ctrl); cudaFree(h->d_goal); cudaFree(h->d_fail); cudaFree(h->d_u8); cudaFree(h->d_small);
+    cudaFree(h->d_ismall);
+    for (int s = 0; s < 3; ++s) cudaFree(h->d_traj[s]);
+    cudaFree(h->d_hist);
+    if (h->h_pin) cudaFreeHost(h->h_pin);
+    if (h->stream) cudaStreamDestroy(h->stream);
+    delete h;
+}
+
+int dmpcb200_set_bounds(dmpcb200_t* h, const double* pmin, const double* pmax) {
+    if (!h || !pmin || !pmax) return fail(DMPCB200_ERR_ARG, "set_bounds: null argument");
+    for (int x = 0; x < 3; ++x) {
+        if (!(pmin[x] < pmax[x])) return fail(DMPCB200_ERR_ARG, "set_bounds: need pmin < pmax");
+        h->dp.pmin[x] = pmin[x];
+        h->dp.pmax[x] = pmax[x];
+    }
+    h->have_bounds = true;
+    drop_graph(h);
+    return 0;
+}
+
+int dmpcb200_set_goals(dmpcb200_t* h, const double* pf) {
+    if (!h || !pf) return fail(DMPCB200_ERR_ARG, "set_goals: null argument");
+    if (int rc = ensure_device(h)) return rc;
+    CK(cudaMemcpyAsync(h->d_pf, pf, 3 * (size_t)h->N * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    h->have_goals = true;
+    return 0;
+}
+
+int dmpcb200_init_horizons(dmpcb200_t* h, const double* po, double* l, double* p1, double* v1, double* a1) {
+    if (!h || !po) return fail(DMPCB200_ERR_ARG, "init_horizons: null argument");
+    if (!h->have_goals) return fail(DMPCB200_ERR_STATE, "init_horizons: call dmpcb200_set_goals first");
+    if (int rc = ensure_device(h)) return rc;
+    const int N = h->N, K = h->K;
+    cudaStream_t s = h->stream;
+    h->cur = 0;
+    double* d_po = h->d_st[1][0];  // staging: the other state buffer
+    CK(cudaMemcpyAsync(d_po, po, 3 * (size_t)N * sizeof(double), cudaMemcpyHostToDevice, s));
+    init_kernel<<<(N + 127) / 128, 128, 0, s>>>(N, K, h->prm.h, h->prm.init_div, d_po, h->d_pf, h->d_l[0],
+                                                h->d_st[0][0], h->d_st[0][1], h->d_st[0][2]);
+    CK(cudaGetLastError());
+    if (l) CK(cudaMemcpyAsync(l, h->d_l[0], (size_t)N * 3 * K * sizeof(double), cudaMemcpyDeviceToHost, s));
+    if (p1) CK(cudaMemcpyAsync(p1, h->d_st[0][0], 3 * (size_t)N * sizeof(double), cudaMemcpyDeviceToHost, s));
+    if (v1) CK(cudaMemcpyAsync(v1, h->d_st[0][1], 3 * (size_t)N * sizeof(double), cudaMemcpyDeviceToHost, s));
+    if (a1) CK(cudaMemcpyAsync(a1, h->d_st[0][2], 3 * (size_t)N * sizeof(double), cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    h->have_init = true;
+    return 0;
+}
+
+int dmpcb200_step_dev(dmpcb200_t* h, const double* d_pk, const double* d_vk, const double* d_ak,
+                      const double* d_l_prev, double* d_l_new, double* d_p1, double* d_v1, double* d_a1,
+                      double* d_v_hor, double* d_a_hor, int32_t* d_status, dmpcb200_diag* d_diag, void* stream) {
+    if (!h || !d_pk || !d_vk || !d_ak || !d_l_prev || !d_l_new || !d_p1 || !d_v1 || !d_a1 || !d_status)
+        return fail(DMPCB200_ERR_ARG, "step_dev: null argument");
+    if (!h->have_goals || !h->have_bounds)
+        return fail(DMPCB200_ERR_STATE, "step_dev: set_goals and set_bounds first");
+    if (((uintptr_t)d_l_prev & 15) != 0) return fail(DMPCB200_ERR_ARG, "step_dev: l_prev must be 16-byte aligned");
+    if (int rc = ensure_device(h)) return rc;
+    cudaStream_t s = (cudaStream_t)stream;
+    const bool padded = (d_l_prev == h->d_l[0] || d_l_prev == h->d_l[1]);
+    StepArgs A = make_args(h, h->n0, h->n1, d_pk, d_vk, d_ak, d_l_prev, d_l_new, d_p1, d_v1, d_a1, d_v_hor, d_a_hor,
+                           d_status, reinterpret_cast<AgentDiag*>(d_diag), padded, nullptr);
+    CK(cudaMemsetAsync(h->d_rescue_next, 0, sizeof(int), s));
+    CK(launch_scan(h, A, s));
+    CK(launch_qp(h, A, s));
+    h->launches = 2;
+    return 0;
+}
+
+int dmpcb200_goal_dev(dmpcb200_t* h, const double* d_p, int ld, double* d_out, void* stream) {
+    if (!h || !d_p || !d_out || ld < 3) return fail(DMPCB200_ERR_ARG, "goal_dev: bad argument");
+    if (int rc = ensure_device(h)) return rc;
+    TailArgs T = make_tail(h, d_p, ld, nullptr, nullptr, nullptr, nullptr, false, nullptr);
+    T.goal_out = d_out;
+    T.fail_out = nullptr;
+    T.rescue_next = nullptr;
+    tail_kernel<<<1, 256, 0, (cudaStream_t)stream>>>(T);
+    CK(cudaGetLastError());
+    return 0;
+}
+
+int dmpcb200_reached_goal(dmpcb200_t* h, const double* p, const double* pf, double tol, double* max_dist,
+                          int32_t* pass) {
+    if (!h || !p || !pf) return fail(DMPCB200_ERR_ARG, "reached_goal: null argument");
+    if (int rc = ensure_device(h)) return rc;
+    cudaStream_t s = h->stream;
+    const size_t sN = 3 * (size_t)h->N * sizeof(double);
+    const int nx = h->cur ^ 1;  // staging: the state buffers that the next step overwrites anyway
+    CK(cudaMemcpyAsync(h->d_st[nx][0], p, sN, cudaMemcpyHostToDevice, s));
+    CK(cudaMemcpyAsync(h->d_st[nx][1], pf, sN, cudaMemcpyHostToDevice, s));
+    TailArgs T = make_tail(h, h->d_st[nx][0], 3, nullptr, nullptr, nullptr, nullptr, false, nullptr);
+    T.pf = h->d_st[nx][1];
+    T.goal_tol = tol;
+    T.fail_out = nullptr;
+    T.rescue_next = nullptr;
+    tail_kernel<<<1, 256, 0, s>>>(T);
+    CK(cudaGetLastError());
+    double out[2] = {0, 0};
+    CK(cudaMemcpyAsync(out, h->d_goal, 2 * sizeof(double), cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    if (max_dist) *max_dist = out[0];
+    if (pass) *pass = out[1] != 0.0;
+    h->launches = 1;
+    return 0;
+}
+
+int dmpcb200_step(dmpcb200_t* h, const double* pk, const double* vk, const double* ak, const double* l_prev,
+                  double* l_new, double* p1, double* v1, double* a1, double* v_hor, double* a_hor,
+                  int32_t* status, dmpcb200_diag* diag, int32_t* first_fail) {
+    if (!h || !pk || !vk || !ak || !l_prev) return fail(DMPCB200_ERR_ARG, "step: null input");
+    if (!h->have_goals || !h->have_bounds) return fail(DMPCB200_ERR_STATE, "step: set_goals and set_bounds first");
+    if (int rc = ensure_device(h)) return rc;
+    const int N = h->N, K = h->K, n3 = 3 * K, n0 = h->n0, NL = h->NL;
+    cudaStream_t s = h->stream;
+    const size_t sN = 3 * (size_t)N * sizeof(double), lB = (size_t)N * n3 * sizeof(double);
+    const int c = 0, nx = 1;
+    CK(cudaMemcpyAsync(h->d_st[c][0], pk, sN, cudaMemcpyHostToDevice, s));
+    CK(cudaMemcpyAsync(h->d_st[c][1], vk, sN, cudaMemcpyHostToDevice, s));
+    CK(cudaMemcpyAsync(h->d_st[c][2], ak, sN, cudaMemcpyHostToDevice, s));
+    CK(cudaMemcpyAsync(h->d_l[c], l_prev, lB, cudaMemcpyHostToDevice, s));
+    if (int rc = ensure_events(h, 4)) return rc;
+    StepArgs A = make_args(h, h->n0, h->n1, h->d_st[c][0], h->d_st[c][1], h->d_st[c][2], h->d_l[c], h->d_l[nx],
+                           h->d_st[nx][0], h->d_st[nx][1], h->d_st[nx][2], (v_hor ? h->d_vhor : nullptr),
+                           (a_hor ? h->d_ahor : nullptr), h->d_status, h->d_diag, true, nullptr);
+    CK(cudaEventRecord(h->ev[0], s));
+    CK(launch_scan(h, A, s));
+    CK(cudaEventRecord(h->ev[1], s));
+    CK(launch_qp(h, A, s));
+    CK(cudaEventRecord(h->ev[2], s));
+    TailArgs T = make_tail(h, nullptr, 3, h->d_status, nullptr, nullptr, nullptr, false, nullptr);
+    tail_kernel<<<1, 256, 0, s>>>(T);
+    CK(cudaGetLastError());
+    CK(cudaEventRecord(h->ev[3], s));
+    // outputs: only the rows of agents n0..n1-1
+    const size_t o3 = 3 * (size_t)n0, b3 = 3 * (size_t)NL * sizeof(double);
+    const size_t oL = (size_t)n0 * n3, bL = (size_t)NL * n3 * sizeof(double);
+    if (l_new) CK(cudaMemcpyAsync(l_new + oL, h->d_l[nx] + oL, bL, cudaMemcpyDeviceToHost, s));
+    if (p1) CK(cudaMemcpyAsync(p1 + o3, h->d_st[nx][0] + o3, b3, cudaMemcpyDeviceToHost, s));
+    if (v1) CK(cudaMemcpyAsync(v1 + o3, h->d_st[nx][1] + o3, b3, cudaMemcpyDeviceToHost, s));
+    if (a1) CK(cudaMemcpyAsync(a1 + o3, h->d_st[nx][2] + o3, b3, cudaMemcpyDeviceToHost, s));
+    if (v_hor) CK(cudaMemcpyAsync(v_hor + oL, h->d_vhor + oL, bL, cudaMemcpyDeviceToHost, s));
+    if (a_hor) CK(cudaMemcpyAsync(a_hor + oL, h->d_ahor + oL, bL, cudaMemcpyDeviceToHost, s));
+    if (status) CK(cudaMemcpyAsync(status + n0, h->d_status + n0, (size_t)NL * sizeof(int), cudaMemcpyDeviceToHost, s));
+    if (diag) CK(cudaMemcpyAsync(diag + n0, h->d_diag + n0, (size_t)NL * sizeof(AgentDiag), cudaMemcpyDeviceToHost, s));
+    int ff = -1;
+    CK(cudaMemcpyAsync(&ff, h->d_fail, sizeof(int), cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    if (first_fail) *first_fail = ff;
+    float a = 0, b = 0, w = 0;
+    cudaEventElapsedTime(&a, h->ev[0], h->ev[1]);
+    cudaEventElapsedTime(&b, h->ev[1], h->ev[2]);
+    cudaEventElapsedTime(&w, h->ev[0], h->ev[3]);
+    h->t_ms[0] = a;
+    h->t_ms[1] = b;
+    h->t_ms[2] = w;
+    h->launches = 3;
+    h->cur = 0;
+    return 0;
+}
+
+int dmpcb200_run(dmpcb200_t* h, int max_steps, int stop_on_fail, int mode, double* traj_p, double* traj_v,
+                 double* traj_a, int32_t* status_hist, int32_t* steps_done, int32_t* reached,
+                 int32_t* first_fail_step, int32_t* first_fail_agent) {
+    if (!h || max_steps < 1) return fail(DMPCB200_ERR_ARG, "run: bad argument");
+    if (h->n0 != 0 || h->n1 != h->N) return fail(DMPCB200_ERR_STATE, "run: needs a handle that owns all agents");
+    if (!h->have_init || !h->have_bounds) return fail(DMPCB200_ERR_STATE, "run: set_bounds and init_horizons first");
+    if (int rc = ensure_device(h)) return rc;
+    const int N = h->N;
+    cudaStream_t s = h->stream;
+    const bool record = traj_p || traj_v || traj_a || status_hist;
+    const bool timed = (mode & 1) != 0;     // per-kernel CUDA events, no graph
+    const bool no_graph = (mode & 2) != 0;  // plain launches
+    if (record) {
+        if (h->traj_S < max_steps || (status_hist && !h->d_hist)) {
+            drop_graph(h);
+            for (int i = 0; i < 3; ++i) {
+                cudaFree(h->d_traj[i]);
+                h->d_traj[i] = nullptr;
+            }
+            cudaFree(h->d_hist);
+            h->d_hist = nullptr;
+            h->traj_S = max_steps;
+            for (int i = 0; i < 3; ++i) CK(dalloc(&h->d_traj[i], 3 * (size_t)(max_steps + 1) * N));
+            CK(dalloc(&h->d_hist, (size_t)max_steps * N));
+        }
+        if (h->hist_on != (status_hist != nullptr)) drop_graph(h);
+        h->hist_on = status_hist != nullptr;
+        // column 0 = current state
+        for (int i = 0; i < 3; ++i)
+            CK(cudaMemcpy2DAsync(h->d_traj[i], 3 * (size_t)(h->traj_S + 1) * sizeof(double), h->d_st[h->cur][i],
+                                 3 * sizeof(double), 3 * sizeof(double), N, cudaMemcpyDeviceToDevice, s));
+    }
+    Ctrl c;
+    std::memset(&c, 0, sizeof(c));
+    c.fail_step = -1;
+    c.fail_agent = -1;
+    c.stop_on_fail = stop_on_fail;
+    c.max_steps = max_steps;
+    CK(cudaMemcpyAsync(h->d_ctrl, &c, sizeof(c), cudaMemcpyHostToDevice, s));
+    CK(cudaMemsetAsync(h->d_rescue_next, 0, sizeof(int), s));
+    if (int rc = ensure_events(h, timed ? 4 * (size_t)max_steps + 2 : 2)) return rc;
+    Ctrl hc = c;
+    const int start_cur = h->cur;
+    int issued = 0;
+    if (!timed && !no_graph) {
+        if (!h->graph || h->graph_record != record) {
+            drop_graph(h);
+            cudaGraph_t g;
+            CK(cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal));
+            int rc = launch_resident_step(h, 0, record, h->d_ctrl, s, nullptr);
+            if (!rc) rc = launch_resident_step(h, 1, record, h->d_ctrl, s, nullptr);
+            cudaError_t e = cudaStreamEndCapture(s, &g);
+            if (rc) return rc;
+            CK(e);
+            CK(cudaGraphInstantiate(&h->graph, g, 0));
+            cudaGraphDestroy(g);
+            h->graph_record = record;
+        }
+    }
+    CK(cudaEventRecord(h->ev[0], s));
+    if (!timed && !no_graph && start_cur == 0) {
+        const int check_every = 8;  // graph launches (= 16 steps) between looks at the control word
+        int since = 0;
+        while (issued < max_steps) {
+            CK(cudaGraphLaunch(h->graph, s));
+            issued += 2;
+            if (++since == check_every && issued < max_steps) {
+                since = 0;
+                CK(cudaMemcpyAsync(&hc, h->d_ctrl, sizeof(hc), cudaMemcpyDeviceToHost, s));
+                CK(cudaStreamSynchronize(s));
+                if (hc.done) break;
+            }
+        }
+    } else {
+        int cur = start_cur;
+        while (issued < max_steps) {
+            cudaEvent_t* evs = timed ? &h->ev[2 + 4 * (size_t)issued] : nullptr;
+            if (int rc = launch_resident_step(h, cur, record, h->d_ctrl, s, evs)) return rc;
+            cur ^= 1;
+            ++issued;
+            if ((issued & 15) == 0 && issued < max_steps) {
+                CK(cudaMemcpyAsync(&hc, h->d_ctrl, sizeof(hc), cudaMemcpyDeviceToHost, s));
+                CK(cudaStreamSynchronize(s));
+                if (hc.done) break;
+            }
+        }
+    }
+    CK(cudaEventRecord(h->ev[1], s));
+    CK(cudaMemcpyAsync(&hc, h->d_ctrl, sizeof(hc), cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    const int steps = hc.step;
+    h->cur = start_cur ^ (steps & 1);
+    float whole = 0;
+    cudaEventElapsedTime(&whole, h->ev[0], h->ev[1]);
+    h->t_ms[0] = h->t_ms[1] = 0;
+    h->t_ms[2] = steps ? whole / steps : 0;
+    if (timed && steps) {
+        double a = 0, b = 0, w = 0;
+        for (int i = 0; i < steps; ++i) {
+            float x;
+            cudaEvent_t* evs = &h->ev[2 + 4 * (size_t)i];
+            cudaEventElapsedTime(&x, evs[0], evs[1]);
+            a += x;
+            cudaEventElapsedTime(&x, evs[1], evs[2]);
+            b += x;
+            cudaEventElapsedTime(&x, evs[0], evs[3]);
+            w += x;
+        }
+        h->t_ms[0] = a / steps;
+        h->t_ms[1] = b / steps;
+        h->t_ms[2] = w / steps;
+    }
+    h->launches = 3 * (int64_t)steps;
+    if (record) {
+        const size_t cols = (size_t)(steps + 1);
+        double* outs[3] = {traj_p, traj_v, traj_a};
+        for (int i = 0; i < 3; ++i)
+            if (outs[i])
+                // device 3 x (S+1) x N -> host 3 x (max_steps+1) x N, first steps+1 columns
+                CK(cudaMemcpy2DAsync(outs[i], 3 * (size_t)(max_steps + 1) * sizeof(double), h->d_traj[i],
+                                     3 * (size_t)(h->traj_S + 1) * sizeof(double), 3 * cols * sizeof(double), N,
+                                     cudaMemcpyDeviceToHost, s));
+        if (status_hist)
+            CK(cudaMemcpyAsync(status_hist, h->d_hist, (size_t)steps * N * sizeof(int), cudaMemcpyDeviceToHost, s));
+        CK(cudaStreamSynchronize(s));
+    }
+    if (steps_done) *steps_done = steps;
+    if (reached) *reached = hc.reached;
+    if (first_fail_step) *first_fail_step = hc.fail_step;
+    if (first_fail_agent) *first_fail_agent = hc.fail_agent;
+    return 0;
+}
+
+int dmpcb200_get_state(dmpcb200_t* h, double* l, double* pk, double* vk, double* ak, int32_t* status,
+                       dmpcb200_diag* diag) {
+    if (!h) return fail(DMPCB200_ERR_ARG, "get_state: null handle");
+    if (int rc = ensure_device(h)) return rc;
+    const int N = h->N, n3 = 3 * h->K;
+    cudaStream_t s = h->stream;
+    const size_t sN = 3 * (size_t)N * sizeof(double);
+    if (l) CK(cudaMemcpyAsync(l, h->d_l[h->cur], (size_t)N * n3 * sizeof(double), cudaMemcpyDeviceToHost, s));
+    if (pk) CK(cudaMemcpyAsync(pk, h->d_st[h->cur][0], sN, cudaMemcpyDeviceToHost, s));
+    if (vk) CK(cudaMemcpyAsync(vk, h->d_st[h->cur][1], sN, cudaMemcpyDeviceToHost, s));
+    if (ak) CK(cudaMemcpyAsync(ak, h->d_st[h->cur][2], sN, cudaMemcpyDeviceToHost, s));
+    if (status) CK(cudaMemcpyAsync(status, h->d_status, (size_t)N * sizeof(int), cudaMemcpyDeviceToHost, s));
+    if (diag) CK(cudaMemcpyAsync(diag, h->d_diag, (size_t)N * sizeof(AgentDiag), cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    return 0;
+}
+
+int dmpcb200_set_state(dmpcb200_t* h, const double* l, const double* pk, const double* vk, const double* ak) {
+    if (!h || !l || !pk || !vk || !ak) return fail(DMPCB200_ERR_ARG, "set_state: null argument");
+    if (!h->have_goals) return fail(DMPCB200_ERR_STATE, "set_state: call dmpcb200_set_goals first");
+    if (int rc = ensure_device(h)) return rc;
+    const int N = h->N, n3 = 3 * h->K;
+    cudaStream_t s = h->stream;
+    const size_t sN = 3 * (size_t)N * sizeof(double);
+    h->cur = 0;
+    CK(cudaMemcpyAsync(h->d_l[0], l, (size_t)N * n3 * sizeof(double), cudaMemcpyHostToDevice, s));
+    CK(cudaMemcpyAsync(h->d_st[0][0], pk, sN, cudaMemcpyHostToDevice, s));
+    CK(cudaMemcpyAsync(h->d_st[0][1], vk, sN, cudaMemcpyHostToDevice, s));
+    CK(cudaMemcpyAsync(h->d_st[0][2], ak, sN, cudaMemcpyHostToDevice, s));
+    CK(cudaStreamSynchronize(s));
+    h->have_init = true;
+    return 0;
+}
+
+int dmpcb200_solve_agent(dmpcb200_t* h, const double* po, const double* pf, const double* vo, const double* ao,
+                         int n, const double* l, double* p, double* v, double* a, int32_t* status,
+                         dmpcb200_diag* diag) {
+    if (!h || !po || !pf || !vo || !ao || !l) return fail(DMPCB200_ERR_ARG, "solve_agent: null argument");
+    if (n < 0 || n >= h->N) return fail(DMPCB200_ERR_ARG, "solve_agent: agent index out of range");
+    if (!h->have_bounds) return fail(DMPCB200_ERR_STATE, "solve_agent: call dmpcb200_set_bounds first");
+    if (int rc = ensure_device(h)) return rc;
+    const int N = h->N, K = h->K, n3 = 3 * K;
+    cudaStream_t s = h->stream;
+    const size_t b3 = 3 * sizeof(double);
+    CK(cudaMemcpyAsync(h->d_st[0][0] + 3 * n, po, b3, cudaMemcpyHostToDevice, s));
+    CK(cudaMemcpyAsync(h->d_st[0][1] + 3 * n, vo, b3, cudaMemcpyHostToDevice, s));
+    CK(cudaMemcpyAsync(h->d_st[0][2] + 3 * n, ao, b3, cudaMemcpyHostToDevice, s));
+    CK(cudaMemcpyAsync(h->d_pf + 3 * n, pf, b3, cudaMemcpyHostToDevice, s));
+    CK(cudaMemcpyAsync(h->d_l[0], l, (size_t)N * n3 * sizeof(double), cudaMemcpyHostToDevice, s));
+    CK(cudaMemsetAsync(h->d_rescue_next, 0, sizeof(int), s));
+    // a batch of one: scratch slot 0 (local index = n - n0 with n0 = n)
+    StepArgs A = make_args(h, n, n + 1, h->d_st[0][0], h->d_st[0][1], h->d_st[0][2], h->d_l[0], h->d_l[1],
+                           h->d_st[1][0], h->d_st[1][1], h->d_st[1][2], h->d_vhor, h->d_ahor, h->d_status,
+                           h->d_diag, true, nullptr);
+    CK(launch_scan(h, A, s));
+    CK(launch_qp(h, A, s));
+    int st = 0;
+    CK(cudaMemcpyAsync(&st, h->d_status + n, sizeof(int), cudaMemcpyDeviceToHost, s));
+    if (p) CK(cudaMemcpyAsync(p, h->d_l[1] + (size_t)n * n3, n3 * sizeof(double), cudaMemcpyDeviceToHost, s));
+    if (v) CK(cudaMemcpyAsync(v, h->d_vhor + (size_t)n * n3, n3 * sizeof(double), cudaMemcpyDeviceToHost, s));
+    if (a) CK(cudaMemcpyAsync(a, h->d_ahor + (size_t)n * n3, n3 * sizeof(double), cudaMemcpyDeviceToHost, s));
+    if (diag) CK(cudaMemcpyAsync(diag, h->d_diag + n, sizeof(AgentDiag), cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    if (status) *status = st;
+    h->have_goals = true;
+    h->launches = 2;
+    return 0;
+}
+
+int dmpcb200_check_coll(dmpcb200_t* h, const double* p3, const double* l, int n, int k, uint8_t* violation,
+                        uint8_t* viol_constr, double* min_dist, int32_t* any_violation) {
+    if (!h || !p3 || !l) return fail(DMPCB200_ERR_ARG, "check_coll: null argument");
+    if (k < 1 || k > h->K || n < 0 || n >= h->N) return fail(DMPCB200_ERR_ARG, "check_coll: k or n out of range");
+    if (int rc = ensure_device(h)) return rc;
+    const int N = h->N, n3 = 3 * h->K;
+    cudaStream_t s = h->stream;
+    CK(cudaMemcpyAsync(h->d_l[0], l, (size_t)N * n3 * sizeof(double), cudaMemcpyHostToDevice, s));
+    check_coll_kernel<<<1, 256, 0, s>>>(h->dp, p3[0], p3[1], p3[2], h->d_l[0], n, k, h->d_u8, h->d_u8 + N,
+                                        h->d_small, h->d_ismall);
+    CK(cudaGetLastError());
+    double md = 0;
+    int any = 0;
+    if (violation) CK(cudaMemcpyAsync(violation, h->d_u8, N, cudaMemcpyDeviceToHost, s));
+    if (viol_constr) CK(cudaMemcpyAsync(viol_constr, h->d_u8 + N, N, cudaMemcpyDeviceToHost, s));
+    CK(cudaMemcpyAsync(&md, h->d_small, sizeof(double), cudaMemcpyDeviceToHost, s));
+    CK(cudaMemcpyAsync(&any, h->d_ismall, sizeof(int), cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    if (min_dist) *min_dist = md;
+    if (any_violation) *any_violation = any;
+    h->launches = 1;
+    return 0;
+}
+
+int dmpcb200_coll_constr(dmpcb200_t* h, const double* p3, const double* po, const double* vo, int n, int k,
+                         const double* l, const uint8_t* mask, int cap, double* Ain, double* bin,
+                         double* prev_dist, int32_t* nrows) {
+    if (!h || !p3 || !po || !vo || !l || !nrows) return fail(DMPCB200_ERR_ARG, "coll_constr: null argument");
+    if (k < 1 || k > h->K || n < 0 || n >= h->N || cap < 1)
+        return fail(DMPCB200_ERR_ARG, "coll_constr: k, n or cap out of range");
+    if (h->prm.variant != DMPCB200_HARD && !mask)
+        return fail(DMPCB200_ERR_ARG, "coll_constr: mask required for this variant");
+    if (h->prm.variant == DMPCB200_SOFT_BOUND2 && k < 2)
+        return fail(DMPCB200_ERR_ARG, "coll_constr: bound2 has no constraint step for k = 1");
+    if (int rc = ensure_device(h)) return rc;
+    const int N = h->N, n3 = 3 * h->K;
+    cudaStream_t s = h->stream;
+    double *d_A = nullptr, *d_b = nullptr;
+    CK(cudaMemcpyAsync(h->d_l[0], l, (size_t)N * n3 * sizeof(double), cudaMemcpyHostToDevice, s));
+    if (mask) CK(cudaMemcpyAsync(h->d_u8, mask, N, cudaMemcpyHostToDevice, s));
+    CK(cudaMallocAsync((void**)&d_A, (size_t)cap * n3 * sizeof(double), s));
+    CK(cudaMallocAsync((void**)&d_b, 2 * (size_t)cap * sizeof(double), s));
+    CK(cudaMemsetAsync(d_A, 0, (size_t)cap * n3 * sizeof(double), s));
+    coll_constr_kernel<<<1, 32, 0, s>>>(h->dp, h->d_tab, p3[0], p3[1], p3[2], po[0], po[1], po[2], vo[0], vo[1],
+                                        vo[2], n, k, h->d_l[0], h->d_u8, cap, d_A, d_b, d_b + cap, h->d_ismall);
+    CK(cudaGetLastError());
+    int nr = 0;
+    CK(cudaMemcpyAsync(&nr, h->d_ismall, sizeof(int), cudaMemcpyDeviceToHost, s));
+    if (Ain) CK(cudaMemcpyAsync(Ain, d_A, (size_t)cap * n3 * sizeof(double), cudaMemcpyDeviceToHost, s));
+    if (bin) CK(cudaMemcpyAsync(bin, d_b, (size_t)cap * sizeof(double), cudaMemcpyDeviceToHost, s));
+    if (prev_dist) CK(cudaMemcpyAsync(prev_dist, d_b + cap, (size_t)cap * sizeof(double), cudaMemcpyDeviceToHost, s));
+    CK(cudaFreeAsync(d_A, s));
+    CK(cudaFreeAsync(d_b, s));
+    CK(cudaStreamSynchronize(s));
+    *nrows = nr;
+    h->launches = 1;
+    if (nr > cap) return fail(DMPCB200_ERR_ARG, "coll_constr: more rows than cap");
+    return 0;
+}
+
+int dmpcb200_prop_state(dmpcb200_t* h, int B, const double* po, const double* vo, const double* a, double* p,
+                        double* v) {
+    if (!h || B < 1 || !po || !vo || !a) return fail(DMPCB200_ERR_ARG, "prop_state: bad argument");
+    if (int rc = ensure_device(h)) return rc;
+    const int n3 = 3 * h->K;
+    cudaStream_t s = h->stream;
+    double* d = nullptr;
+    const size_t nb = (size_t)B * n3;
+    CK(cudaMallocAsync((void**)&d, (3 * nb + 6 * (size_t)B) * sizeof(double), s));
+    double *d_a = d, *d_p = d + nb, *d_v = d + 2 * nb, *d_po = d + 3 * nb, *d_vo = d_po + 3 * (size_t)B;
+    CK(cudaMemcpyAsync(d_a, a, nb * sizeof(double), cudaMemcpyHostToDevice, s));
+    CK(cudaMemcpyAsync(d_po, po, 3 * (size_t)B * sizeof(double), cudaMemcpyHostToDevice, s));
+    CK(cudaMemcpyAsync(d_vo, vo, 3 * (size_t)B * sizeof(double), cudaMemcpyHostToDevice, s));
+    prop_state_kernel<<<(int)((nb + 127) / 128), 128, 0, s>>>(B, h->K, h->d_tab, h->prm.h, d_po, d_vo, d_a, d_p, d_v);
+    CK(cudaGetLastError());
+    if (p) CK(cudaMemcpyAsync(p, d_p, nb * sizeof(double), cudaMemcpyDeviceToHost, s));
+    if (v) CK(cudaMemcpyAsync(v, d_v, nb * sizeof(double), cudaMemcpyDeviceToHost, s));
+    CK(cudaFreeAsync(d, s));
+    CK(cudaStreamSynchronize(s));
+    h->launches = 1;
+    return 0;
+}
+
+int dmpcb200_last_timing(dmpcb200_t* h, double* ms, int64_t* launches) {
+    if (!h) return fail(DMPCB200_ERR_ARG, "last_timing: null handle");
+    if (ms)
+        for (int i = 0; i < 3; ++i) ms[i] = h->t_ms[i];
+    if (launches) *launches = h->launches;
+    return 0;
+}
+
+void* dmpcb200_device_ptr(dmpcb200_t* h, int which) {
+    if (!h) return nullptr;
+    switch (which) {
+        case 0: return h->d_l[h->cur];
+        case 1: return h->d_l[h->cur ^ 1];
+        case 2: return h->d_st[h->cur][0];
+        case 3: return h->d_st[h->cur][1];
+        case 4: return h->d_st[h->cur][2];
+        case 5: return h->d_pf;
+        case 6: return h->d_status;
+        case 7: return h->d_goal;
+        case 8: return h->d_st[h->cur ^ 1][0];
+        case 9: return h->d_st[h->cur ^ 1][1];
+        case 10: return h->d_st[h->cur ^ 1][2];
+        case 11: return h->d_diag;
+        default: return nullptr;
+    }
+}
+
+int dmpcb200_swap_horizons(dmpcb200_t* h) {
+    if (!h) return fail(DMPCB200_ERR_ARG, "swap_horizons: null handle");
+    h->cur ^= 1;
+    return 0;
+}
+
+int dmpcb200_config(dmpcb200_t* h, int32_t* out8) {
+    if (!h || !out8) return fail(DMPCB200_ERR_ARG, "config: null argument");
+    out8[0] = h->W;
+    out8[1] = h->QMAX;
+    out8[2] = h->RCAP;
+    out8[3] = h->RMAX;
+    out8[4] = h->QBIG;
+    out8[5] = h->n_rescue;
+    out8[6] = (int32_t)qp_smem_bytes(h->K, h->W, h->QMAX, h->RCAP);
+    out8[7] = (int32_t)scan_smem_bytes(h->K, kScanW);
+    return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,476 @@
+// dmpc_kernels.cuh -- the sm_100a kernels of the DMPC step.
+//
+//   scan_kernel   (K1)  O(N^2 K) neighbour scan + collision-row build.  One warp per agent, W agents
+//                       per CTA; the neighbour-prediction buffer l (3 x K x N fp64, agent-major)
+//                       is streamed through shared memory in tiles of 32 agents by TMA bulk copies
+//                       (cp.async.bulk + mbarrier, double buffered) and every tile is shared by
+//                       the CTA's W agents.  Lane m of a warp owns neighbour m of the tile.
+//   qp_kernel     (K2)  batched per-agent QP.  One warp per agent; the constant tables of all
+//                       three weight sets are staged once per CTA by one TMA bulk copy; the
+//                       agent's rows, multipliers and Schur inverse live in shared memory
+//                       (qp_core.cuh).  Agents whose active set outgrows the on-chip capacity
+//                       re-solve in a global-memory rescue slot.
+//   tail_kernel   (K3)  ReachedGoal.m reduction, first failing agent, trajectory record, loop
+//                       control word (so the closed loop needs no host synchronisation).
+//   small kernels       initDMPC.m for all agents, the per-agent helper drop-ins.
+//
+// Reference: test/failure_rate.m:99-127 (loop body), solveSoftDMPCbound.m, CheckCollSoftDMPC.m,
+// CollConstrSoftDMPC.m, ReachedGoal.m, initDMPC.m, propStatedmpc.m (dmpc/matlab).
+#pragma once
+#include <cuda_runtime.h>
+
+#include "scan_core.cuh"
+
+namespace dmpc {
+
+constexpr int kTile = 32;  // neighbours per shared-memory tile (= one per lane)
+
+struct ScanRec {
+    int kstar, nv, flag, pad;
+};
+
+// loop control word (device resident)
+struct Ctrl {
+    int step;        // MPC steps completed so far
+    int done;        // set when the loop must stop: kernels become no-ops
+    int reached;     // ReachedGoal
+    int fail_step;   // first step at which some agent failed, -1
+    int fail_agent;  // lowest failing agent of that step, -1
+    int stop_on_fail;
+    int max_steps;
+    int rescue_used;  // global rescue slots handed out (monotone, diagnostics)
+    double goal_dist;
+};
+
+struct StepArgs {
+    DevParams P;
+    int n0, n1;  // agents solved by this launch
+    int RMAX, QMAX, RCAP, QBIG, n_rescue;
+    int tile_padded;  // l_prev is readable up to a multiple of kTile agents
+    const double* l_prev;
+    double* l_new;
+    const double *pk, *vk, *ak, *pf;
+    double *p1, *v1, *a1;
+    double *v_hor, *a_hor;  // optional
+    int* status;
+    AgentDiag* diag;  // optional
+    const double* tab;
+    unsigned* nearmask;  // (n1-n0) x nm_stride
+    size_t nm_stride;
+    ScanRec* scan;  // per local agent
+    double* grow;   // per local agent 5*RMAX
+    int* gkc;       // per local agent RMAX
+    int* gidx;      // per local agent RMAX (neighbour index of each row)
+    double* gscr_d;  // per local agent 3*RMAX
+    int* gscr_i;     // per local agent 4*RMAX
+    unsigned char* rescue;  // n_rescue slots of rescue_bytes
+    size_t rescue_bytes;
+    int* rescue_next;  // slot allocator (reset by the tail kernel)
+    Ctrl* ctrl;        // optional
+};
+
+struct TailArgs {
+    int N, n0, n1, ld;  // p has leading dimension ld (3: packed, 3K: first column of a horizon)
+    double goal_tol;
+    const double* p;
+    const double* pf;
+    const int* status;
+    const double *p1, *v1, *a1;        // recorded into the trajectory (3 x N)
+    double *traj_p, *traj_v, *traj_a;  // optional 3 x (S+1) x N
+    int* status_hist;                  // optional S x N
+    int S;
+    double* goal_out;  // [0] max distance, [1] reached (0/1)
+    int* fail_out;     // first failing agent or -1
+    int* rescue_next;
+    Ctrl* ctrl;  // optional
+};
+
+// ---- PTX helpers: mbarrier + TMA bulk copy ---------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+    return (uint32_t)__cvta_generic_to_shared(p);
+}
+__device__ __forceinline__ void mbar_init(uint64_t* bar, unsigned count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_fence_init() {
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ void tma_bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+    asm volatile(
+        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+            smem_u32(dst)),
+        "l"(src), "r"(bytes), "r"(smem_u32(bar))
+        : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    const uint32_t a = smem_u32(bar);
+    uint32_t ok;
+    do {
+        asm volatile(
+            "{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}"
+            : "=r"(ok)
+            : "r"(a), "r"(parity)
+            : "memory");
+    } while (!ok);
+}
+
+DMPC_HD size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+// ---- K1 -------------------------------------------------------------------------------------
+DMPC_HD size_t scan_smem_bytes(int K, int W) {
+    const int n3 = 3 * K;
+    return 2 * (size_t)kTile * n3 * sizeof(double) + (size_t)W * round_up(n3, 2) * sizeof(double) + 2 * sizeof(uint64_t);
+}
+
+template <int W>
+__global__ void __launch_bounds__(W * 32) scan_kernel(const __grid_constant__ StepArgs A) {
+    if (A.ctrl && A.ctrl->done) return;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    const int K = A.P.K, n3 = 3 * K, n3p = round_up(n3, 2), N = A.P.N;
+    const int tile_d = kTile * n3;
+    const uint32_t tile_bytes = (uint32_t)(tile_d * sizeof(double));  // 32*3K*8: multiple of 16
+    double* tile[2];
+    tile[0] = reinterpret_cast<double*>(smem_raw);
+    tile[1] = tile[0] + tile_d;
+    double* own_all = tile[1] + tile_d;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(own_all + W * n3p);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int li = blockIdx.x * W + warp;
+    const int n = A.n0 + li;
+    const bool valid = n < A.n1;
+    double* own = own_all + warp * n3p;
+
+    if (threadIdx.x == 0) {
+        mbar_init(&bars[0], 1);
+        mbar_init(&bars[1], 1);
+        mbar_fence_init();
+    }
+    if (valid)
+        for (int i = lane; i < n3; i += 32) own[i] = A.l_prev[(size_t)n * n3 + i];
+    __syncthreads();
+
+    const int ntma = A.tile_padded ? (N + kTile - 1) / kTile : N / kTile;
+    if (threadIdx.x == 0) {
+        for (int t = 0; t < 2 && t < ntma; ++t) {
+            mbar_expect_tx(&bars[t], tile_bytes);
+            tma_bulk_g2s(tile[t], A.l_prev + (size_t)t * tile_d, tile_bytes, &bars[t]);
+        }
+    }
+    unsigned* nm = A.nearmask + (size_t)(valid ? li : 0) * A.nm_stride;
+    ScanAcc acc;
+    acc.vmask = 0;
+    acc.md0 = INFINITY;
+    for (int t = 0; t < ntma; ++t) {
+        const int b = t & 1;
+        mbar_wait(&bars[b], (uint32_t)((t >> 1) & 1));
+        const int base = t * kTile;
+        const int cnt = (N - base < kTile) ? (N - base) : kTile;
+        if (valid) scan_tile(A.P, own, n, tile[b], base, cnt, nm, acc);
+        __syncthreads();  // every warp is done with tile[b]
+        if (threadIdx.x == 0 && t + 2 < ntma) {
+            mbar_expect_tx(&bars[b], tile_bytes);
+            tma_bulk_g2s(tile[b], A.l_prev + (size_t)(t + 2) * tile_d, tile_bytes, &bars[b]);
+        }
+    }
+    const int rem_base = ntma * kTile;
+    if (rem_base < N) {
+        // caller-owned buffer without tile padding: the ragged last tile is loaded by the threads
+        const int cnt = N - rem_base;
+        for (int i = threadIdx.x; i < cnt * n3; i += W * 32) tile[0][i] = A.l_prev[(size_t)rem_base * n3 + i];
+        __syncthreads();
+        if (valid) scan_tile(A.P, own, n, tile[0], rem_base, cnt, nm, acc);
+    }
+    if (!valid) return;
+    __syncwarp();
+    const ScanOut so = scan_finish(A.P, own, n, A.l_prev, nm, acc, A.RMAX, A.grow + (size_t)li * 5 * A.RMAX,
+                                   A.gkc + (size_t)li * A.RMAX, A.gidx ? A.gidx + (size_t)li * A.RMAX : nullptr);
+    if (lane == 0) {
+        ScanRec r;
+        r.kstar = so.kstar;
+        r.nv = so.nv;
+        r.flag = so.flag;
+        r.pad = 0;
+        A.scan[li] = r;
+    }
+}
+
+// ---- K2 -------------------------------------------------------------------------------------
+DMPC_HD size_t qp_table_bytes(int K) { return (size_t)(10 * K * K + 2 * K) * sizeof(double); }
+DMPC_HD size_t qp_smem_bytes(int K, int W, int QMAX, int RCAP) {
+    return align_up(qp_table_bytes(K), 16) + (size_t)W * agent_smem_bytes(K, QMAX, RCAP) + 16;
+}
+
+template <int W>
+__global__ void __launch_bounds__(W * 32) qp_kernel(const __grid_constant__ StepArgs A) {
+    if (A.ctrl && A.ctrl->done) return;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    const int K = A.P.K, n3 = 3 * K;
+    const size_t tab_bytes = align_up(qp_table_bytes(K), 16);
+    const size_t per_warp = agent_smem_bytes(K, A.QMAX, A.RCAP);
+    double* tab_s = reinterpret_cast<double*>(smem_raw);
+    uint64_t* bar = reinterpret_cast<uint64_t*>(smem_raw + tab_bytes + (size_t)W * per_warp);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+    if (threadIdx.x == 0) {
+        mbar_init(bar, 1);
+        mbar_fence_init();
+        mbar_expect_tx(bar, (uint32_t)qp_table_bytes(K));
+        tma_bulk_g2s(tab_s, A.tab, (uint32_t)qp_table_bytes(K), bar);
+    }
+    __syncthreads();
+    const int li = blockIdx.x * W + warp;
+    const int n = A.n0 + li;
+    if (n >= A.n1) return;
+
+    const ScanRec sr = A.scan[li];
+    AgentIO io;
+#pragma unroll
+    for (int x = 0; x < 3; ++x) {
+        io.po[x] = A.pk[3 * n + x];
+        io.pf[x] = A.pf[3 * n + x];
+        io.vo[x] = A.vk[3 * n + x];
+        io.ao[x] = A.ak[3 * n + x];
+    }
+    io.kstar = sr.kstar;
+    io.nv = sr.nv;
+    io.scanflag = sr.flag;
+    io.RMAX = A.RMAX;
+    io.grow = A.grow + (size_t)li * 5 * A.RMAX;
+    io.gkc = A.gkc + (size_t)li * A.RMAX;
+    io.gscr_d = A.gscr_d + (size_t)li * 3 * A.RMAX;
+    io.gscr_i = A.gscr_i + (size_t)li * 4 * A.RMAX;
+    io.out_p = A.l_new + (size_t)n * n3;
+    io.out_v = A.v_hor ? A.v_hor + (size_t)n * n3 : nullptr;
+    io.out_a = A.a_hor ? A.a_hor + (size_t)n * n3 : nullptr;
+    io.p1 = A.p1 + 3 * n;
+    io.v1 = A.v1 + 3 * n;
+    io.a1 = A.a1 + 3 * n;
+    io.l_prev_n = A.l_prev + (size_t)n * n3;
+
+    mbar_wait(bar, 0);  // tables have landed
+    AgentDiag dg;
+    int st = agent_solve(A.P, tab_s, smem_raw + tab_bytes + (size_t)warp * per_warp, A.QMAX, A.RCAP, io, &dg);
+    if ((st & ST_OVERFLOW) && !sr.flag && A.rescue) {
+        // active set outgrew the on-chip capacity: re-solve in a global-memory rescue slot
+        int slot = 0;
+        if (lane == 0) slot = atomicAdd(A.rescue_next, 1);
+        slot = __shfl_sync(0xffffffffu, slot, 0);
+        if (slot < A.n_rescue) {
+            if (lane == 0 && A.ctrl) atomicAdd(&A.ctrl->rescue_used, 1);
+            const int it0 = dg.iters;
+            st = agent_solve(A.P, tab_s, A.rescue + (size_t)slot * A.rescue_bytes, A.QBIG, A.RCAP, io, &dg);
+            dg.iters += it0;
+        }
+    }
+    if (lane == 0) {
+        A.status[n] = st;
+        if (A.diag) A.diag[n] = dg;
+    }
+}
+
+// ---- K3 -------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) tail_kernel(const __grid_constant__ TailArgs T) {
+    if (T.ctrl && T.ctrl->done) return;
+    __shared__ double s_md[8];
+    __shared__ int s_ff[8];
+    const int tid = threadIdx.x;
+    const int step = T.ctrl ? T.ctrl->step : 0;
+    double md = 0.0;
+    int ff = 0x7fffffff;
+    for (int n = tid; n < T.N; n += 256) {
+        if (T.p) {
+            // ReachedGoal.m:4-5
+            const double dx = T.p[(size_t)T.ld * n] - T.pf[3 * n];
+            const double dy = T.p[(size_t)T.ld * n + 1] - T.pf[3 * n + 1];
+            const double dz = T.p[(size_t)T.ld * n + 2] - T.pf[3 * n + 2];
+            md = fmax(md, sqrt(dx * dx + dy * dy + dz * dz));
+        }
+        if (T.status && n >= T.n0 && n < T.n1) {
+            const int st = T.status[n];
+            if ((!(st & ST_SOLVED) || (st & ST_OUTBOUND)) && n < ff) ff = n;
+            if (T.status_hist && step < T.S) T.status_hist[(size_t)step * T.N + n] = st;
+        }
+        if (T.traj_p && step < T.S) {
+            const size_t o = 3 * ((size_t)(step + 1) + (size_t)(T.S + 1) * n);
+            for (int x = 0; x < 3; ++x) {
+                T.traj_p[o + x] = T.p1[3 * n + x];
+                T.traj_v[o + x] = T.v1[3 * n + x];
+                T.traj_a[o + x] = T.a1[3 * n + x];
+            }
+        }
+    }
+    for (int o = 16; o; o >>= 1) {
+        md = fmax(md, __shfl_xor_sync(0xffffffffu, md, o));
+        ff = min(ff, __shfl_xor_sync(0xffffffffu, ff, o));
+    }
+    if ((tid & 31) == 0) {
+        s_md[tid >> 5] = md;
+        s_ff[tid >> 5] = ff;
+    }
+    __syncthreads();
+    if (tid == 0) {
+        for (int w = 1; w < 8; ++w) {
+            md = fmax(md, s_md[w]);
+            ff = min(ff, s_ff[w]);
+        }
+        const int reached = (T.p && md < T.goal_tol) ? 1 : 0;
+        if (T.goal_out) {
+            T.goal_out[0] = md;
+            T.goal_out[1] = (double)reached;
+        }
+        if (T.fail_out) *T.fail_out = (ff == 0x7fffffff) ? -1 : ff;
+        if (T.rescue_next) *T.rescue_next = 0;
+        if (T.ctrl) {
+            Ctrl* c = T.ctrl;
+            c->goal_dist = md;
+            if (ff != 0x7fffffff && c->fail_step < 0) {
+                c->fail_step = step;
+                c->fail_agent = ff;
+            }
+            c->step = step + 1;
+            if (reached) {
+                c->reached = 1;
+                c->done = 1;
+            }
+            if (ff != 0x7fffffff && c->stop_on_fail) c->done = 1;
+            if (step + 1 >= c->max_steps) c->done = 1;
+        }
+    }
+}
+
+// ---- initDMPC.m:1-13 for all agents -------------------------------------------------------------
+__global__ void init_kernel(int N, int K, double h, double init_div, const double* __restrict__ po,
+                            const double* __restrict__ pf, double* l, double* pk, double* vk, double* ak) {
+    const int n = blockIdx.x * blockDim.x + threadIdx.x;
+    if (n >= N) return;
+    for (int x = 0; x < 3; ++x) {
+        const double o = po[3 * n + x];
+        const double d = pf[3 * n + x] - o;
+        for (int k = 0; k < K; ++k) {
+            // t = 0:h:(K-1)*h ; p(:,i) = po + 1*t(i)*diff/10
+            const double t = (double)k * h;
+            l[(size_t)n * 3 * K + 3 * k + x] = o + __ddiv_rn(__dmul_rn(t, d), init_div);
+        }
+        pk[3 * n + x] = o;
+        vk[3 * n + x] = 0.0;
+        ak[3 * n + x] = 0.0;
+    }
+}
+
+// ---- CheckCollSoftDMPC.m:1-17 for one agent and one horizon step (helper drop-in) ---------------
+// out_d[0] = min distance, out_i[0] = any(violation)
+__global__ void __launch_bounds__(256) check_coll_kernel(DevParams P, double px, double py, double pz, const double* l,
+                                                         int n, int k1, unsigned char* violation,
+                                                         unsigned char* viol_constr, double* out_d, int* out_i) {
+    __shared__ double s_md[8];
+    __shared__ int s_any[8];
+    const int tid = threadIdx.x;
+    const double thr = neigh_thr(P, k1);
+    double md = INFINITY;
+    int any = 0;
+    for (int i = tid; i < P.N; i += 256) {
+        unsigned char v = 0, vc = 0;
+        if (i != n) {
+            const double* pj = l + 3 * ((size_t)(k1 - 1) + (size_t)P.K * i);
+            const double dist = ell_dist(px - pj[0], py - pj[1], pz - pj[2], P.c);
+            v = dist < P.rmin;
+            vc = dist < thr;
+            md = fmin(md, dist);
+            any |= v;
+        }
+        violation[i] = v;
+        viol_constr[i] = vc;
+    }
+    for (int o = 16; o; o >>= 1) {
+        md = fmin(md, __shfl_xor_sync(0xffffffffu, md, o));
+        any |= __shfl_xor_sync(0xffffffffu, any, o);
+    }
+    if ((tid & 31) == 0) {
+        s_md[tid >> 5] = md;
+        s_any[tid >> 5] = any;
+    }
+    __syncthreads();
+    if (tid == 0) {
+        for (int w = 1; w < 8; ++w) {
+            md = fmin(md, s_md[w]);
+            any |= s_any[w];
+        }
+        out_d[0] = md;
+        out_i[0] = any;
+    }
+}
+
+// ---- CollConstr*DMPC.m for one agent and one horizon step: dense rows like the reference -------
+// one warp; rows in ascending neighbour order.  Ain cap x 3K column-major.
+__global__ void __launch_bounds__(32) coll_constr_kernel(DevParams P, const double* __restrict__ tab, double px,
+                                                         double py, double pz, double po0, double po1, double po2,
+                                                         double vo0, double vo1, double vo2, int n, int k1,
+                                                         const double* l, const unsigned char* mask, int cap,
+                                                         double* Ain, double* bin, double* prev_dist, int* nrows) {
+    const int K = P.K, N = P.N, lane = threadIdx.x;
+    const bool hard = (P.variant == VAR_HARD);
+    const int kc1 = (P.variant == VAR_SOFT_BOUND2) ? k1 - 1 : k1;  // CollConstrSoftDMPC2.m:8
+    const double* lam = tab;
+    const double* tt = tab + K * K;
+    const double c2 = P.c * P.c;
+    int nv = 0;
+    for (int base = 0; base < N; base += 32) {
+        const int i = base + lane;
+        bool hit = false;
+        double dx = 0, dy = 0, dz = 0, dist = 0;
+        if (i < N && i != n && (hard || mask[i])) {
+            const double* pj = l + 3 * ((size_t)(k1 - 1) + (size_t)K * i);
+            dx = px - pj[0];
+            dy = py - pj[1];
+            dz = pz - pj[2];
+            dist = ell_dist(dx, dy, dz, P.c);
+            hit = hard ? (dist < P.hard_radius) : true;
+        }
+        const unsigned bal = __ballot_sync(0xffffffffu, hit);
+        if (hit) {
+            const int slot = nv + __popc(bal & ((1u << lane) - 1u));
+            if (slot < cap) {
+                const double d0 = dx, d1 = dy, d2 = dz / c2;
+                const double dp = d0 * px + d1 * py + d2 * pz;
+                const double tk = (kc1 >= 1) ? tt[kc1 - 1] : 0.0;
+                const double dq = d0 * (po0 + tk * vo0) + d1 * (po1 + tk * vo1) + d2 * (po2 + tk * vo2);
+                const double r = dist * ((P.rmin - dist) + dp / dist) - dq;
+                for (int j = 0; j < K; ++j) {
+                    const double lj = (kc1 >= 1) ? lam[(kc1 - 1) * K + j] : 0.0;
+                    Ain[slot + (size_t)cap * (3 * j + 0)] = -d0 * lj;
+                    Ain[slot + (size_t)cap * (3 * j + 1)] = -d1 * lj;
+                    Ain[slot + (size_t)cap * (3 * j + 2)] = -d2 * lj;
+                }
+                bin[slot] = -r;
+                prev_dist[slot] = dist;
+            }
+        }
+        nv += __popc(bal);
+    }
+    if (lane == 0) *nrows = nv;
+}
+
+// ---- propStatedmpc.m:1-8 for a batch: a 3K x B -> p, v 3K x B -----------------------------------
+__global__ void prop_state_kernel(int B, int K, const double* __restrict__ tab, double h, const double* po,
+                                  const double* vo, const double* a, double* p, double* v) {
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    const int n3 = 3 * K;
+    if (idx >= B * n3) return;
+    const int b = idx / n3, i = idx - b * n3, k = i / 3, x = i - 3 * k;
+    const double* lam = tab;
+    const double* tt = tab + K * K;
+    double sp = 0.0, sv = 0.0;
+    for (int j = 0; j <= k; ++j) {
+        const double aj = a[(size_t)b * n3 + 3 * j + x];
+        sp = fma(lam[k * K + j], aj, sp);
+        sv += h * aj;
+    }
+    p[idx] = sp + (po[3 * b + x] + tt[k] * vo[3 * b + x]);
+    v[idx] = sv + vo[3 * b + x];
+}
+
+}  // namespace dmpc
