@@ -1,0 +1,382 @@
+#!/usr/bin/env python
+"""bench.py -- agent-MPC-steps/s of the DMPC per-agent QP hot path on B200 (BASELINE.json metric).
+
+Workload (config C3 of SURVEY.md section 8d = the configuration the metric is quoted on):
+N = 500 agents, horizon K = 15, soft-constraint DMPC (solveSoftDMPCbound), random point-to-point
+transition in the 1 agent/m^3 arena of test/failure_rate.m:63-64, seed 1003, synthetic.
+A "step" is one MPC time step = one solve of all N per-agent QPs (scan + constraint build + QP +
+propagate); the timed steps are steps W+1 .. W+K of the closed-loop transition that starts at
+initDMPC, so the mix of easy and hard (dense) steps is the workload's own.
+
+Timing: every timed step is bracketed by CUDA events on the launching stream; between steps the L2
+is flushed by writing a 512 MiB buffer (the step's working set is ~0.2 MB, so without the flush
+every step would run out of L2).  value = N * K / sum(step times).  The extra key
+`resident_graph` is the same loop run device-resident through a CUDA graph (no flush, no host
+sync) -- the deployment mode -- reported beside it, not instead of it.
+
+python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--workload C3|N100|N2000|C4]
+Under torchrun (N > 1) the agents are sharded in contiguous blocks with one NCCL all-gather of the
+predicted horizons per step ("strong" scaling: the swarm is fixed).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+
+def b_alg(N, K):
+    """algorithmic bytes per agent-step: every other agent's horizon once, own
+    horizon, state + goal, new horizon + first columns"""
+    return 24 * K * N + 24 * K + 168
+
+
+def peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks + throttle reasons during the timed region (B200_PROFILING.md)"""
+
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index=0):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm = [float(r[0]) for r in self.rows if len(r) >= 6 and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if len(r) >= 6 and r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({names[i] for r in self.rows if len(r) >= 6 for i in range(4) if r[2 + i] == "Active"})
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": reasons, "samples": len(sm)}
+
+
+def workload(name):
+    from multiagent_planning_b200 import scenarios
+    cfg = scenarios.config(name)
+    return cfg
+
+
+def cpu_port_run(cfg, warmup, steps, threads, budget_s=None):
+    """the CPU oracle (port of the reference algorithm) on the same workload: steps W+1..W+K of the
+    transition.  Returns (agent_steps_per_s, steps_done, seconds)."""
+    from oracle import dmpc_oracle as orc
+    P = orc.default_params(cfg["variant"])
+    for k, v in cfg["params"].items():
+        setattr(P, k, v)
+    N, K = cfg["N"], P.K
+    po, pf = cfg["po"], cfg["pf"]
+    l = np.zeros((3, K, N), order="F")
+    for n in range(N):
+        l[:, :, n] = orc.init_dmpc(po[:, n], pf[:, n], P.h, K, P.init_div)[0]
+    pk, vk, ak = l[:, 0, :].copy(), np.zeros((3, N)), np.zeros((3, N))
+    t_total, done = 0.0, 0
+    for k in range(warmup + steps):
+        t0 = time.perf_counter()
+        o = orc.step(P, pk, vk, ak, pf, l, cfg["pmin"], cfg["pmax"], nthreads=threads)
+        dt = time.perf_counter() - t0
+        l, pk, vk, ak = o["l_new"], o["p1"], o["v1"], o["a1"]
+        if k >= warmup:
+            t_total += dt
+            done += 1
+            if budget_s is not None and t_total > budget_s:
+                break
+    return N * done / t_total, done, t_total
+
+
+def run_reference(args):
+    """--impl reference: the reference's MATLAB / C++ implementations cannot run on this box (no
+    MATLAB/Octave; dmpc/cpp needs Eigen, eigen-quadprog, OOQP, CPLEX, Boost).  The CPU arm is the
+    oracle port of the same algorithm with all host threads."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cfg = workload(args.workload)
+    threads = os.cpu_count() or 1
+    v, done, secs = cpu_port_run(cfg, args.warmup, args.steps, threads)
+    P_K = cfg["params"].get("K", 15)
+    line = {
+        "impl": "reference", "metric": "agent-MPC-steps/sec", "value": v, "unit": "agent-steps/s",
+        "n_gpus": args.gpus, "steps": done, "warmup": args.warmup, "ms_per_step": 1e3 * secs / max(done, 1),
+        "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": f"{args.workload}: N={cfg['N']} K={P_K} soft-constraint DMPC (solveSoftDMPCbound), "
+                               "1 agent/m^3 arena, seed 1003, closed-loop steps W+1..W+K"},
+        "cpu_baseline": {"value": v, "unit": "agent-steps/s", "cores": threads, "kind": "port",
+                         "sample": f"{done} MPC steps x {cfg['N']} agents, oracle/liboracle.so, {threads} threads"},
+        "e2e": {"value": v, "unit": "agent-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+def run_single(args):
+    import torch
+    from multiagent_planning_b200 import dmpc
+    cfg = workload(args.workload)
+    N = cfg["N"]
+    P = dmpc.default_params(cfg["variant"], **cfg["params"])
+    K = P.K
+    W, S = args.warmup, args.steps
+    torch.cuda.set_device(0)
+    flush = torch.empty(512 << 20, dtype=torch.uint8, device="cuda")
+    s = dmpc.Solver(N, P, pmin=cfg["pmin"], pmax=cfg["pmax"], pf=cfg["pf"])
+    conf = s.config()
+
+    # ---- device-resident timing with L2 flush between steps (the `value`) ----------------------
+    def flushed_pass():
+        s.init_horizons(cfg["po"])
+        tot = scan = qp = 0.0
+        n = 0
+        for k in range(W + S):
+            flush.zero_()
+            torch.cuda.synchronize()
+            r = s.run(1, mode=1)
+            if r["steps"] != 1:
+                break
+            if k >= W:
+                t = s.last_timing()
+                tot += t["step_ms"]
+                scan += t["scan_ms"]
+                qp += t["qp_ms"]
+                n += 1
+        return tot, scan, qp, n
+
+    flushed_pass()  # whole-pass warm-up (module load, attribute sets, allocator)
+    clk = ClockSampler(0)
+    clk.start()
+    tot, scan, qp, n_timed = flushed_pass()
+    # ---- the same loop as one device-resident CUDA-graph run (no flush, no host sync) -----------
+    s.init_horizons(cfg["po"])
+    s.run(W, mode=0) if W else None
+    r = s.run(S, mode=0)
+    graph_ms = s.last_timing()["step_ms"]
+    graph_steps = r["steps"]
+
+    # ---- end to end through the C-ABI with HOST buffers (pinned), copies inside the timed region
+    s.init_horizons(cfg["po"])
+    pin = lambda shape, dt=torch.float64: torch.empty(shape, dtype=dt).pin_memory().numpy()
+    l_a = pin((N, K, 3)).transpose(2, 1, 0)
+    l_b = pin((N, K, 3)).transpose(2, 1, 0)
+    st = [[pin((N, 3)).T for _ in range(3)] for _ in range(2)]
+    out = dict(status=pin((N,), torch.int32), diag=np.zeros(N, dtype=[("kstar", "i4"), ("nv", "i4"), ("iters", "i4"),
+                                                                     ("nact", "i4")]))
+    l0, p0, v0, a0 = s.init_horizons(cfg["po"])
+    l_a[...] = l0
+    st[0][0][...], st[0][1][...], st[0][2][...] = p0, v0, a0
+    cur, t_e2e = 0, 0.0
+    for k in range(W + S):
+        o = dict(out, l_new=(l_b if cur == 0 else l_a), p1=st[cur ^ 1][0], v1=st[cur ^ 1][1], a1=st[cur ^ 1][2])
+        lp = l_a if cur == 0 else l_b
+        t0 = time.perf_counter()
+        s.step(st[cur][0], st[cur][1], st[cur][2], lp, out=o)
+        dt = time.perf_counter() - t0
+        if k >= W:
+            t_e2e += dt
+        # agents that failed keep their horizon (the library leaves their rows untouched)
+        bad = (o["status"] & 1) == 0
+        if bad.any():
+            o["l_new"][:, :, bad] = lp[:, :, bad]
+            for i in range(3):
+                st[cur ^ 1][i][:, bad] = st[cur][i][:, bad]
+        cur ^= 1
+    clocks = clk.stop()
+    h2d = (9 * N + 3 * K * N) * 8
+    d2h = (3 * K * N + 9 * N) * 8 + 4 * N + 16 * N + 4
+
+    ms_per_step = tot / n_timed
+    value = N * n_timed / (tot * 1e-3)
+    peak, peak_src = peaks()
+    scan_us = 1e3 * scan / n_timed
+    qp_us = 1e3 * qp / n_timed
+    ach_scan = b_alg(N, K) * N / (scan_us * 1e-6) / 1e9
+    ach_step = b_alg(N, K) * N / (ms_per_step * 1e-3) / 1e9
+
+    line = {
+        "metric": "agent-MPC-steps/sec", "value": value, "unit": "agent-steps/s", "n_gpus": 1, "steps": n_timed,
+        "warmup": W, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": f"{args.workload}: N={N} K={K} soft-constraint DMPC (solveSoftDMPCbound), "
+                               "1 agent/m^3 arena, seed 1003, closed-loop steps W+1..W+K",
+                   "l2": "flushed between timed steps (512 MiB write); per-step CUDA events on the launch stream",
+                   "launch": conf},
+        "clocks": clocks,
+        "e2e": {"value": N * S / t_e2e, "unit": "agent-steps/s", "h2d_bytes_per_step": h2d,
+                "d2h_bytes_per_step": d2h, "ms_per_step": 1e3 * t_e2e / S,
+                "api": "dmpcb200_step (host buffers, pinned)"},
+        "gpu_launches": 3 * n_timed,
+        "resident_graph": {"value": N / (graph_ms * 1e-3) if graph_ms else None, "ms_per_step": graph_ms,
+                           "steps": graph_steps, "note": "dmpcb200_run, CUDA graph, L2-warm, no host sync"},
+        "roofline": {"bound": "hbm", "kernel": "scan_kernel<4> (neighbour scan + constraint rows)",
+                     "achieved": ach_scan, "peak": peak, "unit": "GB/s", "frac": ach_scan / peak,
+                     "traffic": None, "peak_source": peak_src, "avg_launch_us": scan_us,
+                     "algorithmic_bytes_per_launch": b_alg(N, K) * N},
+        "roofline_step": {"bound": "hbm", "achieved": ach_step, "peak": peak, "unit": "GB/s",
+                          "frac": ach_step / peak, "note": "B_alg*N over the whole step (scan+QP+tail)"},
+        "kernel_us": {"scan_kernel": scan_us, "qp_kernel": qp_us,
+                      "tail_and_gaps": 1e3 * ms_per_step - scan_us - qp_us,
+                      "share": {"scan": scan_us / (1e3 * ms_per_step), "qp": qp_us / (1e3 * ms_per_step)}},
+    }
+    # ---- CPU baseline: oracle port on a bounded sample of the same workload -----------------------
+    threads = os.cpu_count() or 1
+    v, done, secs = cpu_port_run(cfg, W, S, threads, budget_s=15.0)
+    line["cpu_baseline"] = {"value": v, "unit": "agent-steps/s", "cores": threads, "kind": "port",
+                            "sample": f"steps {W + 1}..{W + done} of the same transition ({done} MPC steps x {N} "
+                                      f"agents, {secs:.1f} s), oracle/liboracle.so with {threads} threads; the "
+                                      "reference's MATLAB / C++ cannot run on this box"}
+    s.close()
+    print(json.dumps(line))
+
+
+def run_multi(args):
+    import torch
+    import torch.distributed as dist
+    from multiagent_planning_b200 import dmpc, sharded
+    rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
+    local = int(os.environ.get("LOCAL_RANK", rank))
+    torch.cuda.set_device(local)
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    cfg = workload(args.workload)
+    N = cfg["N"]
+    P = dmpc.default_params(cfg["variant"], **cfg["params"])
+    K, W, S = P.K, args.warmup, args.steps
+    flush = torch.empty(512 << 20, dtype=torch.uint8, device="cuda")
+    sh = sharded.ShardedDMPC(N, P, cfg["pmin"], cfg["pmax"], cfg["po"], cfg["pf"])
+
+    def one_pass(timed):
+        sh.be.init(cfg["po"])
+        sh.cur = 0
+        evs = []
+        for k in range(W + S):
+            flush.zero_()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            sh.step()
+            e1.record()
+            if k >= W:
+                evs.append((e0, e1))
+        torch.cuda.synchronize()
+        return sum(a.elapsed_time(b) for a, b in evs)
+
+    one_pass(False)
+    clk = ClockSampler(local)
+    if rank == 0:
+        clk.start()
+    dist.barrier()
+    torch.cuda.synchronize()
+    tot = one_pass(True)
+    torch.cuda.synchronize()
+    dist.barrier()
+    t = torch.tensor([tot], dtype=torch.float64, device="cuda")
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    tot = float(t.item())
+    # graph mode: two steps per graph including the NCCL all-gather
+    graph_ms = None
+    try:
+        sh.be.init(cfg["po"])
+        sh.cur = 0
+        for _ in range(2):
+            sh.step()
+        sh.be.init(cfg["po"])
+        sh.cur = 0
+        g = sh.capture_graph()
+        sh.be.init(cfg["po"])
+        for _ in range(W // 2):
+            g.replay()
+        torch.cuda.synchronize()
+        dist.barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(S // 2):
+            g.replay()
+        e1.record()
+        torch.cuda.synchronize()
+        tg = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device="cuda")
+        dist.all_reduce(tg, op=dist.ReduceOp.MAX)
+        graph_ms = float(tg.item()) / (2 * (S // 2))
+    except Exception as ex:  # graph capture of NCCL is an optimisation, not the measured path
+        graph_ms = None
+        graph_err = repr(ex)[:200]
+    clocks = clk.stop() if rank == 0 else None
+    if rank == 0:
+        ms = tot / S
+        peak, peak_src = peaks()
+        ach = b_alg(N, K) * N / (ms * 1e-3) / 1e9
+        line = {
+            "metric": "agent-MPC-steps/sec", "value": N * S / (tot * 1e-3), "unit": "agent-steps/s", "n_gpus": world,
+            "steps": S, "warmup": W, "ms_per_step": ms, "higher_is_better": True, "scaling": "strong",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": f"{args.workload}: N={N} K={K} soft-constraint DMPC (solveSoftDMPCbound), "
+                                   "1 agent/m^3 arena, seed 1003, closed-loop steps W+1..W+K",
+                       "parallelism": f"agents sharded in {world} contiguous blocks of {sh.blk}, one NCCL all-gather "
+                                      f"of {sh.blk * 3 * K * 8} B per rank per step",
+                       "l2": "flushed between timed steps (512 MiB write); per-step CUDA events, max over ranks"},
+            "clocks": clocks,
+            "e2e": {"value": N * S / (tot * 1e-3), "unit": "agent-steps/s", "h2d_bytes_per_step": 0,
+                    "d2h_bytes_per_step": 0,
+                    "note": "multi-GPU loop is device resident; the host-buffer e2e is measured at n_gpus=1"},
+            "gpu_launches": 2 * S,
+            "resident_graph": {"ms_per_step": graph_ms, "value": (N / (graph_ms * 1e-3)) if graph_ms else None,
+                               "note": "torch CUDA graph of two steps incl. NCCL all-gather"},
+            "roofline_step": {"bound": "hbm", "achieved": ach, "peak": peak * world, "unit": "GB/s",
+                              "frac": ach / (peak * world), "peak_source": peak_src},
+            "all_gathers_per_step": sh.n_allgather / max(sh.steps, 1),
+        }
+        print(json.dumps(line))
+    sh.close()
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=120)
+    ap.add_argument("--warmup", type=int, default=4)
+    ap.add_argument("--impl", default="b200")
+    ap.add_argument("--workload", default="C3")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 0)
+    if args.impl == "reference":
+        return run_reference(args)
+    if int(os.environ.get("WORLD_SIZE", "1")) > 1:
+        return run_multi(args)
+    return run_single(args)
+
+
+if __name__ == "__main__":
+    main()

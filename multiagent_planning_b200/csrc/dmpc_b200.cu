@@ -5,6 +5,7 @@
 
 #include <algorithm>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -358,6 +359,10 @@ int dmpcb200_create(const dmpcb200_params* p, int N, int n0, int n1, int device,
         return fail(DMPCB200_ERR_ARG, "create: horizon too long for the on-chip QP workspace");
     }
     h->QMAX = qwant;
+    if (const char* e = getenv("DMPCB200_QMAX")) {  // test hook: shrink the on-chip active-set capacity
+        const int v = atoi(e);
+        if (v >= 2 && v <= qwant) h->QMAX = round_up(v, 2);
+    }
     h->QBIG = round_up(n3 + 2 * std::min(h->RMAX, 256) + 8, 8);
     h->n_rescue = 64;
     h->rescue_bytes = align_up(agent_smem_bytes(K, h->QBIG, h->RCAP), 256);

@@ -26,7 +26,7 @@
 // with M as approximate inverse, removing any drift the explicit-inverse updates accumulated.
 //
 // One warp per agent; all branches are warp-uniform (decided on reduced values).  The same source
-// compiles for the host with one "lane" (tests/host_emul): that build is a debugging aid of the
+// compiles for the host with one "lane" (a test-only build): that build is a debugging aid of the
 // test-suite only and is never part of the product library.
 #pragma once
 

@@ -1,0 +1,108 @@
+"""The device algorithm (scan_core / agent_solve / qp_core .cuh), compiled for the host with one
+lane (tests/host_emul), against the oracle.  CPU-only check of the maths of the CUDA kernels:
+structured Schur-complement dual active set vs the oracle's dense solver."""
+import numpy as np
+import pytest
+
+from tests.conftest import oracle_params
+
+
+def _cmp(orc, emul, P, pk, vk, ak, pf, l, pmin, pmax, tol=1e-9, **kw):
+    o = orc.step(P, pk, vk, ak, pf, l, pmin, pmax)
+    e = emul.step(emul.params_from(P), pk, vk, ak, pf, l, pmin, pmax, **kw)
+    assert np.array_equal(o["status"] & 0xFF, e["status"] & 0xFF)
+    assert np.abs(o["l_new"] - e["l_new"]).max() <= tol
+    assert np.abs(o["p1"] - e["p1"]).max() <= tol and np.abs(o["v1"] - e["v1"]).max() <= tol
+    assert np.abs(o["a1"] - e["a1"]).max() <= tol
+    return o, e
+
+
+@pytest.mark.parametrize("name,variant", [("kat_soft_bound", 0), ("kat_soft_bound2", 1), ("kat_soft_bound", 3)])
+def test_single_step_matches_oracle(orc, emul, golden, name, variant):
+    g = golden[name]
+    P = orc.default_params(variant)
+    _cmp(orc, emul, P, g["pk_prev"], g["vk_prev"], g["ak_prev"], g["pf"], g["l"], g["pmin"], g["pmax"])
+
+
+def test_hard_variant_matches_oracle(orc, emul, golden):
+    g = golden["kat_soft_bound2"]   # N = 100
+    P = orc.default_params(orc.VARIANT_HARD)
+    o = orc.step(P, g["pk_prev"], g["vk_prev"], g["ak_prev"], g["pf"], g["l"], g["pmin"], g["pmax"], n1=40)
+    e = emul.step(emul.params_from(P), g["pk_prev"], g["vk_prev"], g["ak_prev"], g["pf"], g["l"], g["pmin"],
+                  g["pmax"], n1=40, QMAX=128, RCAP=64)
+    assert np.array_equal(o["status"][:40] & 0xFF, e["status"][:40] & 0xFF)
+    assert np.abs(o["l_new"] - e["l_new"]).max() <= 1e-9
+
+
+def test_rows_spill_to_global_and_small_capacity(orc, emul, golden):
+    """RCAP smaller than the row count exercises the in-place global row path; a tiny QMAX must be
+    reported as overflow, never as a wrong answer."""
+    g = golden["kat_soft_bound"]
+    P = orc.default_params(0)
+    _cmp(orc, emul, P, g["pk_prev"], g["vk_prev"], g["ak_prev"], g["pf"], g["l"], g["pmin"], g["pmax"],
+         QMAX=64, RCAP=8)
+    e = emul.step(emul.params_from(P), g["pk_prev"], g["vk_prev"], g["ak_prev"], g["pf"], g["l"], g["pmin"],
+                  g["pmax"], QMAX=4, RCAP=64)
+    o = orc.step(P, g["pk_prev"], g["vk_prev"], g["ak_prev"], g["pf"], g["l"], g["pmin"], g["pmax"])
+    ovf = (e["status"] & 32) != 0
+    assert ovf.any()
+    ok = ~ovf
+    assert np.abs(o["l_new"][:, :, ok] - e["l_new"][:, :, ok]).max() <= 1e-9
+
+
+def test_closed_loop_random_transition(orc, emul):
+    from multiagent_planning_b200 import scenarios
+    N = 60
+    pmin, pmax = scenarios.density_arena(N, density=1.5)
+    po, pf = scenarios.random_test(N, pmin, pmax, 0.35, 2.0, seed=11)
+    P = orc.default_params(0)
+    K = P.K
+    l = np.zeros((3, K, N), order="F")
+    for n in range(N):
+        l[:, :, n] = orc.init_dmpc(po[:, n], pf[:, n], P.h, K, P.init_div)[0]
+    pk, vk, ak = l[:, 0, :].copy(), np.zeros((3, N)), np.zeros((3, N))
+    for k in range(25):
+        o, e = _cmp(orc, emul, P, pk, vk, ak, pf, l, pmin, pmax)
+        l, pk, vk, ak = e["l_new"], e["p1"], e["v1"], e["a1"]
+
+
+def test_edge_cases(orc, emul):
+    P = orc.default_params(0)
+    pmin, pmax = np.array([-2.5, -2.5, 0.2]), np.array([2.5, 2.5, 2.2])
+    # single agent: no neighbours at all
+    po, pf = np.array([[0.0], [0.0], [1.0]]), np.array([[1.0], [1.0], [1.5]])
+    l = np.asfortranarray(orc.init_dmpc(po[:, 0], pf[:, 0], P.h, P.K, 10.0)[0][:, :, None])
+    _cmp(orc, emul, P, po, np.zeros((3, 1)), np.zeros((3, 1)), pf, l, pmin, pmax)
+    # two agents head-on (collision constraint at some k), and goal outside the workspace box
+    po = np.array([[-1.0, 1.0], [0.0, 0.01], [1.0, 1.0]])
+    pf = np.array([[1.0, -1.0], [0.0, 0.0], [1.0, 3.5]])
+    l = np.zeros((3, P.K, 2), order="F")
+    for n in range(2):
+        l[:, :, n] = orc.init_dmpc(po[:, n], pf[:, n], P.h, P.K, 10.0)[0]
+    pk, vk, ak = po.copy(), np.zeros((3, 2)), np.zeros((3, 2))
+    for _ in range(30):
+        o, e = _cmp(orc, emul, P, pk, vk, ak, pf, l, pmin, pmax)
+        l, pk, vk, ak = e["l_new"], e["p1"], e["v1"], e["a1"]
+    # agents that already overlap at k = 1: reference returns coll = 1
+    po = np.array([[0.0, 0.1], [0.0, 0.0], [1.0, 1.0]])
+    l = np.zeros((3, P.K, 2), order="F")
+    for n in range(2):
+        l[:, :, n] = orc.init_dmpc(po[:, n], pf[:, n], P.h, P.K, 10.0)[0]
+    o, e = _cmp(orc, emul, P, po, np.zeros((3, 2)), np.zeros((3, 2)), pf, l, pmin, pmax)
+    assert (e["status"] & 2).all()
+
+
+def test_longer_horizon_k20(orc, emul):
+    from multiagent_planning_b200 import scenarios
+    N = 40
+    pmin, pmax = scenarios.density_arena(N, density=2.0)
+    po, pf = scenarios.random_test(N, pmin, pmax, 0.35, 2.0, seed=5)
+    P = orc.default_params(0)
+    P.K = 20
+    l = np.zeros((3, 20, N), order="F")
+    for n in range(N):
+        l[:, :, n] = orc.init_dmpc(po[:, n], pf[:, n], P.h, 20, P.init_div)[0]
+    pk, vk, ak = l[:, 0, :].copy(), np.zeros((3, N)), np.zeros((3, N))
+    for k in range(8):
+        o, e = _cmp(orc, emul, P, pk, vk, ak, pf, l, pmin, pmax, QMAX=96)
+        l, pk, vk, ak = e["l_new"], e["p1"], e["v1"], e["a1"]

@@ -1,0 +1,380 @@
+"""GPU parity tests: the CUDA path (through the C-ABI of libdmpc_b200.so) against the CPU oracle on
+the same inputs, against the reference's golden MATLAB workspaces, and -- at the full sizes of
+BASELINE.json -- through size-independent properties.  Tolerances:
+  GPU vs oracle, teacher-forced: max |dp| over the horizon <= 1e-6 m, identical status flags;
+  GPU vs MATLAB golden: collision-free agents <= 1e-4 m, colliding agents <= 1e-2 m."""
+import os
+
+import numpy as np
+import pytest
+
+from tests.conftest import oracle_params
+
+pytestmark = pytest.mark.gpu
+
+TOL = 1e-6
+
+
+def _solver(dmpc, g, variant, **kw):
+    P = dmpc.default_params(variant, **kw)
+    N = g["l"].shape[2]
+    return P, dmpc.Solver(N, P, pmin=g["pmin"], pmax=g["pmax"], pf=g["pf"])
+
+
+def _cmp_step(orc, P, s, pk, vk, ak, pf, l, pmin, pmax, tol=TOL):
+    g = s.step(pk, vk, ak, l, want_horizons=True)
+    o = orc.step(oracle_params(orc, P), pk, vk, ak, pf, l, pmin, pmax)
+    n0, n1 = s.n0, s.n1
+    assert np.array_equal(g["status"][n0:n1] & 0xFF, o["status"][n0:n1] & 0xFF)
+    for k in ("l_new", "p1", "v1", "a1"):
+        assert np.abs(g[k] - o[k]).max() <= tol, k
+    assert g["first_fail"] == o["first_fail"]
+    return g, o
+
+
+def test_kat_soft_bound_vs_oracle_and_matlab(dmpc, orc, golden):
+    g = golden["kat_soft_bound"]
+    P, s = _solver(dmpc, g, dmpc.SOFT_BOUND)
+    with s:
+        out, o = _cmp_step(orc, P, s, g["pk_prev"], g["vk_prev"], g["ak_prev"], g["pf"], g["l"], g["pmin"], g["pmax"])
+        ns = int(g["n_solved"])
+        assert out["first_fail"] == ns and out["status"][ns] & dmpc.ST_COLL
+        err = np.abs(out["l_new"][:, :, :ns] - g["new_l"]).max(axis=(0, 1))
+        free = out["diag"]["kstar"][:ns] == 0
+        assert free.sum() == 41
+        assert err[free].max() <= 1e-4 and err[~free].max() <= 1e-2 and np.median(err[~free]) <= 1e-4
+        assert np.abs(out["p1"][:, :ns] - g["pk_new"]).max() <= 1e-3
+        # v, a horizons are consistent with the model: p = A_p a + A_initp [po;vo]
+        A, Av, A0, _ = dmpc.modelMats(P.h, P.K)
+        for n in (0, 5, 100):
+            a = out["a_hor"][:, :, n].reshape(-1, order="F")
+            p = A @ a + A0 @ np.r_[g["pk_prev"][:, n], g["vk_prev"][:, n]]
+            v = Av @ a + np.tile(g["vk_prev"][:, n], P.K)
+            assert np.abs(p - out["l_new"][:, :, n].reshape(-1, order="F")).max() < 1e-12
+            assert np.abs(v - out["v_hor"][:, :, n].reshape(-1, order="F")).max() < 1e-12
+
+
+def test_kat_soft_bound2_vs_oracle_and_matlab(dmpc, orc, golden):
+    g = golden["kat_soft_bound2"]
+    P, s = _solver(dmpc, g, dmpc.SOFT_BOUND2)
+    with s:
+        out, _ = _cmp_step(orc, P, s, g["pk_prev"], g["vk_prev"], g["ak_prev"], g["pf"], g["l"], g["pmin"], g["pmax"])
+        ns = int(g["n_solved"])
+        assert np.abs(out["l_new"][:, :, :ns] - g["new_l"]).max() <= 2e-4
+
+
+@pytest.mark.parametrize("variant", [2, 3])
+def test_hard_variants_vs_oracle(dmpc, orc, golden, variant):
+    g = golden["kat_soft_bound2"]    # N = 100 (BASELINE config 2 shape)
+    P, s = _solver(dmpc, g, variant)
+    with s:
+        _cmp_step(orc, P, s, g["pk_prev"], g["vk_prev"], g["ak_prev"], g["pf"], g["l"], g["pmin"], g["pmax"])
+
+
+def test_cpp_neighbour_mode_vs_oracle(dmpc, orc, golden):
+    """C++ check_collisionsv2 threshold rmin*(1+k/K) (dmpc.cpp:418) as a flag"""
+    g = golden["kat_soft_bound"]
+    P, s = _solver(dmpc, g, dmpc.SOFT_BOUND, neigh_mode=1)
+    with s:
+        _cmp_step(orc, P, s, g["pk_prev"], g["vk_prev"], g["ak_prev"], g["pf"], g["l"], g["pmin"], g["pmax"])
+
+
+def test_matlab_named_surface(dmpc, orc, golden):
+    """solveSoftDMPCbound / CheckCollSoftDMPC / CollConstrSoftDMPC / propStatedmpc / initDMPC /
+    ReachedGoal with the reference's argument lists (1-based n, k)."""
+    g = golden["kat_soft_bound"]
+    l, K, h = g["l"], 15, 0.2
+    A, Av, A0, Delta = dmpc.modelMats(h, K)
+    E1, E2 = np.diag([1, 1, 1 / 2.0]), np.diag([1, 1, 1 / 4.0])
+    O = orc.default_params(0)
+    for n in (1, 2, 17, 120):
+        i = n - 1
+        p, v, a, feas, outb, coll = dmpc.solveSoftDMPCbound(
+            g["pk_prev"][:, i], g["pf"][:, i], g["vk_prev"][:, i], g["ak_prev"][:, i], n, h, l, K, 0.35,
+            g["pmin"], g["pmax"], 1.0, A, A0, A, Av, Delta, 1000, 100, E1, E2, 2, -5e4)
+        assert (feas, outb, coll) == (1, 0, 0) and p.shape == (3, K)
+        assert np.abs(p - g["new_l"][:, :, i]).max() <= 1e-2
+        st, po_, vo_, ao_, _ = orc.solve_agent(O, g["pk_prev"][:, i], g["pf"][:, i], g["vk_prev"][:, i],
+                                               g["ak_prev"][:, i], i, l, g["pmin"], g["pmax"])
+        assert np.abs(p - po_).max() <= TOL and np.abs(v - vo_).max() <= TOL and np.abs(a - ao_).max() <= TOL
+        p2, v2 = dmpc.propStatedmpc(g["pk_prev"][:, i], g["vk_prev"][:, i], a.reshape(-1, order="F"), A0, A, Av)
+        assert np.abs(p2 - p.reshape(-1, order="F")).max() < 1e-12
+        assert np.abs(v2 - v.reshape(-1, order="F")).max() < 1e-12
+    # agent 170: k == 1 violation -> coll = 1 and empty outputs (solveSoftDMPCbound.m:25-32)
+    n = int(g["n_failed"])
+    p, v, a, feas, outb, coll = dmpc.solveSoftDMPCbound(
+        g["pk_prev"][:, n - 1], g["pf"][:, n - 1], g["vk_prev"][:, n - 1], g["ak_prev"][:, n - 1], n, h, l, K, 0.35,
+        g["pmin"], g["pmax"], 1.0, A, A0, A, Av, Delta, 1000, 100, E1, E2, 2, -5e4)
+    assert coll == 1 and feas == 1 and p.size == 0
+    # CheckColl / CollConstr on agent 3 at every horizon step
+    n = 3
+    for k in range(1, K + 1):
+        p3 = l[:, k - 1, n - 1]
+        viol, md, vc = dmpc.CheckCollSoftDMPC(p3, l, n, k, E1, 0.35, 2)
+        oany, ov, ovc, omd = orc.check_coll(O, p3, l, n - 1, k)
+        assert np.array_equal(viol, ov.astype(bool)) and np.array_equal(vc, ovc.astype(bool)) and md == omd
+        if vc.any():
+            Ain, b, pd = dmpc.CollConstrSoftDMPC(p3, g["pk_prev"][:, n - 1], g["vk_prev"][:, n - 1], n, k, l, 0.35,
+                                                 None, A0, E1, E2, 2, vc)
+            oA, ob, opd, _ = orc.coll_constr(O, p3, g["pk_prev"][:, n - 1], g["vk_prev"][:, n - 1], n - 1, k, l,
+                                             mask=vc.astype(np.uint8))
+            assert Ain.shape == oA.shape == (int(vc.sum()), 3 * K)
+            assert np.abs(Ain - oA).max() < 1e-13 and np.abs(b - ob).max() < 1e-12 and np.array_equal(pd, opd)
+    with pytest.raises(dmpc.DmpcError):
+        dmpc.CheckCollSoftDMPC(l[:, 0, 0], l, 1, 1, E1, 0.35, 4)      # order 4 is rejected
+    # initDMPC / ReachedGoal
+    p, v, a = dmpc.initDMPC(g["pk_prev"][:, 0], g["pf"][:, 0], h, K, 150)
+    op, _, _ = orc.init_dmpc(g["pk_prev"][:, 0], g["pf"][:, 0], h, K, 10.0)
+    assert np.array_equal(p, op) and not v.any() and not a.any()
+    pk = np.repeat(g["pf"][:, None, :], 2, axis=1) + 0.003
+    assert dmpc.ReachedGoal(pk, g["pf"], 2, 0.01, 200) is True
+    pk[0, 1, 7] += 0.02
+    assert dmpc.ReachedGoal(pk, g["pf"], 2, 0.01, 200) is False
+    dmpc.close_cached_solvers()
+
+
+def _closed_loop(dmpc, orc, cfg, steps, check_every=1):
+    """device-resident run == host-stepped run; host-stepped teacher-forced vs oracle"""
+    P = dmpc.default_params(cfg["variant"], **cfg["params"])
+    N = cfg["N"]
+    with dmpc.Solver(N, P, pmin=cfg["pmin"], pmax=cfg["pmax"], pf=cfg["pf"]) as s:
+        s.init_horizons(cfg["po"])
+        r = s.run(steps, record=True, status_hist=True)
+        l, pk, vk, ak = s.init_horizons(cfg["po"])
+        assert np.array_equal(r["pk"][:, 0, :], pk)
+        flips = 0
+        for k in range(r["steps"]):
+            if k % check_every == 0:
+                g, o = s.step(pk, vk, ak, l), orc.step(oracle_params(orc, P), pk, vk, ak, cfg["pf"], l, cfg["pmin"],
+                                                       cfg["pmax"], nthreads=4)
+                assert np.array_equal(g["status"] & 0xFF, o["status"] & 0xFF)
+                assert np.abs(g["l_new"] - o["l_new"]).max() <= TOL
+            else:
+                g = s.step(pk, vk, ak, l)
+            assert np.array_equal(r["pk"][:, k + 1, :], g["p1"])       # same kernels, same bits
+            assert np.array_equal(r["vk"][:, k + 1, :], g["v1"]) and np.array_equal(r["ak"][:, k + 1, :], g["a1"])
+            assert np.array_equal(r["status_hist"][k], g["status"])
+            l, pk, vk, ak = g["l_new"], g["p1"], g["v1"], g["a1"]
+        # plain-launch and timed modes give the same trajectory as the graph
+        for mode in (1, 2):
+            s.init_horizons(cfg["po"])
+            r2 = s.run(steps, mode=mode, record=True)
+            assert r2["steps"] == r["steps"] and np.array_equal(r2["pk"], r["pk"])
+        st = s.get_state()
+        assert np.array_equal(st["pk"], pk) and np.array_equal(st["l"], l)
+    return r
+
+
+def test_closed_loop_4_agents_corner_swap(dmpc, orc):
+    """BASELINE config 1 shape: dmpc_soft_bound.m:43-54, 100 fixed steps"""
+    from multiagent_planning_b200 import scenarios
+    cfg = scenarios.config("C1")
+    r = _closed_loop(dmpc, orc, cfg, 100)
+    end = r["pk"][:, -1, :]
+    assert np.sqrt(((end - cfg["pf"]) ** 2).sum(0)).max() < 0.05
+    assert r["first_fail_step"] == -1
+
+
+def test_closed_loop_n100(dmpc, orc):
+    from multiagent_planning_b200 import scenarios
+    cfg = scenarios.config("N100")
+    r = _closed_loop(dmpc, orc, cfg, 149, check_every=3)
+    assert r["reached"] and r["steps"] < 120
+    # early exit at the goal: the loop stopped by itself (ReachedGoal on the device)
+    assert np.sqrt(((r["pk"][:, -1, :] - cfg["pf"]) ** 2).sum(0)).max() < 0.01
+
+
+def test_closed_loop_hard_n100(dmpc, orc):
+    """BASELINE config 2: N=100, 10x10x3 arena, solveHardDMPC"""
+    from multiagent_planning_b200 import scenarios
+    cfg = scenarios.config("C2")
+    _closed_loop(dmpc, orc, cfg, 30, check_every=2)
+
+
+def test_edge_cases(dmpc, orc):
+    pmin, pmax = np.array([-2.5, -2.5, 0.2]), np.array([2.5, 2.5, 2.2])
+    P = dmpc.default_params(0)
+    O = oracle_params(orc, P)
+    # one agent, two agents head-on, overlapping agents, a ragged tile (N = 33), N = 32, N = 65
+    cases = {
+        1: (np.array([[0.0], [0.0], [1.0]]), np.array([[1.0], [1.0], [1.5]])),
+        2: (np.array([[-1.0, 1.0], [0.0, 0.01], [1.0, 1.0]]), np.array([[1.0, -1.0], [0.0, 0.0], [1.0, 3.5]])),
+    }
+    from multiagent_planning_b200 import scenarios
+    for N in (3, 32, 33, 65):
+        a, b = scenarios.density_arena(N, density=3.0)
+        cases[N] = scenarios.random_test(N, a, b, 0.35, 2.0, seed=N) + (a, b)
+    for N, c in cases.items():
+        po, pf = c[0], c[1]
+        lo, hi = (c[2], c[3]) if len(c) == 4 else (pmin, pmax)
+        with dmpc.Solver(N, P, pmin=lo, pmax=hi, pf=pf) as s:
+            l, pk, vk, ak = s.init_horizons(po)
+            for n in range(N):
+                assert np.array_equal(l[:, :, n], orc.init_dmpc(po[:, n], pf[:, n], P.h, P.K, 10.0)[0])
+            for _ in range(12):
+                g, _ = _cmp_step(orc, P, s, pk, vk, ak, pf, l, lo, hi)
+                l, pk, vk, ak = g["l_new"], g["p1"], g["v1"], g["a1"]
+    # overlap at k = 1 -> coll for both
+    po = np.array([[0.0, 0.1], [0.0, 0.0], [1.0, 1.0]])
+    pf = np.array([[1.0, -1.0], [0.0, 0.0], [1.0, 1.0]])
+    with dmpc.Solver(2, P, pmin=pmin, pmax=pmax, pf=pf) as s:
+        l, pk, vk, ak = s.init_horizons(po)
+        g, _ = _cmp_step(orc, P, s, pk, vk, ak, pf, l, pmin, pmax)
+        assert (g["status"] & dmpc.ST_COLL).all() and g["first_fail"] == 0
+        assert np.array_equal(g["l_new"], l) and np.array_equal(g["p1"], pk)
+    # API errors, not crashes
+    with pytest.raises(dmpc.DmpcError):
+        dmpc.Solver(0)
+    with pytest.raises(dmpc.DmpcError):
+        dmpc.Solver(4, dmpc.default_params(0, K=40))
+    with dmpc.Solver(4, P) as s:
+        with pytest.raises(dmpc.DmpcError):
+            s.run(5)                      # no bounds / init yet
+
+
+def test_sharded_handles_equal_whole(dmpc, orc, golden):
+    """agents [n0,n1) per handle (the multi-GPU partition) give the rows of the whole solve"""
+    g = golden["kat_soft_bound"]
+    P, whole = _solver(dmpc, g, 0)
+    with whole:
+        w = whole.step(g["pk_prev"], g["vk_prev"], g["ak_prev"], g["l"])
+    for n0, n1 in ((0, 63), (63, 126), (126, 200)):
+        with dmpc.Solver(200, P, n0=n0, n1=n1, pmin=g["pmin"], pmax=g["pmax"], pf=g["pf"]) as s:
+            o = s.step(g["pk_prev"], g["vk_prev"], g["ak_prev"], g["l"])
+            assert np.array_equal(o["l_new"][:, :, n0:n1], w["l_new"][:, :, n0:n1])
+            assert np.array_equal(o["status"][n0:n1], w["status"][n0:n1])
+            assert np.array_equal(o["l_new"][:, :, :n0], g["l"][:, :, :n0])        # others untouched
+
+
+def test_rescue_path_small_onchip_capacity(dmpc, orc, golden, monkeypatch):
+    """force a tiny on-chip active-set capacity: agents that outgrow it re-solve in the global
+    rescue slots and must still match the oracle"""
+    g = golden["kat_soft_bound"]
+    monkeypatch.setenv("DMPCB200_QMAX", "4")
+    P, s = _solver(dmpc, g, 0)
+    with s:
+        assert s.config()["QMAX"] == 4
+        _cmp_step(orc, P, s, g["pk_prev"], g["vk_prev"], g["ak_prev"], g["pf"], g["l"], g["pmin"], g["pmax"])
+
+
+def test_step_dev_with_caller_owned_unpadded_buffers(dmpc, orc, golden):
+    """dmpcb200_step_dev on torch-owned device memory without tile padding (ragged last tile path)"""
+    import torch
+    g = golden["kat_soft_bound2"]
+    N, K = 100, 15
+    P, s = _solver(dmpc, g, 1)
+    dev = torch.device("cuda", 0)
+    t = lambda a: torch.from_numpy(np.ascontiguousarray(a.T)).to(dev)            # (3,N) -> (N,3)
+    l_prev = torch.from_numpy(np.ascontiguousarray(g["l"].transpose(2, 1, 0))).to(dev)
+    l_new = l_prev.clone()
+    pk, vk, ak = t(g["pk_prev"]), t(g["vk_prev"]), t(g["ak_prev"])
+    p1, v1, a1 = pk.clone(), vk.clone(), ak.clone()
+    st = torch.zeros(N, dtype=torch.int32, device=dev)
+    with s:
+        s.step_dev(pk.data_ptr(), vk.data_ptr(), ak.data_ptr(), l_prev.data_ptr(), l_new.data_ptr(), p1.data_ptr(),
+                   v1.data_ptr(), a1.data_ptr(), st.data_ptr(), stream=torch.cuda.current_stream().cuda_stream)
+        torch.cuda.synchronize()
+        o = orc.step(oracle_params(orc, P), g["pk_prev"], g["vk_prev"], g["ak_prev"], g["pf"], g["l"], g["pmin"],
+                     g["pmax"])
+        assert np.array_equal(st.cpu().numpy() & 0xFF, o["status"] & 0xFF)
+        assert np.abs(l_new.cpu().numpy().transpose(2, 1, 0) - o["l_new"]).max() <= TOL
+        assert np.abs(p1.cpu().numpy().T - o["p1"]).max() <= TOL
+        out = torch.zeros(2, dtype=torch.float64, device=dev)
+        s.goal_dev(l_new.data_ptr(), 3 * K, out.data_ptr(), stream=torch.cuda.current_stream().cuda_stream)
+        md = np.sqrt(((l_new.cpu().numpy()[:, 0, :].T - g["pf"]) ** 2).sum(0)).max()
+        assert abs(out.cpu().numpy()[0] - md) < 1e-12
+
+
+# ---- full-size configurations: size-independent properties --------------------------------------
+def _properties(dmpc, cfg, steps):
+    P = dmpc.default_params(cfg["variant"], **cfg["params"])
+    N, K = cfg["N"], P.K
+    with dmpc.Solver(N, P, pmin=cfg["pmin"], pmax=cfg["pmax"], pf=cfg["pf"]) as s:
+        l, pk, vk, ak = s.init_horizons(cfg["po"])
+        for _ in range(steps):
+            g = s.step(pk, vk, ak, l, want_horizons=True)
+            l, pk, vk, ak = g["l_new"], g["p1"], g["v1"], g["a1"]
+        st = g["status"]
+        ok = (st & dmpc.ST_SOLVED) != 0
+        assert ok.mean() > 0.9 and not (st & (dmpc.ST_QPFAIL | dmpc.ST_OVERFLOW)).any()
+        # feasibility of what was solved: acceleration box, workspace box
+        assert np.abs(g["a_hor"][:, :, ok]).max() <= P.alim + 1e-9
+        lo, hi = cfg["pmin"][:, None, None], cfg["pmax"][:, None, None]
+        assert (g["l_new"][:, :, ok] >= lo - 1e-8).all() and (g["l_new"][:, :, ok] <= hi + 1e-8).all()
+        # permutation equivariance: relabelling the agents permutes the result (unique optimum)
+        rng = np.random.default_rng(0)
+        perm = rng.permutation(N)
+        g1 = s.step(pk, vk, ak, l)
+    with dmpc.Solver(N, P, pmin=cfg["pmin"], pmax=cfg["pmax"], pf=cfg["pf"][:, perm]) as s2:
+        g2 = s2.step(pk[:, perm], vk[:, perm], ak[:, perm], l[:, :, perm])
+    assert np.array_equal(g1["status"][perm] & 0xFF, g2["status"] & 0xFF)
+    assert np.abs(g1["l_new"][:, :, perm] - g2["l_new"]).max() <= 1e-8
+    return g
+
+
+def test_properties_n500_k15(dmpc):
+    from multiagent_planning_b200 import scenarios
+    _properties(dmpc, scenarios.config("C3"), 6)
+
+
+def test_properties_n2000_k20_dense(dmpc):
+    from multiagent_planning_b200 import scenarios
+    _properties(dmpc, scenarios.config("C4"), 4)
+
+
+def test_n500_vs_oracle_dense_steps(dmpc, orc):
+    """the bench workload (N=500, K=15, soft bound): first steps teacher-forced against the oracle"""
+    from multiagent_planning_b200 import scenarios
+    cfg = scenarios.config("C3")
+    P = dmpc.default_params(cfg["variant"])
+    with dmpc.Solver(500, P, pmin=cfg["pmin"], pmax=cfg["pmax"], pf=cfg["pf"]) as s:
+        l, pk, vk, ak = s.init_horizons(cfg["po"])
+        for _ in range(8):
+            g, _ = _cmp_step(orc, P, s, pk, vk, ak, cfg["pf"], l, cfg["pmin"], cfg["pmax"])
+            l, pk, vk, ak = g["l_new"], g["p1"], g["v1"], g["a1"]
+
+
+def _nccl_worker(rank, world, port, q):
+    import torch
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    try:
+        from multiagent_planning_b200 import dmpc, scenarios, sharded
+        cfg = scenarios.config("N100")
+        P = dmpc.default_params(0)
+        sh = sharded.ShardedDMPC(100, P, cfg["pmin"], cfg["pmax"], cfg["po"], cfg["pf"])
+        for _ in range(10):
+            sh.step()
+        torch.cuda.synchronize()
+        if rank == 0:
+            q.put(sh.horizons())
+        dist.barrier()
+    finally:
+        dist.destroy_process_group()
+
+
+def test_two_gpus_nccl_equal_one_gpu(dmpc):
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    import torch.multiprocessing as mp
+    from tests.test_sharded_gloo import _free_port
+    from multiagent_planning_b200 import scenarios
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_nccl_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    l2 = q.get(timeout=300)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    cfg = scenarios.config("N100")
+    with dmpc.Solver(100, dmpc.default_params(0), pmin=cfg["pmin"], pmax=cfg["pmax"], pf=cfg["pf"]) as s:
+        s.init_horizons(cfg["po"])
+        s.run(10)
+        assert np.array_equal(s.get_state()["l"], l2)
