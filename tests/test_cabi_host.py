@@ -94,3 +94,13 @@ def test_scenarios_respect_min_distance():
         assert dist.min() > 0.35
     po2, _ = scenarios.random_test(120, pmin, pmax, 0.35, 2.0, seed=3)
     assert np.array_equal(po, po2)
+
+
+def test_mex_gateway_syntax_against_the_header():
+    """matlab/dmpc_b200_mex.cpp cannot be built here (no MATLAB): syntax-check it against
+    include/dmpc_b200.h with a stub mex.h so that the gateway cannot drift from the C-ABI."""
+    import subprocess
+    r = subprocess.run(["g++", "-std=c++17", "-fsyntax-only", "-Wall", "-I", os.path.join(ROOT, "tests", "mex_stub"),
+                        "-I", os.path.join(ROOT, "include"), os.path.join(ROOT, "matlab", "dmpc_b200_mex.cpp")],
+                       capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
