@@ -32,24 +32,24 @@ DMPC_HD int round_up(int v, int m) { return (v + m - 1) / m * m; }
 // block (all three weight sets, model_tables.h layout) and shared by the block's agents.
 DMPC_HD size_t agent_smem_bytes(int K, int QMAX, int RCAP) {
     const int n3p = round_up(3 * K, 2);
-    size_t nd = 7 * (size_t)n3p + 3 * (size_t)QMAX + (size_t)QMAX * QMAX + 8 * (size_t)RCAP;
-    size_t ni = 2 * (size_t)QMAX + 2 * (size_t)n3p + 5 * (size_t)RCAP;
+    size_t nd = 8 * (size_t)n3p + 18 + 7 * (size_t)QMAX + (size_t)QMAX * QMAX + 9 * (size_t)RCAP;
+    size_t ni = 3 * (size_t)QMAX + 4 * (size_t)n3p + 5 * (size_t)RCAP;
     return nd * sizeof(double) + round_up((int)ni, 4) * sizeof(int);  // multiple of 16 bytes
 }
 
 // layout of the table blob in global memory: see model_tables.h
-DMPC_HD int tab_set_offset(int K, int wset) { return K * K + 2 * K + wset * 3 * K * K; }
+DMPC_HD int tab_set_offset(int K, int wset) { return K * K + 4 * K + wset * 3 * K * K; }
 
 struct AgentIO {
     // inputs
-    double po[3], pf[3], vo[3], ao[3];
+    const double *po, *pf, *vo, *ao;  // 3 each (global)
     int kstar;     // 1-based first violating step (0 none)
     int nv;        // rows produced by the scan
     int scanflag;  // ST_COLL / ST_OVERFLOW from the scan, else 0
     int RMAX;      // stride of the global row arrays
     const double* grow;  // global rows: d0[RMAX] d1[RMAX] d2[RMAX] dist[RMAX] rhs[RMAX]
     const int* gkc;      // global rows: kc[RMAX]
-    double* gscr_d;      // global scratch (used when nv > RCAP): 3*RMAX doubles
+    double* gscr_d;      // global scratch (used when nv > RCAP): 4*RMAX doubles
     int* gscr_i;         // 4*RMAX ints
     // outputs (global), 3K each; v_hor / a_hor may be null
     double *out_p, *out_v, *out_a;
@@ -59,9 +59,11 @@ struct AgentIO {
 
 // All lanes of the warp call this with identical arguments.  Returns the status word.
 // tab: the whole table blob (model_tables.h layout), normally resident in shared memory.
+// KT: compile-time horizon length (0 = run-time P.K).
+template <int KT>
 DMPC_D int agent_solve(const DevParams& P, const double* __restrict__ tab, unsigned char* smem,
                        int QMAX, int RCAP, const AgentIO& io, AgentDiag* diag_out) {
-    const int K = P.K, n3 = 3 * K, n3p = round_up(n3, 2);
+    const int K = KT ? KT : P.K, n3 = 3 * K, n3p = round_up(n3, 2);
     const int lane = lane_id();
     AgentDiag dg;
     dg.kstar = io.kstar;
@@ -75,26 +77,37 @@ DMPC_D int agent_solve(const DevParams& P, const double* __restrict__ tab, unsig
     } else {
         // ---- carve the scratch ---------------------------------------------------------------
         double* dptr = reinterpret_cast<double*>(smem);
-        double* s_p0 = dptr; dptr += n3p;
+        double* s_Punc = dptr; dptr += n3p;
         double* s_aunc = dptr; dptr += n3p;
         double* s_a = dptr; dptr += n3p;
         double* s_P = dptr; dptr += n3p;
         double* s_cbox = dptr; dptr += n3p;
         double* s_cP = dptr; dptr += n3p;
         double* s_z = dptr; dptr += n3p;
+        double* s_Lz = dptr; dptr += n3p;
+        double* s_x0 = dptr; dptr += 12;   // po, pf, vo, ao
+        double* s_bnd = dptr; dptr += 6;   // pmin, pmax
         double* s_u = dptr; dptr += QMAX;
         double* s_g = dptr; dptr += QMAX;
         double* s_r = dptr; dptr += QMAX;
+        double* s_sv0 = dptr; dptr += QMAX;
+        double* s_sv1 = dptr; dptr += QMAX;
+        double* s_sv2 = dptr; dptr += QMAX;
+        double* s_se = dptr; dptr += QMAX;
         double* s_M = dptr; dptr += (size_t)QMAX * QMAX;
         double* s_rows = dptr; dptr += 5 * (size_t)RCAP;
         double* s_rnorm = dptr; dptr += RCAP;
         double* s_eps = dptr; dptr += RCAP;
         double* s_zeps = dptr; dptr += RCAP;
+        double* s_rres = dptr; dptr += RCAP;
         int* iptr = reinterpret_cast<int*>(dptr);
         int* s_act = iptr; iptr += QMAX;
         int* s_ralist = iptr; iptr += QMAX;
-        int* s_mbox = iptr; iptr += n3p;
-        int* s_mws = iptr; iptr += n3p;
+        int* s_sinfo = iptr; iptr += QMAX;
+        int* s_sbl = iptr; iptr += n3p;
+        int* s_sbu = iptr; iptr += n3p;
+        int* s_swl = iptr; iptr += n3p;
+        int* s_swu = iptr; iptr += n3p;
         int* s_rslot = iptr; iptr += RCAP;
         int* s_ubslot = iptr; iptr += RCAP;
         int* s_lbslot = iptr; iptr += RCAP;
@@ -105,7 +118,17 @@ DMPC_D int agent_solve(const DevParams& P, const double* __restrict__ tab, unsig
         const bool soft = (P.variant == VAR_SOFT_BOUND || P.variant == VAR_SOFT_BOUND2);
         // solveHardDMPC quirk: Ain_coll is never empty for N >= 2 -> collision weights always
         const bool any_violation = (P.variant == VAR_HARD) ? (P.N >= 2) : (io.kstar > 0);
-        const double dgx = io.po[0] - io.pf[0], dgy = io.po[1] - io.pf[1], dgz = io.po[2] - io.pf[2];
+        for (int x = lane; x < 3; x += kLanes) {
+            s_x0[x] = io.po[x];
+            s_x0[3 + x] = io.pf[x];
+            s_x0[6 + x] = io.vo[x];
+            s_x0[9 + x] = io.ao[x];
+            s_bnd[x] = P.pmin[x];
+            s_bnd[3 + x] = P.pmax[x];
+        }
+        wsync();
+        const double *x_po = s_x0, *x_pf = s_x0 + 3, *x_vo = s_x0 + 6, *x_ao = s_x0 + 9;
+        const double dgx = x_po[0] - x_pf[0], dgy = x_po[1] - x_pf[1], dgz = x_po[2] - x_pf[2];
         const double dgoal = sqrt(dgx * dgx + dgy * dgy + dgz * dgz);
         int wset;
         double qw, sw;
@@ -117,6 +140,7 @@ DMPC_D int agent_solve(const DevParams& P, const double* __restrict__ tab, unsig
         const double* t_lam = tab;
         const double* t_tt = tab + K * K;
         const double* t_lnorm = tab + K * K + K;
+        const double* t_ilnorm = tab + K * K + 2 * K;
         const double* t_G = tab + tab_set_offset(K, wset);
         const double* t_B = t_G + K * K;
         const double* t_C = t_B + K * K;
@@ -125,7 +149,7 @@ DMPC_D int agent_solve(const DevParams& P, const double* __restrict__ tab, unsig
         const int nv = io.nv;
         const double *rd0, *rd1, *rd2, *rdist, *rrhs;
         const int* rkc;
-        double *rnorm, *eps, *zeps;
+        double *irnorm, *eps, *zeps, *rres;
         int *rslot, *ubslot, *lbslot, *rmat;
         if (nv <= RCAP) {
             for (int f = 0; f < 5; ++f)
@@ -133,12 +157,13 @@ DMPC_D int agent_solve(const DevParams& P, const double* __restrict__ tab, unsig
             for (int j = lane; j < nv; j += kLanes) s_rkc[j] = io.gkc[j];
             rd0 = s_rows; rd1 = s_rows + RCAP; rd2 = s_rows + 2 * RCAP; rdist = s_rows + 3 * RCAP;
             rrhs = s_rows + 4 * RCAP;
-            rkc = s_rkc; rnorm = s_rnorm; eps = s_eps; zeps = s_zeps;
+            rkc = s_rkc; irnorm = s_rnorm; eps = s_eps; zeps = s_zeps; rres = s_rres;
             rslot = s_rslot; ubslot = s_ubslot; lbslot = s_lbslot; rmat = s_rmat;
         } else {
             rd0 = io.grow; rd1 = io.grow + io.RMAX; rd2 = io.grow + 2 * (size_t)io.RMAX;
             rdist = io.grow + 3 * (size_t)io.RMAX; rrhs = io.grow + 4 * (size_t)io.RMAX;
-            rkc = io.gkc; rnorm = io.gscr_d; eps = io.gscr_d + io.RMAX; zeps = io.gscr_d + 2 * (size_t)io.RMAX;
+            rkc = io.gkc; irnorm = io.gscr_d; eps = io.gscr_d + io.RMAX; zeps = io.gscr_d + 2 * (size_t)io.RMAX;
+            rres = io.gscr_d + 3 * (size_t)io.RMAX;
             rslot = io.gscr_i; ubslot = io.gscr_i + io.RMAX; lbslot = io.gscr_i + 2 * (size_t)io.RMAX;
             rmat = io.gscr_i + 3 * (size_t)io.RMAX;
         }
@@ -146,53 +171,69 @@ DMPC_D int agent_solve(const DevParams& P, const double* __restrict__ tab, unsig
         for (int j = lane; j < nv; j += kLanes) {
             const double dd = rd0[j] * rd0[j] + rd1[j] * rd1[j] + rd2[j] * rd2[j];
             const double ln = t_lnorm[rkc[j]];
-            rnorm[j] = sqrt(dd * ln * ln + (soft ? rdist[j] * rdist[j] : 0.0));
+            irnorm[j] = 1.0 / sqrt(dd * ln * ln + (soft ? rdist[j] * rdist[j] : 0.0));
         }
 
-        // ---- p0 = A_initp [po;vo],  a_unc = -G f -------------------------------------------------
+        // ---- a_unc = -G f,  P_unc = A_initp [po;vo] + Lam a_unc ------------------------------------
         // f_x = -2 ( q e_x lamK + s ao_x e_0 ),  e = pf - (po + t_K vo)   (solveSoftDMPCbound.m:82-88)
         for (int i = lane; i < n3; i += kLanes) {
             const int k = i / 3, x = i - 3 * k;
-            s_p0[i] = io.po[x] + t_tt[k] * io.vo[x];
-            const double e = io.pf[x] - (io.po[x] + t_tt[K - 1] * io.vo[x]);
-            s_aunc[i] = 2.0 * qw * e * t_B[k * K + (K - 1)] + 2.0 * sw * io.ao[x] * t_G[k * K];
+            const double e = x_pf[x] - (x_po[x] + t_tt[K - 1] * x_vo[x]);
+            s_aunc[i] = 2.0 * qw * e * t_B[k * K + (K - 1)] + 2.0 * sw * x_ao[x] * t_G[k * K];
+        }
+        wsync();
+        for (int i = lane; i < n3; i += kLanes) {
+            const int k = i / 3, x = i - 3 * k;
+            double s = 0.0;
+            for (int j = 0; j <= k; ++j) s = fma(t_lam[k * K + j], s_aunc[3 * j + x], s);
+            s_Punc[i] = s + (x_po[x] + t_tt[k] * x_vo[x]);
         }
         wsync();
 
-        Qp qp;
+        Qp<KT> qp;
         qp.w.K = K; qp.w.n3 = n3; qp.w.QMAX = QMAX;
-        qp.w.lam = t_lam; qp.w.lnorm = t_lnorm; qp.w.G = t_G; qp.w.B = t_B; qp.w.C = t_C;
+        qp.w.lam = t_lam; qp.w.ilnorm = t_ilnorm; qp.w.G = t_G; qp.w.B = t_B; qp.w.C = t_C;
         qp.w.alim = P.alim; qp.w.soft = soft ? 1 : 0; qp.w.qw = qw; qp.w.sw = sw;
-        for (int x = 0; x < 3; ++x) { qp.w.pmin[x] = P.pmin[x]; qp.w.pmax[x] = P.pmax[x]; }
-        qp.w.p0 = s_p0; qp.w.aunc = s_aunc;
+        qp.w.bnd = s_bnd;
+        qp.w.aunc = s_aunc; qp.w.Punc = s_Punc;
         qp.w.nv = nv;
         qp.w.rd0 = rd0; qp.w.rd1 = rd1; qp.w.rd2 = rd2; qp.w.rdist = rdist; qp.w.rrhs = rrhs;
-        qp.w.rkc = rkc; qp.w.rnorm = rnorm;
-        qp.w.a = s_a; qp.w.P = s_P; qp.w.cbox = s_cbox; qp.w.cP = s_cP; qp.w.z = s_z;
-        qp.w.eps = eps; qp.w.zeps = zeps;
-        qp.w.mbox = s_mbox; qp.w.mws = s_mws;
+        qp.w.rkc = rkc; qp.w.irnorm = irnorm;
+        qp.w.a = s_a; qp.w.P = s_P; qp.w.cbox = s_cbox; qp.w.cP = s_cP; qp.w.z = s_z; qp.w.Lz = s_Lz;
+        qp.w.eps = eps; qp.w.zeps = zeps; qp.w.rres = rres;
+        qp.w.kc_all = (P.variant == VAR_HARD) ? -1 : (io.kstar > 0 ? io.kstar - 1 - (P.variant == VAR_SOFT_BOUND2 ? 1 : 0) : 0);
+        qp.w.sbl = s_sbl; qp.w.sbu = s_sbu; qp.w.swl = s_swl; qp.w.swu = s_swu;
         qp.w.rslot = rslot; qp.w.ubslot = ubslot; qp.w.lbslot = lbslot; qp.w.rmat = rmat;
         qp.w.act = s_act; qp.w.u = s_u; qp.w.g = s_g; qp.w.r = s_r; qp.w.M = s_M;
         qp.w.ralist = s_ralist;
+        qp.w.sv0 = s_sv0; qp.w.sv1 = s_sv1; qp.w.sv2 = s_sv2; qp.w.se = s_se; qp.w.sinfo = s_sinfo;
 
         // ---- retry loop (solveSoftDMPCbound.m:102-155) -------------------------------------------
         double term = P.term, slb = P.slack_lb;
         int tries = 0;
         bool solved = false;
         const int max_iter = 40 * (n3 + nv) + 200;
+        bool warm = false;
         for (;;) {
             qp.w.term = term;
             qp.w.slb = slb;
-            for (int i = lane; i < n3; i += kLanes) {
-                s_a[i] = s_aunc[i];
-                s_mbox[i] = 0;
-                s_mws[i] = 0;
+            if (warm) {
+                // same constraint normals, new (term, slb): keep the active set and its inverse
+                qp.warm_restart();
+            } else {
+                for (int i = lane; i < n3; i += kLanes) {
+                    s_a[i] = s_aunc[i];
+                    s_P[i] = s_Punc[i];
+                    s_sbl[i] = -1; s_sbu[i] = -1; s_swl[i] = -1; s_swu[i] = -1;
+                }
+                for (int j = lane; j < nv; j += kLanes) {
+                    eps[j] = 0.0;
+                    rslot[j] = -1; ubslot[j] = -1; lbslot[j] = -1; rmat[j] = 0;
+                }
+                wsync();
+                qp.reset();
+                qp.rows_refresh();
             }
-            for (int j = lane; j < nv; j += kLanes) {
-                eps[j] = 0.0;
-                rslot[j] = -1; ubslot[j] = -1; lbslot[j] = -1; rmat[j] = 0;
-            }
-            wsync();
             const QpResult r = qp.solve(max_iter);
             dg.iters += r.iters;
             dg.nact = r.q;
@@ -205,6 +246,7 @@ DMPC_D int agent_solve(const DevParams& P, const double* __restrict__ tab, unsig
             slb *= 2.0;
             term *= 2.0;
             if (++tries >= P.max_tries) break;
+            warm = true;
         }
         status |= (tries & 0xff) << 8;
         if (solved) {
@@ -214,7 +256,7 @@ DMPC_D int agent_solve(const DevParams& P, const double* __restrict__ tab, unsig
                 const int k = i / 3, x = i - 3 * k;
                 double sv = 0.0;
                 for (int j = 0; j <= k; ++j) sv += P.h * s_a[3 * j + x];
-                const double vv = sv + io.vo[x];
+                const double vv = sv + x_vo[x];
                 io.out_p[i] = s_P[i];
                 if (io.out_v) io.out_v[i] = vv;
                 if (io.out_a) io.out_a[i] = s_a[i];
@@ -226,8 +268,9 @@ DMPC_D int agent_solve(const DevParams& P, const double* __restrict__ tab, unsig
             }
             // is_inbounds.m on the first predicted position
             bool inb = true;
+#pragma unroll
             for (int x = 0; x < 3; ++x)
-                inb = inb && (s_P[x] < P.pmax[x] + P.inb_tol) && (s_P[x] > P.pmin[x] - P.inb_tol);
+                inb = inb && (s_P[x] < s_bnd[3 + x] + P.inb_tol) && (s_P[x] > s_bnd[x] - P.inb_tol);
             if (!inb) status |= ST_OUTBOUND;
         } else if (!(status & ST_QPFAIL)) {
             status |= ST_INFEASIBLE;
@@ -236,12 +279,11 @@ DMPC_D int agent_solve(const DevParams& P, const double* __restrict__ tab, unsig
     if (!(status & ST_SOLVED)) {
         // the reference returns empty p,v,a: the caller keeps the old horizon and state
         for (int i = lane; i < n3; i += kLanes) io.out_p[i] = io.l_prev_n[i];
-        if (lane == 0)
-            for (int x = 0; x < 3; ++x) {
-                io.p1[x] = io.po[x];
-                io.v1[x] = io.vo[x];
-                io.a1[x] = io.ao[x];
-            }
+        for (int x = lane; x < 3; x += kLanes) {
+            io.p1[x] = io.po[x];
+            io.v1[x] = io.vo[x];
+            io.a1[x] = io.ao[x];
+        }
     }
     if (diag_out && lane == 0) *diag_out = dg;
     return status;

@@ -103,6 +103,7 @@ StepArgs make_args(dmpcb200_t* h, int n0, int n1, const double* pk, const double
                    double* a_hor, int* status, AgentDiag* diag, bool padded, Ctrl* ctrl) {
     StepArgs A;
     A.P = h->dp;
+    A.thr = make_scan_thr(h->dp);
     A.n0 = n0;
     A.n1 = n1;
     A.RMAX = h->RMAX;
@@ -141,41 +142,48 @@ StepArgs make_args(dmpcb200_t* h, int n0, int n1, const double* pk, const double
 }
 
 template <int W>
-cudaError_t launch_scan_w(const StepArgs& A, int nl, size_t smem, cudaStream_t s) {
+cudaError_t launch_scan_w(const StepArgs& A, int nl, int K, cudaStream_t s) {
     static bool attr_done = false;
     if (!attr_done) {
         cudaError_t e = cudaFuncSetAttribute(scan_kernel<W>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
         if (e != cudaSuccess) return e;
         attr_done = true;
     }
-    scan_kernel<W><<<(nl + W - 1) / W, W * 32, smem, s>>>(A);
+    const int stages = scan_stages(K, A.P.N);
+    scan_kernel<W><<<(nl + W - 1) / W, W * 32, scan_smem_bytes(K, W, stages), s>>>(A, stages);
     return cudaGetLastError();
 }
-template <int W>
+template <int W, int KT>
 cudaError_t launch_qp_w(const StepArgs& A, int nl, size_t smem, cudaStream_t s) {
     static bool attr_done = false;
     if (!attr_done) {
-        cudaError_t e = cudaFuncSetAttribute(qp_kernel<W>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        cudaError_t e =
+            cudaFuncSetAttribute(qp_kernel<W, KT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
         if (e != cudaSuccess) return e;
         attr_done = true;
     }
-    qp_kernel<W><<<(nl + W - 1) / W, W * 32, smem, s>>>(A);
+    qp_kernel<W, KT><<<(nl + W - 1) / W, W * 32, smem, s>>>(A);
     return cudaGetLastError();
 }
 
-constexpr int kScanW = 4;
-
+// 4 agents per CTA while that still gives every agent its own SM sub-partition, 8 beyond
 cudaError_t launch_scan(dmpcb200_t* h, const StepArgs& A, cudaStream_t s) {
-    return launch_scan_w<kScanW>(A, A.n1 - A.n0, scan_smem_bytes(h->K, kScanW), s);
+    const int nl = A.n1 - A.n0;
+    if (nl <= 4 * 148) return launch_scan_w<4>(A, nl, h->K, s);
+    return launch_scan_w<8>(A, nl, h->K, s);
 }
+// horizon lengths 15 and 20 (the reference's configurations) are compiled with the horizon as a
+// compile-time constant (fully unrolled table products); anything else takes the generic kernel
 cudaError_t launch_qp(dmpcb200_t* h, const StepArgs& A, cudaStream_t s) {
     const int nl = A.n1 - A.n0;
     const size_t smem = qp_smem_bytes(h->K, h->W, h->QMAX, h->RCAP);
+    if (h->K == 15 && h->W == 4) return launch_qp_w<4, 15>(A, nl, smem, s);
+    if (h->K == 20 && h->W == 3) return launch_qp_w<3, 20>(A, nl, smem, s);
     switch (h->W) {
-        case 4: return launch_qp_w<4>(A, nl, smem, s);
-        case 3: return launch_qp_w<3>(A, nl, smem, s);
-        case 2: return launch_qp_w<2>(A, nl, smem, s);
-        default: return launch_qp_w<1>(A, nl, smem, s);
+        case 4: return launch_qp_w<4, 0>(A, nl, smem, s);
+        case 3: return launch_qp_w<3, 0>(A, nl, smem, s);
+        case 2: return launch_qp_w<2, 0>(A, nl, smem, s);
+        default: return launch_qp_w<1, 0>(A, nl, smem, s);
     }
 }
 
@@ -398,7 +406,7 @@ int dmpcb200_create(const dmpcb200_params* p, int N, int n0, int n1, int device,
     if ((e = dalloc(&h->d_grow, NL * 5 * h->RMAX)) != cudaSuccess) return bail(e, "rows");
     if ((e = dalloc(&h->d_gkc, NL * h->RMAX)) != cudaSuccess) return bail(e, "rows kc");
     if ((e = dalloc(&h->d_gidx, NL * h->RMAX)) != cudaSuccess) return bail(e, "rows idx");
-    if ((e = dalloc(&h->d_gscr_d, NL * 3 * h->RMAX)) != cudaSuccess) return bail(e, "row scratch");
+    if ((e = dalloc(&h->d_gscr_d, NL * 4 * h->RMAX)) != cudaSuccess) return bail(e, "row scratch");
     if ((e = dalloc(&h->d_gscr_i, NL * 4 * h->RMAX)) != cudaSuccess) return bail(e, "row scratch");
     if ((e = dalloc(&h->d_rescue, h->rescue_bytes * h->n_rescue)) != cudaSuccess) return bail(e, "rescue");
     if ((e = dalloc(&h->d_rescue_next, 1)) != cudaSuccess) return bail(e, "rescue counter");
@@ -906,6 +914,19 @@ int dmpcb200_swap_horizons(dmpcb200_t* h) {
     return 0;
 }
 
+/* profiling builds (-DDMPC_PROF) only: cycles[0..15], counts[16..31] of the QP phases; reset after read */
+int dmpcb200_prof_read(uint64_t* out32) {
+#ifdef DMPC_PROF
+    unsigned long long z[32] = {0};
+    if (cudaMemcpyFromSymbol(out32, g_prof, sizeof(z)) != cudaSuccess) return DMPCB200_ERR_CUDA;
+    if (cudaMemcpyToSymbol(g_prof, z, sizeof(z)) != cudaSuccess) return DMPCB200_ERR_CUDA;
+    return 0;
+#else
+    (void)out32;
+    return DMPCB200_ERR_STATE;
+#endif
+}
+
 int dmpcb200_config(dmpcb200_t* h, int32_t* out8) {
     if (!h || !out8) return fail(DMPCB200_ERR_ARG, "config: null argument");
     out8[0] = h->W;
@@ -915,7 +936,7 @@ int dmpcb200_config(dmpcb200_t* h, int32_t* out8) {
     out8[4] = h->QBIG;
     out8[5] = h->n_rescue;
     out8[6] = (int32_t)qp_smem_bytes(h->K, h->W, h->QMAX, h->RCAP);
-    out8[7] = (int32_t)scan_smem_bytes(h->K, kScanW);
+    out8[7] = (int32_t)scan_smem_bytes(h->K, (h->NL <= 4 * 148) ? 4 : 8, scan_stages(h->K, h->N));
     return 0;
 }
 

@@ -44,6 +44,7 @@ struct Ctrl {
 
 struct StepArgs {
     DevParams P;
+    ScanThr thr;  // exact squared distance thresholds (scan_core.cuh)
     int n0, n1;  // agents solved by this launch
     int RMAX, QMAX, RCAP, QBIG, n_rescue;
     int tile_padded;  // l_prev is readable up to a multiple of kTile agents
@@ -61,7 +62,7 @@ struct StepArgs {
     double* grow;   // per local agent 5*RMAX
     int* gkc;       // per local agent RMAX
     int* gidx;      // per local agent RMAX (neighbour index of each row)
-    double* gscr_d;  // per local agent 3*RMAX
+    double* gscr_d;  // per local agent 4*RMAX
     int* gscr_i;     // per local agent 4*RMAX
     unsigned char* rescue;  // n_rescue slots of rescue_bytes
     size_t rescue_bytes;
@@ -121,22 +122,32 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
 DMPC_HD size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
 // ---- K1 -------------------------------------------------------------------------------------
-DMPC_HD size_t scan_smem_bytes(int K, int W) {
+constexpr int kScanMaxStages = 24;
+// ring depth: as many 32-agent tiles as fit in ~200 KB of shared memory (N = 500, K = 15: the whole
+// neighbour buffer, 16 tiles, is in flight at once; the TMA round trip is paid once, not per tile)
+DMPC_HD int scan_stages(int K, int N) {
+    const size_t tile_bytes = (size_t)kTile * 3 * K * sizeof(double);
+    int s = (int)((200u * 1024u) / tile_bytes);
+    const int ntiles = (N + kTile - 1) / kTile;
+    if (s > ntiles) s = ntiles;
+    if (s > kScanMaxStages) s = kScanMaxStages;
+    return s < 1 ? 1 : s;
+}
+DMPC_HD size_t scan_smem_bytes(int K, int W, int stages) {
     const int n3 = 3 * K;
-    return 2 * (size_t)kTile * n3 * sizeof(double) + (size_t)W * round_up(n3, 2) * sizeof(double) + 2 * sizeof(uint64_t);
+    return (size_t)stages * kTile * n3 * sizeof(double) + (size_t)W * round_up(n3, 2) * sizeof(double) +
+           kScanMaxStages * sizeof(uint64_t);
 }
 
 template <int W>
-__global__ void __launch_bounds__(W * 32) scan_kernel(const __grid_constant__ StepArgs A) {
+__global__ void __launch_bounds__(W * 32) scan_kernel(const __grid_constant__ StepArgs A, int stages) {
     if (A.ctrl && A.ctrl->done) return;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const int K = A.P.K, n3 = 3 * K, n3p = round_up(n3, 2), N = A.P.N;
     const int tile_d = kTile * n3;
     const uint32_t tile_bytes = (uint32_t)(tile_d * sizeof(double));  // 32*3K*8: multiple of 16
-    double* tile[2];
-    tile[0] = reinterpret_cast<double*>(smem_raw);
-    tile[1] = tile[0] + tile_d;
-    double* own_all = tile[1] + tile_d;
+    double* tiles = reinterpret_cast<double*>(smem_raw);
+    double* own_all = tiles + (size_t)stages * tile_d;
     uint64_t* bars = reinterpret_cast<uint64_t*>(own_all + W * n3p);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int li = blockIdx.x * W + warp;
@@ -144,45 +155,47 @@ __global__ void __launch_bounds__(W * 32) scan_kernel(const __grid_constant__ St
     const bool valid = n < A.n1;
     double* own = own_all + warp * n3p;
 
+    const int ntma = A.tile_padded ? (N + kTile - 1) / kTile : N / kTile;
     if (threadIdx.x == 0) {
-        mbar_init(&bars[0], 1);
-        mbar_init(&bars[1], 1);
+        for (int b = 0; b < stages; ++b) mbar_init(&bars[b], 1);
         mbar_fence_init();
+        for (int t = 0; t < stages && t < ntma; ++t) {
+            mbar_expect_tx(&bars[t], tile_bytes);
+            tma_bulk_g2s(tiles + (size_t)t * tile_d, A.l_prev + (size_t)t * tile_d, tile_bytes, &bars[t]);
+        }
     }
     if (valid)
         for (int i = lane; i < n3; i += 32) own[i] = A.l_prev[(size_t)n * n3 + i];
-    __syncthreads();
+    __syncthreads();  // barrier init + own horizons visible
 
-    const int ntma = A.tile_padded ? (N + kTile - 1) / kTile : N / kTile;
-    if (threadIdx.x == 0) {
-        for (int t = 0; t < 2 && t < ntma; ++t) {
-            mbar_expect_tx(&bars[t], tile_bytes);
-            tma_bulk_g2s(tile[t], A.l_prev + (size_t)t * tile_d, tile_bytes, &bars[t]);
-        }
-    }
     unsigned* nm = A.nearmask + (size_t)(valid ? li : 0) * A.nm_stride;
     ScanAcc acc;
     acc.vmask = 0;
-    acc.md0 = INFINITY;
+    acc.coll0 = 0;
+    const bool refill = ntma > stages;
     for (int t = 0; t < ntma; ++t) {
-        const int b = t & 1;
-        mbar_wait(&bars[b], (uint32_t)((t >> 1) & 1));
+        const int b = t % stages;
+        mbar_wait(&bars[b], (uint32_t)((t / stages) & 1));
         const int base = t * kTile;
         const int cnt = (N - base < kTile) ? (N - base) : kTile;
-        if (valid) scan_tile(A.P, own, n, tile[b], base, cnt, nm, acc);
-        __syncthreads();  // every warp is done with tile[b]
-        if (threadIdx.x == 0 && t + 2 < ntma) {
-            mbar_expect_tx(&bars[b], tile_bytes);
-            tma_bulk_g2s(tile[b], A.l_prev + (size_t)(t + 2) * tile_d, tile_bytes, &bars[b]);
+        if (valid) scan_tile(A.P, &A.thr, own, n, tiles + (size_t)b * tile_d, base, cnt, nm, acc);
+        if (refill) {
+            __syncthreads();  // every warp is done with stage b
+            if (threadIdx.x == 0 && t + stages < ntma) {
+                mbar_expect_tx(&bars[b], tile_bytes);
+                tma_bulk_g2s(tiles + (size_t)b * tile_d, A.l_prev + (size_t)(t + stages) * tile_d, tile_bytes,
+                             &bars[b]);
+            }
         }
     }
     const int rem_base = ntma * kTile;
     if (rem_base < N) {
         // caller-owned buffer without tile padding: the ragged last tile is loaded by the threads
         const int cnt = N - rem_base;
-        for (int i = threadIdx.x; i < cnt * n3; i += W * 32) tile[0][i] = A.l_prev[(size_t)rem_base * n3 + i];
         __syncthreads();
-        if (valid) scan_tile(A.P, own, n, tile[0], rem_base, cnt, nm, acc);
+        for (int i = threadIdx.x; i < cnt * n3; i += W * 32) tiles[i] = A.l_prev[(size_t)rem_base * n3 + i];
+        __syncthreads();
+        if (valid) scan_tile(A.P, &A.thr, own, n, tiles, rem_base, cnt, nm, acc);
     }
     if (!valid) return;
     __syncwarp();
@@ -199,16 +212,16 @@ __global__ void __launch_bounds__(W * 32) scan_kernel(const __grid_constant__ St
 }
 
 // ---- K2 -------------------------------------------------------------------------------------
-DMPC_HD size_t qp_table_bytes(int K) { return (size_t)(10 * K * K + 2 * K) * sizeof(double); }
+DMPC_HD size_t qp_table_bytes(int K) { return (size_t)(10 * K * K + 4 * K) * sizeof(double); }
 DMPC_HD size_t qp_smem_bytes(int K, int W, int QMAX, int RCAP) {
     return align_up(qp_table_bytes(K), 16) + (size_t)W * agent_smem_bytes(K, QMAX, RCAP) + 16;
 }
 
-template <int W>
-__global__ void __launch_bounds__(W * 32) qp_kernel(const __grid_constant__ StepArgs A) {
+template <int W, int KT>
+__global__ void __launch_bounds__(W * 32, 1) qp_kernel(const __grid_constant__ StepArgs A) {
     if (A.ctrl && A.ctrl->done) return;
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    const int K = A.P.K, n3 = 3 * K;
+    const int K = KT ? KT : A.P.K, n3 = 3 * K;
     const size_t tab_bytes = align_up(qp_table_bytes(K), 16);
     const size_t per_warp = agent_smem_bytes(K, A.QMAX, A.RCAP);
     double* tab_s = reinterpret_cast<double*>(smem_raw);
@@ -228,20 +241,17 @@ __global__ void __launch_bounds__(W * 32) qp_kernel(const __grid_constant__ Step
 
     const ScanRec sr = A.scan[li];
     AgentIO io;
-#pragma unroll
-    for (int x = 0; x < 3; ++x) {
-        io.po[x] = A.pk[3 * n + x];
-        io.pf[x] = A.pf[3 * n + x];
-        io.vo[x] = A.vk[3 * n + x];
-        io.ao[x] = A.ak[3 * n + x];
-    }
+    io.po = A.pk + 3 * n;
+    io.pf = A.pf + 3 * n;
+    io.vo = A.vk + 3 * n;
+    io.ao = A.ak + 3 * n;
     io.kstar = sr.kstar;
     io.nv = sr.nv;
     io.scanflag = sr.flag;
     io.RMAX = A.RMAX;
     io.grow = A.grow + (size_t)li * 5 * A.RMAX;
     io.gkc = A.gkc + (size_t)li * A.RMAX;
-    io.gscr_d = A.gscr_d + (size_t)li * 3 * A.RMAX;
+    io.gscr_d = A.gscr_d + (size_t)li * 4 * A.RMAX;
     io.gscr_i = A.gscr_i + (size_t)li * 4 * A.RMAX;
     io.out_p = A.l_new + (size_t)n * n3;
     io.out_v = A.v_hor ? A.v_hor + (size_t)n * n3 : nullptr;
@@ -253,18 +263,23 @@ __global__ void __launch_bounds__(W * 32) qp_kernel(const __grid_constant__ Step
 
     mbar_wait(bar, 0);  // tables have landed
     AgentDiag dg;
-    int st = agent_solve(A.P, tab_s, smem_raw + tab_bytes + (size_t)warp * per_warp, A.QMAX, A.RCAP, io, &dg);
-    if ((st & ST_OVERFLOW) && !sr.flag && A.rescue) {
-        // active set outgrew the on-chip capacity: re-solve in a global-memory rescue slot
+    int st = 0, it0 = 0;
+    // attempt 0: on-chip workspace; attempt 1 (only if the active set outgrew it): a global-memory
+    // rescue slot with capacity QBIG.  One call site, so the solver exists once in the kernel image.
+    unsigned char* scratch = smem_raw + tab_bytes + (size_t)warp * per_warp;
+    int cap = A.QMAX;
+    for (int attempt = 0; attempt < 2; ++attempt) {
+        st = agent_solve<KT>(A.P, tab_s, scratch, cap, A.RCAP, io, &dg);
+        dg.iters += it0;
+        if (attempt || !(st & ST_OVERFLOW) || sr.flag || !A.rescue) break;
         int slot = 0;
         if (lane == 0) slot = atomicAdd(A.rescue_next, 1);
         slot = __shfl_sync(0xffffffffu, slot, 0);
-        if (slot < A.n_rescue) {
-            if (lane == 0 && A.ctrl) atomicAdd(&A.ctrl->rescue_used, 1);
-            const int it0 = dg.iters;
-            st = agent_solve(A.P, tab_s, A.rescue + (size_t)slot * A.rescue_bytes, A.QBIG, A.RCAP, io, &dg);
-            dg.iters += it0;
-        }
+        if (slot >= A.n_rescue) break;
+        if (lane == 0 && A.ctrl) atomicAdd(&A.ctrl->rescue_used, 1);
+        it0 = dg.iters;
+        scratch = A.rescue + (size_t)slot * A.rescue_bytes;
+        cap = A.QBIG;
     }
     if (lane == 0) {
         A.status[n] = st;

@@ -79,6 +79,7 @@ void build_tables(double h, int K, const double qs[3][2], std::vector<double>& o
         long double s = 0;
         for (int j = 0; j < K; ++j) s += (long double)lam[k * K + j] * lam[k * K + j];
         out[K * K + K + k] = (double)sqrtl(s);
+        out[K * K + 2 * K + k] = 1.0 / out[K * K + K + k];
     }
     typedef long double ld;
     std::vector<ld> Hm((size_t)K * K), L((size_t)K * K), Li((size_t)K * K), Gm((size_t)K * K),

@@ -16,9 +16,10 @@ namespace dmpc {
 //   [0, K*K)            lam   row-major lam[k*K + j] = A_p(3k+d, 3j+d)
 //   [K*K, K*K+K)        tt    tt[k] = A_initp(3k+d, 3+d) = (k+1) h (summed like the reference)
 //   [.., +K)            lnorm lnorm[k] = || lam[k,:] ||_2
+//   [.., +K)            ilnorm = 1 / lnorm
 //   then for each weight set w = 0 (far), 1 (near), 2 (collision):  G, B, C  (K*K each, row-major)
-inline int tables_set_offset(int K, int w) { return K * K + 2 * K + w * 3 * K * K; }
-inline int tables_size(int K) { return K * K + 2 * K + 9 * K * K; }
+inline int tables_set_offset(int K, int w) { return K * K + 4 * K + w * 3 * K * K; }
+inline int tables_size(int K) { return K * K + 4 * K + 9 * K * K; }
 
 // qs[w] = {q, s} for w = far, near, collision
 void build_tables(double h, int K, const double qs[3][2], std::vector<double>& out);

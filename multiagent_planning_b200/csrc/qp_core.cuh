@@ -17,17 +17,21 @@
 // G = H_K^{-1}, B = G Lam', C = Lam G Lam' (model_tables.h).  Neither H, nor a factor of it, nor a
 // dense constraint row is ever formed.  We carry M = S^{-1} explicitly (q x q, shared memory):
 //   add constraint    -> bordering update of M      (rank 1, no dependent chain)
-//   drop constraint   -> Schur downdate + swap-remove
-// so one iteration is a handful of warp-wide q x q sweeps; lanes own rows of M.  Slack upper
-// bounds (eps_j <= 0) all start active (the slack's free optimum is -term/2 >> 0); they are kept
-// IMPLICIT (not stored in M: they are decoupled from everything until row j is touched) and are
-// materialised lazily, so q stays ~ (#active box) + 2 (#touched rows).
+//   drop constraint   -> Schur downdate + swap-remove; the step data r = M g and delta = z'Hz
+//                        follow by rank-1 formulas (no new matrix-vector product)
+// Slack upper bounds (eps_j <= 0) all start active (the slack's free optimum is -term/2 >> 0); they
+// are kept IMPLICIT (not stored in M: they are decoupled from everything until row j is touched)
+// and are materialised lazily, so q stays ~ (#active box) + 2 (#touched rows).
 // A final "polish" re-synthesises x from the multipliers (x = x_unc + H^{-1} N u) and refines u
 // with M as approximate inverse, removing any drift the explicit-inverse updates accumulated.
 //
-// One warp per agent; all branches are warp-uniform (decided on reduced values).  The same source
-// compiles for the host with one "lane" (a test-only build): that build is a debugging aid of the
-// test-suite only and is never part of the product library.
+// One warp per agent; all branches are warp-uniform (decided on reduced values).  A warp is alone
+// on its SM sub-partition, so the code is organised for instruction-level parallelism: the horizon
+// length is a template parameter (fully unrolled table products), the primal direction z and its
+// position image Lam z come out of ONE pass over the tables (positions are updated incrementally,
+// never recomputed), arg-reductions use redux.sync on ordered integer keys.
+// The same source compiles for the host with one "lane" (a test-only build): that build is a
+// debugging aid of the test-suite only and is never part of the product library.
 #pragma once
 
 #include <math.h>
@@ -39,9 +43,31 @@
 #if defined(__CUDACC__)
 #define DMPC_HD __host__ __device__ __forceinline__
 #define DMPC_D __device__ __forceinline__
+#define DMPC_COLD __device__ __forceinline__
 #else
 #define DMPC_HD inline
 #define DMPC_D inline
+#define DMPC_COLD
+#endif
+
+#if defined(DMPC_PROF) && defined(__CUDACC__)
+// per-phase cycle accounting (profiling builds only): lane 0 of every warp accumulates into g_prof
+__device__ unsigned long long g_prof[32];
+#endif
+#if defined(DMPC_PROF) && defined(__CUDA_ARCH__)
+#define PROF_BEGIN() long long prof_t0 = clock64()
+#define PROF(i)                                                              \
+    do {                                                                     \
+        const long long prof_t1 = clock64();                                 \
+        if (lane_id() == 0) {                                                \
+            atomicAdd(&g_prof[i], (unsigned long long)(prof_t1 - prof_t0));  \
+            atomicAdd(&g_prof[16 + (i)], 1ull);                              \
+        }                                                                    \
+        prof_t0 = clock64();                                                 \
+    } while (0)
+#else
+#define PROF_BEGIN()
+#define PROF(i)
 #endif
 
 namespace dmpc {
@@ -61,18 +87,36 @@ DMPC_D double wmax(double v) {
     for (int o = 16; o; o >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, o));
     return v;
 }
-// (value, index) arg-min; ties -> smaller index; result identical in every lane
-DMPC_D void wargmin(double& v, int& idx) {
-#pragma unroll
-    for (int o = 16; o; o >>= 1) {
-        double ov = __shfl_xor_sync(0xffffffffu, v, o);
-        int oi = __shfl_xor_sync(0xffffffffu, idx, o);
-        if (ov < v || (ov == v && oi < idx)) {
-            v = ov;
-            idx = oi;
-        }
-    }
+// arg-max / arg-min over the warp of a NON-NEGATIVE double (its bit pattern is monotone as an
+// integer): two 32-bit redux + a ballot.  has = this lane takes part.  Returns the winning lane or
+// -1; ties -> lowest lane.  v is replaced by the extremum.
+DMPC_D int warg_max_nonneg(double& v, bool has) {
+    const unsigned long long key = has ? (unsigned long long)__double_as_longlong(v) : 0ull;
+    const unsigned hi = (unsigned)(key >> 32), lo = (unsigned)key;
+    const unsigned mhi = __reduce_max_sync(0xffffffffu, hi);
+    const unsigned mlo = __reduce_max_sync(0xffffffffu, (hi == mhi) ? lo : 0u);
+    const unsigned bal = __ballot_sync(0xffffffffu, has && hi == mhi && lo == mlo);
+    v = __longlong_as_double((long long)(((unsigned long long)mhi << 32) | mlo));
+    return bal ? (__ffs(bal) - 1) : -1;
 }
+DMPC_D int warg_min_nonneg(double& v, bool has) {
+    const unsigned long long key = has ? (unsigned long long)__double_as_longlong(v) : ~0ull;
+    const unsigned hi = (unsigned)(key >> 32), lo = (unsigned)key;
+    const unsigned mhi = __reduce_min_sync(0xffffffffu, hi);
+    const unsigned mlo = __reduce_min_sync(0xffffffffu, (hi == mhi) ? lo : 0xffffffffu);
+    const unsigned bal = __ballot_sync(0xffffffffu, has && hi == mhi && lo == mlo);
+    v = __longlong_as_double((long long)(((unsigned long long)mhi << 32) | mlo));
+    return bal ? (__ffs(bal) - 1) : -1;
+}
+// max over the warp of a NON-NEGATIVE double, accurate to 2^-20 relative (one redux on the high word):
+// used for thresholds only
+DMPC_D double wmax_approx_nonneg(double v) {
+    const unsigned hi = (unsigned)(((unsigned long long)__double_as_longlong(v)) >> 32);
+    const unsigned mhi = __reduce_max_sync(0xffffffffu, hi);
+    return __longlong_as_double((long long)((unsigned long long)mhi << 32));
+}
+DMPC_D double frcp(double x) { return __drcp_rn(x); }  // no IEEE division sequence on the critical path
+DMPC_D int wbcast(int v, int src) { return __shfl_sync(0xffffffffu, v, src); }
 DMPC_D unsigned wballot(bool p) { return __ballot_sync(0xffffffffu, p); }
 DMPC_D int popc_below(unsigned m) { return __popc(m & ((1u << (threadIdx.x & 31u)) - 1u)); }
 DMPC_D int popc_all(unsigned m) { return __popc(m); }
@@ -82,7 +126,11 @@ constexpr int kLanes = 1;
 inline void wsync() {}
 inline double wsum(double v) { return v; }
 inline double wmax(double v) { return v; }
-inline void wargmin(double&, int&) {}
+inline int warg_max_nonneg(double&, bool has) { return has ? 0 : -1; }
+inline int warg_min_nonneg(double&, bool has) { return has ? 0 : -1; }
+inline double wmax_approx_nonneg(double v) { return v; }
+inline double frcp(double x) { return 1.0 / x; }
+inline int wbcast(int v, int) { return v; }
 inline unsigned wballot(bool p) { return p ? 1u : 0u; }
 inline int popc_below(unsigned) { return 0; }
 inline int popc_all(unsigned m) { return (int)(m & 1u); }
@@ -99,27 +147,33 @@ enum { QP_OK = 0, QP_INFEASIBLE = 1, QP_ITERCAP = 2, QP_OVERFLOW = 3 };
 struct QpWs {
     int K, n3, QMAX;
     // constant tables of the agent's weight set (shared memory), row-major K x K
-    const double *lam, *lnorm, *G, *B, *C;
+    const double *lam, *ilnorm, *G, *B, *C;  // ilnorm[k] = 1 / || lam[k,:] ||
     // problem data
     double alim, term, slb;
-    double qw, sw;  // terminal-position and input-variation weights of the set in use
-    double pmin[3], pmax[3];
-    int soft;  // rows carry a slack variable
-    const double* p0;    // n3: po + tt[k] vo
+    double qw, sw;       // terminal-position and input-variation weights of the set in use
+    const double* bnd;   // workspace box: pmin[0..2], pmax[3..5]
+    int soft;            // rows carry a slack variable
     const double* aunc;  // n3: unconstrained optimum of a
+    const double* Punc;  // n3: p0 + Lam aunc
     // collision rows (SoA)
     int nv;
     const double *rd0, *rd1, *rd2, *rdist, *rrhs;
     const int* rkc;  // 0-based horizon index the row acts on
-    double* rnorm;   // norm of the dense row (constraint selection is on normalised violation)
+    double* irnorm;  // 1 / norm of the dense row (constraint selection is on normalised violation)
     // mutable per-agent state
-    double *a, *P, *cbox, *cP, *z;
+    double *a, *P, *cbox, *cP, *z, *Lz;
     double *eps, *zeps;
-    int *mbox, *mws;                      // per i: bit0 lower active, bit1 upper active
+    double* rres;  // residual of every row at the current x (maintained incrementally)
+    int kc_all;    // >= 0: every row acts on this horizon index (soft variants); -1: mixed (hard)
+    int *sbl, *sbu, *swl, *swu;           // per i: slot of the active lower/upper box / workspace bound or -1
     int *rslot, *ubslot, *lbslot, *rmat;  // per row: slot in the active list or -1; materialised?
     int* act;                             // active list: constraint codes
+    // per-slot record of the constraint normal: n = v (3-vector) at horizon index k in a-space
+    // (space 0) or position space (space 1), plus e on slack j (sinfo packs space | k<<1 | (j+1)<<9)
+    double *sv0, *sv1, *sv2, *se;
+    int* sinfo;
     double *u, *g, *r, *M;                // multipliers, scratch, M = (N'H^-1 N)^-1 (ld = QMAX)
-    int* ralist;                          // scratch: slots of active rows
+    int* ralist;                          // rows that are in the active list (row indices)
 };
 
 struct QpResult {
@@ -128,88 +182,81 @@ struct QpResult {
     int q;
 };
 
-// decoded candidate constraint p (uniform across the warp)
+// decoded constraint (uniform across the warp): normal = v at horizon index k of a-space (space 0) or
+// position space (space 1), plus e on slack j;  nph = n' H^{-1} n
 struct PInfo {
-    int type, idx, k, x, j, kc;
-    double sig, d0, d1, d2, dist, nph;
+    int type, idx, space, k, j;
+    double v0, v1, v2, e, nph;
 };
+DMPC_HD int pack_info(int space, int k, int j) { return space | (k << 1) | ((j + 1) << 9); }
 
+// KT = compile-time horizon length (0: use the run-time value)
+template <int KT>
 struct Qp {
     QpWs w;
-    int q, nmat;
+    int q, nmat, nra, nbox, npos;  // active-set size, materialised slack bounds, active rows / box / (ws+rows)
 
-    // ---- H^{-1} n_p lookups ---------------------------------------------------------------
-    // a-space entry i=(k,x) of H^{-1} n_p
+    DMPC_D int KK() const { return KT ? KT : w.K; }
+    DMPC_D int N3() const { return KT ? 3 * KT : w.n3; }  // compile-time trip counts for the entry loops
+
+    // ---- H^{-1} n_p lookups: the tables G, B, C are contiguous (K*K apart) ---------------------------
+    // a-space entry (k,x) of H^{-1} n_p:  v_x * (space ? B[k][kp] : G[k][kp])
     DMPC_D double hA(const PInfo& p, int k, int x) const {
-        const int K = w.K;
-        switch (p.type) {
-            case T_BOXL:
-            case T_BOXU: return (x == p.x) ? p.sig * w.G[k * K + p.k] : 0.0;
-            case T_WSL:
-            case T_WSU: return (x == p.x) ? p.sig * w.B[k * K + p.k] : 0.0;
-            case T_ROW: {
-                const double dx = (x == 0) ? p.d0 : ((x == 1) ? p.d1 : p.d2);
-                return dx * w.B[k * K + p.kc];
-            }
-            default: return 0.0;
-        }
+        const int K = KK();
+        const double vx = (x == 0) ? p.v0 : ((x == 1) ? p.v1 : p.v2);
+        return vx * w.G[p.space * K * K + k * K + p.k];
     }
-    // P-space image (Lam H^{-1} n_p) entry (k,x)
+    // position image (Lam H^{-1} n_p) entry (k,x):  v_x * (space ? C[kp][k] : B[kp][k])   (C symmetric)
     DMPC_D double hP(const PInfo& p, int k, int x) const {
-        const int K = w.K;
-        switch (p.type) {
-            case T_BOXL:
-            case T_BOXU: return (x == p.x) ? p.sig * w.B[p.k * K + k] : 0.0;
-            case T_WSL:
-            case T_WSU: return (x == p.x) ? p.sig * w.C[k * K + p.k] : 0.0;
-            case T_ROW: {
-                const double dx = (x == 0) ? p.d0 : ((x == 1) ? p.d1 : p.d2);
-                return dx * w.C[k * K + p.kc];
-            }
-            default: return 0.0;
-        }
+        const int K = KK();
+        const double vx = (x == 0) ? p.v0 : ((x == 1) ? p.v1 : p.v2);
+        return vx * w.G[(1 + p.space) * K * K + p.k * K + k];
     }
     // slack-space entry j of H^{-1} n_p  (slack Hessian is 2)
-    DMPC_D double hE(const PInfo& p, int j) const {
-        if (j != p.j) return 0.0;
-        switch (p.type) {
-            case T_ROW: return w.soft ? -0.5 * p.dist : 0.0;
-            case T_SUB: return -0.5;
-            case T_SLB: return 0.5;
-            default: return 0.0;
-        }
-    }
+    DMPC_D double hE(const PInfo& p, int j) const { return (j == p.j) ? 0.5 * p.e : 0.0; }
 
     DMPC_D PInfo decode(int code) const {
         PInfo p;
         p.type = code_type(code);
         p.idx = code_idx(code);
-        p.k = p.x = 0;
+        p.space = 0;
+        p.k = 0;
         p.j = -1;
-        p.kc = 0;
-        p.sig = 1.0;
-        p.d0 = p.d1 = p.d2 = p.dist = 0.0;
-        const int K = w.K;
+        p.v0 = p.v1 = p.v2 = p.e = 0.0;
+        const int K = KK();
         if (p.type <= T_WSU) {
             p.k = p.idx / 3;
-            p.x = p.idx - 3 * p.k;
-            p.sig = (p.type == T_BOXL || p.type == T_WSL) ? 1.0 : -1.0;
-            p.nph = (p.type <= T_BOXU) ? w.G[p.k * K + p.k] : w.C[p.k * K + p.k];
+            const int x = p.idx - 3 * p.k;
+            const double sig = (p.type == T_BOXL || p.type == T_WSL) ? 1.0 : -1.0;
+            p.v0 = (x == 0) ? sig : 0.0;
+            p.v1 = (x == 1) ? sig : 0.0;
+            p.v2 = (x == 2) ? sig : 0.0;
+            p.space = (p.type >= T_WSL) ? 1 : 0;
+            p.nph = w.G[2 * p.space * K * K + p.k * K + p.k];  // G[k][k] or C[k][k]
         } else {
             p.j = p.idx;
             if (p.type == T_ROW) {
-                p.d0 = w.rd0[p.j];
-                p.d1 = w.rd1[p.j];
-                p.d2 = w.rd2[p.j];
-                p.dist = w.rdist[p.j];
-                p.kc = w.rkc[p.j];
-                p.nph = (p.d0 * p.d0 + p.d1 * p.d1 + p.d2 * p.d2) * w.C[p.kc * K + p.kc] +
-                        (w.soft ? 0.5 * p.dist * p.dist : 0.0);
+                p.v0 = w.rd0[p.j];
+                p.v1 = w.rd1[p.j];
+                p.v2 = w.rd2[p.j];
+                p.e = w.soft ? -w.rdist[p.j] : 0.0;
+                p.k = w.rkc[p.j];
+                p.space = 1;
+                p.nph = (p.v0 * p.v0 + p.v1 * p.v1 + p.v2 * p.v2) * w.C[p.k * K + p.k] + 0.5 * p.e * p.e;
             } else {
+                p.e = (p.type == T_SUB) ? -1.0 : 1.0;
                 p.nph = 0.5;
             }
         }
         return p;
+    }
+    // store the record of constraint p in slot s (one lane)
+    DMPC_D void put_record(int s, const PInfo& p) {
+        w.sv0[s] = p.v0;
+        w.sv1[s] = p.v1;
+        w.sv2[s] = p.v2;
+        w.se[s] = p.e;
+        w.sinfo[s] = pack_info(p.space, p.k, p.j);
     }
 
     // residual c'x - b of a constraint at the current x (>= 0 feasible)
@@ -218,8 +265,8 @@ struct Qp {
         switch (t) {
             case T_BOXL: return w.a[i] + w.alim;
             case T_BOXU: return w.alim - w.a[i];
-            case T_WSL: return w.P[i] - w.pmin[i % 3];
-            case T_WSU: return w.pmax[i % 3] - w.P[i];
+            case T_WSL: return w.P[i] - w.bnd[i % 3];
+            case T_WSU: return w.bnd[3 + i % 3] - w.P[i];
             case T_ROW: {
                 const int kc = w.rkc[i];
                 double s = w.rd0[i] * w.P[3 * kc] + w.rd1[i] * w.P[3 * kc + 1] +
@@ -232,76 +279,109 @@ struct Qp {
         }
     }
 
-    // P = p0 + Lam a
-    DMPC_D void update_P() {
-        const int K = w.K;
-        for (int i = lane_id(); i < w.n3; i += kLanes) {
-            const int k = i / 3, x = i - 3 * k;
-            double s = 0.0;
-            for (int j = 0; j <= k; ++j) s = fma(w.lam[k * K + j], w.a[3 * j + x], s);
-            w.P[i] = s + w.p0[i];
-        }
+    // recompute every row residual from P and eps (after a re-synthesis of x)
+    DMPC_D void rows_refresh() {
+        for (int j = lane_id(); j < w.nv; j += kLanes) w.rres[j] = resid(mk_code(T_ROW, j));
         wsync();
     }
 
     // cbox / cP <- sum over the active set of coef_s * (normal of slot s), split by basis:
     //   cbox: coefficients on unit vectors e_i (box constraints)
     //   cP  : coefficients on rows of Lam (workspace constraints and collision rows)
-    DMPC_D void accumulate(const double* coef) {
-        for (int i = lane_id(); i < w.n3; i += kLanes) {
-            w.cbox[i] = 0.0;
-            w.cP[i] = 0.0;
-        }
-        wsync();
-        // compact list of active row slots (for the gather below)
-        int nra = 0;
-        for (int base = 0; base < q; base += kLanes) {
-            const int s = base + lane_id();
-            bool isrow = false;
-            if (s < q) {
-                const int c = w.act[s];
-                const int t = code_type(c), i = code_idx(c);
-                if (t == T_BOXL) w.cbox[i] = coef[s];
-                else if (t == T_BOXU) w.cbox[i] = -coef[s];
-                else if (t == T_WSL) w.cP[i] = coef[s];
-                else if (t == T_WSU) w.cP[i] = -coef[s];
-                else if (t == T_ROW) isrow = true;
+    // Gather form: every entry looks its (at most four) slots up; rows come from the active-row list.
+    DMPC_D void coefs(const double* coef) {
+        double rs0 = 0.0, rs1 = 0.0, rs2 = 0.0;
+        const bool red = (nra > 1) && (w.kc_all >= 0) && (kLanes > 1);
+        if (red) {
+            // every row sits on horizon index kc_all: sum_j coef_j d_j is three warp sums
+            for (int e = lane_id(); e < nra; e += kLanes) {
+                const int j = w.ralist[e];
+                const double c = coef[w.rslot[j]];
+                rs0 = fma(c, w.rd0[j], rs0);
+                rs1 = fma(c, w.rd1[j], rs1);
+                rs2 = fma(c, w.rd2[j], rs2);
             }
-            const unsigned m = wballot(isrow);
-            if (isrow) w.ralist[nra + popc_below(m)] = s;
-            nra += popc_all(m);
+            rs0 = wsum(rs0);
+            rs1 = wsum(rs1);
+            rs2 = wsum(rs2);
         }
-        wsync();
-        if (nra) {
-            for (int i = lane_id(); i < w.n3; i += kLanes) {
-                const int k = i / 3, x = i - 3 * k;
-                double acc = 0.0;
+        for (int i = lane_id(); i < N3(); i += kLanes) {
+            const int sl = w.sbl[i], su = w.sbu[i], wl = w.swl[i], wu = w.swu[i];
+            double cb = 0.0, cp = 0.0;
+            if (sl >= 0) cb = coef[sl];
+            if (su >= 0) cb -= coef[su];
+            if (wl >= 0) cp = coef[wl];
+            if (wu >= 0) cp -= coef[wu];
+            const int k = i / 3, x = i - 3 * k;
+            if (red) {
+                if (k == w.kc_all) cp += (x == 0) ? rs0 : ((x == 1) ? rs1 : rs2);
+            } else if (nra) {
                 for (int e = 0; e < nra; ++e) {
-                    const int s = w.ralist[e];
-                    const int j = code_idx(w.act[s]);
+                    const int j = w.ralist[e];
                     if (w.rkc[j] == k) {
                         const double dx = (x == 0) ? w.rd0[j] : ((x == 1) ? w.rd1[j] : w.rd2[j]);
-                        acc = fma(coef[s], dx, acc);
+                        cp = fma(coef[w.rslot[j]], dx, cp);
                     }
                 }
-                w.cP[i] += acc;
             }
-            wsync();
+            w.cbox[i] = cb;
+            w.cP[i] = cp;
         }
+        wsync();
     }
 
-    // out_i = base_i + sgn * (G cbox + B cP)_i     (a-space image of the accumulated normals)
-    DMPC_D void apply_Hinv(double* out, const double* base, double sgn, const PInfo* hp) {
-        const int K = w.K;
-        for (int i = lane_id(); i < w.n3; i += kLanes) {
+    // ONE pass over the tables:  oa_i = ba_i + sgn (G cbox + B cP)_i      (a-space)
+    //                            oP_i = bP_i + sgn (B' cbox + C cP)_i     (position image: Lam x a-space)
+    // hp != null: the bases are H^{-1} n_p / Lam H^{-1} n_p of the candidate constraint.
+    DMPC_D void apply(double* oa, double* oP, const double* ba, const double* bP, double sgn, const PInfo* hp) {
+        const int K = KK();
+        const bool hb = nbox > 0, hpz = npos > 0;
+        for (int i = lane_id(); i < N3(); i += kLanes) {
             const int k = i / 3, x = i - 3 * k;
-            double s = 0.0;
-            for (int j = 0; j < K; ++j) {
-                s = fma(w.G[k * K + j], w.cbox[3 * j + x], s);
-                s = fma(w.B[k * K + j], w.cP[3 * j + x], s);
+            double a0 = 0.0, a1 = 0.0, p0 = 0.0, p1 = 0.0;
+            if (hb) {
+#pragma unroll
+                for (int j = 0; j < K; ++j) {
+                    const double c = w.cbox[3 * j + x];
+                    a0 = fma(w.G[k * K + j], c, a0);
+                    p0 = fma(w.B[j * K + k], c, p0);
+                }
             }
-            const double b = hp ? hA(*hp, k, x) : base[i];
-            out[i] = b + sgn * s;
+            if (hpz) {
+#pragma unroll
+                for (int j = 0; j < K; ++j) {
+                    const double c = w.cP[3 * j + x];
+                    a1 = fma(w.B[k * K + j], c, a1);
+                    p1 = fma(w.C[k * K + j], c, p1);
+                }
+            }
+            const double b_a = hp ? hA(*hp, k, x) : ba[i];
+            const double b_P = hp ? hP(*hp, k, x) : bP[i];
+            oa[i] = b_a + sgn * (a0 + a1);
+            oP[i] = b_P + sgn * (p0 + p1);
+        }
+        wsync();
+    }
+
+    // Same result as coefs(r) + apply(z, Lz, -1, &p) by a loop over the active slots instead of the
+    // dense table products: cheaper while the active set is small.
+    //   z_i  = hA(p)_i - sum_s r_s v_s[x] TA_s[k][k_s],   TA_s = G (a-space slot) | B (position slot)
+    //   Lz_i = hP(p)_i - sum_s r_s v_s[x] TP_s[k_s][k],   TP_s = B               | C
+    DMPC_D void direction_sparse(const PInfo& p) {
+        const int K = KK(), KK2 = K * K;
+        for (int i = lane_id(); i < N3(); i += kLanes) {
+            const int k = i / 3, x = i - 3 * k;
+            const double* sv = (x == 0) ? w.sv0 : ((x == 1) ? w.sv1 : w.sv2);
+            double za = hA(p, k, x), zl = hP(p, k, x);
+            for (int s = 0; s < q; ++s) {
+                const int info = w.sinfo[s];
+                const int sp = info & 1, ks = (info >> 1) & 0xff;
+                const double c = w.r[s] * sv[s];
+                za = fma(-c, w.G[sp * KK2 + k * K + ks], za);
+                zl = fma(-c, w.G[(1 + sp) * KK2 + ks * K + k], zl);
+            }
+            w.z[i] = za;
+            w.Lz[i] = zl;
         }
         wsync();
     }
@@ -309,74 +389,69 @@ struct Qp {
     DMPC_D void set_active(int code, int slot) {
         const int t = code_type(code), i = code_idx(code);
         switch (t) {
-            case T_BOXL: w.mbox[i] |= 1; break;
-            case T_BOXU: w.mbox[i] |= 2; break;
-            case T_WSL: w.mws[i] |= 1; break;
-            case T_WSU: w.mws[i] |= 2; break;
+            case T_BOXL: w.sbl[i] = slot; break;
+            case T_BOXU: w.sbu[i] = slot; break;
+            case T_WSL: w.swl[i] = slot; break;
+            case T_WSU: w.swu[i] = slot; break;
             case T_ROW: w.rslot[i] = slot; break;
             case T_SUB: w.ubslot[i] = slot; break;
             default: w.lbslot[i] = slot; break;
         }
     }
-    DMPC_D void clear_active(int code) {
-        const int t = code_type(code), i = code_idx(code);
-        switch (t) {
-            case T_BOXL: w.mbox[i] &= ~1; break;
-            case T_BOXU: w.mbox[i] &= ~2; break;
-            case T_WSL: w.mws[i] &= ~1; break;
-            case T_WSU: w.mws[i] &= ~2; break;
-            case T_ROW: w.rslot[i] = -1; break;
-            case T_SUB: w.ubslot[i] = -1; break;
-            default: w.lbslot[i] = -1; break;
+    // bookkeeping of the uniform counters when a constraint enters (+1) / leaves (-1) the active list
+    DMPC_D void count_active(int code, int d) {
+        const int t = code_type(code);
+        if (t <= T_BOXU) nbox += d;
+        else if (t <= T_ROW) npos += d;
+        if (t == T_ROW) {
+            const int j = code_idx(code);
+            if (d > 0) {
+                if (lane_id() == 0) w.ralist[nra] = j;
+                ++nra;
+            } else {
+                int pos = 0;  // swap-remove j from the row list
+                for (int e = 0; e < nra; ++e)
+                    if (w.ralist[e] == j) pos = e;
+                wsync();
+                if (lane_id() == 0) w.ralist[pos] = w.ralist[nra - 1];
+                --nra;
+            }
         }
     }
 
     // most violated (normalised) inactive constraint; returns code or -1
     DMPC_D int most_violated(double tol, double* sp_out) {
         double best = -tol;
-        int bcode = 0x7fffffff;
-        for (int i = lane_id(); i < w.n3; i += kLanes) {
-            const int x = i % 3, k = i / 3;
-            const int mb = w.mbox[i], mw = w.mws[i];
-            const double ai = w.a[i], Pi = w.P[i];
-            const double iln = 1.0 / w.lnorm[k];
-            double s;
-            if (!(mb & 1)) {
-                s = ai + w.alim;
-                if (s < best) { best = s; bcode = mk_code(T_BOXL, i); }
-            }
-            if (!(mb & 2)) {
-                s = w.alim - ai;
-                if (s < best) { best = s; bcode = mk_code(T_BOXU, i); }
-            }
-            if (!(mw & 1)) {
-                s = Pi - w.pmin[x];
-                if (s * iln < best) { best = s * iln; bcode = mk_code(T_WSL, i); }
-            }
-            if (!(mw & 2)) {
-                s = w.pmax[x] - Pi;
-                if (s * iln < best) { best = s * iln; bcode = mk_code(T_WSU, i); }
-            }
+        int bcode = -1;
+        for (int i = lane_id(); i < N3(); i += kLanes) {
+            const int k = i / 3, x = i - 3 * k;
+            const double ai = w.a[i], Pi = w.P[i], iln = w.ilnorm[k];
+            const double lo = w.bnd[x], hi = w.bnd[3 + x];
+            const double v0 = (w.sbl[i] < 0) ? ai + w.alim : INFINITY;
+            const double v1 = (w.sbu[i] < 0) ? w.alim - ai : INFINITY;
+            const double v2 = (w.swl[i] < 0) ? (Pi - lo) * iln : INFINITY;
+            const double v3 = (w.swu[i] < 0) ? (hi - Pi) * iln : INFINITY;
+            const double m01 = fmin(v0, v1), m23 = fmin(v2, v3);
+            const int t01 = (v1 < v0) ? T_BOXU : T_BOXL, t23 = (v3 < v2) ? T_WSU : T_WSL;
+            const double m = fmin(m01, m23);
+            const int t = (m23 < m01) ? t23 : t01;
+            if (m < best) { best = m; bcode = mk_code(t, i); }
         }
         for (int j = lane_id(); j < w.nv; j += kLanes) {
             if (w.rslot[j] < 0) {
-                const double s = resid(mk_code(T_ROW, j));
-                const double sn = s / w.rnorm[j];
+                const double sn = w.rres[j] * w.irnorm[j];
                 if (sn < best) { best = sn; bcode = mk_code(T_ROW, j); }
             }
             if (w.soft && w.rmat[j]) {
-                if (w.ubslot[j] < 0) {
-                    const double s = -w.eps[j];
-                    if (s < best) { best = s; bcode = mk_code(T_SUB, j); }
-                }
-                if (w.lbslot[j] < 0) {
-                    const double s = w.eps[j] - w.slb;
-                    if (s < best) { best = s; bcode = mk_code(T_SLB, j); }
-                }
+                const double ej = w.eps[j];
+                if (w.ubslot[j] < 0 && -ej < best) { best = -ej; bcode = mk_code(T_SUB, j); }
+                if (w.lbslot[j] < 0 && ej - w.slb < best) { best = ej - w.slb; bcode = mk_code(T_SLB, j); }
             }
         }
-        wargmin(best, bcode);
-        if (bcode == 0x7fffffff) return -1;
+        double viol = -best;  // > tol when this lane found something
+        const int src = warg_max_nonneg(viol, bcode >= 0);
+        if (src < 0) return -1;
+        bcode = wbcast(bcode, src);
         *sp_out = resid(bcode);  // recomputed uniformly by every lane
         return bcode;
     }
@@ -393,26 +468,45 @@ struct Qp {
             w.act[q] = code;
             w.u[q] = uval;
             set_active(code, q);
+            put_record(q, decode(code));
         }
+        count_active(code, +1);
         wsync();
         ++q;
     }
 
-    // drop slot l: Schur downdate of M, then move the last slot into l
-    DMPC_D void drop_slot(int l) {
+    // drop slot l: Schur downdate of M, then move the last slot into l.  With vec the vector r = M g
+    // (vec = w.r, of the pending candidate) or the multipliers (vec = w.u, warm restart) follow by the
+    // same rank-1 formula  vec' = vec - M(:,l) vec_l / M_ll.  Uses w.g as scratch (column l of M).
+    DMPC_D void drop_slot(int l, double* vec) {
         const int Q = w.QMAX;
-        const double inv = 1.0 / w.M[l + Q * l];
+        const bool upd_r = vec != nullptr;
+        const double inv = frcp(w.M[l + Q * l]);
+        const double rl = upd_r ? vec[l] : 0.0;
+        for (int j = lane_id(); j < q; j += kLanes) w.g[j] = w.M[j + Q * l];
+        wsync();
         for (int i = lane_id(); i < q; i += kLanes) {
             if (i == l) continue;
-            const double ci = w.M[i + Q * l] * inv;
-            for (int j = 0; j < q; ++j) {
-                if (j == l) continue;
-                w.M[i + Q * j] = fma(-ci, w.M[j + Q * l], w.M[i + Q * j]);
+            const double ci = w.g[i] * inv;
+            if (upd_r) vec[i] = fma(-ci, rl, vec[i]);
+            int j = 0;
+            for (; j + 3 < q; j += 4) {
+                const double m0 = w.g[j], m1 = w.g[j + 1], m2 = w.g[j + 2], m3 = w.g[j + 3];
+                const double v0 = w.M[i + Q * j], v1 = w.M[i + Q * (j + 1)], v2 = w.M[i + Q * (j + 2)],
+                             v3 = w.M[i + Q * (j + 3)];
+                w.M[i + Q * j] = fma(-ci, m0, v0);
+                w.M[i + Q * (j + 1)] = fma(-ci, m1, v1);
+                w.M[i + Q * (j + 2)] = fma(-ci, m2, v2);
+                w.M[i + Q * (j + 3)] = fma(-ci, m3, v3);
             }
+            for (; j < q; ++j) w.M[i + Q * j] = fma(-ci, w.g[j], w.M[i + Q * j]);
         }
-        wsync();
+        // row / column l are garbage now: they are overwritten or discarded below
         const int last = q - 1;
-        if (lane_id() == 0) clear_active(w.act[l]);
+        const int cl = w.act[l];
+        wsync();
+        if (lane_id() == 0) set_active(cl, -1);
+        count_active(cl, -1);
         wsync();
         if (l != last) {
             for (int i = lane_id(); i < last; i += kLanes) {
@@ -426,6 +520,12 @@ struct Qp {
                 const int c = w.act[last];
                 w.act[l] = c;
                 w.u[l] = w.u[last];
+                w.r[l] = w.r[last];
+                w.sv0[l] = w.sv0[last];
+                w.sv1[l] = w.sv1[last];
+                w.sv2[l] = w.sv2[last];
+                w.se[l] = w.se[last];
+                w.sinfo[l] = w.sinfo[last];
                 set_active(c, l);
             }
         }
@@ -435,8 +535,8 @@ struct Qp {
 
     // x (a, eps, P) re-synthesised from the multipliers:  x = x_unc + H^{-1} N u
     DMPC_D void synth_from_u() {
-        accumulate(w.u);
-        apply_Hinv(w.a, w.aunc, 1.0, nullptr);
+        coefs(w.u);
+        apply(w.a, w.P, w.aunc, w.Punc, 1.0, nullptr);
         if (w.soft) {
             for (int j = lane_id(); j < w.nv; j += kLanes) {
                 if (!w.rmat[j]) continue;  // implicit upper bound: eps = 0
@@ -449,57 +549,69 @@ struct Qp {
             }
         }
         wsync();
-        update_P();
+        rows_refresh();
     }
 
-    // g[s] = n_{act[s]}' H^{-1} n_p for s < cnt   (an entry of the Schur complement S: all lookups)
+    // g[s] = n_{act[s]}' H^{-1} n_p for s < cnt   (an entry of the Schur complement S: one table lookup)
+    //   a-part: (v_s . v_p) * T[ks][kp],  T = G (a,a) | B (a,P) | B' (P,a) | C (P,P);  slack part: e_s e_p / 2
     DMPC_D void gvec(const PInfo& p, int cnt) {
+        const int K = KK(), KK2 = K * K;
         for (int s = lane_id(); s < cnt; s += kLanes) {
-            const int c = w.act[s];
-            const int t = code_type(c), i = code_idx(c);
-            double gv;
-            if (t <= T_BOXU) gv = ((t == T_BOXL) ? 1.0 : -1.0) * hA(p, i / 3, i % 3);
-            else if (t <= T_WSU) gv = ((t == T_WSL) ? 1.0 : -1.0) * hP(p, i / 3, i % 3);
-            else if (t == T_ROW) {
-                const int kc = w.rkc[i];
-                gv = w.rd0[i] * hP(p, kc, 0) + w.rd1[i] * hP(p, kc, 1) + w.rd2[i] * hP(p, kc, 2);
-                if (w.soft) gv -= w.rdist[i] * hE(p, i);
-            } else if (t == T_SUB) gv = -hE(p, i);
-            else gv = hE(p, i);
+            const int info = w.sinfo[s];
+            const int sp = info & 1, ks = (info >> 1) & 0xff, js = (info >> 9) - 1;
+            const double dot = w.sv0[s] * p.v0 + w.sv1[s] * p.v1 + w.sv2[s] * p.v2;
+            const int idx = (sp > p.space) ? (p.k * K + ks) : (ks * K + p.k);
+            double gv = dot * w.G[(sp + p.space) * KK2 + idx];
+            if (js >= 0 && js == p.j) gv = fma(0.5 * w.se[s], p.e, gv);
             w.g[s] = gv;
         }
         wsync();
     }
 
-    // r = M[0:cnt,0:cnt] g ; returns g'r and max|r| (uniform)
-    DMPC_D void mat_vec(int cnt, double* gr_out, double* rmax_out) {
+    // r = M[0:cnt,0:cnt] g.  Returns g'r (NEED_GR, one reduction) or 0; *rmax_out (optional) gets
+    // max |r_i| to 2^-20 relative (one redux) for the ratio-test threshold.
+    template <bool NEED_GR>
+    DMPC_D double mat_vec(int cnt, double* rmax_out) {
         const int Q = w.QMAX;
-        double gr = 0.0, rmax = 0.0;
+        double gr = 0.0, rm = 0.0;
         for (int i = lane_id(); i < cnt; i += kLanes) {
-            double s0 = 0.0, s1 = 0.0;
+            double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
             int j = 0;
-            for (; j + 1 < cnt; j += 2) {
+            for (; j + 3 < cnt; j += 4) {
                 s0 = fma(w.M[i + Q * j], w.g[j], s0);
                 s1 = fma(w.M[i + Q * (j + 1)], w.g[j + 1], s1);
+                s2 = fma(w.M[i + Q * (j + 2)], w.g[j + 2], s2);
+                s3 = fma(w.M[i + Q * (j + 3)], w.g[j + 3], s3);
             }
-            if (j < cnt) s0 = fma(w.M[i + Q * j], w.g[j], s0);
-            const double ri = s0 + s1;
+            for (; j < cnt; ++j) s0 = fma(w.M[i + Q * j], w.g[j], s0);
+            const double ri = (s0 + s1) + (s2 + s3);
             w.r[i] = ri;
-            gr = fma(w.g[i], ri, gr);
-            rmax = fmax(rmax, fabs(ri));
+            if (NEED_GR) gr = fma(w.g[i], ri, gr);
+            rm = fmax(rm, fabs(ri));
         }
-        *gr_out = wsum(gr);
-        *rmax_out = wmax(rmax);
+        if (NEED_GR) gr = wsum(gr);
+        if (rmax_out) *rmax_out = wmax_approx_nonneg(rm);
         wsync();
+        return gr;
     }
 
     // bordering update: M <- inverse of [[S, g],[g', nph]] given r = M g and delta = nph - g'r
     DMPC_D void border(int cnt, double delta) {
         const int Q = w.QMAX;
-        const double id = 1.0 / delta;
+        const double id = frcp(delta);
         for (int i = lane_id(); i < cnt; i += kLanes) {
             const double ci = w.r[i] * id;
-            for (int j = 0; j < cnt; ++j) w.M[i + Q * j] = fma(ci, w.r[j], w.M[i + Q * j]);
+            int j = 0;
+            for (; j + 3 < cnt; j += 4) {
+                const double r0 = w.r[j], r1 = w.r[j + 1], r2 = w.r[j + 2], r3 = w.r[j + 3];
+                const double v0 = w.M[i + Q * j], v1 = w.M[i + Q * (j + 1)], v2 = w.M[i + Q * (j + 2)],
+                             v3 = w.M[i + Q * (j + 3)];
+                w.M[i + Q * j] = fma(ci, r0, v0);
+                w.M[i + Q * (j + 1)] = fma(ci, r1, v1);
+                w.M[i + Q * (j + 2)] = fma(ci, r2, v2);
+                w.M[i + Q * (j + 3)] = fma(ci, r3, v3);
+            }
+            for (; j < cnt; ++j) w.M[i + Q * j] = fma(ci, w.r[j], w.M[i + Q * j]);
             w.M[i + Q * cnt] = -ci;
             w.M[cnt + Q * i] = -ci;
         }
@@ -508,43 +620,37 @@ struct Qp {
     }
 
     // rebuild M exactly from the active list (S entries are lookups): removes accumulated drift
-    DMPC_D void refresh() {
+    DMPC_COLD void refresh() {
         for (int s = 0; s < q; ++s) {
             const PInfo p = decode(w.act[s]);
+            if (lane_id() == 0) put_record(s, p);
             gvec(p, s);
-            double gr, rmax;
-            mat_vec(s, &gr, &rmax);
+            const double gr = mat_vec<true>(s, nullptr);
             double delta = p.nph - gr;
             if (!(delta > 1e-14 * p.nph)) delta = 1e-14 * p.nph;
             border(s, delta);
         }
     }
 
-    // z'Hz for the a-part of z: H_K = 2 (q lamK lamK' + s Delta'Delta + I) -- a sum of squares
-    DMPC_D double zHz() const {
-        const int K = w.K;
-        const double* lamK = w.lam + (K - 1) * K;
-        double loc = 0.0, t0 = 0.0, t1 = 0.0, t2 = 0.0;
-        for (int i = lane_id(); i < w.n3; i += kLanes) {
-            const int k = i / 3, x = i - 3 * k;
+    // z'Hz for the a-part of z: H_K = 2 (q lamK lamK' + s Delta'Delta + I) -- a sum of squares; the
+    // terminal term lamK'z_x is entry (K-1, x) of Lam z, which apply() already produced.
+    // extra: lane-local part of the slack contribution (added before the single reduction)
+    DMPC_D double zHz(double extra) const {
+        const int K = KK();
+        double loc = extra;
+        for (int i = lane_id(); i < N3(); i += kLanes) {
             const double zi = w.z[i];
-            const double dz = zi - ((k > 0) ? w.z[i - 3] : 0.0);
+            const double dz = zi - ((i >= 3) ? w.z[i - 3] : 0.0);
             loc = fma(zi, zi, loc);
             loc = fma(w.sw * dz, dz, loc);
-            const double lz = lamK[k] * zi;
-            if (x == 0) t0 += lz;
-            else if (x == 1) t1 += lz;
-            else t2 += lz;
         }
         loc = wsum(loc);
-        t0 = wsum(t0);
-        t1 = wsum(t1);
-        t2 = wsum(t2);
+        const double t0 = w.Lz[3 * (K - 1)], t1 = w.Lz[3 * (K - 1) + 1], t2 = w.Lz[3 * (K - 1) + 2];
         return 2.0 * (loc + w.qw * (t0 * t0 + t1 * t1 + t2 * t2));
     }
 
     // returns max residual of the active constraints after refinement
-    DMPC_D double polish() {
+    DMPC_COLD double polish() {
         double mx = 0.0;
         for (int round = 0; round < 4; ++round) {
             synth_from_u();
@@ -560,44 +666,113 @@ struct Qp {
             printf("  polish round %d q %d max resid %.3e\n", round, q, mx);
 #endif
             if (!(mx > 1e-13)) break;
-            double gr, rmax;
-            mat_vec(q, &gr, &rmax);
+            mat_vec<false>(q, nullptr);
             for (int i = lane_id(); i < q; i += kLanes) w.u[i] -= w.r[i];
             wsync();
         }
         return mx;
     }
 
+    // Warm restart after the slack data (term, slb) changed: the acceleration-box and workspace
+    // constraints of the old active set are kept (their part of the problem does not depend on term
+    // or slb), everything that involves a slack goes back to the implicit start (rows inactive,
+    // eps = 0 held by the implicit upper bounds).  M is rebuilt for the kept set, the multipliers
+    // of the equality-constrained problem on it are u = M (b - N' x_unc), constraints with a negative
+    // multiplier are dropped (rank-1 updates of u and M) until u >= 0, and x is re-synthesised: a
+    // valid starting pair for solve() (x minimises the objective on the active set, u >= 0).
+    DMPC_COLD void warm_restart() {
+        int m = 0;
+        for (int s2 = 0; s2 < q; ++s2) {
+            const int c = w.act[s2];
+            wsync();
+            if (code_type(c) <= T_WSU) {
+                if (lane_id() == 0) {
+                    w.act[m] = c;
+                    set_active(c, m);
+                }
+                ++m;
+            }
+        }
+        q = m;
+        nmat = 0;
+        nra = 0;
+        npos = 0;
+        nbox = 0;
+        for (int s2 = 0; s2 < q; ++s2) {
+            if (code_type(w.act[s2]) <= T_BOXU) ++nbox;
+            else ++npos;
+        }
+        for (int j = lane_id(); j < w.nv; j += kLanes) {
+            w.eps[j] = 0.0;
+            w.rslot[j] = -1;
+            w.ubslot[j] = -1;
+            w.lbslot[j] = -1;
+            w.rmat[j] = 0;
+        }
+        for (int i = lane_id(); i < N3(); i += kLanes) {
+            w.a[i] = w.aunc[i];
+            w.P[i] = w.Punc[i];
+        }
+        wsync();
+        refresh();
+        for (int s2 = lane_id(); s2 < q; s2 += kLanes) w.g[s2] = -resid(w.act[s2]);
+        wsync();
+        mat_vec<false>(q, nullptr);
+        for (int i = lane_id(); i < q; i += kLanes) w.u[i] = w.r[i];
+        wsync();
+        for (;;) {
+            double neg = 0.0;
+            int l = -1;
+            for (int i = lane_id(); i < q; i += kLanes) {
+                const double ui = w.u[i];
+                if (ui < 0.0 && (l < 0 || -ui > neg)) { neg = -ui; l = i; }
+            }
+            const int src = warg_max_nonneg(neg, l >= 0);
+            if (src < 0) break;
+            l = wbcast(l, src);
+            drop_slot(l, w.u);
+        }
+        synth_from_u();
+    }
+
+    // start state: nothing active
+    DMPC_D void reset() {
+        q = 0;
+        nmat = 0;
+        nra = 0;
+        nbox = 0;
+        npos = 0;
+    }
+
     // ---- the solver ---------------------------------------------------------------------------
-    // expects: w.a = aunc, eps = 0, masks cleared, rslot/ubslot/lbslot = -1, rmat = 0
+    // expects: a = aunc, P = Punc, eps = 0, slot maps = -1, rmat = 0, reset() called
     DMPC_D QpResult solve(int max_iter) {
         const int Q = w.QMAX;
         const double feas_tol = 1e-10;
         const double dep_tol = 1e-9;    // on delta = z'Hz relative to n_p'H^{-1}n_p
         const double ill_tol = 1e-5;    // adds below this mark M for an exact rebuild
-        q = 0;
-        nmat = 0;
         int iters = 0, npolish = 0;
         bool polished = false, dirty = false;
         QpResult res;
-        update_P();
+        res.rc = QP_OK;
+        PROF_BEGIN();
         for (;;) {
             double sp;
+            PROF(0);
             const int pcode = most_violated(feas_tol, &sp);
+            PROF(1);
             if (pcode < 0) {
-                if (!polished && q > 0) {
-                    if (dirty) { refresh(); dirty = false; }
-                    double mx = polish();
-                    if (mx > 1e-9) {
-                        refresh();
-                        mx = polish();
-                    }
-                    polished = true;
-                    if (++npolish > 8) { res.rc = QP_ITERCAP; break; }
-                    continue;
+                if (polished || q == 0) break;  // optimal
+                // x is re-synthesised from the multipliers; a poor residual triggers one exact rebuild
+                for (int pass = 0; pass < 2; ++pass) {
+                    if (dirty || pass) refresh();
+                    dirty = false;
+                    if (!(polish() > 1e-9)) break;
                 }
-                res.rc = QP_OK;
-                break;
+                polished = true;
+                PROF(2);
+                if (++npolish > 8) { res.rc = QP_ITERCAP; break; }
+                continue;
             }
             polished = false;
             PInfo p = decode(pcode);
@@ -605,66 +780,117 @@ struct Qp {
                 // materialise the (active) slack upper bound of this row: isolated so far,
                 // S entry 1/2 -> M entry 2, multiplier -term - 2 eps = -term
                 if (q + 2 > Q) { res.rc = QP_OVERFLOW; break; }
+                const double e0 = w.eps[p.j];
+                wsync();
                 if (lane_id() == 0) w.rmat[p.j] = 1;
-                append_isolated(mk_code(T_SUB, p.j), -w.term - 2.0 * w.eps[p.j], 2.0);
+                append_isolated(mk_code(T_SUB, p.j), -w.term - 2.0 * e0, 2.0);
                 ++nmat;
             }
             if (q + 1 > Q) { res.rc = QP_OVERFLOW; break; }
+            PROF(3);
             double up = 0.0;
-            bool failed = false, added = false;
+            double rmax = 0.0;    // max |r_i| (approximate)
+            double delta = 0.0;   // z'Hz of the current direction (valid when have_z)
+            bool need_r = true;   // r = M g must be (re)computed from scratch
+            bool have_z = false;  // z / Lz / zeps / delta describe the current active set
+            bool failed = false, added = false, rebuilt = false;
             while (!added) {
-                if (++iters > max_iter) { res.rc = QP_ITERCAP; failed = true; break; }
-                gvec(p, q);
-                double gr, rmax;
-                mat_vec(q, &gr, &rmax);
-                // primal direction z = H^{-1}(n_p - N r); delta = n_p'z = z'Hz (no cancellation)
-                accumulate(w.r);
-                apply_Hinv(w.z, nullptr, -1.0, &p);
-                double de = 0.0;
-                if (w.soft) {
-                    for (int j = lane_id(); j < w.nv; j += kLanes) {
-                        if (!w.rmat[j]) continue;
-                        double ze = hE(p, j);
-                        const int sr = w.rslot[j], su = w.ubslot[j], sl = w.lbslot[j];
-                        if (sr >= 0) ze += 0.5 * w.rdist[j] * w.r[sr];
-                        if (su >= 0) ze += 0.5 * w.r[su];
-                        if (sl >= 0) ze -= 0.5 * w.r[sl];
-                        w.zeps[j] = ze;
-                        de = fma(ze, ze, de);
-                    }
-                    de = 2.0 * wsum(de);
+                if (need_r) {
+                    if (dirty) { refresh(); dirty = false; }
+                    gvec(p, q);
+                    PROF(4);
+                    mat_vec<false>(q, &rmax);
+                    PROF(5);
+                    need_r = false;
+                    have_z = false;
                 }
-                const double delta = zHz() + de;
+                if (++iters > max_iter) { res.rc = QP_ITERCAP; failed = true; break; }
+                // primal direction z = H^{-1}(n_p - N r); delta = n_p'z = z'Hz (no cancellation).  After a
+                // drop, delta grows by r_l^2 / M_ll exactly: while that keeps it below the dependence
+                // threshold no direction is needed (no primal step is taken).
+                if (!have_z) {
+                    if (q <= 8) {
+                        direction_sparse(p);
+                        PROF(6);
+                    } else {
+                        coefs(w.r);
+                        apply(w.z, w.Lz, nullptr, nullptr, -1.0, &p);
+                        PROF(7);
+                    }
+                    double de = 0.0;
+                    if (w.soft) {
+                        for (int j = lane_id(); j < w.nv; j += kLanes) {
+                            if (!w.rmat[j]) continue;
+                            double ze = hE(p, j);
+                            const int sr = w.rslot[j], su = w.ubslot[j], sl = w.lbslot[j];
+                            if (sr >= 0) ze += 0.5 * w.rdist[j] * w.r[sr];
+                            if (su >= 0) ze += 0.5 * w.r[su];
+                            if (sl >= 0) ze -= 0.5 * w.r[sl];
+                            w.zeps[j] = ze;
+                            de = fma(ze, ze, de);
+                        }
+                    }
+                    delta = zHz(de);
+                    have_z = true;
+                    PROF(8);
+                    // In exact arithmetic 0 <= delta <= n_p'H^{-1}n_p.  Anything else (or a NaN) means the
+                    // explicit inverse has lost its accuracy -- it happens inside infeasible problems,
+                    // where near-dependent constraints produce giant steps: rebuild M exactly once for
+                    // this candidate; if that does not cure it the problem is reported infeasible.
+                    if (!(delta <= 1.000001 * p.nph)) {
+                        if (rebuilt) { res.rc = QP_INFEASIBLE; failed = true; break; }
+                        rebuilt = true;
+                        dirty = true;
+                        need_r = true;
+                        continue;
+                    }
+                }
 #ifdef DMPC_DEBUG
-                printf("it %d p type %d idx %d sp %.3e nph %.3e delta %.3e (schur %.3e) q %d\n", iters, p.type, p.idx, sp, p.nph, delta, p.nph - gr, q);
+                printf("it %d p type %d idx %d sp %.3e nph %.3e delta %.3e q %d\n", iters, p.type, p.idx, sp, p.nph,
+                       delta, q);
 #endif
                 const bool dependent = !(delta > dep_tol * p.nph) || (q >= w.n3 + nmat);
-                // dual ratio test
-                double t1 = INFINITY;
-                int ldrop = 0x7fffffff;
+                // dual ratio test: smallest u_i / r_i over r_i > 0
                 const double rthr = 1e-12 * rmax;
+                double t1 = INFINITY;
+                int ldrop = -1;
                 for (int i = lane_id(); i < q; i += kLanes) {
                     const double ri = w.r[i];
                     if (ri > rthr) {
-                        const double t = fmax(w.u[i], 0.0) / ri;
-                        if (t < t1) { t1 = t; ldrop = i; }
+                        const double t = fmax(w.u[i], 0.0) * frcp(ri);
+                        if (ldrop < 0 || t < t1) { t1 = t; ldrop = i; }
                     }
                 }
-                wargmin(t1, ldrop);
-                const double t2 = dependent ? INFINITY : (-sp / delta);
+                {
+                    const int src = warg_min_nonneg(t1, ldrop >= 0);
+                    ldrop = (src >= 0) ? wbcast(ldrop, src) : -1;
+                    if (src < 0) t1 = INFINITY;
+                }
+                PROF(9);
+                const double t2 = dependent ? INFINITY : (-sp * frcp(delta));
                 const double t = (t1 < t2) ? t1 : t2;
-                if (!(t < INFINITY)) { res.rc = QP_INFEASIBLE; failed = true; break; }
+                if (!(t < INFINITY)) { res.rc = QP_INFEASIBLE; failed = true; break; }  // also catches NaN
                 if (!dependent) {
-                    for (int i = lane_id(); i < w.n3; i += kLanes) w.a[i] = fma(t, w.z[i], w.a[i]);
-                    if (w.soft)
-                        for (int j = lane_id(); j < w.nv; j += kLanes)
-                            if (w.rmat[j]) w.eps[j] = fma(t, w.zeps[j], w.eps[j]);
-                    wsync();
-                    update_P();
+                    for (int i = lane_id(); i < N3(); i += kLanes) {
+                        w.a[i] = fma(t, w.z[i], w.a[i]);
+                        w.P[i] = fma(t, w.Lz[i], w.P[i]);
+                    }
+                    // rows: residual_j += t n_j'z = t (d_j . Lz[kc_j] - dist_j zeps_j)
+                    for (int j = lane_id(); j < w.nv; j += kLanes) {
+                        const int kc = w.rkc[j];
+                        double nz = w.rd0[j] * w.Lz[3 * kc] + w.rd1[j] * w.Lz[3 * kc + 1] + w.rd2[j] * w.Lz[3 * kc + 2];
+                        if (w.soft && w.rmat[j]) {
+                            const double ze = w.zeps[j];
+                            w.eps[j] = fma(t, ze, w.eps[j]);
+                            nz = fma(-w.rdist[j], ze, nz);
+                        }
+                        w.rres[j] = fma(t, nz, w.rres[j]);
+                    }
                 }
                 for (int i = lane_id(); i < q; i += kLanes) w.u[i] = fma(-t, w.r[i], w.u[i]);
                 up += t;
                 wsync();
+                PROF(10);
                 if (!dependent && t2 <= t1) {
                     // full step: constraint p becomes active
                     border(q, delta);
@@ -672,15 +898,30 @@ struct Qp {
                         w.act[q] = pcode;
                         w.u[q] = up;
                         set_active(pcode, q);
+                        put_record(q, p);
                     }
+                    count_active(pcode, +1);
                     wsync();
                     ++q;
                     added = true;
                     if (delta < ill_tol * p.nph) dirty = true;
+                    PROF(11);
                 } else {
-                    drop_slot(ldrop);
-                    if (dirty) { refresh(); dirty = false; }
+                    const double rl = w.r[ldrop], mll = w.M[ldrop + Q * ldrop];
+                    wsync();
+                    drop_slot(ldrop, w.r);
+                    if (dirty) {
+                        need_r = true;  // rebuild M, then r from scratch
+                    } else if (dependent && (q < w.n3 + nmat)) {
+                        // delta' = delta + r_l^2 / M_ll: while still dependent keep dropping without a direction
+                        const double dn = fmax(delta, 0.0) + rl * rl * frcp(mll);
+                        if (dn > 0.25 * dep_tol * p.nph) have_z = false;
+                        else delta = dn;
+                    } else {
+                        have_z = false;
+                    }
                     if (!dependent) sp = resid(pcode);
+                    PROF(12);
                 }
             }
             if (failed) break;

@@ -41,40 +41,112 @@ DMPC_D double ell_dist(double dx, double dy, double dz, double c) {
     const double ez = dz / c;
     return sqrt(add_rn(add_rn(mul_rn(dx, dx), mul_rn(dy, dy)), mul_rn(ez, ez)));
 }
+// the rounded sum of squares under the square root of ell_dist (same rounding sequence)
+DMPC_D double ell_sq(double dx, double dy, double dz, double c) {
+    const double ez = dz / c;
+    return add_rn(add_rn(mul_rn(dx, dx), mul_rn(dy, dy)), mul_rn(ez, ez));
+}
 
 // neighbour threshold at 1-based step k (CheckCollSoftDMPC.m:12 ; C++ dmpc.cpp:418)
-DMPC_D double neigh_thr(const DevParams& P, int k1) {
+DMPC_HD double neigh_thr(const DevParams& P, int k1) {
     if (P.variant == VAR_HARD) return P.hard_radius;  // CollConstrHardDMPC.m:19
     if (P.neigh_mode == 1) return P.rmin * (1.0 + (double)(k1 - 1) / P.K);
     return P.rmin * P.neigh_factor;
 }
 
+// Exact squared thresholds.  sqrt is monotone and correctly rounded, so for a threshold r
+//     fl(sqrt(s)) < r   <=>   s < T(r),   T(r) = min { t : fl(sqrt(t)) >= r }.
+// With T the scan never takes a square root; with a cheap FMA estimate of s it never divides
+// either unless the pair is close enough to matter -- and the decisions stay bit-identical to
+// evaluating the reference's formula in plain C.
+struct ScanThr {
+    double T_viol;       // dist < rmin
+    double T_coll;       // dist < rmin - coll_tol   (k = 1 only, solveSoftDMPCbound.m:25)
+    double T_near[32];   // dist < neigh_thr(k)
+    // two-sided bands around the thresholds for decisions taken on the FMA estimate of s
+    double Tv_lo, Tv_hi, Tc_lo, Tc_hi;
+    double Tn_lo[32], Tn_hi[32];
+    double inv_c;
+};
+
+inline double sq_threshold(double r) {
+    if (!(r > 0.0)) return 0.0;  // dist < r is never true
+    double t = r * r;
+    while (sqrt(t) >= r) t = nextafter(t, 0.0);
+    while (sqrt(t) < r) t = nextafter(t, INFINITY);
+    return t;
+}
+
+inline ScanThr make_scan_thr(const DevParams& P) {
+    ScanThr T;
+    const double lo = 1.0 - 1e-12, hi = 1.0 + 1e-12;  // the estimate is good to a few ulp
+    T.T_viol = sq_threshold(P.rmin);
+    T.T_coll = sq_threshold(P.rmin - P.coll_tol);
+    T.Tv_lo = T.T_viol * lo;
+    T.Tv_hi = T.T_viol * hi;
+    T.Tc_lo = T.T_coll * lo;
+    T.Tc_hi = T.T_coll * hi;
+    for (int k = 0; k < 32; ++k) {
+        T.T_near[k] = (k < P.K) ? sq_threshold(neigh_thr(P, k + 1)) : 0.0;
+        T.Tn_lo[k] = T.T_near[k] * lo;
+        T.Tn_hi[k] = T.T_near[k] * hi;
+    }
+    T.inv_c = 1.0 / P.c;
+    return T;
+}
+
 struct ScanAcc {
     unsigned vmask;  // per lane: bit k set if some neighbour of this lane violates at step k
-    double md0;      // per lane: min distance at step 1
+    unsigned coll0;  // per lane: some neighbour is closer than rmin - coll_tol at step 1
 };
 
 // Accumulate `cnt` neighbours starting at global index ibase whose horizons lie at tile
 // (cnt x K x 3 doubles, same layout as l).  own = this agent's previous horizon (3K doubles).
-// nearmask[i] (i global) receives the K-bit near mask.
-DMPC_D void scan_tile(const DevParams& P, const double* __restrict__ own, int n,
+// nearmask[i] (i global) receives the K-bit near mask.  thr: ScanThr (kernel parameter space).
+// Branch-free: every decision is taken on an FMA estimate of s against the two-sided bands; only an
+// estimate that falls INSIDE a band (relative width 2e-12 -- practically never) sends the pair through
+// the reference's exact rounding sequence (division included), so all decisions stay bit-identical.
+DMPC_D void scan_tile(const DevParams& P, const ScanThr* __restrict__ thr, const double* __restrict__ own, int n,
                       const double* __restrict__ tile, int ibase, int cnt, unsigned* nearmask,
                       ScanAcc& acc) {
     const int K = P.K;
+    const double inv_c = thr->inv_c, Tv_lo = thr->Tv_lo, Tv_hi = thr->Tv_hi;
     for (int m = lane_id(); m < cnt; m += kLanes) {
         const int i = ibase + m;
         unsigned nm = 0;
         if (i != n) {
             const double* pj = tile + (size_t)m * 3 * K;
-            unsigned vm = 0;
+            unsigned vm = 0, amb = 0;
+#pragma unroll 5
             for (int k = 0; k < K; ++k) {
                 const double dx = own[3 * k] - pj[3 * k];
                 const double dy = own[3 * k + 1] - pj[3 * k + 1];
                 const double dz = own[3 * k + 2] - pj[3 * k + 2];
-                const double dist = ell_dist(dx, dy, dz, P.c);
-                if (dist < P.rmin) vm |= 1u << k;
-                if (dist < neigh_thr(P, k + 1)) nm |= 1u << k;
-                if (k == 0) acc.md0 = fmin(acc.md0, dist);
+                const double ez = dz * inv_c;
+                const double est = fma(ez, ez, fma(dy, dy, dx * dx));  // estimate of s, good to a few ulp
+                const double Tnl = thr->Tn_lo[k], Tnh = thr->Tn_hi[k];
+                vm |= (est < Tv_lo ? 1u : 0u) << k;
+                nm |= (est < Tnl ? 1u : 0u) << k;
+                amb |= ((est >= Tv_lo && est < Tv_hi) || (est >= Tnl && est < Tnh)) ? 1u : 0u;
+            }
+            {   // k = 0 again for the rmin - coll_tol test (solveSoftDMPCbound.m:25)
+                const double dx = own[0] - pj[0], dy = own[1] - pj[1], dz = own[2] - pj[2];
+                const double ez = dz * inv_c;
+                const double est = fma(ez, ez, fma(dy, dy, dx * dx));
+                if (est < thr->Tc_lo) acc.coll0 = 1u;
+                amb |= (est >= thr->Tc_lo && est < thr->Tc_hi) ? 1u : 0u;
+            }
+            if (amb) {
+                // some estimate sits within 1e-12 of a threshold: redo this neighbour exactly
+                vm = 0;
+                nm = 0;
+                for (int k = 0; k < K; ++k) {
+                    const double s = ell_sq(own[3 * k] - pj[3 * k], own[3 * k + 1] - pj[3 * k + 1],
+                                            own[3 * k + 2] - pj[3 * k + 2], P.c);
+                    if (s < thr->T_viol) vm |= 1u << k;
+                    if (s < thr->T_near[k]) nm |= 1u << k;
+                    if (k == 0 && s < thr->T_coll) acc.coll0 = 1u;
+                }
             }
             acc.vmask |= vm;
         }
@@ -86,7 +158,6 @@ struct ScanOut {
     int kstar;     // 1-based, 0 = none
     int nv;        // rows written
     int flag;      // 0 / ST_COLL / ST_OVERFLOW
-    double md0;
 };
 
 // Decide the first violating step and emit rows.  l = full horizon buffer (global).
@@ -100,7 +171,7 @@ DMPC_D ScanOut scan_finish(const DevParams& P, const double* __restrict__ own, i
     o.nv = 0;
     o.flag = 0;
     const unsigned vm = wor(acc.vmask);
-    o.md0 = wmin(acc.md0);
+    const unsigned coll0 = wor(acc.coll0);
     const bool soft = (P.variant == VAR_SOFT_BOUND || P.variant == VAR_SOFT_BOUND2);
     const double c2 = P.c * P.c;
     int kfirst = 0, klast = -1, kshift = 0;
@@ -111,7 +182,7 @@ DMPC_D ScanOut scan_finish(const DevParams& P, const double* __restrict__ own, i
         o.kstar = 0;
     } else {
         unsigned m = vm;
-        if (soft && (m & 1u) && o.md0 < P.rmin - P.coll_tol) {
+        if (soft && (m & 1u) && coll0) {
             // solveSoftDMPCbound.m:25-32: predicted collision at the very next step
             o.kstar = 1;
             o.flag = ST_COLL;

@@ -37,22 +37,20 @@ extern "C" int emul_step(const dmpcb200_params* p, int N, int n0, int n1, const 
     const double qs[3][2] = {{p->Q_far, p->S_free}, {p->Q_near, p->S_free}, {p->Q1, p->S1}};
     build_tables(p->h, K, qs, tab);
     std::vector<unsigned char> smem(agent_smem_bytes(K, QMAX, RCAP) + 64);
+    const ScanThr thr = make_scan_thr(D);
     std::vector<unsigned> nearmask(N);
-    std::vector<double> grow(5 * (size_t)RMAX), gscr_d(3 * (size_t)RMAX);
+    std::vector<double> grow(5 * (size_t)RMAX), gscr_d(4 * (size_t)RMAX);
     std::vector<int> gkc(RMAX), gidx(RMAX), gscr_i(4 * (size_t)RMAX);
     for (int n = n0; n < n1; ++n) {
         const double* own = l_prev + (size_t)3 * K * n;
         ScanAcc acc;
         acc.vmask = 0;
-        acc.md0 = INFINITY;
-        scan_tile(D, own, n, l_prev, 0, N, nearmask.data(), acc);
+        acc.coll0 = 0;
+        scan_tile(D, &thr, own, n, l_prev, 0, N, nearmask.data(), acc);
         ScanOut so = scan_finish(D, own, n, l_prev, nearmask.data(), acc, RMAX, grow.data(), gkc.data(),
                                  gidx.data());
         AgentIO io;
-        for (int x = 0; x < 3; ++x) {
-            io.po[x] = pk[3 * n + x]; io.pf[x] = pf[3 * n + x];
-            io.vo[x] = vk[3 * n + x]; io.ao[x] = ak[3 * n + x];
-        }
+        io.po = pk + 3 * n; io.pf = pf + 3 * n; io.vo = vk + 3 * n; io.ao = ak + 3 * n;
         io.kstar = so.kstar; io.nv = so.nv; io.scanflag = so.flag; io.RMAX = RMAX;
         io.grow = grow.data(); io.gkc = gkc.data(); io.gscr_d = gscr_d.data(); io.gscr_i = gscr_i.data();
         io.out_p = l_new + (size_t)3 * K * n;
@@ -61,7 +59,7 @@ extern "C" int emul_step(const dmpcb200_params* p, int N, int n0, int n1, const 
         io.p1 = p1 + 3 * n; io.v1 = v1 + 3 * n; io.a1 = a1 + 3 * n;
         io.l_prev_n = own;
         AgentDiag dg;
-        status[n] = agent_solve(D, tab.data(), smem.data(), QMAX, RCAP, io, &dg);
+        status[n] = agent_solve<0>(D, tab.data(), smem.data(), QMAX, RCAP, io, &dg);
         if (diag) { diag[4 * n] = dg.kstar; diag[4 * n + 1] = dg.nv; diag[4 * n + 2] = dg.iters; diag[4 * n + 3] = dg.nact; }
     }
     return 0;
