@@ -15,7 +15,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 _CSRC = os.path.join(_HERE, "csrc")
 LIB_PATH = os.path.join(_HERE, "libdmpc_b200.so")
 SOURCES = ["dmpc_b200.cu", "model_tables.cpp"]
-HEADERS = ["dmpc_kernels.cuh", "scan_core.cuh", "agent_solve.cuh", "qp_core.cuh", "model_tables.h",
+HEADERS = ["dmpc_kernels.cuh", "scan_core.cuh", "agent_solve.cuh", "qp_core.cuh", "qp_warp.cuh", "model_tables.h",
            os.path.join("..", "..", "include", "dmpc_b200.h")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "-shared", "-diag-suppress", "177"]

@@ -178,13 +178,10 @@ cudaError_t launch_qp(dmpcb200_t* h, const StepArgs& A, cudaStream_t s) {
     const int nl = A.n1 - A.n0;
     const size_t smem = qp_smem_bytes(h->K, h->W, h->QMAX, h->RCAP);
     if (h->K == 15 && h->W == 4) return launch_qp_w<4, 15>(A, nl, smem, s);
-    if (h->K == 20 && h->W == 3) return launch_qp_w<3, 20>(A, nl, smem, s);
-    switch (h->W) {
-        case 4: return launch_qp_w<4, 0>(A, nl, smem, s);
-        case 3: return launch_qp_w<3, 0>(A, nl, smem, s);
-        case 2: return launch_qp_w<2, 0>(A, nl, smem, s);
-        default: return launch_qp_w<1, 0>(A, nl, smem, s);
-    }
+    if (h->K == 20 && h->W == 4) return launch_qp_w<4, 20>(A, nl, smem, s);
+    // W = 4 for every horizon up to 21, 3 beyond (the tables grow with K^2)
+    if (h->W == 4) return launch_qp_w<4, 0>(A, nl, smem, s);
+    return launch_qp_w<3, 0>(A, nl, smem, s);
 }
 
 TailArgs make_tail(dmpcb200_t* h, const double* p, int ld, const int* status, const double* p1, const double* v1,
@@ -354,10 +351,10 @@ int dmpcb200_create(const dmpcb200_params* p, int N, int n0, int n1, int device,
     else h->RMAX = std::min(std::max(N - 1, 1), 256);
     h->RMAX = round_up(h->RMAX, 2);
     h->RCAP = 64;
-    const int qwant = round_up(n3 + 16, 8);
+    const int qwant = std::min(round_up(n3 + 16, 8), 64);  // on-chip active-set capacity (qp_warp.cuh: 64)
     const size_t smem_max = 227 * 1024;
     h->W = 0;
-    for (int w : {4, 3, 2, 1})
+    for (int w : {4, 3})
         if (qp_smem_bytes(K, w, qwant, h->RCAP) <= smem_max) {
             h->W = w;
             break;

@@ -20,6 +20,7 @@
 #include <cuda_runtime.h>
 
 #include "scan_core.cuh"
+#include "qp_warp.cuh"
 
 namespace dmpc {
 
@@ -213,8 +214,13 @@ __global__ void __launch_bounds__(W * 32) scan_kernel(const __grid_constant__ St
 
 // ---- K2 -------------------------------------------------------------------------------------
 DMPC_HD size_t qp_table_bytes(int K) { return (size_t)(10 * K * K + 4 * K) * sizeof(double); }
+// per-agent workspace: the register-resident solver's (qp_warp.cuh) or the generic solver's, whichever is larger
+DMPC_HD size_t qp_agent_bytes(int K, int QMAX, int RCAP) {
+    const size_t a = agent_smem_bytes(K, QMAX, RCAP), b = align_up(qw_smem_bytes(), 16);
+    return a > b ? a : b;
+}
 DMPC_HD size_t qp_smem_bytes(int K, int W, int QMAX, int RCAP) {
-    return align_up(qp_table_bytes(K), 16) + (size_t)W * agent_smem_bytes(K, QMAX, RCAP) + 16;
+    return align_up(qp_table_bytes(K), 16) + (size_t)W * qp_agent_bytes(K, QMAX, RCAP) + 16;
 }
 
 template <int W, int KT>
@@ -223,7 +229,7 @@ __global__ void __launch_bounds__(W * 32, 1) qp_kernel(const __grid_constant__ S
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const int K = KT ? KT : A.P.K, n3 = 3 * K;
     const size_t tab_bytes = align_up(qp_table_bytes(K), 16);
-    const size_t per_warp = agent_smem_bytes(K, A.QMAX, A.RCAP);
+    const size_t per_warp = qp_agent_bytes(K, A.QMAX, A.RCAP);
     double* tab_s = reinterpret_cast<double*>(smem_raw);
     uint64_t* bar = reinterpret_cast<uint64_t*>(smem_raw + tab_bytes + (size_t)W * per_warp);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -264,22 +270,37 @@ __global__ void __launch_bounds__(W * 32, 1) qp_kernel(const __grid_constant__ S
     mbar_wait(bar, 0);  // tables have landed
     AgentDiag dg;
     int st = 0, it0 = 0;
-    // attempt 0: on-chip workspace; attempt 1 (only if the active set outgrew it): a global-memory
-    // rescue slot with capacity QBIG.  One call site, so the solver exists once in the kernel image.
     unsigned char* scratch = smem_raw + tab_bytes + (size_t)warp * per_warp;
+    // fast path: the register-resident warp solver (qp_warp.cuh) -- every agent of the soft variants whose
+    // rows fit.  The generic solver (qp_core.cuh) takes the rest: solveHardDMPC (rows on many horizon
+    // steps), more than 64 rows, and -- in a global-memory rescue slot of capacity QBIG -- agents whose
+    // active set outgrew the on-chip capacity.  One call site, so the generic solver exists once.
+    const bool fast_ok = (n3 <= kQW) && (sr.nv <= kQW) && (A.P.variant != VAR_HARD) && !sr.flag;
+    bool generic = !fast_ok, rescue = false;
     int cap = A.QMAX;
-    for (int attempt = 0; attempt < 2; ++attempt) {
-        st = agent_solve<KT>(A.P, tab_s, scratch, cap, A.RCAP, io, &dg);
+    if (fast_ok) {
+        st = agent_solve_fast<KT>(A.P, tab_s, scratch, A.QMAX, io, &dg);
+        if ((st & ST_OVERFLOW) && A.rescue) {
+            generic = true;
+            rescue = true;
+            it0 = dg.iters;
+        }
+    }
+    while (generic) {
+        if (rescue) {
+            int slot = 0;
+            if (lane == 0) slot = atomicAdd(A.rescue_next, 1);
+            slot = __shfl_sync(0xffffffffu, slot, 0);
+            if (slot >= A.n_rescue) break;
+            if (lane == 0 && A.ctrl) atomicAdd(&A.ctrl->rescue_used, 1);
+            scratch = A.rescue + (size_t)slot * A.rescue_bytes;
+            cap = A.QBIG;
+        }
+        st = agent_solve<0>(A.P, tab_s, scratch, cap, A.RCAP, io, &dg);
         dg.iters += it0;
-        if (attempt || !(st & ST_OVERFLOW) || sr.flag || !A.rescue) break;
-        int slot = 0;
-        if (lane == 0) slot = atomicAdd(A.rescue_next, 1);
-        slot = __shfl_sync(0xffffffffu, slot, 0);
-        if (slot >= A.n_rescue) break;
-        if (lane == 0 && A.ctrl) atomicAdd(&A.ctrl->rescue_used, 1);
+        if (rescue || !(st & ST_OVERFLOW) || sr.flag || !A.rescue) break;
+        rescue = true;
         it0 = dg.iters;
-        scratch = A.rescue + (size_t)slot * A.rescue_bytes;
-        cap = A.QBIG;
     }
     if (lane == 0) {
         A.status[n] = st;

@@ -1,0 +1,1130 @@
+// qp_warp.cuh -- register-resident warp solver for one agent's DMPC QP (the fast path of K2).
+//
+// Same problem and same method as qp_core.cuh (solveSoftDMPCbound.m:60-155 of the reference: the
+// QP handed to quadprog, and its infeasible-retry loop) -- a Goldfarb-Idnani dual active-set
+// iteration in Schur-complement form with the explicit inverse M = (N' H^-1 N)^-1 and table
+// lookups for every entry of N' H^-1 N -- but laid out for ONE WARP THAT IS ALONE ON ITS SM
+// SUB-PARTITION, i.e. for latency, not throughput:
+//   * every lane owns two primal entries (i = lane, lane + 32), two collision rows and two
+//     active-set slots; the iterate (a, P = p0 + Lam a, slacks, row residuals, multipliers) lives in
+//     REGISTERS, never in memory;
+//   * shared memory holds only what other lanes must see: M (row stride 66 doubles so that a lane
+//     streams its own row with conflict-free 128-bit loads), the broadcast vectors g, r, the
+//     coefficient vectors of the direction, the static row data and the slot records;
+//   * the workspace pointers are derived from the kernel's shared-memory base, so every access is
+//     an LDS/STS with a 32-bit address (the generic solver of qp_core.cuh goes through 64-bit
+//     generic loads because its scratch may live in global memory);
+//   * a retry of the reference's loop (slack bound x2, penalty x2) keeps the WHOLE active set and
+//     its inverse: the constraint normals do not depend on (term, slb), only the right-hand sides
+//     and the slack part of the unconstrained optimum do, so the multipliers of the old active set
+//     are one matrix-vector product away and the iteration resumes from there.
+// Capacity: 3K <= 64 entries, <= 64 rows that all act on one horizon index (every variant except
+// solveHardDMPC), <= 64 active constraints.  Anything else is solved by the generic solver.
+//
+// The file compiles for the host with one "lane" that owns all 64 items (tests/host_emul): that
+// build is a debugging aid of the test-suite and is never part of the product library.
+#pragma once
+#include "agent_solve.cuh"
+
+namespace dmpc {
+
+constexpr int kQW = 64;             // capacity: entries, rows, slots
+constexpr int kMS = 66;             // row stride of M in doubles
+constexpr int kEPL = kQW / kLanes;  // items per lane: 2 on the device, 64 in the host build
+constexpr unsigned kNone = 0xffu;
+
+#if defined(__CUDA_ARCH__)
+#define QW_FOR(h) _Pragma("unroll") for (int h = 0; h < kEPL; ++h)
+DMPC_D double wshfl(double v, int src) { return __shfl_sync(0xffffffffu, v, src); }
+DMPC_D void wsum3(double& x0, double& x1, double& x2) {
+#pragma unroll
+    for (int o = 16; o; o >>= 1) {
+        x0 += __shfl_xor_sync(0xffffffffu, x0, o);
+        x1 += __shfl_xor_sync(0xffffffffu, x1, o);
+        x2 += __shfl_xor_sync(0xffffffffu, x2, o);
+    }
+}
+#else
+#define QW_FOR(h) for (int h = 0; h < kEPL; ++h)
+inline double wshfl(double v, int) { return v; }
+inline void wsum3(double&, double&, double&) {}
+#endif
+
+DMPC_HD int qw_item(int h) { return lane_id() + h * kLanes; }
+DMPC_HD unsigned qw_getb(unsigned m, int b) { return (m >> (8 * b)) & 0xffu; }
+DMPC_HD unsigned qw_setb(unsigned m, int b, unsigned v) { return (m & ~(0xffu << (8 * b))) | (v << (8 * b)); }
+
+// doubles / ints of shared memory the fast solver needs per agent
+DMPC_HD size_t qw_smem_doubles() { return (size_t)kQW * kMS + 16 * (size_t)kQW; }
+DMPC_HD size_t qw_smem_ints() { return 3 * (size_t)kQW; }
+DMPC_HD size_t qw_smem_bytes() { return qw_smem_doubles() * sizeof(double) + qw_smem_ints() * sizeof(int); }
+
+template <int KT>
+struct QpW {
+    // ---- uniform problem data ---------------------------------------------------------------------
+    int K, n3, nv, soft, kc_all, qcap;
+    double alim, term, slb, qw, sw;
+    const double *ilnorm, *G, *B, *C;  // tables of the weight set in use (shared memory)
+    // ---- shared-memory workspace ---------------------------------------------------------------------
+    double *M, *gs, *rs, *cb, *cp, *zs, *Ls;
+    double *rd0, *rd1, *rd2, *rdist, *rrhs, *rirn;  // static row data
+    double *sv0, *sv1, *sv2, *se;                   // slot records (normal of the constraint in the slot)
+    int *rkc, *sinfo, *act;
+    // ---- per-lane state ---------------------------------------------------------------------------
+    double a[kEPL], P[kEPL], z[kEPL], L[kEPL], aunc[kEPL], Punc[kEPL];
+    double elo[kEPL], ehi[kEPL], eiln[kEPL];  // workspace box and 1/||lam[k,:]|| of the entry
+    double eps[kEPL], rres[kEPL], zeps[kEPL];
+    double u[kEPL], r[kEPL];
+    unsigned emap[kEPL];  // bytes: slot of BOXL, BOXU, WSL, WSU of the entry (0xff: inactive)
+    unsigned rmap[kEPL];  // bytes: slot of ROW, SUB, SLB of the row (0xff: inactive), materialised flag
+    int ek[kEPL], ex[kEPL];
+    int q, nmat, nra, nbox, npos;
+
+    DMPC_D int KK() const { return KT ? KT : K; }
+
+    DMPC_D void carve(unsigned char* smem) {
+        double* d = reinterpret_cast<double*>(smem);
+        M = d; d += (size_t)kQW * kMS;
+        gs = d; d += kQW; rs = d; d += kQW; cb = d; d += kQW; cp = d; d += kQW; zs = d; d += kQW; Ls = d; d += kQW;
+        rd0 = d; d += kQW; rd1 = d; d += kQW; rd2 = d; d += kQW; rdist = d; d += kQW; rrhs = d; d += kQW;
+        rirn = d; d += kQW;
+        sv0 = d; d += kQW; sv1 = d; d += kQW; sv2 = d; d += kQW; se = d; d += kQW;
+        int* ip = reinterpret_cast<int*>(d);
+        rkc = ip; ip += kQW; sinfo = ip; ip += kQW; act = ip; ip += kQW;
+    }
+
+    // ---- value of item idx of a per-lane array, on every lane -----------------------------------
+    DMPC_D double item_d(const double* arr, int idx) const {
+#if defined(__CUDA_ARCH__)
+        double v = arr[0];
+#pragma unroll
+        for (int h = 1; h < kEPL; ++h)
+            if ((idx >> 5) == h) v = arr[h];
+        return wshfl(v, idx & 31);
+#else
+        return arr[idx];
+#endif
+    }
+
+    // ---- constraint decoding -------------------------------------------------------------------
+    DMPC_D PInfo decode(int code) const {
+        PInfo p;
+        p.type = code_type(code);
+        p.idx = code_idx(code);
+        p.space = 0;
+        p.k = 0;
+        p.j = -1;
+        p.v0 = p.v1 = p.v2 = p.e = 0.0;
+        const int Kk = KK();
+        if (p.type <= T_WSU) {
+            p.k = p.idx / 3;
+            const int x = p.idx - 3 * p.k;
+            const double sig = (p.type == T_BOXL || p.type == T_WSL) ? 1.0 : -1.0;
+            p.v0 = (x == 0) ? sig : 0.0;
+            p.v1 = (x == 1) ? sig : 0.0;
+            p.v2 = (x == 2) ? sig : 0.0;
+            p.space = (p.type >= T_WSL) ? 1 : 0;
+            p.nph = G[2 * p.space * Kk * Kk + p.k * Kk + p.k];  // G[k][k] or C[k][k]
+        } else {
+            p.j = p.idx;
+            if (p.type == T_ROW) {
+                p.v0 = rd0[p.j];
+                p.v1 = rd1[p.j];
+                p.v2 = rd2[p.j];
+                p.e = soft ? -rdist[p.j] : 0.0;
+                p.k = rkc[p.j];
+                p.space = 1;
+                p.nph = (p.v0 * p.v0 + p.v1 * p.v1 + p.v2 * p.v2) * C[p.k * Kk + p.k] + 0.5 * p.e * p.e;
+            } else {
+                p.e = (p.type == T_SUB) ? -1.0 : 1.0;
+                p.nph = 0.5;
+            }
+        }
+        return p;
+    }
+    DMPC_D void put_record(int s, const PInfo& p) {  // one lane
+        sv0[s] = p.v0;
+        sv1[s] = p.v1;
+        sv2[s] = p.v2;
+        se[s] = p.e;
+        sinfo[s] = pack_info(p.space, p.k, p.j);
+    }
+
+    DMPC_D void set_active(int code, unsigned slot) {
+        const int t = code_type(code), i = code_idx(code);
+        QW_FOR(h) {
+            if (i == qw_item(h)) {
+                if (t <= T_WSU) emap[h] = qw_setb(emap[h], t, slot);
+                else rmap[h] = qw_setb(rmap[h], t - T_ROW, slot);
+            }
+        }
+    }
+    DMPC_D void count_active(int code, int d) {
+        const int t = code_type(code);
+        if (t <= T_BOXU) nbox += d;
+        else if (t <= T_ROW) npos += d;
+        if (t == T_ROW) nra += d;
+    }
+
+    // residual c'x - b of a constraint at the current x (>= 0 feasible), from the owner's registers
+    DMPC_D double resid_code(int code) const {
+        const int t = code_type(code), i = code_idx(code);
+        double v = 0.0;
+        QW_FOR(h) {
+            if (i == qw_item(h)) {
+                switch (t) {
+                    case T_BOXL: v = a[h] + alim; break;
+                    case T_BOXU: v = alim - a[h]; break;
+                    case T_WSL: v = P[h] - elo[h]; break;
+                    case T_WSU: v = ehi[h] - P[h]; break;
+                    case T_ROW: v = rres[h]; break;
+                    case T_SUB: v = -eps[h]; break;
+                    default: v = eps[h] - slb; break;
+                }
+            }
+        }
+        return wshfl(v, i & (kLanes - 1));
+    }
+
+    // ---- most violated (normalised) inactive constraint; returns code or -1 -----------------------
+    DMPC_D int most_violated(double tol, double* sp_out) const {
+        double best = -tol, braw = 0.0;
+        int bcode = -1;
+        QW_FOR(h) {
+            const int i = qw_item(h);
+            if (i < n3) {
+                const unsigned m = emap[h];
+                const double ai = a[h], Pi = P[h], iln = eiln[h];
+                const double r0 = ai + alim, r1 = alim - ai, r2 = Pi - elo[h], r3 = ehi[h] - Pi;
+                const double v0 = (qw_getb(m, 0) == kNone) ? r0 : INFINITY;
+                const double v1 = (qw_getb(m, 1) == kNone) ? r1 : INFINITY;
+                const double v2 = (qw_getb(m, 2) == kNone) ? r2 * iln : INFINITY;
+                const double v3 = (qw_getb(m, 3) == kNone) ? r3 * iln : INFINITY;
+                const double m01 = fmin(v0, v1), m23 = fmin(v2, v3);
+                const int t01 = (v1 < v0) ? T_BOXU : T_BOXL, t23 = (v3 < v2) ? T_WSU : T_WSL;
+                const double raw01 = (v1 < v0) ? r1 : r0, raw23 = (v3 < v2) ? r3 : r2;
+                const double mm = fmin(m01, m23);
+                if (mm < best) {
+                    best = mm;
+                    bcode = mk_code((m23 < m01) ? t23 : t01, i);
+                    braw = (m23 < m01) ? raw23 : raw01;
+                }
+            }
+        }
+        QW_FOR(h) {
+            const int j = qw_item(h);
+            if (j < nv) {
+                const unsigned m = rmap[h];
+                if (qw_getb(m, 0) == kNone) {
+                    const double sn = rres[h] * rirn[j];
+                    if (sn < best) { best = sn; bcode = mk_code(T_ROW, j); braw = rres[h]; }
+                }
+                if (soft && qw_getb(m, 3)) {
+                    const double ej = eps[h];
+                    if (qw_getb(m, 1) == kNone && -ej < best) { best = -ej; bcode = mk_code(T_SUB, j); braw = -ej; }
+                    if (qw_getb(m, 2) == kNone && ej - slb < best) { best = ej - slb; bcode = mk_code(T_SLB, j); braw = ej - slb; }
+                }
+            }
+        }
+        double viol = -best;
+        const int src = warg_max_nonneg(viol, bcode >= 0);
+        if (src < 0) return -1;
+        *sp_out = wshfl(braw, src);
+        return wbcast(bcode, src);
+    }
+
+    // ---- g[s] = n_{act[s]}' H^{-1} n_p for s < cnt, into gs (zero padded to a multiple of 4) ---------
+    DMPC_D void gvec(const PInfo& p, int cnt) {
+        const int Kk = KK(), KK2 = Kk * Kk;
+        const int cnt4 = (cnt + 3) & ~3;
+        QW_FOR(h) {
+            const int s = qw_item(h);
+            if (s < cnt) {
+                const int info = sinfo[s];
+                const int sp = info & 1, ks = (info >> 1) & 0xff, js = (info >> 9) - 1;
+                const double dot = sv0[s] * p.v0 + sv1[s] * p.v1 + sv2[s] * p.v2;
+                const int idx = (sp > p.space) ? (p.k * Kk + ks) : (ks * Kk + p.k);
+                double gv = dot * G[(sp + p.space) * KK2 + idx];
+                if (js >= 0 && js == p.j) gv = fma(0.5 * se[s], p.e, gv);
+                gs[s] = gv;
+            } else if (s < cnt4) {
+                gs[s] = 0.0;
+            }
+        }
+        wsync();
+    }
+
+    // ---- r = M[0:cnt,0:cnt] gs into the registers and into rs (zero padded).  Returns g'r (NEED_GR) --
+    template <bool NEED_GR>
+    DMPC_D double mat_vec(int cnt, double* rmax_out) {
+        const int cnt4 = (cnt + 3) & ~3;
+        double gr = 0.0, rm = 0.0;
+        QW_FOR(h) {
+            const int s = qw_item(h);
+            if (h * kLanes < cnt) {  // uniform: this half of the slots is in use
+                double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+                if (s < cnt) {
+                    const double* Mr = M + (size_t)s * kMS;
+#pragma unroll 2
+                    for (int j = 0; j < cnt4; j += 4) {
+                        s0 = fma(Mr[j], gs[j], s0);
+                        s1 = fma(Mr[j + 1], gs[j + 1], s1);
+                        s2 = fma(Mr[j + 2], gs[j + 2], s2);
+                        s3 = fma(Mr[j + 3], gs[j + 3], s3);
+                    }
+                }
+                const double ri = (s0 + s1) + (s2 + s3);
+                r[h] = ri;
+                if (s < cnt4) rs[s] = (s < cnt) ? ri : 0.0;
+                if (NEED_GR && s < cnt) gr = fma(gs[s], ri, gr);
+                rm = fmax(rm, fabs(ri));
+            } else {
+                r[h] = 0.0;
+                if (s < cnt4) rs[s] = 0.0;
+            }
+        }
+        if (NEED_GR) gr = wsum(gr);
+        if (rmax_out) *rmax_out = wmax_approx_nonneg(rm);
+        wsync();
+        return gr;
+    }
+
+    // ---- bordering update: M <- inverse of [[S, g],[g', nph]] given r (registers + rs), delta -------
+    DMPC_D void border(int cnt, double delta) {
+        const int cnt4 = (cnt + 3) & ~3;
+        const double id = frcp(delta);
+        QW_FOR(h) {
+            const int s = qw_item(h);
+            if (s < cnt) {
+                const double ci = r[h] * id;
+                double* Mr = M + (size_t)s * kMS;
+#pragma unroll 2
+                for (int j = 0; j < cnt4; j += 4) {
+                    const double m0 = Mr[j], m1 = Mr[j + 1], m2 = Mr[j + 2], m3 = Mr[j + 3];
+                    Mr[j] = fma(ci, rs[j], m0);
+                    Mr[j + 1] = fma(ci, rs[j + 1], m1);
+                    Mr[j + 2] = fma(ci, rs[j + 2], m2);
+                    Mr[j + 3] = fma(ci, rs[j + 3], m3);
+                }
+                Mr[cnt] = -ci;  // after the loop: cnt may lie inside the padded range
+                M[(size_t)cnt * kMS + s] = -ci;
+            }
+        }
+        if (lane_id() == 0) M[(size_t)cnt * kMS + cnt] = id;
+        wsync();
+    }
+
+    // ---- append a slot that is decoupled from all others (a slack upper bound): M row/col = (0, diag) --
+    DMPC_D void append_isolated(int code, double uval, double mdiag) {
+        const PInfo p = decode(code);
+        if (lane_id() == 0) {
+            M[(size_t)q * kMS + q] = mdiag;  // the unused part of M is kept zero
+            act[q] = code;
+            put_record(q, p);
+        }
+        QW_FOR(h) if (q == qw_item(h)) u[h] = uval;
+        set_active(code, (unsigned)q);
+        count_active(code, +1);
+        wsync();
+        ++q;
+    }
+
+    // ---- drop slot l: Schur downdate of M, swap-remove.  vec (r or u, per-lane registers) follows by
+    //      vec' = vec - M(:,l) vec_l / M_ll.  vec_l is passed in (uniform). ------------------------------
+    DMPC_D void drop_slot(int l, double* vec, double vl, double* other) {
+        const int last = q - 1;
+        const int q4 = (q + 3) & ~3;
+        const double inv = frcp(M[(size_t)l * kMS + l]);
+        // column l (= row l, M is symmetric) as broadcast vector
+        QW_FOR(h) {
+            const int s = qw_item(h);
+            if (s < q) gs[s] = M[(size_t)l * kMS + s];
+            else if (s < q4) gs[s] = 0.0;
+        }
+        wsync();
+        QW_FOR(h) {
+            const int s = qw_item(h);
+            if (s < q && s != l) {
+                const double ci = gs[s] * inv;
+                vec[h] = fma(-ci, vl, vec[h]);
+                double* Mr = M + (size_t)s * kMS;
+#pragma unroll 2
+                for (int j = 0; j < q4; j += 4) {
+                    const double m0 = Mr[j], m1 = Mr[j + 1], m2 = Mr[j + 2], m3 = Mr[j + 3];
+                    Mr[j] = fma(-ci, gs[j], m0);
+                    Mr[j + 1] = fma(-ci, gs[j + 1], m1);
+                    Mr[j + 2] = fma(-ci, gs[j + 2], m2);
+                    Mr[j + 3] = fma(-ci, gs[j + 3], m3);
+                }
+            }
+        }
+        const int cl = act[l], clast = act[last];
+        // values of the last slot that travel with it (vec, other: per-lane registers)
+        const double vec_last = item_d(vec, last);
+        const double oth_last = other ? item_d(other, last) : 0.0;
+        wsync();
+        set_active(cl, kNone);
+        count_active(cl, -1);
+        if (l != last) {
+            // move slot `last` into l: row/column `last` of M, record, code, vec, other
+            QW_FOR(h) {
+                const int s = qw_item(h);
+                if (s < last && s != l) {
+                    const double v = M[(size_t)s * kMS + last];
+                    M[(size_t)s * kMS + l] = v;
+                    M[(size_t)l * kMS + s] = v;
+                }
+                if (s == l) {
+                    vec[h] = vec_last;
+                    if (other) other[h] = oth_last;
+                }
+            }
+            if (lane_id() == 0) {
+                M[(size_t)l * kMS + l] = M[(size_t)last * kMS + last];
+                act[l] = clast;
+                sv0[l] = sv0[last];
+                sv1[l] = sv1[last];
+                sv2[l] = sv2[last];
+                se[l] = se[last];
+                sinfo[l] = sinfo[last];
+            }
+            set_active(clast, (unsigned)l);
+        }
+        wsync();
+        // keep the unused part of M zero: clear row / column `last`
+        QW_FOR(h) {
+            const int s = qw_item(h);
+            if (s <= last) {
+                M[(size_t)s * kMS + last] = 0.0;
+                M[(size_t)last * kMS + s] = 0.0;
+            }
+            if (s == last) {
+                vec[h] = 0.0;
+                if (other) other[h] = 0.0;
+            }
+        }
+        wsync();
+        --q;
+    }
+
+    // ---- cb / cp <- sum over the active set of coef_s * (normal of slot s), coef = rs -----------------
+    //   cb: coefficients on unit vectors e_i (acceleration box)
+    //   cp: coefficients on rows of Lam (workspace constraints and collision rows at kc_all)
+    DMPC_D void coefs() {
+        double D0 = 0.0, D1 = 0.0, D2 = 0.0;
+        if (nra) {
+            QW_FOR(h) {
+                const int j = qw_item(h);
+                const unsigned sr = qw_getb(rmap[h], 0);
+                if (j < nv && sr != kNone) {
+                    const double c = rs[sr];
+                    D0 = fma(c, rd0[j], D0);
+                    D1 = fma(c, rd1[j], D1);
+                    D2 = fma(c, rd2[j], D2);
+                }
+            }
+            wsum3(D0, D1, D2);
+        }
+        QW_FOR(h) {
+            const int i = qw_item(h);
+            if (i < n3) {
+                const unsigned m = emap[h];
+                const unsigned sl = qw_getb(m, 0), su = qw_getb(m, 1), wl = qw_getb(m, 2), wu = qw_getb(m, 3);
+                double c_b = 0.0, c_p = 0.0;
+                if (sl != kNone) c_b = rs[sl];
+                if (su != kNone) c_b -= rs[su];
+                if (wl != kNone) c_p = rs[wl];
+                if (wu != kNone) c_p -= rs[wu];
+                if (nra && ek[h] == kc_all) c_p += (ex[h] == 0) ? D0 : ((ex[h] == 1) ? D1 : D2);
+                cb[i] = c_b;
+                cp[i] = c_p;
+            }
+        }
+        wsync();
+    }
+
+    // ---- ONE pass over the tables:  oa_i = ba_i + sgn (G cb + B cp)_i,  oP_i = bP_i + sgn (B' cb + C cp)_i
+    //      hp != null: the bases are H^{-1} n_p / Lam H^{-1} n_p of the candidate constraint -------------
+    DMPC_D void apply(double* oa, double* oP, const double* ba, const double* bP, double sgn, const PInfo* hp) {
+        const int Kk = KK(), KK2 = Kk * Kk;
+        const bool hb = nbox > 0, hpz = npos > 0;
+        QW_FOR(h) {
+            const int i = qw_item(h);
+            if (i < n3) {
+                const int k = ek[h], x = ex[h];
+                double a0 = 0.0, a1 = 0.0, p0 = 0.0, p1 = 0.0;
+                if (hb) {
+#pragma unroll
+                    for (int j = 0; j < Kk; ++j) {
+                        const double c = cb[3 * j + x];
+                        a0 = fma(G[k * Kk + j], c, a0);
+                        p0 = fma(B[j * Kk + k], c, p0);
+                    }
+                }
+                if (hpz) {
+#pragma unroll
+                    for (int j = 0; j < Kk; ++j) {
+                        const double c = cp[3 * j + x];
+                        a1 = fma(B[k * Kk + j], c, a1);
+                        p1 = fma(C[k * Kk + j], c, p1);
+                    }
+                }
+                double b_a, b_P;
+                if (hp) {
+                    const double vx = (x == 0) ? hp->v0 : ((x == 1) ? hp->v1 : hp->v2);
+                    b_a = vx * G[hp->space * KK2 + k * Kk + hp->k];
+                    b_P = vx * G[(1 + hp->space) * KK2 + hp->k * Kk + k];
+                } else {
+                    b_a = ba[h];
+                    b_P = bP[h];
+                }
+                oa[h] = b_a + sgn * (a0 + a1);
+                oP[h] = b_P + sgn * (p0 + p1);
+            }
+        }
+    }
+
+    // ---- primal direction z = H^{-1}(n_p - N r), Lz, zeps; returns delta = z'Hz ----------------------
+    DMPC_D double direction(const PInfo& p) {
+        coefs();
+        apply(z, L, nullptr, nullptr, -1.0, &p);
+        QW_FOR(h) {
+            const int i = qw_item(h);
+            if (i < n3) {
+                zs[i] = z[h];
+                Ls[i] = L[h];
+            }
+        }
+        double loc = 0.0;
+        if (soft) {
+            QW_FOR(h) {
+                const int j = qw_item(h);
+                const unsigned m = rmap[h];
+                double ze = 0.0;
+                if (j < nv && qw_getb(m, 3)) {
+                    ze = (j == p.j) ? 0.5 * p.e : 0.0;
+                    const unsigned sr = qw_getb(m, 0), su = qw_getb(m, 1), sl = qw_getb(m, 2);
+                    if (sr != kNone) ze += 0.5 * rdist[j] * rs[sr];
+                    if (su != kNone) ze += 0.5 * rs[su];
+                    if (sl != kNone) ze -= 0.5 * rs[sl];
+                    loc = fma(ze, ze, loc);
+                }
+                zeps[h] = ze;
+            }
+        }
+        wsync();
+        // z'Hz, H_K = 2 (q lamK lamK' + s Delta'Delta + I): a sum of squares (no cancellation)
+        QW_FOR(h) {
+            const int i = qw_item(h);
+            if (i < n3) {
+                const double zi = z[h];
+                const double dz = zi - ((i >= 3) ? zs[i - 3] : 0.0);
+                loc = fma(zi, zi, loc);
+                loc = fma(sw * dz, dz, loc);
+            }
+        }
+        loc = wsum(loc);
+        const int Kk = KK();
+        const double t0 = Ls[3 * (Kk - 1)], t1 = Ls[3 * (Kk - 1) + 1], t2 = Ls[3 * (Kk - 1) + 2];
+        return 2.0 * (loc + qw * (t0 * t0 + t1 * t1 + t2 * t2));
+    }
+
+    // ---- x (a, eps, P) re-synthesised from the multipliers: x = x_unc + H^{-1} N u; residuals of the
+    //      rows refreshed.  Leaves a in zs, P in Ls, eps in cb, rres in cp (shared copies). ------------
+    DMPC_D void synth_from_u() {
+        const int q4 = (q + 3) & ~3;
+        QW_FOR(h) {
+            const int s = qw_item(h);
+            if (s < q4) rs[s] = (s < q) ? u[h] : 0.0;
+        }
+        wsync();
+        coefs();
+        apply(a, P, aunc, Punc, 1.0, nullptr);
+        wsync();  // everybody is done reading cb / cp
+        QW_FOR(h) {
+            const int i = qw_item(h);
+            if (i < n3) {
+                zs[i] = a[h];
+                Ls[i] = P[h];
+            }
+        }
+        if (soft) {
+            QW_FOR(h) {
+                const int j = qw_item(h);
+                const unsigned m = rmap[h];
+                double e = 0.0;  // implicit upper bound: eps = 0
+                if (j < nv && qw_getb(m, 3)) {
+                    e = -0.5 * term;
+                    const unsigned sr = qw_getb(m, 0), su = qw_getb(m, 1), sl = qw_getb(m, 2);
+                    if (sr != kNone) e -= 0.5 * rdist[j] * rs[sr];
+                    if (su != kNone) e -= 0.5 * rs[su];
+                    if (sl != kNone) e += 0.5 * rs[sl];
+                }
+                eps[h] = e;
+            }
+        }
+        wsync();
+        rows_refresh();
+    }
+
+    // recompute every row residual from P (shared copy in Ls) and eps; publishes eps -> cb, rres -> cp
+    DMPC_D void rows_refresh() {
+        QW_FOR(h) {
+            const int j = qw_item(h);
+            if (j < nv) {
+                const int kc = rkc[j];
+                double s = rd0[j] * Ls[3 * kc] + rd1[j] * Ls[3 * kc + 1] + rd2[j] * Ls[3 * kc + 2] - rrhs[j];
+                if (soft) s -= rdist[j] * eps[h];
+                rres[h] = s;
+                cb[j] = eps[h];
+                cp[j] = s;
+            }
+        }
+        wsync();
+    }
+
+    // residual of the constraint in slot s from the shared copies (after synth_from_u)
+    DMPC_D double resid_shared(int code) const {
+        const int t = code_type(code), i = code_idx(code);
+        switch (t) {
+            case T_BOXL: return zs[i] + alim;
+            case T_BOXU: return alim - zs[i];
+            case T_WSL: return Ls[i] - pmin_of(i);
+            case T_WSU: return pmax_of(i) - Ls[i];
+            case T_ROW: return cp[i];
+            case T_SUB: return -cb[i];
+            default: return cb[i] - slb;
+        }
+    }
+    double bnd6[6];  // pmin, pmax (uniform)
+    DMPC_D double pmin_of(int i) const { const int x = i % 3; return (x == 0) ? bnd6[0] : ((x == 1) ? bnd6[1] : bnd6[2]); }
+    DMPC_D double pmax_of(int i) const { const int x = i % 3; return (x == 0) ? bnd6[3] : ((x == 1) ? bnd6[4] : bnd6[5]); }
+
+    // rebuild M exactly from the slot records (S entries are lookups): removes accumulated drift
+    DMPC_COLD void refresh() {
+        for (int s = 0; s < q; ++s) {
+            PInfo p;
+            {
+                const int info = sinfo[s];
+                p.space = info & 1;
+                p.k = (info >> 1) & 0xff;
+                p.j = (info >> 9) - 1;
+                p.v0 = sv0[s];
+                p.v1 = sv1[s];
+                p.v2 = sv2[s];
+                p.e = se[s];
+                p.type = 0;
+                p.idx = 0;
+                const int Kk = KK();
+                p.nph = (p.v0 * p.v0 + p.v1 * p.v1 + p.v2 * p.v2) * G[2 * p.space * Kk * Kk + p.k * Kk + p.k] +
+                        0.5 * p.e * p.e;
+            }
+            // clear row / column s (it may hold garbage of a broken-down update)
+            QW_FOR(h) {
+                const int i = qw_item(h);
+                if (i <= s) {
+                    M[(size_t)i * kMS + s] = 0.0;
+                    M[(size_t)s * kMS + i] = 0.0;
+                }
+            }
+            wsync();
+            gvec(p, s);
+            const double gr = mat_vec<true>(s, nullptr);
+            double delta = p.nph - gr;
+            if (!(delta > 1e-14 * p.nph)) delta = 1e-14 * p.nph;
+            border(s, delta);
+        }
+    }
+
+    // returns max residual of the active constraints after refinement
+    DMPC_COLD double polish() {
+        double mx = 0.0;
+        for (int round = 0; round < 4; ++round) {
+            synth_from_u();
+            mx = 0.0;
+            const int q4 = (q + 3) & ~3;
+            QW_FOR(h) {
+                const int s = qw_item(h);
+                if (s < q) {
+                    const double v = resid_shared(act[s]);
+                    gs[s] = v;
+                    mx = fmax(mx, fabs(v));
+                } else if (s < q4) {
+                    gs[s] = 0.0;
+                }
+            }
+            mx = wmax(mx);
+            wsync();
+            if (!(mx > 1e-13)) break;
+            mat_vec<false>(q, nullptr);
+            QW_FOR(h) u[h] -= r[h];
+        }
+        return mx;
+    }
+
+    // ---- start state: x = x_unc, nothing active ----------------------------------------------------
+    DMPC_D void cold_start() {
+        q = 0;
+        nmat = 0;
+        nra = 0;
+        nbox = 0;
+        npos = 0;
+        QW_FOR(h) {
+            a[h] = aunc[h];
+            P[h] = Punc[h];
+            z[h] = 0.0;
+            L[h] = 0.0;
+            eps[h] = 0.0;
+            zeps[h] = 0.0;
+            u[h] = 0.0;
+            r[h] = 0.0;
+            emap[h] = 0xffffffffu;
+            rmap[h] = 0x00ffffffu;
+            const int i = qw_item(h);
+            if (i < n3) Ls[i] = Punc[h];
+        }
+        // the unused part of M is zero at all times
+        for (int e = lane_id(); e < kQW * kMS; e += kLanes) M[e] = 0.0;
+        wsync();
+        rows_refresh();
+    }
+
+    // ---- restart after the slack data (term, slb) changed: the acceleration-box and workspace
+    //      constraints of the old active set are kept (their part of the problem does not depend on
+    //      term or slb), everything that involves a slack goes back to the implicit start (rows
+    //      inactive, eps = 0 held by the implicit upper bounds).  M is rebuilt for the kept set, the
+    //      multipliers of the equality-constrained problem on it are u = M (b - N' x_unc), constraints
+    //      with a negative multiplier are dropped (rank-1 updates of u and M) until u >= 0, and x is
+    //      re-synthesised: a valid starting pair for solve().  Returns false if the state is not
+    //      usable (the caller then starts cold). ------------------------------------------------------
+    DMPC_COLD bool warm_restart() {
+        int m = 0;
+        nbox = 0;
+        npos = 0;
+        for (int s2 = 0; s2 < q; ++s2) {
+            const int c = act[s2];
+            wsync();
+            if (code_type(c) <= T_WSU) {
+                if (lane_id() == 0 && m != s2) {
+                    act[m] = c;
+                    sv0[m] = sv0[s2];
+                    sv1[m] = sv1[s2];
+                    sv2[m] = sv2[s2];
+                    se[m] = se[s2];
+                    sinfo[m] = sinfo[s2];
+                }
+                set_active(c, (unsigned)m);
+                if (code_type(c) <= T_BOXU) ++nbox;
+                else ++npos;
+                ++m;
+            }
+        }
+        q = m;
+        nmat = 0;
+        nra = 0;
+        for (int e = lane_id(); e < kQW * kMS; e += kLanes) M[e] = 0.0;
+        QW_FOR(h) {
+            const int i = qw_item(h);
+            if (i < n3) {
+                zs[i] = aunc[h];
+                Ls[i] = Punc[h];
+            }
+            a[h] = aunc[h];
+            P[h] = Punc[h];
+            eps[h] = 0.0;
+            zeps[h] = 0.0;
+            rmap[h] = 0x00ffffffu;
+        }
+        wsync();
+        refresh();
+        rows_refresh();
+        const int q4 = (q + 3) & ~3;
+        QW_FOR(h) {
+            const int s = qw_item(h);
+            if (s < q) gs[s] = -resid_shared(act[s]);
+            else if (s < q4) gs[s] = 0.0;
+        }
+        wsync();
+        mat_vec<false>(q, nullptr);
+        double bad = 0.0;
+        QW_FOR(h) {
+            u[h] = r[h];
+            if (!(fabs(r[h]) < 1e300)) bad = 1.0;
+        }
+        if (wmax(bad) > 0.0) return false;
+        for (;;) {
+            double neg = 0.0;
+            int l = -1;
+            QW_FOR(h) {
+                const int s = qw_item(h);
+                if (s < q && u[h] < 0.0 && (l < 0 || -u[h] > neg)) { neg = -u[h]; l = s; }
+            }
+            const int src = warg_max_nonneg(neg, l >= 0);
+            if (src < 0) break;
+            l = wbcast(l, src);
+            const double ul = item_d(u, l);
+            wsync();
+            drop_slot(l, u, ul, nullptr);
+        }
+        synth_from_u();
+        return true;
+    }
+
+    // ---- the solver -----------------------------------------------------------------------------
+    // expects a valid GI state: x minimises the objective on the active set, u >= 0
+    DMPC_D QpResult solve(int max_iter, bool* m_valid_out) {
+        const double feas_tol = 1e-10;
+        const double dep_tol = 1e-9;   // on delta = z'Hz relative to n_p'H^{-1}n_p
+        const double ill_tol = 1e-5;   // adds below this mark M for an exact rebuild
+        int iters = 0, npolish = 0;
+        bool polished = false, dirty = false, m_valid = true;
+        QpResult res;
+        res.rc = QP_OK;
+        PROF_BEGIN();
+        for (;;) {
+            double sp;
+            PROF(0);
+            const int pcode = most_violated(feas_tol, &sp);
+            PROF(1);
+            if (pcode < 0) {
+                if (polished || q == 0) break;  // optimal
+                for (int pass = 0; pass < 2; ++pass) {
+                    if (dirty || pass) refresh();
+                    dirty = false;
+                    if (!(polish() > 1e-9)) break;
+                }
+                polished = true;
+                PROF(2);
+                if (++npolish > 8) { res.rc = QP_ITERCAP; break; }
+                continue;
+            }
+            polished = false;
+            PInfo p = decode(pcode);
+            if (p.type == T_ROW && soft && !qw_getb(item_u(rmap, p.j), 3)) {
+                // materialise the (active) slack upper bound of this row: isolated so far,
+                // S entry 1/2 -> M entry 2, multiplier -term - 2 eps
+                if (q + 2 > qcap) { res.rc = QP_OVERFLOW; break; }
+                const double e0 = item_d(eps, p.j);
+                QW_FOR(h) if (p.j == qw_item(h)) rmap[h] = qw_setb(rmap[h], 3, 1u);
+                append_isolated(mk_code(T_SUB, p.j), -term - 2.0 * e0, 2.0);
+                ++nmat;
+            }
+            if (q + 1 > qcap) { res.rc = QP_OVERFLOW; break; }
+            PROF(3);
+            double up = 0.0, rmax = 0.0, delta = 0.0;
+            bool need_r = true, have_z = false, failed = false, added = false, rebuilt = false;
+            while (!added) {
+                if (need_r) {
+                    if (dirty) { refresh(); dirty = false; }
+                    gvec(p, q);
+                    PROF(4);
+                    mat_vec<false>(q, &rmax);
+                    PROF(5);
+                    need_r = false;
+                    have_z = false;
+                }
+                if (++iters > max_iter) { res.rc = QP_ITERCAP; failed = true; break; }
+                if (!have_z) {
+                    delta = direction(p);
+                    have_z = true;
+                    PROF(7);
+                    // In exact arithmetic 0 <= delta <= n_p'H^{-1}n_p.  Anything else (or a NaN) means the
+                    // explicit inverse has lost its accuracy: rebuild M exactly once for this candidate;
+                    // if that does not cure it the problem is reported infeasible.
+                    if (!(delta <= 1.000001 * p.nph)) {
+                        if (rebuilt) { res.rc = QP_INFEASIBLE; failed = true; m_valid = false; break; }
+                        rebuilt = true;
+                        dirty = true;
+                        need_r = true;
+                        continue;
+                    }
+                }
+                const bool dependent = !(delta > dep_tol * p.nph) || (q >= n3 + nmat);
+                // dual ratio test: smallest u_i / r_i over r_i > 0
+                const double rthr = 1e-12 * rmax;
+                double t1 = INFINITY;
+                int ldrop = -1;
+                QW_FOR(h) {
+                    const int s = qw_item(h);
+                    const double ri = r[h];
+                    if (s < q && ri > rthr) {
+                        const double t = fmax(u[h], 0.0) * frcp(ri);
+                        if (ldrop < 0 || t < t1) { t1 = t; ldrop = s; }
+                    }
+                }
+                {
+                    const int src = warg_min_nonneg(t1, ldrop >= 0);
+                    ldrop = (src >= 0) ? wbcast(ldrop, src) : -1;
+                    if (src < 0) t1 = INFINITY;
+                }
+                PROF(9);
+                const double t2 = dependent ? INFINITY : (-sp * frcp(delta));
+                const double t = (t1 < t2) ? t1 : t2;
+                if (!(t < INFINITY)) {  // also catches NaN
+                    res.rc = QP_INFEASIBLE;
+                    failed = true;
+                    if (!(t == t) || !(delta == delta)) m_valid = false;
+                    break;
+                }
+                if (!dependent) {
+                    QW_FOR(h) {
+                        a[h] = fma(t, z[h], a[h]);
+                        P[h] = fma(t, L[h], P[h]);
+                    }
+                    // rows: residual_j += t n_j'z = t (d_j . Lz[kc_j] - dist_j zeps_j)
+                    QW_FOR(h) {
+                        const int j = qw_item(h);
+                        if (j < nv) {
+                            const int kc = rkc[j];
+                            double nz = rd0[j] * Ls[3 * kc] + rd1[j] * Ls[3 * kc + 1] + rd2[j] * Ls[3 * kc + 2];
+                            if (soft) {
+                                const double ze = zeps[h];
+                                eps[h] = fma(t, ze, eps[h]);
+                                nz = fma(-rdist[j], ze, nz);
+                            }
+                            rres[h] = fma(t, nz, rres[h]);
+                        }
+                    }
+                }
+                QW_FOR(h) u[h] = fma(-t, r[h], u[h]);
+                up += t;
+                PROF(10);
+                if (!dependent && t2 <= t1) {
+                    // full step: constraint p becomes active
+                    border(q, delta);
+                    if (lane_id() == 0) {
+                        act[q] = pcode;
+                        put_record(q, p);
+                    }
+                    QW_FOR(h) if (q == qw_item(h)) u[h] = up;
+                    set_active(pcode, (unsigned)q);
+                    count_active(pcode, +1);
+                    wsync();
+                    ++q;
+                    added = true;
+                    if (delta < ill_tol * p.nph) dirty = true;
+                    PROF(11);
+                } else {
+                    const double rl = rs[ldrop], mll = M[(size_t)ldrop * kMS + ldrop];
+                    wsync();
+                    drop_slot(ldrop, r, rl, u);
+                    if (dirty) {
+                        need_r = true;  // rebuild M, then r from scratch
+                    } else {
+                        // r changed by the rank-1 formula: publish it again
+                        const int q4 = (q + 3) & ~3;
+                        QW_FOR(h) {
+                            const int s = qw_item(h);
+                            if (s < q4) rs[s] = (s < q) ? r[h] : 0.0;
+                        }
+                        wsync();
+                        if (dependent && (q < n3 + nmat)) {
+                            // delta' = delta + r_l^2 / M_ll: while still dependent keep dropping without a direction
+                            const double dn = fmax(delta, 0.0) + rl * rl * frcp(mll);
+                            if (dn > 0.25 * dep_tol * p.nph) have_z = false;
+                            else delta = dn;
+                        } else {
+                            have_z = false;
+                        }
+                    }
+                    if (!dependent) sp = resid_code(pcode);
+                    PROF(12);
+                }
+            }
+            if (failed) break;
+        }
+        res.iters = iters;
+        res.q = q;
+        if (m_valid_out) *m_valid_out = m_valid;
+        return res;
+    }
+
+    DMPC_D unsigned item_u(const unsigned* arr, int idx) const {
+#if defined(__CUDA_ARCH__)
+        unsigned v = arr[0];
+#pragma unroll
+        for (int h = 1; h < kEPL; ++h)
+            if ((idx >> 5) == h) v = arr[h];
+        return __shfl_sync(0xffffffffu, v, idx & 31);
+#else
+        return arr[idx];
+#endif
+    }
+};
+
+// ---- one agent's MPC step after the neighbour scan, fast path ---------------------------------------
+// Preconditions (checked by the caller): 3K <= 64, io.nv <= 64, variant != VAR_HARD, io.scanflag == 0.
+// tab: the whole table blob in shared memory; smem: qw_smem_bytes() of per-agent workspace.
+// Same contract as agent_solve() (agent_solve.cuh); returns the status word (ST_OVERFLOW: the active set
+// outgrew qcap -- the caller re-solves with the generic solver).
+template <int KT>
+DMPC_D int agent_solve_fast(const DevParams& Pm, const double* __restrict__ tab, unsigned char* smem, int qcap,
+                            const AgentIO& io, AgentDiag* diag_out) {
+    const int K = KT ? KT : Pm.K, n3 = 3 * K;
+    AgentDiag dg;
+    dg.kstar = io.kstar;
+    dg.nv = io.nv;
+    dg.iters = 0;
+    dg.nact = 0;
+    int status = 0;
+
+    QpW<KT> qp;
+    qp.carve(smem);
+    const bool soft = (Pm.variant == VAR_SOFT_BOUND || Pm.variant == VAR_SOFT_BOUND2);
+    const bool any_violation = io.kstar > 0;
+    double x_po[3], x_pf[3], x_vo[3], x_ao[3];
+#pragma unroll
+    for (int x = 0; x < 3; ++x) {
+        x_po[x] = io.po[x];
+        x_pf[x] = io.pf[x];
+        x_vo[x] = io.vo[x];
+        x_ao[x] = io.ao[x];
+        qp.bnd6[x] = Pm.pmin[x];
+        qp.bnd6[3 + x] = Pm.pmax[x];
+    }
+    // ---- weights (solveSoftDMPCbound.m:43-58) -------------------------------------------------------
+    const double dgx = x_po[0] - x_pf[0], dgy = x_po[1] - x_pf[1], dgz = x_po[2] - x_pf[2];
+    const double dgoal = sqrt(dgx * dgx + dgy * dgy + dgz * dgz);
+    int wset;
+    double qw, sw;
+    if (!any_violation && dgoal >= Pm.near_radius) { wset = 0; qw = Pm.Q_far; sw = Pm.S_free; }
+    else if (!any_violation) { wset = 1; qw = Pm.Q_near; sw = Pm.S_free; }
+    else { wset = 2; qw = Pm.Q1; sw = Pm.S1; }
+    const double* t_lam = tab;
+    const double* t_tt = tab + K * K;
+    const double* t_lnorm = tab + K * K + K;
+    const double* t_G = tab + tab_set_offset(K, wset);
+    qp.K = K; qp.n3 = n3; qp.nv = io.nv; qp.soft = soft ? 1 : 0;
+    qp.kc_all = io.kstar > 0 ? io.kstar - 1 - (Pm.variant == VAR_SOFT_BOUND2 ? 1 : 0) : 0;
+    qp.alim = Pm.alim; qp.qw = qw; qp.sw = sw;
+    qp.qcap = qcap < kQW ? qcap : kQW;
+    qp.ilnorm = tab + K * K + 2 * K; qp.G = t_G; qp.B = t_G + K * K; qp.C = t_G + 2 * K * K;
+
+    // ---- rows: global SoA (scan output) -> shared ---------------------------------------------------
+    const int nv = io.nv;
+    QW_FOR(h) {
+        const int j = qw_item(h);
+        if (j < nv) {
+            const double d0 = io.grow[j], d1 = io.grow[(size_t)io.RMAX + j], d2 = io.grow[2 * (size_t)io.RMAX + j];
+            const double dist = io.grow[3 * (size_t)io.RMAX + j];
+            const int kc = io.gkc[j];
+            qp.rd0[j] = d0; qp.rd1[j] = d1; qp.rd2[j] = d2; qp.rdist[j] = dist;
+            qp.rrhs[j] = io.grow[4 * (size_t)io.RMAX + j];
+            qp.rkc[j] = kc;
+            const double dd = d0 * d0 + d1 * d1 + d2 * d2;
+            const double ln = t_lnorm[kc];
+            qp.rirn[j] = 1.0 / sqrt(dd * ln * ln + (soft ? dist * dist : 0.0));
+        }
+    }
+    // ---- a_unc = -G f,  P_unc = A_initp [po;vo] + Lam a_unc  (solveSoftDMPCbound.m:82-88) ------------
+    QW_FOR(h) {
+        const int i = qw_item(h);
+        const int k = i / 3, x = i - 3 * k;
+        qp.ek[h] = k;
+        qp.ex[h] = x;
+        double au = 0.0;
+        qp.elo[h] = 0.0; qp.ehi[h] = 0.0; qp.eiln[h] = 0.0;
+        if (i < n3) {
+            const double pox = (x == 0) ? x_po[0] : ((x == 1) ? x_po[1] : x_po[2]);
+            const double pfx = (x == 0) ? x_pf[0] : ((x == 1) ? x_pf[1] : x_pf[2]);
+            const double vox = (x == 0) ? x_vo[0] : ((x == 1) ? x_vo[1] : x_vo[2]);
+            const double aox = (x == 0) ? x_ao[0] : ((x == 1) ? x_ao[1] : x_ao[2]);
+            const double e = pfx - (pox + t_tt[K - 1] * vox);
+            au = 2.0 * qw * e * qp.B[k * K + (K - 1)] + 2.0 * sw * aox * qp.G[k * K];
+            qp.zs[i] = au;
+            qp.elo[h] = qp.pmin_of(i);
+            qp.ehi[h] = qp.pmax_of(i);
+            qp.eiln[h] = qp.ilnorm[k];
+        }
+        qp.aunc[h] = au;
+    }
+    wsync();
+    QW_FOR(h) {
+        const int i = qw_item(h);
+        double pu = 0.0;
+        if (i < n3) {
+            const int k = qp.ek[h], x = qp.ex[h];
+            const double pox = (x == 0) ? x_po[0] : ((x == 1) ? x_po[1] : x_po[2]);
+            const double vox = (x == 0) ? x_vo[0] : ((x == 1) ? x_vo[1] : x_vo[2]);
+            double s = 0.0;
+            for (int j = 0; j <= k; ++j) s = fma(t_lam[k * K + j], qp.zs[3 * j + x], s);
+            pu = s + (pox + t_tt[k] * vox);
+        }
+        qp.Punc[h] = pu;
+    }
+    wsync();
+
+    // ---- retry loop (solveSoftDMPCbound.m:102-155) ---------------------------------------------------
+    double term = Pm.term, slb = Pm.slack_lb;
+    int tries = 0;
+    bool solved = false, warm = false, m_valid = true;
+    const int max_iter = 40 * (n3 + nv) + 200;
+    for (;;) {
+        qp.term = term;
+        qp.slb = slb;
+        if (!(warm && qp.warm_restart())) qp.cold_start();
+        const QpResult r = qp.solve(max_iter, &m_valid);
+        dg.iters += r.iters;
+        dg.nact = r.q;
+        if (r.rc == QP_OK) { solved = true; break; }
+        if (r.rc == QP_ITERCAP) { status |= ST_QPFAIL; break; }
+        if (r.rc == QP_OVERFLOW) { status |= ST_QPFAIL | ST_OVERFLOW; break; }
+        // infeasible: soft variants with slack double the slack bound and the penalty and retry;
+        // otherwise the reference only loosens quadprog's tolerance or gives up.
+        if (!(soft && nv > 0)) break;
+        slb *= 2.0;
+        term *= 2.0;
+        if (++tries >= Pm.max_tries) break;
+        warm = true;
+    }
+    status |= (tries & 0xff) << 8;
+    if (solved) {
+        status |= ST_SOLVED;
+        // propStatedmpc.m: p = A_p a + A_initp [po;vo] (= P), v = A_v a + vo
+        wsync();
+        QW_FOR(h) {
+            const int i = qw_item(h);
+            if (i < n3) qp.zs[i] = qp.a[h];
+        }
+        wsync();
+        QW_FOR(h) {
+            const int i = qw_item(h);
+            if (i < n3) {
+                const int k = qp.ek[h], x = qp.ex[h];
+                const double vox = (x == 0) ? x_vo[0] : ((x == 1) ? x_vo[1] : x_vo[2]);
+                double sv = 0.0;
+                for (int j = 0; j <= k; ++j) sv += Pm.h * qp.zs[3 * j + x];
+                const double vv = sv + vox;
+                io.out_p[i] = qp.P[h];
+                if (io.out_v) io.out_v[i] = vv;
+                if (io.out_a) io.out_a[i] = qp.a[h];
+                if (k == 0) {
+                    io.p1[x] = qp.P[h];
+                    io.v1[x] = vv;
+                    io.a1[x] = qp.a[h];
+                }
+            }
+        }
+        // is_inbounds.m on the first predicted position
+        bool inb = true;
+#pragma unroll
+        for (int x = 0; x < 3; ++x) {
+            const double p1x = qp.item_d(qp.P, x);
+            inb = inb && (p1x < qp.bnd6[3 + x] + Pm.inb_tol) && (p1x > qp.bnd6[x] - Pm.inb_tol);
+        }
+        if (!inb) status |= ST_OUTBOUND;
+    } else {
+        if (!(status & ST_QPFAIL)) status |= ST_INFEASIBLE;
+        // the reference returns empty p,v,a: the caller keeps the old horizon and state
+        for (int i = lane_id(); i < n3; i += kLanes) io.out_p[i] = io.l_prev_n[i];
+        for (int x = lane_id(); x < 3; x += kLanes) {
+            io.p1[x] = io.po[x];
+            io.v1[x] = io.vo[x];
+            io.a1[x] = io.ao[x];
+        }
+    }
+    if (diag_out && lane_id() == 0) *diag_out = dg;
+    return status;
+}
+
+}  // namespace dmpc

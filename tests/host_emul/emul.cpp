@@ -5,6 +5,7 @@
 // sequentially.  This lets the CPU test-suite (-m "not gpu") check the ALGORITHM against the
 // oracle where no GPU exists.  It is a debugging aid: it is built by tests/ into
 // tests/host_emul/libemul.so, never linked into libdmpc_b200.so and never imported by the package.
+#include <algorithm>
 #include <cstdlib>
 #include <cstring>
 #include <vector>
@@ -12,6 +13,7 @@
 #include "../../include/dmpc_b200.h"
 #include "../../multiagent_planning_b200/csrc/model_tables.h"
 #include "../../multiagent_planning_b200/csrc/scan_core.cuh"
+#include "../../multiagent_planning_b200/csrc/qp_warp.cuh"
 
 using namespace dmpc;
 
@@ -36,7 +38,11 @@ extern "C" int emul_step(const dmpcb200_params* p, int N, int n0, int n1, const 
     std::vector<double> tab;
     const double qs[3][2] = {{p->Q_far, p->S_free}, {p->Q_near, p->S_free}, {p->Q1, p->S1}};
     build_tables(p->h, K, qs, tab);
-    std::vector<unsigned char> smem(agent_smem_bytes(K, QMAX, RCAP) + 64);
+    // QMAX < 0: the register-resident solver of qp_warp.cuh (capacity -QMAX) where its preconditions
+    // hold, the generic solver elsewhere -- the dispatch of qp_kernel
+    const bool fast = QMAX < 0;
+    if (fast) QMAX = -QMAX;
+    std::vector<unsigned char> smem(std::max(agent_smem_bytes(K, QMAX, RCAP), qw_smem_bytes()) + 64);
     const ScanThr thr = make_scan_thr(D);
     std::vector<unsigned> nearmask(N);
     std::vector<double> grow(5 * (size_t)RMAX), gscr_d(4 * (size_t)RMAX);
@@ -59,7 +65,10 @@ extern "C" int emul_step(const dmpcb200_params* p, int N, int n0, int n1, const 
         io.p1 = p1 + 3 * n; io.v1 = v1 + 3 * n; io.a1 = a1 + 3 * n;
         io.l_prev_n = own;
         AgentDiag dg;
-        status[n] = agent_solve<0>(D, tab.data(), smem.data(), QMAX, RCAP, io, &dg);
+        if (fast && 3 * K <= kQW && so.nv <= kQW && D.variant != VAR_HARD && !so.flag)
+            status[n] = agent_solve_fast<0>(D, tab.data(), smem.data(), QMAX, io, &dg);
+        else
+            status[n] = agent_solve<0>(D, tab.data(), smem.data(), QMAX, RCAP, io, &dg);
         if (diag) { diag[4 * n] = dg.kstar; diag[4 * n + 1] = dg.nv; diag[4 * n + 2] = dg.iters; diag[4 * n + 3] = dg.nact; }
     }
     return 0;

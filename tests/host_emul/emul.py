@@ -28,7 +28,7 @@ def build(force=False):
     srcs = [os.path.join(_HERE, "emul.cpp"),
             os.path.join(_ROOT, "multiagent_planning_b200/csrc/model_tables.cpp")]
     deps = srcs + [os.path.join(_ROOT, "multiagent_planning_b200/csrc", f)
-                   for f in ("qp_core.cuh", "agent_solve.cuh", "scan_core.cuh", "model_tables.h")]
+                   for f in ("qp_core.cuh", "qp_warp.cuh", "agent_solve.cuh", "scan_core.cuh", "model_tables.h")]
     if force or not os.path.exists(so) or any(os.path.getmtime(d) > os.path.getmtime(so) for d in deps):
         subprocess.check_call(["g++", "-O2", "-fPIC", "-std=c++17", "-ffp-contract=off", "-shared",
                                "-o", so] + srcs)
