@@ -14,10 +14,14 @@
 //   * the workspace pointers are derived from the kernel's shared-memory base, so every access is
 //     an LDS/STS with a 32-bit address (the generic solver of qp_core.cuh goes through 64-bit
 //     generic loads because its scratch may live in global memory);
-//   * a retry of the reference's loop (slack bound x2, penalty x2) keeps the WHOLE active set and
-//     its inverse: the constraint normals do not depend on (term, slb), only the right-hand sides
-//     and the slack part of the unconstrained optimum do, so the multipliers of the old active set
-//     are one matrix-vector product away and the iteration resumes from there.
+//   * the reference's infeasible-retry loop (slack bound x2, penalty x2, solveSoftDMPCbound.m:135-153)
+//     is short-cut by an exact necessary condition: all collision rows of an agent act on the SAME
+//     predicted position y = P[kc], so a try can only be feasible if the 3-D polytope
+//     { y in reach box : d_j . y >= rhs_j + dist_j slb } is non-empty.  A 3-variable dual active-set
+//     iteration (relaxed_infeasible) proves emptiness with a Farkas certificate in ~10 cheap
+//     iterations; tries that are certainly infeasible are skipped without running the 45-variable
+//     solver on them (it would need ~100 iterations to find out).  A try that passes the test is
+//     solved normally, so the outcome is the reference's in every case.
 // Capacity: 3K <= 64 entries, <= 64 rows that all act on one horizon index (every variant except
 // solveHardDMPC), <= 64 active constraints.  Anything else is solved by the generic solver.
 //
@@ -662,6 +666,166 @@ struct QpW {
         return mx;
     }
 
+    // ---- necessary condition for feasibility at slack bound sl (< 0) ---------------------------------
+    // Every collision row acts on y = P[kc_all] (3-vector).  Whatever the accelerations do,
+    //     y_x in [ylo_x, yhi_x]  (acceleration box through row kc of Lam, and the workspace box),
+    // and row j needs d_j . y >= rhs_j + dist_j eps_j with eps_j >= sl, i.e. d_j . y >= rhs_j + dist_j sl.
+    // Returns true only if that 3-D polytope is CERTAINLY empty (then the full QP is infeasible):
+    // a dual active-set iteration on  min |y - yc|^2  over the polytope ends either at a feasible point
+    // (return false) or with a constraint p whose normal is a non-positive combination of <= 3 active
+    // normals -- a Farkas certificate, checked with a margin against the size of the box.  Every lane
+    // runs the same 3-D arithmetic; only the search for the most violated constraint is spread.
+    DMPC_COLD bool relaxed_infeasible(double sl, const double* ylo, const double* yhi) {
+        double y[3], nA[3][3] = {{0, 0, 0}, {0, 0, 0}, {0, 0, 0}}, bA[3] = {0, 0, 0}, uA[3] = {0, 0, 0};
+        int cA[3] = {-1, -1, -1};
+        int qa = 0;
+        double rad = 0.0;
+#pragma unroll
+        for (int x = 0; x < 3; ++x) {
+            if (!(ylo[x] <= yhi[x])) return false;  // degenerate box: let the solver decide
+            y[x] = 0.5 * (ylo[x] + yhi[x]);
+            rad += fmax(fabs(ylo[x]), fabs(yhi[x]));
+        }
+        for (int it = 0; it < 64; ++it) {
+            // most violated constraint, normalised: rows j (code j), box lower x (code 64+x), upper (67+x)
+            double best = -1e-9;
+            int bcode = -1;
+            QW_FOR(h) {
+                const int j = qw_item(h);
+                if (j < nv && !(qa > 0 && j == cA[0]) && !(qa > 1 && j == cA[1]) && !(qa > 2 && j == cA[2])) {
+                    const double d0 = rd0[j], d1 = rd1[j], d2 = rd2[j];
+                    const double v = (d0 * y[0] + d1 * y[1] + d2 * y[2] - (rrhs[j] + rdist[j] * sl)) /
+                                     sqrt(d0 * d0 + d1 * d1 + d2 * d2);
+                    if (v < best) { best = v; bcode = j; }
+                }
+            }
+            if (lane_id() == 0) {
+#pragma unroll
+                for (int x = 0; x < 3; ++x) {
+                    const double vl = y[x] - ylo[x], vu = yhi[x] - y[x];
+                    const bool al = (qa > 0 && cA[0] == 64 + x) || (qa > 1 && cA[1] == 64 + x) || (qa > 2 && cA[2] == 64 + x);
+                    const bool au = (qa > 0 && cA[0] == 67 + x) || (qa > 1 && cA[1] == 67 + x) || (qa > 2 && cA[2] == 67 + x);
+                    if (!al && vl < best) { best = vl; bcode = 64 + x; }
+                    if (!au && vu < best) { best = vu; bcode = 67 + x; }
+                }
+            }
+            double viol = -best;
+            const int src = warg_max_nonneg(viol, bcode >= 0);
+            if (src < 0) return false;  // y is feasible: the polytope is not empty
+            const int pc = wbcast(bcode, src);
+            double np[3], bp;
+            if (pc < 64) {
+                np[0] = rd0[pc]; np[1] = rd1[pc]; np[2] = rd2[pc];
+                bp = rrhs[pc] + rdist[pc] * sl;
+            } else {
+                const int x = (pc - 64) % 3;
+                const double sg = (pc < 67) ? 1.0 : -1.0;
+                np[0] = (x == 0) ? sg : 0.0; np[1] = (x == 1) ? sg : 0.0; np[2] = (x == 2) ? sg : 0.0;
+                bp = (pc < 67) ? ((x == 0) ? ylo[0] : ((x == 1) ? ylo[1] : ylo[2]))
+                               : -((x == 0) ? yhi[0] : ((x == 1) ? yhi[1] : yhi[2]));
+            }
+            const double npp = np[0] * np[0] + np[1] * np[1] + np[2] * np[2];
+            double sp = np[0] * y[0] + np[1] * y[1] + np[2] * y[2] - bp;
+            double up = 0.0;
+            for (int inner = 0; inner < 8; ++inner) {
+                // r = (N'N)^-1 N' n_p by Cramer / closed forms (qa <= 3), z = n_p - N r
+                double g[3] = {0.0, 0.0, 0.0}, r3[3] = {0.0, 0.0, 0.0};
+                double S[3][3], det;
+#pragma unroll
+                for (int i = 0; i < 3; ++i) {
+#pragma unroll
+                    for (int k = 0; k < 3; ++k)
+                        S[i][k] = (i < qa && k < qa) ? nA[i][0] * nA[k][0] + nA[i][1] * nA[k][1] + nA[i][2] * nA[k][2]
+                                                     : ((i == k) ? 1.0 : 0.0);
+                    if (i < qa) g[i] = nA[i][0] * np[0] + nA[i][1] * np[1] + nA[i][2] * np[2];
+                }
+                {
+                    // inverse of the 3x3 (padded with identity) Gram matrix by cofactors
+                    const double c00 = S[1][1] * S[2][2] - S[1][2] * S[2][1];
+                    const double c01 = S[1][2] * S[2][0] - S[1][0] * S[2][2];
+                    const double c02 = S[1][0] * S[2][1] - S[1][1] * S[2][0];
+                    det = S[0][0] * c00 + S[0][1] * c01 + S[0][2] * c02;
+                    const double id = 1.0 / det;
+                    const double c11 = S[0][0] * S[2][2] - S[0][2] * S[2][0];
+                    const double c12 = S[0][1] * S[2][0] - S[0][0] * S[2][1];
+                    const double c22 = S[0][0] * S[1][1] - S[0][1] * S[1][0];
+                    r3[0] = (c00 * g[0] + c01 * g[1] + c02 * g[2]) * id;
+                    r3[1] = (c01 * g[0] + c11 * g[1] + c12 * g[2]) * id;
+                    r3[2] = (c02 * g[0] + c12 * g[1] + c22 * g[2]) * id;
+                }
+                double z[3];
+#pragma unroll
+                for (int x = 0; x < 3; ++x) {
+                    z[x] = np[x];
+#pragma unroll
+                    for (int i = 0; i < 3; ++i)
+                        if (i < qa) z[x] -= r3[i] * nA[i][x];
+                }
+                const double delta = z[0] * z[0] + z[1] * z[1] + z[2] * z[2];
+                const bool dependent = !(delta > 1e-10 * npp) || qa == 3;
+                double t1 = INFINITY;
+                int ld = -1;
+#pragma unroll
+                for (int i = 0; i < 3; ++i)
+                    if (i < qa && r3[i] > 1e-12) {
+                        const double t = fmax(uA[i], 0.0) / r3[i];
+                        if (t < t1) { t1 = t; ld = i; }
+                    }
+                const double t2 = dependent ? INFINITY : -sp / delta;
+                if (!(t1 < INFINITY) && !(t2 < INFINITY)) {
+                    // n_p = sum r_i n_i + z with r_i <= 1e-12: Farkas multipliers lam_p = 1, lam_i = -r_i >= 0.
+                    // sum lam n = z (tiny), so feasibility would need  z . y >= b_p - sum r_i b_i : impossible
+                    // inside the box if the right-hand side exceeds |z| * (size of the box) by a margin.
+                    if (!(det == det) || !(delta == delta)) return false;
+                    double cert = bp;
+                    bool ok = true;
+#pragma unroll
+                    for (int i = 0; i < 3; ++i)
+                        if (i < qa) {
+                            cert -= r3[i] * bA[i];
+                            if (r3[i] > 0.0) ok = false;  // (0, 1e-12]: not a clean certificate
+                        }
+                    return ok && (cert > sqrt(delta) * rad + 1e-9 * (fabs(bp) + 1.0));
+                }
+                const double t = (t1 < t2) ? t1 : t2;
+                if (!dependent) {
+#pragma unroll
+                    for (int x = 0; x < 3; ++x) y[x] = fma(t, z[x], y[x]);
+                    sp = fma(t, delta, sp);
+                }
+#pragma unroll
+                for (int i = 0; i < 3; ++i)
+                    if (i < qa) uA[i] = fma(-t, r3[i], uA[i]);
+                up += t;
+                if (!dependent && t2 <= t1) {
+                    nA[qa][0] = np[0]; nA[qa][1] = np[1]; nA[qa][2] = np[2];
+                    bA[qa] = bp;
+                    uA[qa] = up;
+                    cA[qa] = pc;
+                    ++qa;
+                    break;
+                }
+                // drop ld: move the last active constraint into its place
+#pragma unroll
+                for (int i = 0; i < 3; ++i)
+                    if (i == ld) {
+                        const int la = qa - 1;
+#pragma unroll
+                        for (int k = 0; k < 3; ++k)
+                            if (k == la) {
+                                nA[i][0] = nA[k][0]; nA[i][1] = nA[k][1]; nA[i][2] = nA[k][2];
+                                bA[i] = bA[k];
+                                uA[i] = uA[k];
+                                cA[i] = cA[k];
+                            }
+                    }
+                --qa;
+                if (inner == 7) return false;  // no decision: let the solver decide
+            }
+        }
+        return false;
+    }
+
     // ---- start state: x = x_unc, nothing active ----------------------------------------------------
     DMPC_D void cold_start() {
         q = 0;
@@ -1059,7 +1223,31 @@ DMPC_D int agent_solve_fast(const DevParams& Pm, const double* __restrict__ tab,
     int tries = 0;
     bool solved = false, warm = false, m_valid = true;
     const int max_iter = 40 * (n3 + nv) + 200;
+    // reach box of y = P[kc]: |a| <= alim through row kc of Lam (all entries positive), and the workspace
+    double ylo[3], yhi[3];
+    const bool relax = soft && nv > 0;
+    if (relax) {
+        const int kc = qp.kc_all;
+        double l1 = 0.0;
+        for (int j = 0; j <= kc; ++j) l1 += t_lam[kc * K + j];
+        l1 *= Pm.alim * (1.0 + 1e-12);
+#pragma unroll
+        for (int x = 0; x < 3; ++x) {
+            const double c0 = x_po[x] + t_tt[kc] * x_vo[x];
+            const double pad = 1e-12 * (fabs(c0) + l1);
+            ylo[x] = fmax(c0 - l1 - pad, qp.bnd6[x]);
+            yhi[x] = fmin(c0 + l1 + pad, qp.bnd6[3 + x]);
+        }
+    }
+    bool give_up = false;
     for (;;) {
+        // skip the tries that the 3-D necessary condition proves infeasible (with a 1e-6 margin on slb)
+        while (relax && qp.relaxed_infeasible(slb * (1.0 + 1e-6), ylo, yhi)) {
+            slb *= 2.0;
+            term *= 2.0;
+            if (++tries >= Pm.max_tries) { give_up = true; break; }
+        }
+        if (give_up) break;
         qp.term = term;
         qp.slb = slb;
         if (!(warm && qp.warm_restart())) qp.cold_start();
