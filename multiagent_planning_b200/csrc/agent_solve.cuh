@@ -39,6 +39,10 @@ DMPC_HD size_t agent_smem_bytes(int K, int QMAX, int RCAP) {
 
 // layout of the table blob in global memory: see model_tables.h
 DMPC_HD int tab_set_offset(int K, int wset) { return K * K + 4 * K + wset * 3 * K * K; }
+// the blob of the register-resident solver (header copy padded to 4 doubles + interleaved T4 per set)
+DMPC_HD int tab_fast_offset(int K) { return (K * K + 4 * K + 9 * K * K + 3) / 4 * 4; }
+DMPC_HD int tab_fast_header(int K) { return (K * K + 4 * K + 3) / 4 * 4; }
+DMPC_HD int tab_fast_size(int K) { return tab_fast_header(K) + 12 * K * K; }
 
 struct AgentIO {
     // inputs

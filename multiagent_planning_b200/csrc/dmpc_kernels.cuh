@@ -213,7 +213,8 @@ __global__ void __launch_bounds__(W * 32) scan_kernel(const __grid_constant__ St
 }
 
 // ---- K2 -------------------------------------------------------------------------------------
-DMPC_HD size_t qp_table_bytes(int K) { return (size_t)(10 * K * K + 4 * K) * sizeof(double); }
+// shared-memory tables of K2: the blob of the register-resident solver (multiple of 32 bytes)
+DMPC_HD size_t qp_table_bytes(int K) { return (size_t)tab_fast_size(K) * sizeof(double); }
 // per-agent workspace: the register-resident solver's (qp_warp.cuh) or the generic solver's, whichever is larger
 DMPC_HD size_t qp_agent_bytes(int K, int QMAX, int RCAP) {
     const size_t a = agent_smem_bytes(K, QMAX, RCAP), b = align_up(qw_smem_bytes(), 16);
@@ -238,7 +239,7 @@ __global__ void __launch_bounds__(W * 32, 1) qp_kernel(const __grid_constant__ S
         mbar_init(bar, 1);
         mbar_fence_init();
         mbar_expect_tx(bar, (uint32_t)qp_table_bytes(K));
-        tma_bulk_g2s(tab_s, A.tab, (uint32_t)qp_table_bytes(K), bar);
+        tma_bulk_g2s(tab_s, A.tab + tab_fast_offset(K), (uint32_t)qp_table_bytes(K), bar);
     }
     __syncthreads();
     const int li = blockIdx.x * W + warp;
@@ -296,7 +297,7 @@ __global__ void __launch_bounds__(W * 32, 1) qp_kernel(const __grid_constant__ S
             scratch = A.rescue + (size_t)slot * A.rescue_bytes;
             cap = A.QBIG;
         }
-        st = agent_solve<0>(A.P, tab_s, scratch, cap, A.RCAP, io, &dg);
+        st = agent_solve<0>(A.P, A.tab, scratch, cap, A.RCAP, io, &dg);  // tables from global memory (L1/L2)
         dg.iters += it0;
         if (rescue || !(st & ST_OVERFLOW) || sr.flag || !A.rescue) break;
         rescue = true;

@@ -148,6 +148,23 @@ void build_tables(double h, int K, const double qs[3][2], std::vector<double>& o
                 C[i * K + k] = C[k * K + i];
             }
     }
+    // the shared-memory blob of the register-resident solver: header copy + interleaved T4 per weight set
+    double* F = out.data() + tables_fast_offset(K);
+    for (int i = 0; i < K * K + 4 * K; ++i) F[i] = out[i];
+    for (int w = 0; w < 3; ++w) {
+        const double* G = out.data() + tables_set_offset(K, w);
+        const double* B = G + K * K;
+        const double* C = B + K * K;
+        double* T4 = F + tables_fast_header(K) + (size_t)w * 4 * K * K;
+        for (int k = 0; k < K; ++k)
+            for (int j = 0; j < K; ++j) {
+                double* t = T4 + 4 * ((size_t)k * K + j);
+                t[0] = G[k * K + j];
+                t[1] = B[k * K + j];
+                t[2] = B[j * K + k];
+                t[3] = C[k * K + j];
+            }
+    }
 }
 
 }  // namespace dmpc

@@ -18,8 +18,17 @@ namespace dmpc {
 //   [.., +K)            lnorm lnorm[k] = || lam[k,:] ||_2
 //   [.., +K)            ilnorm = 1 / lnorm
 //   then for each weight set w = 0 (far), 1 (near), 2 (collision):  G, B, C  (K*K each, row-major)
+//   [tables_fast_offset(K), +tables_fast_size(K))   the blob the register-resident solver (qp_warp.cuh)
+//       stages in shared memory with ONE bulk copy: a copy of the header (lam, tt, lnorm, ilnorm, padded to a
+//       multiple of 4 doubles) followed, per weight set, by the interleaved table
+//           T4[k][j] = { G[k][j], B[k][j], B[j][k], C[k][j] }        (32-byte records, row-major in k, j)
+//       so that one 128-bit-pair load fetches everything the direction needs for (k, j).
 inline int tables_set_offset(int K, int w) { return K * K + 4 * K + w * 3 * K * K; }
-inline int tables_size(int K) { return K * K + 4 * K + 9 * K * K; }
+inline int tables_base_size(int K) { return K * K + 4 * K + 9 * K * K; }
+inline int tables_fast_offset(int K) { return (tables_base_size(K) + 3) / 4 * 4; }
+inline int tables_fast_header(int K) { return (K * K + 4 * K + 3) / 4 * 4; }
+inline int tables_fast_size(int K) { return tables_fast_header(K) + 12 * K * K; }
+inline int tables_size(int K) { return tables_fast_offset(K) + tables_fast_size(K); }
 
 // qs[w] = {q, s} for w = far, near, collision
 void build_tables(double h, int K, const double qs[3][2], std::vector<double>& out);

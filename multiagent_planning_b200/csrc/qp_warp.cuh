@@ -30,6 +30,23 @@
 #pragma once
 #include "agent_solve.cuh"
 
+#if defined(DMPC_PROF) && defined(__CUDA_ARCH__)
+// profiling builds: account only the iterations of large active sets (the critical agents)
+#undef PROF
+#define PROF(i)                                                              \
+    do {                                                                     \
+        const long long prof_t1 = clock64();                                 \
+        if (lane_id() == 0 && q >= DMPC_PROF_QMIN) {                         \
+            atomicAdd(&g_prof[i], (unsigned long long)(prof_t1 - prof_t0));  \
+            atomicAdd(&g_prof[16 + (i)], 1ull);                              \
+        }                                                                    \
+        prof_t0 = clock64();                                                 \
+    } while (0)
+#ifndef DMPC_PROF_QMIN
+#define DMPC_PROF_QMIN 0
+#endif
+#endif
+
 namespace dmpc {
 
 constexpr int kQW = 64;             // capacity: entries, rows, slots
@@ -54,6 +71,26 @@ inline double wshfl(double v, int) { return v; }
 inline void wsum3(double&, double&, double&) {}
 #endif
 
+#if defined(__CUDA_ARCH__)
+typedef double2 Dbl2;
+DMPC_D Dbl2 ld2(const double* p) { return *reinterpret_cast<const double2*>(p); }
+DMPC_D void st2(double* p, Dbl2 v) { *reinterpret_cast<double2*>(p) = v; }
+// 1/x for normal-range x: MUFU.RCP64H seed + two Newton steps, no slow path, no branch
+DMPC_D double qw_rcp(double x) {
+    double y;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+    double e = fma(-x, y, 1.0);
+    y = fma(y, e, y);
+    e = fma(-x, y, 1.0);
+    return fma(y, e, y);
+}
+#else
+struct Dbl2 { double x, y; };
+inline Dbl2 ld2(const double* p) { Dbl2 v; v.x = p[0]; v.y = p[1]; return v; }
+inline void st2(double* p, Dbl2 v) { p[0] = v.x; p[1] = v.y; }
+inline double qw_rcp(double x) { return 1.0 / x; }
+#endif
+
 DMPC_HD int qw_item(int h) { return lane_id() + h * kLanes; }
 DMPC_HD unsigned qw_getb(unsigned m, int b) { return (m >> (8 * b)) & 0xffu; }
 DMPC_HD unsigned qw_setb(unsigned m, int b, unsigned v) { return (m & ~(0xffu << (8 * b))) | (v << (8 * b)); }
@@ -68,9 +105,9 @@ struct QpW {
     // ---- uniform problem data ---------------------------------------------------------------------
     int K, n3, nv, soft, kc_all, qcap;
     double alim, term, slb, qw, sw;
-    const double *ilnorm, *G, *B, *C;  // tables of the weight set in use (shared memory)
+    const double *ilnorm, *T4;  // shared memory: 1/||lam[k,:]||, interleaved {G,B,B',C}[k][j] of the weight set in use
     // ---- shared-memory workspace ---------------------------------------------------------------------
-    double *M, *gs, *rs, *cb, *cp, *zs, *Ls;
+    double *M, *gs, *rs, *cb, *cp, *cbp, *zs, *Ls;  // cbp = cb..cp as one array of (cb, cp) pairs
     double *rd0, *rd1, *rd2, *rdist, *rrhs, *rirn;  // static row data
     double *sv0, *sv1, *sv2, *se;                   // slot records (normal of the constraint in the slot)
     int *rkc, *sinfo, *act;
@@ -89,7 +126,7 @@ struct QpW {
     DMPC_D void carve(unsigned char* smem) {
         double* d = reinterpret_cast<double*>(smem);
         M = d; d += (size_t)kQW * kMS;
-        gs = d; d += kQW; rs = d; d += kQW; cb = d; d += kQW; cp = d; d += kQW; zs = d; d += kQW; Ls = d; d += kQW;
+        gs = d; d += kQW; rs = d; d += kQW; cb = d; cbp = d; d += kQW; cp = d; d += kQW; zs = d; d += kQW; Ls = d; d += kQW;
         rd0 = d; d += kQW; rd1 = d; d += kQW; rd2 = d; d += kQW; rdist = d; d += kQW; rrhs = d; d += kQW;
         rirn = d; d += kQW;
         sv0 = d; d += kQW; sv1 = d; d += kQW; sv2 = d; d += kQW; se = d; d += kQW;
@@ -128,7 +165,7 @@ struct QpW {
             p.v1 = (x == 1) ? sig : 0.0;
             p.v2 = (x == 2) ? sig : 0.0;
             p.space = (p.type >= T_WSL) ? 1 : 0;
-            p.nph = G[2 * p.space * Kk * Kk + p.k * Kk + p.k];  // G[k][k] or C[k][k]
+            p.nph = T4[4 * (p.k * Kk + p.k) + 3 * p.space];  // G[k][k] or C[k][k]
         } else {
             p.j = p.idx;
             if (p.type == T_ROW) {
@@ -138,7 +175,7 @@ struct QpW {
                 p.e = soft ? -rdist[p.j] : 0.0;
                 p.k = rkc[p.j];
                 p.space = 1;
-                p.nph = (p.v0 * p.v0 + p.v1 * p.v1 + p.v2 * p.v2) * C[p.k * Kk + p.k] + 0.5 * p.e * p.e;
+                p.nph = (p.v0 * p.v0 + p.v1 * p.v1 + p.v2 * p.v2) * T4[4 * (p.k * Kk + p.k) + 3] + 0.5 * p.e * p.e;
             } else {
                 p.e = (p.type == T_SUB) ? -1.0 : 1.0;
                 p.nph = 0.5;
@@ -191,43 +228,53 @@ struct QpW {
     }
 
     // ---- most violated (normalised) inactive constraint; returns code or -1 -----------------------
+    // (written with selects only: no data-dependent branch)
     DMPC_D int most_violated(double tol, double* sp_out) const {
         double best = -tol, braw = 0.0;
         int bcode = -1;
         QW_FOR(h) {
             const int i = qw_item(h);
-            if (i < n3) {
-                const unsigned m = emap[h];
-                const double ai = a[h], Pi = P[h], iln = eiln[h];
-                const double r0 = ai + alim, r1 = alim - ai, r2 = Pi - elo[h], r3 = ehi[h] - Pi;
-                const double v0 = (qw_getb(m, 0) == kNone) ? r0 : INFINITY;
-                const double v1 = (qw_getb(m, 1) == kNone) ? r1 : INFINITY;
-                const double v2 = (qw_getb(m, 2) == kNone) ? r2 * iln : INFINITY;
-                const double v3 = (qw_getb(m, 3) == kNone) ? r3 * iln : INFINITY;
-                const double m01 = fmin(v0, v1), m23 = fmin(v2, v3);
-                const int t01 = (v1 < v0) ? T_BOXU : T_BOXL, t23 = (v3 < v2) ? T_WSU : T_WSL;
-                const double raw01 = (v1 < v0) ? r1 : r0, raw23 = (v3 < v2) ? r3 : r2;
-                const double mm = fmin(m01, m23);
-                if (mm < best) {
-                    best = mm;
-                    bcode = mk_code((m23 < m01) ? t23 : t01, i);
-                    braw = (m23 < m01) ? raw23 : raw01;
-                }
-            }
+            const bool ok = i < n3;
+            const unsigned m = emap[h];
+            const double ai = a[h], Pi = P[h], iln = eiln[h];
+            const double r0 = ai + alim, r1 = alim - ai, r2 = Pi - elo[h], r3 = ehi[h] - Pi;
+            const double v0 = (ok && qw_getb(m, 0) == kNone) ? r0 : INFINITY;
+            const double v1 = (ok && qw_getb(m, 1) == kNone) ? r1 : INFINITY;
+            const double v2 = (ok && qw_getb(m, 2) == kNone) ? r2 * iln : INFINITY;
+            const double v3 = (ok && qw_getb(m, 3) == kNone) ? r3 * iln : INFINITY;
+            const bool u01 = v1 < v0, u23 = v3 < v2;
+            const double m01 = u01 ? v1 : v0, m23 = u23 ? v3 : v2;
+            const double raw01 = u01 ? r1 : r0, raw23 = u23 ? r3 : r2;
+            const int t01 = u01 ? T_BOXU : T_BOXL, t23 = u23 ? T_WSU : T_WSL;
+            const bool w = m23 < m01;
+            const double mm = w ? m23 : m01;
+            const bool better = mm < best;
+            best = better ? mm : best;
+            bcode = better ? mk_code(w ? t23 : t01, i) : bcode;
+            braw = better ? (w ? raw23 : raw01) : braw;
         }
-        QW_FOR(h) {
-            const int j = qw_item(h);
-            if (j < nv) {
+        if (nv > 0) {
+            QW_FOR(h) {
+                const int j = qw_item(h);
+                const bool ok = j < nv;
                 const unsigned m = rmap[h];
-                if (qw_getb(m, 0) == kNone) {
-                    const double sn = rres[h] * rirn[j];
-                    if (sn < best) { best = sn; bcode = mk_code(T_ROW, j); braw = rres[h]; }
-                }
-                if (soft && qw_getb(m, 3)) {
-                    const double ej = eps[h];
-                    if (qw_getb(m, 1) == kNone && -ej < best) { best = -ej; bcode = mk_code(T_SUB, j); braw = -ej; }
-                    if (qw_getb(m, 2) == kNone && ej - slb < best) { best = ej - slb; bcode = mk_code(T_SLB, j); braw = ej - slb; }
-                }
+                const double rr = rres[h], ej = eps[h];
+                const double sn = (ok && qw_getb(m, 0) == kNone) ? rr * rirn[j & (kQW - 1)] : INFINITY;
+                const bool mat = ok && soft && qw_getb(m, 3);
+                const double su = (mat && qw_getb(m, 1) == kNone) ? -ej : INFINITY;
+                const double sl = (mat && qw_getb(m, 2) == kNone) ? ej - slb : INFINITY;
+                bool better = sn < best;
+                best = better ? sn : best;
+                bcode = better ? mk_code(T_ROW, j) : bcode;
+                braw = better ? rr : braw;
+                better = su < best;
+                best = better ? su : best;
+                bcode = better ? mk_code(T_SUB, j) : bcode;
+                braw = better ? su : braw;
+                better = sl < best;
+                best = better ? sl : best;
+                bcode = better ? mk_code(T_SLB, j) : bcode;
+                braw = better ? sl : braw;
             }
         }
         double viol = -best;
@@ -237,55 +284,56 @@ struct QpW {
         return wbcast(bcode, src);
     }
 
-    // ---- g[s] = n_{act[s]}' H^{-1} n_p for s < cnt, into gs (zero padded to a multiple of 4) ---------
+    // ---- g[s] = n_{act[s]}' H^{-1} n_p for s < cnt, into gs; gs[s] = 0 for every other slot of the halves
+    //      in use.  One table record per slot: T4[ks][kp][2 sp + space]. --------------------------------
     DMPC_D void gvec(const PInfo& p, int cnt) {
-        const int Kk = KK(), KK2 = Kk * Kk;
+        const int Kk = KK();
         const int cnt4 = (cnt + 3) & ~3;
         QW_FOR(h) {
-            const int s = qw_item(h);
-            if (s < cnt) {
-                const int info = sinfo[s];
+            if (h * kLanes < cnt4) {  // uniform
+                const int s = qw_item(h);
+                const int info = sinfo[s];  // (records of unused slots hold valid stale data)
                 const int sp = info & 1, ks = (info >> 1) & 0xff, js = (info >> 9) - 1;
                 const double dot = sv0[s] * p.v0 + sv1[s] * p.v1 + sv2[s] * p.v2;
-                const int idx = (sp > p.space) ? (p.k * Kk + ks) : (ks * Kk + p.k);
-                double gv = dot * G[(sp + p.space) * KK2 + idx];
-                if (js >= 0 && js == p.j) gv = fma(0.5 * se[s], p.e, gv);
-                gs[s] = gv;
-            } else if (s < cnt4) {
-                gs[s] = 0.0;
+                double gv = dot * T4[4 * (ks * Kk + p.k) + 2 * sp + p.space];
+                gv = (js >= 0 && js == p.j) ? fma(0.5 * se[s], p.e, gv) : gv;
+                gs[s] = (s < cnt) ? gv : 0.0;
             }
         }
         wsync();
     }
 
-    // ---- r = M[0:cnt,0:cnt] gs into the registers and into rs (zero padded).  Returns g'r (NEED_GR) --
+    // ---- r = M gs into the registers and into rs.  Rows of M beyond the active set are zero (invariant)
+    //      and gs is zero there, so no lane needs a bound check.  Returns g'r (NEED_GR) ------------------
     template <bool NEED_GR>
     DMPC_D double mat_vec(int cnt, double* rmax_out) {
         const int cnt4 = (cnt + 3) & ~3;
+        double acc[kEPL][4];
+        QW_FOR(h) { acc[h][0] = 0.0; acc[h][1] = 0.0; acc[h][2] = 0.0; acc[h][3] = 0.0; }
+#pragma unroll 2
+        for (int j = 0; j < cnt4; j += 4) {
+            const Dbl2 g01 = ld2(gs + j), g23 = ld2(gs + j + 2);
+            QW_FOR(h) {
+                if (h * kLanes < cnt) {  // uniform
+                    const double* Mr = M + (size_t)qw_item(h) * kMS + j;
+                    const Dbl2 m01 = ld2(Mr), m23 = ld2(Mr + 2);
+                    acc[h][0] = fma(m01.x, g01.x, acc[h][0]);
+                    acc[h][1] = fma(m01.y, g01.y, acc[h][1]);
+                    acc[h][2] = fma(m23.x, g23.x, acc[h][2]);
+                    acc[h][3] = fma(m23.y, g23.y, acc[h][3]);
+                }
+            }
+        }
         double gr = 0.0, rm = 0.0;
         QW_FOR(h) {
             const int s = qw_item(h);
-            if (h * kLanes < cnt) {  // uniform: this half of the slots is in use
-                double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
-                if (s < cnt) {
-                    const double* Mr = M + (size_t)s * kMS;
-#pragma unroll 2
-                    for (int j = 0; j < cnt4; j += 4) {
-                        s0 = fma(Mr[j], gs[j], s0);
-                        s1 = fma(Mr[j + 1], gs[j + 1], s1);
-                        s2 = fma(Mr[j + 2], gs[j + 2], s2);
-                        s3 = fma(Mr[j + 3], gs[j + 3], s3);
-                    }
-                }
-                const double ri = (s0 + s1) + (s2 + s3);
-                r[h] = ri;
-                if (s < cnt4) rs[s] = (s < cnt) ? ri : 0.0;
-                if (NEED_GR && s < cnt) gr = fma(gs[s], ri, gr);
-                rm = fmax(rm, fabs(ri));
-            } else {
-                r[h] = 0.0;
-                if (s < cnt4) rs[s] = 0.0;
+            const double ri = (acc[h][0] + acc[h][1]) + (acc[h][2] + acc[h][3]);
+            r[h] = ri;
+            if (h * kLanes < cnt4) {  // uniform
+                rs[s] = ri;
+                if (NEED_GR) gr = fma(gs[s], ri, gr);
             }
+            rm = fmax(rm, fabs(ri));
         }
         if (NEED_GR) gr = wsum(gr);
         if (rmax_out) *rmax_out = wmax_approx_nonneg(rm);
@@ -293,28 +341,37 @@ struct QpW {
         return gr;
     }
 
-    // ---- bordering update: M <- inverse of [[S, g],[g', nph]] given r (registers + rs), delta -------
+    // ---- bordering update: M <- inverse of [[S, g],[g', nph]] given r (registers + rs), delta.
+    //      r is zero beyond the active set, so every lane of the halves in use runs the same code. --------
     DMPC_D void border(int cnt, double delta) {
         const int cnt4 = (cnt + 3) & ~3;
-        const double id = frcp(delta);
-        QW_FOR(h) {
-            const int s = qw_item(h);
-            if (s < cnt) {
-                const double ci = r[h] * id;
-                double* Mr = M + (size_t)s * kMS;
+        const double id = qw_rcp(delta);
+        double ci[kEPL];
+        QW_FOR(h) ci[h] = r[h] * id;
 #pragma unroll 2
-                for (int j = 0; j < cnt4; j += 4) {
-                    const double m0 = Mr[j], m1 = Mr[j + 1], m2 = Mr[j + 2], m3 = Mr[j + 3];
-                    Mr[j] = fma(ci, rs[j], m0);
-                    Mr[j + 1] = fma(ci, rs[j + 1], m1);
-                    Mr[j + 2] = fma(ci, rs[j + 2], m2);
-                    Mr[j + 3] = fma(ci, rs[j + 3], m3);
+        for (int j = 0; j < cnt4; j += 4) {
+            const Dbl2 r01 = ld2(rs + j), r23 = ld2(rs + j + 2);
+            QW_FOR(h) {
+                if (h * kLanes < cnt) {  // uniform
+                    double* Mr = M + (size_t)qw_item(h) * kMS + j;
+                    Dbl2 m01 = ld2(Mr), m23 = ld2(Mr + 2);
+                    m01.x = fma(ci[h], r01.x, m01.x);
+                    m01.y = fma(ci[h], r01.y, m01.y);
+                    m23.x = fma(ci[h], r23.x, m23.x);
+                    m23.y = fma(ci[h], r23.y, m23.y);
+                    st2(Mr, m01);
+                    st2(Mr + 2, m23);
                 }
-                Mr[cnt] = -ci;  // after the loop: cnt may lie inside the padded range
-                M[(size_t)cnt * kMS + s] = -ci;
             }
         }
-        if (lane_id() == 0) M[(size_t)cnt * kMS + cnt] = id;
+        QW_FOR(h) {
+            if (h * kLanes <= cnt) {  // uniform: the half of the new slot included
+                const int s = qw_item(h);
+                const double v = (s == cnt) ? id : -ci[h];  // lanes beyond the set write (-)0
+                M[(size_t)s * kMS + cnt] = v;
+                M[(size_t)cnt * kMS + s] = v;
+            }
+        }
         wsync();
     }
 
@@ -326,7 +383,7 @@ struct QpW {
             act[q] = code;
             put_record(q, p);
         }
-        QW_FOR(h) if (q == qw_item(h)) u[h] = uval;
+        QW_FOR(h) u[h] = (q == qw_item(h)) ? uval : u[h];
         set_active(code, (unsigned)q);
         count_active(code, +1);
         wsync();
@@ -338,27 +395,34 @@ struct QpW {
     DMPC_D void drop_slot(int l, double* vec, double vl, double* other) {
         const int last = q - 1;
         const int q4 = (q + 3) & ~3;
-        const double inv = frcp(M[(size_t)l * kMS + l]);
-        // column l (= row l, M is symmetric) as broadcast vector
+        const double inv = qw_rcp(M[(size_t)l * kMS + l]);
+        // column l (= row l, M is symmetric) as broadcast vector; zero beyond the set (invariant of M)
         QW_FOR(h) {
-            const int s = qw_item(h);
-            if (s < q) gs[s] = M[(size_t)l * kMS + s];
-            else if (s < q4) gs[s] = 0.0;
+            if (h * kLanes < q4) {
+                const int s = qw_item(h);
+                gs[s] = M[(size_t)l * kMS + s];
+            }
         }
         wsync();
+        double ci[kEPL];
         QW_FOR(h) {
             const int s = qw_item(h);
-            if (s < q && s != l) {
-                const double ci = gs[s] * inv;
-                vec[h] = fma(-ci, vl, vec[h]);
-                double* Mr = M + (size_t)s * kMS;
+            ci[h] = (h * kLanes < q4 && s != l) ? gs[s & (kQW - 1)] * inv : 0.0;
+            vec[h] = fma(-ci[h], vl, vec[h]);
+        }
 #pragma unroll 2
-                for (int j = 0; j < q4; j += 4) {
-                    const double m0 = Mr[j], m1 = Mr[j + 1], m2 = Mr[j + 2], m3 = Mr[j + 3];
-                    Mr[j] = fma(-ci, gs[j], m0);
-                    Mr[j + 1] = fma(-ci, gs[j + 1], m1);
-                    Mr[j + 2] = fma(-ci, gs[j + 2], m2);
-                    Mr[j + 3] = fma(-ci, gs[j + 3], m3);
+        for (int j = 0; j < q4; j += 4) {
+            const Dbl2 g01 = ld2(gs + j), g23 = ld2(gs + j + 2);
+            QW_FOR(h) {
+                if (h * kLanes < q) {  // uniform
+                    double* Mr = M + (size_t)qw_item(h) * kMS + j;
+                    Dbl2 m01 = ld2(Mr), m23 = ld2(Mr + 2);
+                    m01.x = fma(-ci[h], g01.x, m01.x);
+                    m01.y = fma(-ci[h], g01.y, m01.y);
+                    m23.x = fma(-ci[h], g23.x, m23.x);
+                    m23.y = fma(-ci[h], g23.y, m23.y);
+                    st2(Mr, m01);
+                    st2(Mr + 2, m23);
                 }
             }
         }
@@ -378,10 +442,8 @@ struct QpW {
                     M[(size_t)s * kMS + l] = v;
                     M[(size_t)l * kMS + s] = v;
                 }
-                if (s == l) {
-                    vec[h] = vec_last;
-                    if (other) other[h] = oth_last;
-                }
+                vec[h] = (s == l) ? vec_last : vec[h];
+                if (other) other[h] = (s == l) ? oth_last : other[h];
             }
             if (lane_id() == 0) {
                 M[(size_t)l * kMS + l] = M[(size_t)last * kMS + last];
@@ -402,89 +464,86 @@ struct QpW {
                 M[(size_t)s * kMS + last] = 0.0;
                 M[(size_t)last * kMS + s] = 0.0;
             }
-            if (s == last) {
-                vec[h] = 0.0;
-                if (other) other[h] = 0.0;
-            }
+            vec[h] = (s == last) ? 0.0 : vec[h];
+            if (other) other[h] = (s == last) ? 0.0 : other[h];
         }
         wsync();
         --q;
     }
 
-    // ---- cb / cp <- sum over the active set of coef_s * (normal of slot s), coef = rs -----------------
+    // ---- coefficient vectors of N c for c = rs (per slot): pairs (cb, cp) at cbp[2 (x K + k)]
     //   cb: coefficients on unit vectors e_i (acceleration box)
     //   cp: coefficients on rows of Lam (workspace constraints and collision rows at kc_all)
     DMPC_D void coefs() {
         double D0 = 0.0, D1 = 0.0, D2 = 0.0;
         if (nra) {
             QW_FOR(h) {
-                const int j = qw_item(h);
+                const int j = qw_item(h) & (kQW - 1);
                 const unsigned sr = qw_getb(rmap[h], 0);
-                if (j < nv && sr != kNone) {
-                    const double c = rs[sr];
-                    D0 = fma(c, rd0[j], D0);
-                    D1 = fma(c, rd1[j], D1);
-                    D2 = fma(c, rd2[j], D2);
-                }
+                const double c = (sr != kNone) ? rs[sr & (kQW - 1)] : 0.0;  // rows beyond nv are never active
+                D0 = fma(c, rd0[j], D0);
+                D1 = fma(c, rd1[j], D1);
+                D2 = fma(c, rd2[j], D2);
             }
             wsum3(D0, D1, D2);
         }
+        const int Kk = KK();
         QW_FOR(h) {
             const int i = qw_item(h);
-            if (i < n3) {
-                const unsigned m = emap[h];
-                const unsigned sl = qw_getb(m, 0), su = qw_getb(m, 1), wl = qw_getb(m, 2), wu = qw_getb(m, 3);
-                double c_b = 0.0, c_p = 0.0;
-                if (sl != kNone) c_b = rs[sl];
-                if (su != kNone) c_b -= rs[su];
-                if (wl != kNone) c_p = rs[wl];
-                if (wu != kNone) c_p -= rs[wu];
-                if (nra && ek[h] == kc_all) c_p += (ex[h] == 0) ? D0 : ((ex[h] == 1) ? D1 : D2);
-                cb[i] = c_b;
-                cp[i] = c_p;
-            }
+            const unsigned m = emap[h];
+            const unsigned sl = qw_getb(m, 0), su = qw_getb(m, 1), wl = qw_getb(m, 2), wu = qw_getb(m, 3);
+            const double c0 = rs[sl & (kQW - 1)], c1 = rs[su & (kQW - 1)], c2 = rs[wl & (kQW - 1)],
+                         c3 = rs[wu & (kQW - 1)];
+            Dbl2 cc;
+            cc.x = ((sl != kNone) ? c0 : 0.0) - ((su != kNone) ? c1 : 0.0);
+            cc.y = ((wl != kNone) ? c2 : 0.0) - ((wu != kNone) ? c3 : 0.0);
+            const double dx = (ex[h] == 0) ? D0 : ((ex[h] == 1) ? D1 : D2);
+            cc.y += (nra && ek[h] == kc_all) ? dx : 0.0;
+            if (i < n3) st2(cbp + 2 * (ex[h] * Kk + ek[h]), cc);
         }
         wsync();
     }
 
-    // ---- ONE pass over the tables:  oa_i = ba_i + sgn (G cb + B cp)_i,  oP_i = bP_i + sgn (B' cb + C cp)_i
+    // ---- ONE pass over the interleaved table:  oa_i = ba_i + sgn (G cb + B cp)_i,
+    //                                            oP_i = bP_i + sgn (B' cb + C cp)_i
     //      hp != null: the bases are H^{-1} n_p / Lam H^{-1} n_p of the candidate constraint -------------
     DMPC_D void apply(double* oa, double* oP, const double* ba, const double* bP, double sgn, const PInfo* hp) {
-        const int Kk = KK(), KK2 = Kk * Kk;
-        const bool hb = nbox > 0, hpz = npos > 0;
+        const int Kk = KK();
+        double sa[kEPL][2], sP[kEPL][2];
+        const double* tp[kEPL];
+        const double* cq[kEPL];
         QW_FOR(h) {
-            const int i = qw_item(h);
-            if (i < n3) {
-                const int k = ek[h], x = ex[h];
-                double a0 = 0.0, a1 = 0.0, p0 = 0.0, p1 = 0.0;
-                if (hb) {
+            const int kk = (qw_item(h) < n3) ? ek[h] : 0;
+            tp[h] = T4 + 4 * (kk * Kk);
+            cq[h] = cbp + 2 * (ex[h] * Kk);
+            sa[h][0] = sa[h][1] = sP[h][0] = sP[h][1] = 0.0;
+        }
 #pragma unroll
-                    for (int j = 0; j < Kk; ++j) {
-                        const double c = cb[3 * j + x];
-                        a0 = fma(G[k * Kk + j], c, a0);
-                        p0 = fma(B[j * Kk + k], c, p0);
-                    }
+        for (int j = 0; j < Kk; ++j) {
+            QW_FOR(h) {
+                if (h * kLanes < n3) {  // uniform
+                    const Dbl2 t01 = ld2(tp[h] + 4 * j), t23 = ld2(tp[h] + 4 * j + 2), c = ld2(cq[h] + 2 * j);
+                    sa[h][0] = fma(t01.x, c.x, sa[h][0]);
+                    sa[h][1] = fma(t01.y, c.y, sa[h][1]);
+                    sP[h][0] = fma(t23.x, c.x, sP[h][0]);
+                    sP[h][1] = fma(t23.y, c.y, sP[h][1]);
                 }
-                if (hpz) {
-#pragma unroll
-                    for (int j = 0; j < Kk; ++j) {
-                        const double c = cp[3 * j + x];
-                        a1 = fma(B[k * Kk + j], c, a1);
-                        p1 = fma(C[k * Kk + j], c, p1);
-                    }
-                }
-                double b_a, b_P;
-                if (hp) {
-                    const double vx = (x == 0) ? hp->v0 : ((x == 1) ? hp->v1 : hp->v2);
-                    b_a = vx * G[hp->space * KK2 + k * Kk + hp->k];
-                    b_P = vx * G[(1 + hp->space) * KK2 + hp->k * Kk + k];
-                } else {
-                    b_a = ba[h];
-                    b_P = bP[h];
-                }
-                oa[h] = b_a + sgn * (a0 + a1);
-                oP[h] = b_P + sgn * (p0 + p1);
             }
+        }
+        QW_FOR(h) {
+            double b_a, b_P;
+            if (hp) {
+                const int x = ex[h];
+                const double vx = (x == 0) ? hp->v0 : ((x == 1) ? hp->v1 : hp->v2);
+                const double* t = tp[h] + 4 * hp->k;
+                b_a = vx * t[hp->space];
+                b_P = vx * t[2 + hp->space];
+            } else {
+                b_a = ba[h];
+                b_P = bP[h];
+            }
+            oa[h] = b_a + sgn * (sa[h][0] + sa[h][1]);
+            oP[h] = b_P + sgn * (sP[h][0] + sP[h][1]);
         }
     }
 
@@ -494,38 +553,39 @@ struct QpW {
         apply(z, L, nullptr, nullptr, -1.0, &p);
         QW_FOR(h) {
             const int i = qw_item(h);
-            if (i < n3) {
+            if (h * kLanes < n3) {  // uniform; entries beyond n3 of a half in use land in the padding
                 zs[i] = z[h];
                 Ls[i] = L[h];
             }
         }
         double loc = 0.0;
-        if (soft) {
+        if (soft && nmat) {
             QW_FOR(h) {
-                const int j = qw_item(h);
+                const int j = qw_item(h) & (kQW - 1);
                 const unsigned m = rmap[h];
-                double ze = 0.0;
-                if (j < nv && qw_getb(m, 3)) {
-                    ze = (j == p.j) ? 0.5 * p.e : 0.0;
-                    const unsigned sr = qw_getb(m, 0), su = qw_getb(m, 1), sl = qw_getb(m, 2);
-                    if (sr != kNone) ze += 0.5 * rdist[j] * rs[sr];
-                    if (su != kNone) ze += 0.5 * rs[su];
-                    if (sl != kNone) ze -= 0.5 * rs[sl];
-                    loc = fma(ze, ze, loc);
-                }
+                const unsigned sr = qw_getb(m, 0), su = qw_getb(m, 1), sl = qw_getb(m, 2);
+                const double c0 = rs[sr & (kQW - 1)], c1 = rs[su & (kQW - 1)], c2 = rs[sl & (kQW - 1)];
+                double ze = (j == p.j) ? 0.5 * p.e : 0.0;
+                ze += (sr != kNone) ? 0.5 * rdist[j] * c0 : 0.0;
+                ze += (su != kNone) ? 0.5 * c1 : 0.0;
+                ze -= (sl != kNone) ? 0.5 * c2 : 0.0;
+                ze = qw_getb(m, 3) ? ze : 0.0;  // not materialised: eps is held at 0 by its implicit bound
+                loc = fma(ze, ze, loc);
                 zeps[h] = ze;
             }
+        } else {
+            QW_FOR(h) zeps[h] = 0.0;
         }
         wsync();
         // z'Hz, H_K = 2 (q lamK lamK' + s Delta'Delta + I): a sum of squares (no cancellation)
         QW_FOR(h) {
             const int i = qw_item(h);
-            if (i < n3) {
-                const double zi = z[h];
-                const double dz = zi - ((i >= 3) ? zs[i - 3] : 0.0);
-                loc = fma(zi, zi, loc);
-                loc = fma(sw * dz, dz, loc);
-            }
+            const bool ok = i < n3;
+            const double zi = ok ? z[h] : 0.0;
+            const double zp = (ok && i >= 3) ? zs[(i - 3) & (kQW - 1)] : 0.0;
+            const double dz = zi - zp;
+            loc = fma(zi, zi, loc);
+            loc = fma(sw * dz, dz, loc);
         }
         loc = wsum(loc);
         const int Kk = KK();
@@ -573,11 +633,11 @@ struct QpW {
 
     // recompute every row residual from P (shared copy in Ls) and eps; publishes eps -> cb, rres -> cp
     DMPC_D void rows_refresh() {
+        const double l0 = Ls[3 * kc_all], l1 = Ls[3 * kc_all + 1], l2 = Ls[3 * kc_all + 2];
         QW_FOR(h) {
             const int j = qw_item(h);
             if (j < nv) {
-                const int kc = rkc[j];
-                double s = rd0[j] * Ls[3 * kc] + rd1[j] * Ls[3 * kc + 1] + rd2[j] * Ls[3 * kc + 2] - rrhs[j];
+                double s = rd0[j] * l0 + rd1[j] * l1 + rd2[j] * l2 - rrhs[j];
                 if (soft) s -= rdist[j] * eps[h];
                 rres[h] = s;
                 cb[j] = eps[h];
@@ -620,7 +680,7 @@ struct QpW {
                 p.type = 0;
                 p.idx = 0;
                 const int Kk = KK();
-                p.nph = (p.v0 * p.v0 + p.v1 * p.v1 + p.v2 * p.v2) * G[2 * p.space * Kk * Kk + p.k * Kk + p.k] +
+                p.nph = (p.v0 * p.v0 + p.v1 * p.v1 + p.v2 * p.v2) * T4[4 * (p.k * Kk + p.k) + 3 * p.space] +
                         0.5 * p.e * p.e;
             }
             // clear row / column s (it may hold garbage of a broken-down update)
@@ -844,8 +904,15 @@ struct QpW {
             r[h] = 0.0;
             emap[h] = 0xffffffffu;
             rmap[h] = 0x00ffffffu;
+            rres[h] = 0.0;
             const int i = qw_item(h);
             if (i < n3) Ls[i] = Punc[h];
+            // slot records of unused slots are read (and discarded) by the branch-free loops: keep them valid
+            if (i < kQW) {
+                sinfo[i] = 0; act[i] = 0;
+                sv0[i] = 0.0; sv1[i] = 0.0; sv2[i] = 0.0; se[i] = 0.0;
+                gs[i] = 0.0; rs[i] = 0.0; cb[i] = 0.0; cp[i] = 0.0;
+            }
         }
         // the unused part of M is zero at all times
         for (int e = lane_id(); e < kQW * kMS; e += kLanes) M[e] = 0.0;
@@ -988,6 +1055,25 @@ struct QpW {
                     have_z = false;
                 }
                 if (++iters > max_iter) { res.rc = QP_ITERCAP; failed = true; break; }
+                // dual ratio test: smallest u_i / r_i over r_i > 0 (needs u and r only: issued before the
+                // direction so that its latency hides behind the table products)
+                const double rthr = 1e-12 * rmax;
+                double t1 = INFINITY;
+                int ldrop = -1;
+                QW_FOR(h) {
+                    const int s = qw_item(h);
+                    const double ri = r[h];
+                    const bool ok = s < q && ri > rthr;
+                    const double t = ok ? fmax(u[h], 0.0) * qw_rcp(ok ? ri : 1.0) : INFINITY;
+                    const bool better = ok && (ldrop < 0 || t < t1);
+                    t1 = better ? t : t1;
+                    ldrop = better ? s : ldrop;
+                }
+                {
+                    const int src = warg_min_nonneg(t1, ldrop >= 0);
+                    ldrop = (src >= 0) ? wbcast(ldrop, src) : -1;
+                    if (src < 0) t1 = INFINITY;
+                }
                 if (!have_z) {
                     delta = direction(p);
                     have_z = true;
@@ -1004,25 +1090,8 @@ struct QpW {
                     }
                 }
                 const bool dependent = !(delta > dep_tol * p.nph) || (q >= n3 + nmat);
-                // dual ratio test: smallest u_i / r_i over r_i > 0
-                const double rthr = 1e-12 * rmax;
-                double t1 = INFINITY;
-                int ldrop = -1;
-                QW_FOR(h) {
-                    const int s = qw_item(h);
-                    const double ri = r[h];
-                    if (s < q && ri > rthr) {
-                        const double t = fmax(u[h], 0.0) * frcp(ri);
-                        if (ldrop < 0 || t < t1) { t1 = t; ldrop = s; }
-                    }
-                }
-                {
-                    const int src = warg_min_nonneg(t1, ldrop >= 0);
-                    ldrop = (src >= 0) ? wbcast(ldrop, src) : -1;
-                    if (src < 0) t1 = INFINITY;
-                }
                 PROF(9);
-                const double t2 = dependent ? INFINITY : (-sp * frcp(delta));
+                const double t2 = dependent ? INFINITY : (-sp * qw_rcp(delta));
                 const double t = (t1 < t2) ? t1 : t2;
                 if (!(t < INFINITY)) {  // also catches NaN
                     res.rc = QP_INFEASIBLE;
@@ -1035,17 +1104,15 @@ struct QpW {
                         a[h] = fma(t, z[h], a[h]);
                         P[h] = fma(t, L[h], P[h]);
                     }
-                    // rows: residual_j += t n_j'z = t (d_j . Lz[kc_j] - dist_j zeps_j)
-                    QW_FOR(h) {
-                        const int j = qw_item(h);
-                        if (j < nv) {
-                            const int kc = rkc[j];
-                            double nz = rd0[j] * Ls[3 * kc] + rd1[j] * Ls[3 * kc + 1] + rd2[j] * Ls[3 * kc + 2];
-                            if (soft) {
-                                const double ze = zeps[h];
-                                eps[h] = fma(t, ze, eps[h]);
-                                nz = fma(-rdist[j], ze, nz);
-                            }
+                    // rows: residual_j += t n_j'z = t (d_j . Lz[kc] - dist_j zeps_j)   (all rows act on kc_all)
+                    if (nv > 0) {
+                        const double l0 = Ls[3 * kc_all], l1 = Ls[3 * kc_all + 1], l2 = Ls[3 * kc_all + 2];
+                        QW_FOR(h) {
+                            const int j = qw_item(h) & (kQW - 1);
+                            double nz = rd0[j] * l0 + rd1[j] * l1 + rd2[j] * l2;
+                            const double ze = zeps[h];  // 0 unless soft and materialised
+                            eps[h] = fma(t, ze, eps[h]);
+                            nz = fma(-rdist[j], ze, nz);
                             rres[h] = fma(t, nz, rres[h]);
                         }
                     }
@@ -1084,7 +1151,7 @@ struct QpW {
                         wsync();
                         if (dependent && (q < n3 + nmat)) {
                             // delta' = delta + r_l^2 / M_ll: while still dependent keep dropping without a direction
-                            const double dn = fmax(delta, 0.0) + rl * rl * frcp(mll);
+                            const double dn = fmax(delta, 0.0) + rl * rl * qw_rcp(mll);
                             if (dn > 0.25 * dep_tol * p.nph) have_z = false;
                             else delta = dn;
                         } else {
@@ -1157,12 +1224,13 @@ DMPC_D int agent_solve_fast(const DevParams& Pm, const double* __restrict__ tab,
     const double* t_lam = tab;
     const double* t_tt = tab + K * K;
     const double* t_lnorm = tab + K * K + K;
-    const double* t_G = tab + tab_set_offset(K, wset);
+    // tab: the shared-memory blob of model_tables.h (header padded to 4 doubles, then T4 per weight set)
+    const double* t_T4 = tab + tab_fast_header(K) + (size_t)wset * 4 * K * K;
     qp.K = K; qp.n3 = n3; qp.nv = io.nv; qp.soft = soft ? 1 : 0;
     qp.kc_all = io.kstar > 0 ? io.kstar - 1 - (Pm.variant == VAR_SOFT_BOUND2 ? 1 : 0) : 0;
     qp.alim = Pm.alim; qp.qw = qw; qp.sw = sw;
     qp.qcap = qcap < kQW ? qcap : kQW;
-    qp.ilnorm = tab + K * K + 2 * K; qp.G = t_G; qp.B = t_G + K * K; qp.C = t_G + 2 * K * K;
+    qp.ilnorm = tab + K * K + 2 * K; qp.T4 = t_T4;
 
     // ---- rows: global SoA (scan output) -> shared ---------------------------------------------------
     const int nv = io.nv;
@@ -1178,6 +1246,10 @@ DMPC_D int agent_solve_fast(const DevParams& Pm, const double* __restrict__ tab,
             const double dd = d0 * d0 + d1 * d1 + d2 * d2;
             const double ln = t_lnorm[kc];
             qp.rirn[j] = 1.0 / sqrt(dd * ln * ln + (soft ? dist * dist : 0.0));
+        } else if (j < kQW) {
+            // rows beyond nv are read (and discarded) by the branch-free loops: keep them finite
+            qp.rd0[j] = 0.0; qp.rd1[j] = 0.0; qp.rd2[j] = 0.0; qp.rdist[j] = 0.0; qp.rrhs[j] = 0.0; qp.rirn[j] = 0.0;
+            qp.rkc[j] = 0;
         }
     }
     // ---- a_unc = -G f,  P_unc = A_initp [po;vo] + Lam a_unc  (solveSoftDMPCbound.m:82-88) ------------
@@ -1194,7 +1266,7 @@ DMPC_D int agent_solve_fast(const DevParams& Pm, const double* __restrict__ tab,
             const double vox = (x == 0) ? x_vo[0] : ((x == 1) ? x_vo[1] : x_vo[2]);
             const double aox = (x == 0) ? x_ao[0] : ((x == 1) ? x_ao[1] : x_ao[2]);
             const double e = pfx - (pox + t_tt[K - 1] * vox);
-            au = 2.0 * qw * e * qp.B[k * K + (K - 1)] + 2.0 * sw * aox * qp.G[k * K];
+            au = 2.0 * qw * e * t_T4[4 * (k * K + (K - 1)) + 1] + 2.0 * sw * aox * t_T4[4 * (k * K)];
             qp.zs[i] = au;
             qp.elo[h] = qp.pmin_of(i);
             qp.ehi[h] = qp.pmax_of(i);
