@@ -238,7 +238,7 @@ def run_single(args):
         "e2e": {"value": N * S / t_e2e, "unit": "agent-steps/s", "h2d_bytes_per_step": h2d,
                 "d2h_bytes_per_step": d2h, "ms_per_step": 1e3 * t_e2e / S,
                 "api": "dmpcb200_step (host buffers, pinned)"},
-        "gpu_launches": 3 * n_timed,
+        "gpu_launches": 2 * n_timed,
         "resident_graph": {"value": N / (graph_ms * 1e-3) if graph_ms else None, "ms_per_step": graph_ms,
                            "steps": graph_steps, "note": "dmpcb200_run, CUDA graph, L2-warm, no host sync"},
         "roofline": {"bound": "hbm", "kernel": "scan_kernel<4> (neighbour scan + constraint rows)",

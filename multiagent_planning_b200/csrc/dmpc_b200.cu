@@ -66,6 +66,7 @@ struct dmpcb200_handle {
     int *d_gkc = nullptr, *d_gidx = nullptr, *d_gscr_i = nullptr;
     unsigned char* d_rescue = nullptr;
     int* d_rescue_next = nullptr;
+    unsigned* d_done = nullptr;  // CTA arrival counter of the fused tail
     Ctrl* d_ctrl = nullptr;
     double* d_goal = nullptr;  // 2 doubles
     int* d_fail = nullptr;
@@ -138,39 +139,54 @@ StepArgs make_args(dmpcb200_t* h, int n0, int n1, const double* pk, const double
     A.rescue_bytes = h->rescue_bytes;
     A.rescue_next = h->d_rescue_next;
     A.ctrl = ctrl;
+    A.fuse_tail = 0;
+    A.done_cnt = h->d_done;
     return A;
 }
 
-template <int W>
+template <int W, int S, int KT>
 cudaError_t launch_scan_w(const StepArgs& A, int nl, int K, cudaStream_t s) {
     static bool attr_done = false;
     if (!attr_done) {
-        cudaError_t e = cudaFuncSetAttribute(scan_kernel<W>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        cudaError_t e =
+            cudaFuncSetAttribute(scan_kernel<W, S, KT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
         if (e != cudaSuccess) return e;
         attr_done = true;
     }
-    const int stages = scan_stages(K, A.P.N);
-    scan_kernel<W><<<(nl + W - 1) / W, W * 32, scan_smem_bytes(K, W, stages), s>>>(A, stages);
+    int stages = scan_stages(K, A.P.N);
+    if (stages > S) stages = stages / S * S;  // rounds of S tiles map onto distinct stages
+    scan_kernel<W, S, KT><<<(nl + W - 1) / W, W * S * 32, scan_smem_bytes(K, W, stages), s>>>(A, stages);
     return cudaGetLastError();
 }
 template <int W, int KT>
 cudaError_t launch_qp_w(const StepArgs& A, int nl, size_t smem, cudaStream_t s) {
-    static bool attr_done = false;
-    if (!attr_done) {
+    static size_t attr_smem = 0;
+    if (attr_smem < smem) {  // (the kernel also has a few hundred bytes of static shared memory)
         cudaError_t e =
-            cudaFuncSetAttribute(qp_kernel<W, KT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+            cudaFuncSetAttribute(qp_kernel<W, KT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
-        attr_done = true;
+        attr_smem = smem;
     }
     qp_kernel<W, KT><<<(nl + W - 1) / W, W * 32, smem, s>>>(A);
     return cudaGetLastError();
 }
 
-// 4 agents per CTA while that still gives every agent its own SM sub-partition, 8 beyond
+// 4 agents x 4 warps per CTA while one wave of CTAs covers the swarm, 8 agents x 2 warps beyond;
+// the reference's horizons (15, 20) are compiled with the horizon as a constant
 cudaError_t launch_scan(dmpcb200_t* h, const StepArgs& A, cudaStream_t s) {
     const int nl = A.n1 - A.n0;
-    if (nl <= 4 * 148) return launch_scan_w<4>(A, nl, h->K, s);
-    return launch_scan_w<8>(A, nl, h->K, s);
+    if (nl <= 4 * 148) {
+        static const int variant = getenv("DMPCB200_SCAN") ? atoi(getenv("DMPCB200_SCAN")) : 0;  // tuning hook
+        if (h->K == 15 && variant == 1) return launch_scan_w<4, 4, 15>(A, nl, h->K, s);
+        if (h->K == 15 && variant == 2) return launch_scan_w<4, 2, 15>(A, nl, h->K, s);
+        if (h->K == 15 && variant == 3) return launch_scan_w<4, 4, 0>(A, nl, h->K, s);
+        if (h->K == 15) return launch_scan_w<4, 3, 15>(A, nl, h->K, s);
+        if (h->K == 20) return launch_scan_w<4, 2, 20>(A, nl, h->K, s);
+        return launch_scan_w<4, 4, 0>(A, nl, h->K, s);
+    }
+    if (h->K == 15) return launch_scan_w<8, 2, 15>(A, nl, h->K, s);
+    if (h->K == 20) return launch_scan_w<8, 1, 20>(A, nl, h->K, s);
+    return launch_scan_w<8, 2, 0>(A, nl, h->K, s);
 }
 // horizon lengths 15 and 20 (the reference's configurations) are compiled with the horizon as a
 // compile-time constant (fully unrolled table products); anything else takes the generic kernel
@@ -216,15 +232,13 @@ int launch_resident_step(dmpcb200_t* h, int cur, bool record, Ctrl* ctrl, cudaSt
     StepArgs A = make_args(h, h->n0, h->n1, h->d_st[cur][0], h->d_st[cur][1], h->d_st[cur][2], h->d_l[cur],
                            h->d_l[nx], h->d_st[nx][0], h->d_st[nx][1], h->d_st[nx][2], nullptr, nullptr,
                            h->d_status, h->d_diag, true, ctrl);
+    A.T = make_tail(h, h->d_st[nx][0], 3, h->d_status, h->d_st[nx][0], h->d_st[nx][1], h->d_st[nx][2], record, ctrl);
+    A.fuse_tail = 1;
     if (evs) CK(cudaEventRecord(evs[0], s));
     CK(launch_scan(h, A, s));
     if (evs) CK(cudaEventRecord(evs[1], s));
-    CK(launch_qp(h, A, s));
+    CK(launch_qp(h, A, s));  // the tail of the step runs in the last CTA of the QP kernel
     if (evs) CK(cudaEventRecord(evs[2], s));
-    TailArgs T = make_tail(h, h->d_st[nx][0], 3, h->d_status, h->d_st[nx][0], h->d_st[nx][1], h->d_st[nx][2],
-                           record, ctrl);
-    tail_kernel<<<1, 256, 0, s>>>(T);
-    CK(cudaGetLastError());
     if (evs) CK(cudaEventRecord(evs[3], s));
     return 0;
 }
@@ -407,6 +421,7 @@ int dmpcb200_create(const dmpcb200_params* p, int N, int n0, int n1, int device,
     if ((e = dalloc(&h->d_gscr_i, NL * 4 * h->RMAX)) != cudaSuccess) return bail(e, "row scratch");
     if ((e = dalloc(&h->d_rescue, h->rescue_bytes * h->n_rescue)) != cudaSuccess) return bail(e, "rescue");
     if ((e = dalloc(&h->d_rescue_next, 1)) != cudaSuccess) return bail(e, "rescue counter");
+    if ((e = dalloc(&h->d_done, 1)) != cudaSuccess) return bail(e, "done counter");
     if ((e = dalloc(&h->d_ctrl, 1)) != cudaSuccess) return bail(e, "ctrl");
     if ((e = dalloc(&h->d_goal, 2)) != cudaSuccess) return bail(e, "goal");
     if ((e = dalloc(&h->d_fail, 1)) != cudaSuccess) return bail(e, "fail");
@@ -431,7 +446,7 @@ void dmpcb200_destroy(dmpcb200_t* h) {
     cudaFree(h->d_pf); cudaFree(h->d_vhor); cudaFree(h->d_ahor); cudaFree(h->d_status); cudaFree(h->d_diag);
     cudaFree(h->d_nearmask); cudaFree(h->d_scan); cudaFree(h->d_grow); cudaFree(h->d_gkc); cudaFree(h->d_gidx);
     cudaFree(h->d_gscr_d); cudaFree(h->d_gscr_i); cudaFree(h->d_rescue); cudaFree(h->d_rescue_next);
-    cudaFree(h->d_ctrl); cudaFree(h->d_goal); cudaFree(h->d_fail); cudaFree(h->d_u8); cudaFree(h->d_small);
+    cudaFree(h->d_done); cudaFree(h->d_ctrl); cudaFree(h->d_goal); cudaFree(h->d_fail); cudaFree(h->d_u8); cudaFree(h->d_small);
     cudaFree(h->d_ismall);
     for (int s = 0; s < 3; ++s) cudaFree(h->d_traj[s]);
     cudaFree(h->d_hist);
@@ -557,14 +572,13 @@ int dmpcb200_step(dmpcb200_t* h, const double* pk, const double* vk, const doubl
     StepArgs A = make_args(h, h->n0, h->n1, h->d_st[c][0], h->d_st[c][1], h->d_st[c][2], h->d_l[c], h->d_l[nx],
                            h->d_st[nx][0], h->d_st[nx][1], h->d_st[nx][2], (v_hor ? h->d_vhor : nullptr),
                            (a_hor ? h->d_ahor : nullptr), h->d_status, h->d_diag, true, nullptr);
+    A.T = make_tail(h, nullptr, 3, h->d_status, nullptr, nullptr, nullptr, false, nullptr);
+    A.fuse_tail = 1;  // first failing agent + rescue-slot reset in the last CTA of the QP kernel
     CK(cudaEventRecord(h->ev[0], s));
     CK(launch_scan(h, A, s));
     CK(cudaEventRecord(h->ev[1], s));
     CK(launch_qp(h, A, s));
     CK(cudaEventRecord(h->ev[2], s));
-    TailArgs T = make_tail(h, nullptr, 3, h->d_status, nullptr, nullptr, nullptr, false, nullptr);
-    tail_kernel<<<1, 256, 0, s>>>(T);
-    CK(cudaGetLastError());
     CK(cudaEventRecord(h->ev[3], s));
     // outputs: only the rows of agents n0..n1-1
     const size_t o3 = 3 * (size_t)n0, b3 = 3 * (size_t)NL * sizeof(double);
@@ -588,7 +602,7 @@ int dmpcb200_step(dmpcb200_t* h, const double* pk, const double* vk, const doubl
     h->t_ms[0] = a;
     h->t_ms[1] = b;
     h->t_ms[2] = w;
-    h->launches = 3;
+    h->launches = 2;
     h->cur = 0;
     return 0;
 }
@@ -705,7 +719,7 @@ int dmpcb200_run(dmpcb200_t* h, int max_steps, int stop_on_fail, int mode, doubl
         h->t_ms[1] = b / steps;
         h->t_ms[2] = w / steps;
     }
-    h->launches = 3 * (int64_t)steps;
+    h->launches = 2 * (int64_t)steps;
     if (record) {
         const size_t cols = (size_t)(steps + 1);
         double* outs[3] = {traj_p, traj_v, traj_a};

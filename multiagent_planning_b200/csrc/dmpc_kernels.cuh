@@ -43,6 +43,22 @@ struct Ctrl {
     double goal_dist;
 };
 
+struct TailArgs {
+    int N, n0, n1, ld;  // p has leading dimension ld (3: packed, 3K: first column of a horizon)
+    double goal_tol;
+    const double* p;
+    const double* pf;
+    const int* status;
+    const double *p1, *v1, *a1;        // recorded into the trajectory (3 x N)
+    double *traj_p, *traj_v, *traj_a;  // optional 3 x (S+1) x N
+    int* status_hist;                  // optional S x N
+    int S;
+    double* goal_out;  // [0] max distance, [1] reached (0/1)
+    int* fail_out;     // first failing agent or -1
+    int* rescue_next;
+    Ctrl* ctrl;  // optional
+};
+
 struct StepArgs {
     DevParams P;
     ScanThr thr;  // exact squared distance thresholds (scan_core.cuh)
@@ -69,22 +85,10 @@ struct StepArgs {
     size_t rescue_bytes;
     int* rescue_next;  // slot allocator (reset by the tail kernel)
     Ctrl* ctrl;        // optional
-};
-
-struct TailArgs {
-    int N, n0, n1, ld;  // p has leading dimension ld (3: packed, 3K: first column of a horizon)
-    double goal_tol;
-    const double* p;
-    const double* pf;
-    const int* status;
-    const double *p1, *v1, *a1;        // recorded into the trajectory (3 x N)
-    double *traj_p, *traj_v, *traj_a;  // optional 3 x (S+1) x N
-    int* status_hist;                  // optional S x N
-    int S;
-    double* goal_out;  // [0] max distance, [1] reached (0/1)
-    int* fail_out;     // first failing agent or -1
-    int* rescue_next;
-    Ctrl* ctrl;  // optional
+    // K3 fused into K2: the last CTA of the QP kernel to finish runs the step's tail (optional)
+    int fuse_tail;
+    unsigned* done_cnt;
+    TailArgs T;
 };
 
 // ---- PTX helpers: mbarrier + TMA bulk copy ---------------------------------------------------
@@ -137,24 +141,29 @@ DMPC_HD int scan_stages(int K, int N) {
 DMPC_HD size_t scan_smem_bytes(int K, int W, int stages) {
     const int n3 = 3 * K;
     return (size_t)stages * kTile * n3 * sizeof(double) + (size_t)W * round_up(n3, 2) * sizeof(double) +
-           kScanMaxStages * sizeof(uint64_t);
+           kScanMaxStages * sizeof(uint64_t) + 64 * 2 * sizeof(unsigned);
 }
 
-template <int W>
-__global__ void __launch_bounds__(W * 32) scan_kernel(const __grid_constant__ StepArgs A, int stages) {
+// W agents per CTA, S warps per agent (each takes every S-th neighbour tile: 4 x the warps of a
+// warp-per-agent layout hide the LDS / fp64 latencies of the distance loop), KT = compile-time horizon
+// (the agent's own horizon then lives in registers) or 0.
+template <int W, int S, int KT>
+__global__ void __launch_bounds__(W * S * 32) scan_kernel(const __grid_constant__ StepArgs A, int stages) {
     if (A.ctrl && A.ctrl->done) return;
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    const int K = A.P.K, n3 = 3 * K, n3p = round_up(n3, 2), N = A.P.N;
+    const int K = KT ? KT : A.P.K, n3 = 3 * K, n3p = round_up(n3, 2), N = A.P.N;
     const int tile_d = kTile * n3;
     const uint32_t tile_bytes = (uint32_t)(tile_d * sizeof(double));  // 32*3K*8: multiple of 16
     double* tiles = reinterpret_cast<double*>(smem_raw);
     double* own_all = tiles + (size_t)stages * tile_d;
     uint64_t* bars = reinterpret_cast<uint64_t*>(own_all + W * n3p);
+    unsigned* s_acc = reinterpret_cast<unsigned*>(bars + kScanMaxStages);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int li = blockIdx.x * W + warp;
+    const int ag = warp / S, sub = warp - ag * S;
+    const int li = blockIdx.x * W + ag;
     const int n = A.n0 + li;
     const bool valid = n < A.n1;
-    double* own = own_all + warp * n3p;
+    double* own = own_all + ag * n3p;
 
     const int ntma = A.tile_padded ? (N + kTile - 1) / kTile : N / kTile;
     if (threadIdx.x == 0) {
@@ -165,27 +174,43 @@ __global__ void __launch_bounds__(W * 32) scan_kernel(const __grid_constant__ St
             tma_bulk_g2s(tiles + (size_t)t * tile_d, A.l_prev + (size_t)t * tile_d, tile_bytes, &bars[t]);
         }
     }
-    if (valid)
+    if (valid && sub == 0)
         for (int i = lane; i < n3; i += 32) own[i] = A.l_prev[(size_t)n * n3 + i];
     __syncthreads();  // barrier init + own horizons visible
+
+    double ow[KT ? 3 * KT : 1];
+    if (KT) {
+#pragma unroll
+        for (int i = 0; i < 3 * KT; ++i) ow[i] = own[i];
+    }
+    const double* ownp = KT ? ow : own;
 
     unsigned* nm = A.nearmask + (size_t)(valid ? li : 0) * A.nm_stride;
     ScanAcc acc;
     acc.vmask = 0;
     acc.coll0 = 0;
     const bool refill = ntma > stages;
-    for (int t = 0; t < ntma; ++t) {
-        const int b = t % stages;
-        mbar_wait(&bars[b], (uint32_t)((t / stages) & 1));
-        const int base = t * kTile;
-        const int cnt = (N - base < kTile) ? (N - base) : kTile;
-        if (valid) scan_tile(A.P, &A.thr, own, n, tiles + (size_t)b * tile_d, base, cnt, nm, acc);
+    for (int t0 = 0; t0 < ntma; t0 += S) {
+        const int t = t0 + sub;
+        if (t < ntma) {
+            const int b = t % stages;
+            mbar_wait(&bars[b], (uint32_t)((t / stages) & 1));
+            const int base = t * kTile;
+            const int cnt = (N - base < kTile) ? (N - base) : kTile;
+            if (valid) scan_tile_hw<KT>(A.P, &A.thr, ownp, n, tiles + (size_t)b * tile_d, base, cnt, nm, acc);
+        }
         if (refill) {
-            __syncthreads();  // every warp is done with stage b
-            if (threadIdx.x == 0 && t + stages < ntma) {
-                mbar_expect_tx(&bars[b], tile_bytes);
-                tma_bulk_g2s(tiles + (size_t)b * tile_d, A.l_prev + (size_t)(t + stages) * tile_d, tile_bytes,
-                             &bars[b]);
+            __syncthreads();  // every warp is done with the stages of this round
+            if (threadIdx.x == 0) {
+                for (int i = 0; i < S; ++i) {
+                    const int tt = t0 + i;
+                    if (tt < ntma && tt + stages < ntma) {
+                        const int b = tt % stages;
+                        mbar_expect_tx(&bars[b], tile_bytes);
+                        tma_bulk_g2s(tiles + (size_t)b * tile_d, A.l_prev + (size_t)(tt + stages) * tile_d, tile_bytes,
+                                     &bars[b]);
+                    }
+                }
             }
         }
     }
@@ -194,12 +219,25 @@ __global__ void __launch_bounds__(W * 32) scan_kernel(const __grid_constant__ St
         // caller-owned buffer without tile padding: the ragged last tile is loaded by the threads
         const int cnt = N - rem_base;
         __syncthreads();
-        for (int i = threadIdx.x; i < cnt * n3; i += W * 32) tiles[i] = A.l_prev[(size_t)rem_base * n3 + i];
+        for (int i = threadIdx.x; i < cnt * n3; i += W * S * 32) tiles[i] = A.l_prev[(size_t)rem_base * n3 + i];
         __syncthreads();
-        if (valid) scan_tile(A.P, &A.thr, own, n, tiles, rem_base, cnt, nm, acc);
+        if (valid && sub == 0) scan_tile_hw<KT>(A.P, &A.thr, ownp, n, tiles, rem_base, cnt, nm, acc);
     }
-    if (!valid) return;
-    __syncwarp();
+    // combine the S partial results of an agent (the barrier also publishes the siblings' near masks)
+    {
+        const unsigned vm = wor(acc.vmask), c0 = wor(acc.coll0);
+        if (lane == 0) {
+            s_acc[2 * warp] = vm;
+            s_acc[2 * warp + 1] = c0;
+        }
+    }
+    __syncthreads();
+    if (!valid || sub != 0) return;
+#pragma unroll
+    for (int i = 1; i < S; ++i) {
+        acc.vmask |= s_acc[2 * (warp + i)];
+        acc.coll0 |= s_acc[2 * (warp + i) + 1];
+    }
     const ScanOut so = scan_finish(A.P, own, n, A.l_prev, nm, acc, A.RMAX, A.grow + (size_t)li * 5 * A.RMAX,
                                    A.gkc + (size_t)li * A.RMAX, A.gidx ? A.gidx + (size_t)li * A.RMAX : nullptr);
     if (lane == 0) {
@@ -210,6 +248,83 @@ __global__ void __launch_bounds__(W * 32) scan_kernel(const __grid_constant__ St
         r.pad = 0;
         A.scan[li] = r;
     }
+}
+
+// ---- K3 (defined first: K2 runs it in its last CTA) --------------------------------------------
+// body of K3 for a CTA of NT threads (NT <= 512).  The inputs may have been written by other CTAs of the
+// SAME kernel (fused tail): they are read with ld.global.cg (L2), never from a stale L1 line.
+template <int NT>
+__device__ __forceinline__ void tail_body(const TailArgs& T) {
+    __shared__ double s_md[16];
+    __shared__ int s_ff[16];
+    const int tid = threadIdx.x;
+    const int step = T.ctrl ? T.ctrl->step : 0;
+    double md = 0.0;
+    int ff = 0x7fffffff;
+    for (int n = tid; n < T.N; n += NT) {
+        if (T.p) {
+            // ReachedGoal.m:4-5
+            const double dx = __ldcg(T.p + (size_t)T.ld * n) - T.pf[3 * n];
+            const double dy = __ldcg(T.p + (size_t)T.ld * n + 1) - T.pf[3 * n + 1];
+            const double dz = __ldcg(T.p + (size_t)T.ld * n + 2) - T.pf[3 * n + 2];
+            md = fmax(md, sqrt(dx * dx + dy * dy + dz * dz));
+        }
+        if (T.status && n >= T.n0 && n < T.n1) {
+            const int st = __ldcg(T.status + n);
+            if ((!(st & ST_SOLVED) || (st & ST_OUTBOUND)) && n < ff) ff = n;
+            if (T.status_hist && step < T.S) T.status_hist[(size_t)step * T.N + n] = st;
+        }
+        if (T.traj_p && step < T.S) {
+            const size_t o = 3 * ((size_t)(step + 1) + (size_t)(T.S + 1) * n);
+            for (int x = 0; x < 3; ++x) {
+                T.traj_p[o + x] = __ldcg(T.p1 + 3 * n + x);
+                T.traj_v[o + x] = __ldcg(T.v1 + 3 * n + x);
+                T.traj_a[o + x] = __ldcg(T.a1 + 3 * n + x);
+            }
+        }
+    }
+    for (int o = 16; o; o >>= 1) {
+        md = fmax(md, __shfl_xor_sync(0xffffffffu, md, o));
+        ff = min(ff, __shfl_xor_sync(0xffffffffu, ff, o));
+    }
+    if ((tid & 31) == 0) {
+        s_md[tid >> 5] = md;
+        s_ff[tid >> 5] = ff;
+    }
+    __syncthreads();
+    if (tid == 0) {
+        for (int w = 1; w < NT / 32; ++w) {
+            md = fmax(md, s_md[w]);
+            ff = min(ff, s_ff[w]);
+        }
+        const int reached = (T.p && md < T.goal_tol) ? 1 : 0;
+        if (T.goal_out) {
+            T.goal_out[0] = md;
+            T.goal_out[1] = (double)reached;
+        }
+        if (T.fail_out) *T.fail_out = (ff == 0x7fffffff) ? -1 : ff;
+        if (T.rescue_next) *T.rescue_next = 0;
+        if (T.ctrl) {
+            Ctrl* c = T.ctrl;
+            c->goal_dist = md;
+            if (ff != 0x7fffffff && c->fail_step < 0) {
+                c->fail_step = step;
+                c->fail_agent = ff;
+            }
+            c->step = step + 1;
+            if (reached) {
+                c->reached = 1;
+                c->done = 1;
+            }
+            if (ff != 0x7fffffff && c->stop_on_fail) c->done = 1;
+            if (step + 1 >= c->max_steps) c->done = 1;
+        }
+    }
+}
+
+__global__ void __launch_bounds__(256) tail_kernel(const __grid_constant__ TailArgs T) {
+    if (T.ctrl && T.ctrl->done) return;
+    tail_body<256>(T);
 }
 
 // ---- K2 -------------------------------------------------------------------------------------
@@ -244,8 +359,7 @@ __global__ void __launch_bounds__(W * 32, 1) qp_kernel(const __grid_constant__ S
     __syncthreads();
     const int li = blockIdx.x * W + warp;
     const int n = A.n0 + li;
-    if (n >= A.n1) return;
-
+    if (n < A.n1) {
     const ScanRec sr = A.scan[li];
     AgentIO io;
     io.po = A.pk + 3 * n;
@@ -307,78 +421,23 @@ __global__ void __launch_bounds__(W * 32, 1) qp_kernel(const __grid_constant__ S
         A.status[n] = st;
         if (A.diag) A.diag[n] = dg;
     }
+    }  // n < A.n1
+    if (A.fuse_tail) {
+        // the last CTA to arrive has every agent's result behind it: it runs the tail of the step
+        __shared__ int s_last;
+        __threadfence();
+        __syncthreads();
+        if (threadIdx.x == 0) s_last = (atomicAdd(A.done_cnt, 1u) == gridDim.x - 1) ? 1 : 0;
+        __syncthreads();
+        if (s_last) {
+            __threadfence();
+            tail_body<W * 32>(A.T);
+            if (threadIdx.x == 0) *A.done_cnt = 0;
+        }
+    }
 }
 
 // ---- K3 -------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) tail_kernel(const __grid_constant__ TailArgs T) {
-    if (T.ctrl && T.ctrl->done) return;
-    __shared__ double s_md[8];
-    __shared__ int s_ff[8];
-    const int tid = threadIdx.x;
-    const int step = T.ctrl ? T.ctrl->step : 0;
-    double md = 0.0;
-    int ff = 0x7fffffff;
-    for (int n = tid; n < T.N; n += 256) {
-        if (T.p) {
-            // ReachedGoal.m:4-5
-            const double dx = T.p[(size_t)T.ld * n] - T.pf[3 * n];
-            const double dy = T.p[(size_t)T.ld * n + 1] - T.pf[3 * n + 1];
-            const double dz = T.p[(size_t)T.ld * n + 2] - T.pf[3 * n + 2];
-            md = fmax(md, sqrt(dx * dx + dy * dy + dz * dz));
-        }
-        if (T.status && n >= T.n0 && n < T.n1) {
-            const int st = T.status[n];
-            if ((!(st & ST_SOLVED) || (st & ST_OUTBOUND)) && n < ff) ff = n;
-            if (T.status_hist && step < T.S) T.status_hist[(size_t)step * T.N + n] = st;
-        }
-        if (T.traj_p && step < T.S) {
-            const size_t o = 3 * ((size_t)(step + 1) + (size_t)(T.S + 1) * n);
-            for (int x = 0; x < 3; ++x) {
-                T.traj_p[o + x] = T.p1[3 * n + x];
-                T.traj_v[o + x] = T.v1[3 * n + x];
-                T.traj_a[o + x] = T.a1[3 * n + x];
-            }
-        }
-    }
-    for (int o = 16; o; o >>= 1) {
-        md = fmax(md, __shfl_xor_sync(0xffffffffu, md, o));
-        ff = min(ff, __shfl_xor_sync(0xffffffffu, ff, o));
-    }
-    if ((tid & 31) == 0) {
-        s_md[tid >> 5] = md;
-        s_ff[tid >> 5] = ff;
-    }
-    __syncthreads();
-    if (tid == 0) {
-        for (int w = 1; w < 8; ++w) {
-            md = fmax(md, s_md[w]);
-            ff = min(ff, s_ff[w]);
-        }
-        const int reached = (T.p && md < T.goal_tol) ? 1 : 0;
-        if (T.goal_out) {
-            T.goal_out[0] = md;
-            T.goal_out[1] = (double)reached;
-        }
-        if (T.fail_out) *T.fail_out = (ff == 0x7fffffff) ? -1 : ff;
-        if (T.rescue_next) *T.rescue_next = 0;
-        if (T.ctrl) {
-            Ctrl* c = T.ctrl;
-            c->goal_dist = md;
-            if (ff != 0x7fffffff && c->fail_step < 0) {
-                c->fail_step = step;
-                c->fail_agent = ff;
-            }
-            c->step = step + 1;
-            if (reached) {
-                c->reached = 1;
-                c->done = 1;
-            }
-            if (ff != 0x7fffffff && c->stop_on_fail) c->done = 1;
-            if (step + 1 >= c->max_steps) c->done = 1;
-        }
-    }
-}
-
 // ---- initDMPC.m:1-13 for all agents -------------------------------------------------------------
 __global__ void init_kernel(int N, int K, double h, double init_div, const double* __restrict__ po,
                             const double* __restrict__ pf, double* l, double* pk, double* vk, double* ak) {

@@ -15,6 +15,8 @@
 // decisions (dist < rmin, first violating k, neighbour set) are bit-identical to a plain C
 // evaluation of the reference's formula.
 #pragma once
+#include <string.h>
+
 #include "agent_solve.cuh"
 
 namespace dmpc {
@@ -67,7 +69,19 @@ struct ScanThr {
     double Tv_lo, Tv_hi, Tc_lo, Tc_hi;
     double Tn_lo[32], Tn_hi[32];
     double inv_c;
+    // high 32 bits of the exact thresholds, minus 1: decisions on the high word of the estimate
+    // (scan_tile_hw).  he - h*_m (unsigned):  negative -> surely below;  0,1,2 -> ambiguous;  else surely above
+    unsigned hv_m, hc_m, hn_m[32];
 };
+DMPC_HD unsigned hi_word(double v) {
+#if defined(__CUDA_ARCH__)
+    return (unsigned)__double2hiint(v);
+#else
+    unsigned long long b;
+    memcpy(&b, &v, sizeof b);
+    return (unsigned)(b >> 32);
+#endif
+}
 
 inline double sq_threshold(double r) {
     if (!(r > 0.0)) return 0.0;  // dist < r is never true
@@ -92,6 +106,9 @@ inline ScanThr make_scan_thr(const DevParams& P) {
         T.Tn_hi[k] = T.T_near[k] * hi;
     }
     T.inv_c = 1.0 / P.c;
+    T.hv_m = hi_word(T.T_viol) - 1u;
+    T.hc_m = hi_word(T.T_coll) - 1u;
+    for (int k = 0; k < 32; ++k) T.hn_m[k] = hi_word(T.T_near[k]) - 1u;
     return T;
 }
 
@@ -152,6 +169,60 @@ DMPC_D void scan_tile(const DevParams& P, const ScanThr* __restrict__ thr, const
         }
         nearmask[i] = nm;
     }
+}
+
+// Same contract as scan_tile for ONE neighbour per lane (cnt <= kLanes), decisions taken on the HIGH WORD
+// of the FMA estimate of s with integer compares: for positive doubles  s < T  <=>  hi(s) < hi(T)  unless
+// the high words are within 1 of each other -- only then (relative distance to a threshold < 2^-19, and
+// the estimate is good to a few ulp) the pair goes through the reference's exact rounding sequence.  The
+// fp64 pipe sees 7 operations per (neighbour, step); everything else is 32-bit integer work.
+// KT: compile-time horizon (own[] then lives in registers after unrolling); 0 = run-time P.K.
+template <int KT>
+DMPC_D void scan_tile_hw(const DevParams& P, const ScanThr* __restrict__ thr, const double* __restrict__ own, int n,
+                         const double* __restrict__ tile, int ibase, int cnt, unsigned* nearmask, ScanAcc& acc) {
+    const int K = KT ? KT : P.K;
+    const int m = lane_id();
+    const int i = ibase + m;
+    if (m >= cnt) return;
+    unsigned nm = 0;
+    if (i != n) {
+        const double* pj = tile + (size_t)m * 3 * K;
+        const double inv_c = thr->inv_c;
+        const unsigned hv_m = thr->hv_m;
+        unsigned vm = 0, amb = 0, c0 = 0;
+#pragma unroll
+        for (int k = 0; k < K; ++k) {
+            const double dx = own[3 * k] - pj[3 * k];
+            const double dy = own[3 * k + 1] - pj[3 * k + 1];
+            const double ez = (own[3 * k + 2] - pj[3 * k + 2]) * inv_c;
+            const unsigned he = hi_word(fma(ez, ez, fma(dy, dy, dx * dx)));
+            const unsigned xv = he - hv_m, xn = he - thr->hn_m[k];
+            vm |= ((int)xv < 0 ? 1u : 0u) << k;
+            nm |= ((int)xn < 0 ? 1u : 0u) << k;
+            amb |= (xv <= 2u || xn <= 2u) ? 1u : 0u;
+            if (k == 0) {  // rmin - coll_tol test of the first step (solveSoftDMPCbound.m:25)
+                const unsigned xc = he - thr->hc_m;
+                c0 = ((int)xc < 0) ? 1u : 0u;
+                amb |= (xc <= 2u) ? 1u : 0u;
+            }
+        }
+        if (amb) {
+            // some estimate sits next to a threshold: redo this neighbour exactly
+            vm = 0;
+            nm = 0;
+            c0 = 0;
+            for (int k = 0; k < K; ++k) {
+                const double s = ell_sq(own[3 * k] - pj[3 * k], own[3 * k + 1] - pj[3 * k + 1],
+                                        own[3 * k + 2] - pj[3 * k + 2], P.c);
+                if (s < thr->T_viol) vm |= 1u << k;
+                if (s < thr->T_near[k]) nm |= 1u << k;
+                if (k == 0 && s < thr->T_coll) c0 = 1u;
+            }
+        }
+        acc.vmask |= vm;
+        acc.coll0 |= c0;
+    }
+    nearmask[i] = nm;
 }
 
 struct ScanOut {
