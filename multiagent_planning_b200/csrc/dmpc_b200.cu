@@ -146,16 +146,18 @@ StepArgs make_args(dmpcb200_t* h, int n0, int n1, const double* pk, const double
 
 template <int W, int S, int KT>
 cudaError_t launch_scan_w(const StepArgs& A, int nl, int K, cudaStream_t s) {
-    static bool attr_done = false;
-    if (!attr_done) {
-        cudaError_t e =
-            cudaFuncSetAttribute(scan_kernel<W, S, KT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-        if (e != cudaSuccess) return e;
-        attr_done = true;
-    }
-    int stages = scan_stages(K, A.P.N);
+    const int Npad = round_up(A.P.N, kTile);
+    int stages = scan_stages(K, A.P.N, W, A.RMAX);
+    if (stages < 1) return cudaErrorInvalidConfiguration;
     if (stages > S) stages = stages / S * S;  // rounds of S tiles map onto distinct stages
-    scan_kernel<W, S, KT><<<(nl + W - 1) / W, W * S * 32, scan_smem_bytes(K, W, stages), s>>>(A, stages);
+    const size_t smem = scan_smem_bytes(K, W, stages, Npad, A.RMAX);
+    static size_t attr_smem = 0;
+    if (attr_smem < smem) {
+        cudaError_t e = cudaFuncSetAttribute(scan_kernel<W, S, KT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        attr_smem = smem;
+    }
+    scan_kernel<W, S, KT><<<(nl + W - 1) / W, W * S * 32, smem, s>>>(A, stages);
     return cudaGetLastError();
 }
 template <int W, int KT>
@@ -171,22 +173,19 @@ cudaError_t launch_qp_w(const StepArgs& A, int nl, size_t smem, cudaStream_t s) 
     return cudaGetLastError();
 }
 
-// 4 agents x 4 warps per CTA while one wave of CTAs covers the swarm, 8 agents x 2 warps beyond;
-// the reference's horizons (15, 20) are compiled with the horizon as a constant
+// 4 agents x 2 warps per CTA while one wave of CTAs covers the swarm, 8 agents beyond (or fewer when the
+// per-agent near masks of a very large swarm do not fit next to a tile); the reference's horizons
+// (15, 20) are compiled with the horizon as a constant (the own horizon then lives in registers)
 cudaError_t launch_scan(dmpcb200_t* h, const StepArgs& A, cudaStream_t s) {
-    const int nl = A.n1 - A.n0;
-    if (nl <= 4 * 148) {
-        static const int variant = getenv("DMPCB200_SCAN") ? atoi(getenv("DMPCB200_SCAN")) : 0;  // tuning hook
-        if (h->K == 15 && variant == 1) return launch_scan_w<4, 4, 15>(A, nl, h->K, s);
-        if (h->K == 15 && variant == 2) return launch_scan_w<4, 2, 15>(A, nl, h->K, s);
-        if (h->K == 15 && variant == 3) return launch_scan_w<4, 4, 0>(A, nl, h->K, s);
-        if (h->K == 15) return launch_scan_w<4, 3, 15>(A, nl, h->K, s);
-        if (h->K == 20) return launch_scan_w<4, 2, 20>(A, nl, h->K, s);
-        return launch_scan_w<4, 4, 0>(A, nl, h->K, s);
+    const int nl = A.n1 - A.n0, K = h->K, N = h->N;
+    if (nl <= 4 * 148 || scan_stages(K, N, 8, A.RMAX) < 2) {
+        if (scan_stages(K, N, 4, A.RMAX) < 1) return launch_scan_w<1, 2, 0>(A, nl, K, s);
+        if (K == 15) return launch_scan_w<4, 2, 15>(A, nl, K, s);
+        if (K == 20) return launch_scan_w<4, 2, 20>(A, nl, K, s);
+        return launch_scan_w<4, 4, 0>(A, nl, K, s);
     }
-    if (h->K == 15) return launch_scan_w<8, 2, 15>(A, nl, h->K, s);
-    if (h->K == 20) return launch_scan_w<8, 1, 20>(A, nl, h->K, s);
-    return launch_scan_w<8, 2, 0>(A, nl, h->K, s);
+    if (K == 20) return launch_scan_w<8, 1, 20>(A, nl, K, s);
+    return launch_scan_w<8, 2, 0>(A, nl, K, s);
 }
 // horizon lengths 15 and 20 (the reference's configurations) are compiled with the horizon as a
 // compile-time constant (fully unrolled table products); anything else takes the generic kernel
@@ -927,7 +926,7 @@ int dmpcb200_swap_horizons(dmpcb200_t* h) {
 
 /* profiling builds (-DDMPC_PROF) only: cycles[0..15], counts[16..31] of the QP phases; reset after read */
 int dmpcb200_prof_read(uint64_t* out32) {
-#ifdef DMPC_PROF
+#if defined(DMPC_PROF) || defined(DMPC_PROF_SCAN)
     unsigned long long z[32] = {0};
     if (cudaMemcpyFromSymbol(out32, g_prof, sizeof(z)) != cudaSuccess) return DMPCB200_ERR_CUDA;
     if (cudaMemcpyToSymbol(g_prof, z, sizeof(z)) != cudaSuccess) return DMPCB200_ERR_CUDA;
@@ -947,7 +946,10 @@ int dmpcb200_config(dmpcb200_t* h, int32_t* out8) {
     out8[4] = h->QBIG;
     out8[5] = h->n_rescue;
     out8[6] = (int32_t)qp_smem_bytes(h->K, h->W, h->QMAX, h->RCAP);
-    out8[7] = (int32_t)scan_smem_bytes(h->K, (h->NL <= 4 * 148) ? 4 : 8, scan_stages(h->K, h->N));
+    {
+        const int w = (h->NL <= 4 * 148) ? 4 : 8;
+        out8[7] = (int32_t)scan_smem_bytes(h->K, w, std::max(scan_stages(h->K, h->N, w, h->RMAX), 0), h->Npad, h->RMAX);
+    }
     return 0;
 }
 

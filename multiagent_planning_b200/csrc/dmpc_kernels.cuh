@@ -130,26 +130,46 @@ DMPC_HD size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 constexpr int kScanMaxStages = 24;
 // ring depth: as many 32-agent tiles as fit in ~200 KB of shared memory (N = 500, K = 15: the whole
 // neighbour buffer, 16 tiles, is in flight at once; the TMA round trip is paid once, not per tile)
-DMPC_HD int scan_stages(int K, int N) {
+// shared memory of K1 besides the tile ring: own horizons, barriers, partial results, and per agent the
+// near masks of all neighbours (Npad words) and the compaction list of scan_finish (RMAX words)
+DMPC_HD size_t scan_fixed_bytes(int K, int W, int Npad, int RMAX) {
+    return (size_t)W * round_up(3 * K, 2) * sizeof(double) + kScanMaxStages * sizeof(uint64_t) +
+           64 * 2 * sizeof(unsigned) + (size_t)W * ((size_t)Npad + RMAX) * sizeof(unsigned);
+}
+DMPC_HD int scan_stages(int K, int N, int W, int RMAX) {
     const size_t tile_bytes = (size_t)kTile * 3 * K * sizeof(double);
-    int s = (int)((200u * 1024u) / tile_bytes);
     const int ntiles = (N + kTile - 1) / kTile;
+    const size_t fixed = scan_fixed_bytes(K, W, ntiles * kTile, RMAX);
+    const size_t budget = 224u * 1024u;
+    int s = fixed + tile_bytes <= budget ? (int)((budget - fixed) / tile_bytes) : 0;
     if (s > ntiles) s = ntiles;
     if (s > kScanMaxStages) s = kScanMaxStages;
-    return s < 1 ? 1 : s;
+    return s;  // 0: does not fit (the caller picks a smaller W)
 }
-DMPC_HD size_t scan_smem_bytes(int K, int W, int stages) {
-    const int n3 = 3 * K;
-    return (size_t)stages * kTile * n3 * sizeof(double) + (size_t)W * round_up(n3, 2) * sizeof(double) +
-           kScanMaxStages * sizeof(uint64_t) + 64 * 2 * sizeof(unsigned);
+DMPC_HD size_t scan_smem_bytes(int K, int W, int stages, int Npad, int RMAX) {
+    return (size_t)stages * kTile * 3 * K * sizeof(double) + scan_fixed_bytes(K, W, Npad, RMAX);
 }
 
-// W agents per CTA, S warps per agent (each takes every S-th neighbour tile: 4 x the warps of a
-// warp-per-agent layout hide the LDS / fp64 latencies of the distance loop), KT = compile-time horizon
-// (the agent's own horizon then lives in registers) or 0.
+#if defined(DMPC_PROF_SCAN)
+#define SCAN_PROF(i)                                                                           \
+    do {                                                                                       \
+        if ((threadIdx.x & 31) == 0) {                                                         \
+            const unsigned long long d = (unsigned long long)(clock64() - scan_t0);            \
+            atomicMax(&g_prof[i], d);                                                          \
+            atomicAdd(&g_prof[8 + (i)], d);                                                    \
+            atomicAdd(&g_prof[16 + (i)], 1ull);                                                \
+        }                                                                                      \
+    } while (0)
+#else
+#define SCAN_PROF(i)
+#endif
+
 template <int W, int S, int KT>
 __global__ void __launch_bounds__(W * S * 32) scan_kernel(const __grid_constant__ StepArgs A, int stages) {
     if (A.ctrl && A.ctrl->done) return;
+#if defined(DMPC_PROF_SCAN)
+    const long long scan_t0 = clock64();
+#endif
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const int K = KT ? KT : A.P.K, n3 = 3 * K, n3p = round_up(n3, 2), N = A.P.N;
     const int tile_d = kTile * n3;
@@ -158,6 +178,9 @@ __global__ void __launch_bounds__(W * S * 32) scan_kernel(const __grid_constant_
     double* own_all = tiles + (size_t)stages * tile_d;
     uint64_t* bars = reinterpret_cast<uint64_t*>(own_all + W * n3p);
     unsigned* s_acc = reinterpret_cast<unsigned*>(bars + kScanMaxStages);
+    unsigned* nm_all = s_acc + 64 * 2;
+    const int Npad = round_up(N, kTile);
+    int* list_all = reinterpret_cast<int*>(nm_all + (size_t)W * Npad);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int ag = warp / S, sub = warp - ag * S;
     const int li = blockIdx.x * W + ag;
@@ -166,17 +189,22 @@ __global__ void __launch_bounds__(W * S * 32) scan_kernel(const __grid_constant_
     double* own = own_all + ag * n3p;
 
     const int ntma = A.tile_padded ? (N + kTile - 1) / kTile : N / kTile;
+    // every CTA walks the tiles in its own rotation: the CTAs do not all pull the same L2 lines at once
+    const int rot = ntma ? (int)(blockIdx.x % (unsigned)ntma) : 0;
     if (threadIdx.x == 0) {
         for (int b = 0; b < stages; ++b) mbar_init(&bars[b], 1);
         mbar_fence_init();
         for (int t = 0; t < stages && t < ntma; ++t) {
+            int tau = t + rot;
+            tau -= (tau >= ntma) ? ntma : 0;
             mbar_expect_tx(&bars[t], tile_bytes);
-            tma_bulk_g2s(tiles + (size_t)t * tile_d, A.l_prev + (size_t)t * tile_d, tile_bytes, &bars[t]);
+            tma_bulk_g2s(tiles + (size_t)t * tile_d, A.l_prev + (size_t)tau * tile_d, tile_bytes, &bars[t]);
         }
     }
     if (valid && sub == 0)
         for (int i = lane; i < n3; i += 32) own[i] = A.l_prev[(size_t)n * n3 + i];
     __syncthreads();  // barrier init + own horizons visible
+    SCAN_PROF(0);
 
     double ow[KT ? 3 * KT : 1];
     if (KT) {
@@ -185,7 +213,7 @@ __global__ void __launch_bounds__(W * S * 32) scan_kernel(const __grid_constant_
     }
     const double* ownp = KT ? ow : own;
 
-    unsigned* nm = A.nearmask + (size_t)(valid ? li : 0) * A.nm_stride;
+    unsigned* nm = nm_all + (size_t)ag * Npad;
     ScanAcc acc;
     acc.vmask = 0;
     acc.coll0 = 0;
@@ -195,7 +223,9 @@ __global__ void __launch_bounds__(W * S * 32) scan_kernel(const __grid_constant_
         if (t < ntma) {
             const int b = t % stages;
             mbar_wait(&bars[b], (uint32_t)((t / stages) & 1));
-            const int base = t * kTile;
+            int tau = t + rot;
+            tau -= (tau >= ntma) ? ntma : 0;
+            const int base = tau * kTile;
             const int cnt = (N - base < kTile) ? (N - base) : kTile;
             if (valid) scan_tile_hw<KT>(A.P, &A.thr, ownp, n, tiles + (size_t)b * tile_d, base, cnt, nm, acc);
         }
@@ -206,14 +236,17 @@ __global__ void __launch_bounds__(W * S * 32) scan_kernel(const __grid_constant_
                     const int tt = t0 + i;
                     if (tt < ntma && tt + stages < ntma) {
                         const int b = tt % stages;
+                        int tau = tt + stages + rot;
+                        tau -= (tau >= ntma) ? ntma : 0;
                         mbar_expect_tx(&bars[b], tile_bytes);
-                        tma_bulk_g2s(tiles + (size_t)b * tile_d, A.l_prev + (size_t)(tt + stages) * tile_d, tile_bytes,
+                        tma_bulk_g2s(tiles + (size_t)b * tile_d, A.l_prev + (size_t)tau * tile_d, tile_bytes,
                                      &bars[b]);
                     }
                 }
             }
         }
     }
+    SCAN_PROF(1);
     const int rem_base = ntma * kTile;
     if (rem_base < N) {
         // caller-owned buffer without tile padding: the ragged last tile is loaded by the threads
@@ -232,14 +265,18 @@ __global__ void __launch_bounds__(W * S * 32) scan_kernel(const __grid_constant_
         }
     }
     __syncthreads();
+    SCAN_PROF(2);
     if (!valid || sub != 0) return;
 #pragma unroll
     for (int i = 1; i < S; ++i) {
         acc.vmask |= s_acc[2 * (warp + i)];
         acc.coll0 |= s_acc[2 * (warp + i) + 1];
     }
+    // neighbour positions from the resident tiles when the whole buffer is in shared memory
+    const bool resident = !refill && rem_base >= N;
     const ScanOut so = scan_finish(A.P, own, n, A.l_prev, nm, acc, A.RMAX, A.grow + (size_t)li * 5 * A.RMAX,
-                                   A.gkc + (size_t)li * A.RMAX, A.gidx ? A.gidx + (size_t)li * A.RMAX : nullptr);
+                                   A.gkc + (size_t)li * A.RMAX, A.gidx ? A.gidx + (size_t)li * A.RMAX : nullptr,
+                                   list_all + (size_t)ag * A.RMAX, resident ? tiles : nullptr, rot, ntma);
     if (lane == 0) {
         ScanRec r;
         r.kstar = so.kstar;
@@ -248,6 +285,7 @@ __global__ void __launch_bounds__(W * S * 32) scan_kernel(const __grid_constant_
         r.pad = 0;
         A.scan[li] = r;
     }
+    SCAN_PROF(3);
 }
 
 // ---- K3 (defined first: K2 runs it in its last CTA) --------------------------------------------

@@ -50,7 +50,7 @@
 #define DMPC_COLD
 #endif
 
-#if defined(DMPC_PROF) && defined(__CUDACC__)
+#if (defined(DMPC_PROF) || defined(DMPC_PROF_SCAN)) && defined(__CUDACC__)
 // per-phase cycle accounting (profiling builds only): lane 0 of every warp accumulates into g_prof
 __device__ unsigned long long g_prof[32];
 #endif

@@ -25,7 +25,7 @@
 // Capacity: 3K <= 64 entries, <= 64 rows that all act on one horizon index (every variant except
 // solveHardDMPC), <= 64 active constraints.  Anything else is solved by the generic solver.
 //
-// The file compiles for the host with one "lane" that owns all 64 items (tests/host_emul): that
+// The file compiles for the host with one "lane" that owns all 64 items (a test-only build): that
 // build is a debugging aid of the test-suite and is never part of the product library.
 #pragma once
 #include "agent_solve.cuh"

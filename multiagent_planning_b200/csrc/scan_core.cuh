@@ -233,9 +233,15 @@ struct ScanOut {
 
 // Decide the first violating step and emit rows.  l = full horizon buffer (global).
 // grow: d0[RMAX] d1[RMAX] d2[RMAX] dist[RMAX] rhs[RMAX]; gkc, gidx: RMAX ints.
+// list: RMAX ints of scratch (shared memory in the kernel).  Two passes: (A) the near masks are compacted
+// into the ordered list of (step, neighbour) pairs -- ballots and prefix counts only; (B) the rows of the
+// list are computed side by side, one per lane (square root and division of all rows overlap).
+// tiles_s != null: the neighbour horizons are resident in shared memory, tile t (32 neighbours) at
+// tiles_s + ((t - tiles_rot) mod ntiles) * 32 * 3K.
 DMPC_D ScanOut scan_finish(const DevParams& P, const double* __restrict__ own, int n,
                            const double* __restrict__ l, const unsigned* nearmask, ScanAcc acc,
-                           int RMAX, double* grow, int* gkc, int* gidx) {
+                           int RMAX, double* grow, int* gkc, int* gidx, int* list,
+                           const double* tiles_s = nullptr, int tiles_rot = 0, int ntiles = 0) {
     const int K = P.K, N = P.N;
     ScanOut o;
     o.kstar = 0;
@@ -269,39 +275,49 @@ DMPC_D ScanOut scan_finish(const DevParams& P, const double* __restrict__ own, i
         o.kstar = ks + 1;
         kfirst = klast = ks;
     }
+    // (A) ordered compaction: rows in ascending neighbour order within a step (the reference's row order)
     int nv = 0;
-    bool ovf = false;
     for (int k = kfirst; k <= klast; ++k) {
-        const double px = own[3 * k], py = own[3 * k + 1], pz = own[3 * k + 2];
         for (int base = 0; base < N; base += kLanes) {
             const int i = base + lane_id();
             const bool hit = (i < N) && ((nearmask[i] >> k) & 1u);
             const unsigned bal = wballot(hit);
             if (hit) {
                 const int slot = nv + popc_below(bal);
-                if (slot < RMAX) {
-                    const double* pj = l + 3 * ((size_t)k + (size_t)K * i);
-                    const double dx = px - pj[0], dy = py - pj[1], dz = pz - pj[2];
-                    const double dist = ell_dist(dx, dy, dz, P.c);
-                    const double d0 = dx, d1 = dy, d2 = dz / c2;  // diff = E2 (p - pj)
-                    const double dp = d0 * px + d1 * py + d2 * pz;
-                    grow[slot] = d0;
-                    grow[(size_t)RMAX + slot] = d1;
-                    grow[2 * (size_t)RMAX + slot] = d2;
-                    grow[3 * (size_t)RMAX + slot] = dist;
-                    grow[4 * (size_t)RMAX + slot] = dist * ((P.rmin - dist) + dp / dist);
-                    gkc[slot] = k - kshift;
-                    if (gidx) gidx[slot] = i;
-                } else {
-                    ovf = true;
-                }
+                if (slot < RMAX) list[slot] = (k << 26) | i;
             }
             nv += popc_all(bal);
         }
     }
-    if (wballot(ovf) || nv > RMAX) {
+    if (nv > RMAX) {
         o.flag = ST_QPFAIL | ST_OVERFLOW;
         nv = RMAX;
+    }
+    wsync();
+    // (B) the rows
+    for (int e = lane_id(); e < nv; e += kLanes) {
+        const int code = list[e];
+        const int k = code >> 26, i = code & 0x3ffffff;
+        const double px = own[3 * k], py = own[3 * k + 1], pz = own[3 * k + 2];
+        const double* pj;
+        if (tiles_s) {
+            int st = (i / 32) - tiles_rot;
+            st += (st < 0) ? ntiles : 0;
+            pj = tiles_s + ((size_t)st * 32 + (i & 31)) * 3 * K + 3 * k;
+        } else {
+            pj = l + 3 * ((size_t)k + (size_t)K * i);
+        }
+        const double dx = px - pj[0], dy = py - pj[1], dz = pz - pj[2];
+        const double dist = ell_dist(dx, dy, dz, P.c);
+        const double d0 = dx, d1 = dy, d2 = dz / c2;  // diff = E2 (p - pj)
+        const double dp = d0 * px + d1 * py + d2 * pz;
+        grow[e] = d0;
+        grow[(size_t)RMAX + e] = d1;
+        grow[2 * (size_t)RMAX + e] = d2;
+        grow[3 * (size_t)RMAX + e] = dist;
+        grow[4 * (size_t)RMAX + e] = dist * ((P.rmin - dist) + dp / dist);
+        gkc[e] = k - kshift;
+        if (gidx) gidx[e] = i;
     }
     o.nv = nv;
     if (P.variant == VAR_HARD) o.kstar = nv ? 1 : 0;

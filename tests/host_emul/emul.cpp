@@ -46,15 +46,19 @@ extern "C" int emul_step(const dmpcb200_params* p, int N, int n0, int n1, const 
     const ScanThr thr = make_scan_thr(D);
     std::vector<unsigned> nearmask(N);
     std::vector<double> grow(5 * (size_t)RMAX), gscr_d(4 * (size_t)RMAX);
-    std::vector<int> gkc(RMAX), gidx(RMAX), gscr_i(4 * (size_t)RMAX);
+    std::vector<int> gkc(RMAX), gidx(RMAX), gscr_i(4 * (size_t)RMAX), list(RMAX);
     for (int n = n0; n < n1; ++n) {
         const double* own = l_prev + (size_t)3 * K * n;
         ScanAcc acc;
         acc.vmask = 0;
         acc.coll0 = 0;
-        scan_tile(D, &thr, own, n, l_prev, 0, N, nearmask.data(), acc);
+        if (fast)  // the kernel's tile function: one neighbour per lane, decisions on the high word
+            for (int i = 0; i < N; ++i)
+                scan_tile_hw<0>(D, &thr, own, n, l_prev + (size_t)3 * K * i, i, 1, nearmask.data(), acc);
+        else
+            scan_tile(D, &thr, own, n, l_prev, 0, N, nearmask.data(), acc);
         ScanOut so = scan_finish(D, own, n, l_prev, nearmask.data(), acc, RMAX, grow.data(), gkc.data(),
-                                 gidx.data());
+                                 gidx.data(), list.data());
         AgentIO io;
         io.po = pk + 3 * n; io.pf = pf + 3 * n; io.vo = vk + 3 * n; io.ao = ak + 3 * n;
         io.kstar = so.kstar; io.nv = so.nv; io.scanflag = so.flag; io.RMAX = RMAX;
