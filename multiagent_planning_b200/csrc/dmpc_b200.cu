@@ -180,6 +180,9 @@ cudaError_t launch_scan(dmpcb200_t* h, const StepArgs& A, cudaStream_t s) {
     const int nl = A.n1 - A.n0, K = h->K, N = h->N;
     if (nl <= 4 * 148 || scan_stages(K, N, 8, A.RMAX) < 2) {
         if (scan_stages(K, N, 4, A.RMAX) < 1) return launch_scan_w<1, 2, 0>(A, nl, K, s);
+        static const int variant = getenv("DMPCB200_SCAN") ? atoi(getenv("DMPCB200_SCAN")) : 0;  // tuning hook
+        if (variant == 1) return launch_scan_w<8, 2, 0>(A, nl, K, s);
+        if (variant == 2) return launch_scan_w<4, 4, 0>(A, nl, K, s);
         if (K == 15) return launch_scan_w<4, 2, 15>(A, nl, K, s);
         if (K == 20) return launch_scan_w<4, 2, 20>(A, nl, K, s);
         return launch_scan_w<4, 4, 0>(A, nl, K, s);

@@ -169,6 +169,7 @@ __global__ void __launch_bounds__(W * S * 32) scan_kernel(const __grid_constant_
     if (A.ctrl && A.ctrl->done) return;
 #if defined(DMPC_PROF_SCAN)
     const long long scan_t0 = clock64();
+    long long scan_wait = 0;
 #endif
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const int K = KT ? KT : A.P.K, n3 = 3 * K, n3p = round_up(n3, 2), N = A.P.N;
@@ -222,7 +223,13 @@ __global__ void __launch_bounds__(W * S * 32) scan_kernel(const __grid_constant_
         const int t = t0 + sub;
         if (t < ntma) {
             const int b = t % stages;
+#if defined(DMPC_PROF_SCAN)
+            const long long w0 = clock64();
+#endif
             mbar_wait(&bars[b], (uint32_t)((t / stages) & 1));
+#if defined(DMPC_PROF_SCAN)
+            scan_wait += clock64() - w0;
+#endif
             int tau = t + rot;
             tau -= (tau >= ntma) ? ntma : 0;
             const int base = tau * kTile;
@@ -247,6 +254,13 @@ __global__ void __launch_bounds__(W * S * 32) scan_kernel(const __grid_constant_
         }
     }
     SCAN_PROF(1);
+#if defined(DMPC_PROF_SCAN)
+    if ((threadIdx.x & 31) == 0) {
+        atomicMax(&g_prof[4], (unsigned long long)scan_wait);
+        atomicAdd(&g_prof[12], (unsigned long long)scan_wait);
+        atomicAdd(&g_prof[20], 1ull);
+    }
+#endif
     const int rem_base = ntma * kTile;
     if (rem_base < N) {
         // caller-owned buffer without tile padding: the ragged last tile is loaded by the threads

@@ -11,7 +11,7 @@ L = _lib.lib()
 cfg = scenarios.config(sys.argv[1] if len(sys.argv) > 1 else "C3")
 steps = int(sys.argv[2]) if len(sys.argv) > 2 else 12
 P = dmpc.default_params(cfg["variant"], **cfg["params"])
-names = ["setup (barriers, TMA issue, own)", "tile loop", "combine barrier", "scan_finish (rows)"]
+names = ["setup (barriers, TMA issue, own)", "tile loop", "combine barrier", "scan_finish (rows)", "of which mbarrier wait"]
 with dmpc.Solver(cfg["N"], P, pmin=cfg["pmin"], pmax=cfg["pmax"], pf=cfg["pf"]) as s:
     s.init_horizons(cfg["po"])
     out = (C.c_uint64 * 32)()
@@ -22,4 +22,4 @@ with dmpc.Solver(cfg["N"], P, pmin=cfg["pmin"], pmax=cfg["pmax"], pf=cfg["pf"]) 
         L.dmpcb200_prof_read(out)
         o = np.array(out[:], dtype=np.float64)
         print("step %2d  " % k + "  ".join("%s: max %6.0f mean %6.0f" % (names[i].split(" (")[0], o[i], o[8 + i] / max(o[16 + i], 1))
-                                          for i in range(4)), " timing", s.last_timing()["scan_ms"])
+                                          for i in range(5)), " timing", s.last_timing()["scan_ms"])
