@@ -200,6 +200,11 @@ int dmpcb200_prop_state(dmpcb200_t* h, int B, const double* po, const double* vo
  * the steps of the call; launches[0] = number of kernels launched. */
 int dmpcb200_last_timing(dmpcb200_t* h, double* ms, int64_t* launches);
 
+/* host-side phases of the last dmpcb200_step, microseconds: us4[0] pack the inputs into the pinned staging
+ * block, us4[1] submit (one H2D copy, two kernels, one D2H copy), us4[2] wait for the stream, us4[3] hand the
+ * rows to the caller's arrays. */
+int dmpcb200_last_host_timing(dmpcb200_t* h, double* us4);
+
 /* raw device pointers of the handle's resident state (for host frameworks that own streams):
  * which: 0 l_cur, 1 l_next, 2 pk, 3 vk, 4 ak, 5 pf, 6 status, 7 goal_out(2 doubles),
  *        8 pk_next, 9 vk_next, 10 ak_next, 11 diag */

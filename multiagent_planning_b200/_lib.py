@@ -107,6 +107,7 @@ def lib():
         "dmpcb200_coll_constr": ([vp, dp, dp, dp, I, I, dp, u8p, I, dp, dp, dp, ip], I),
         "dmpcb200_prop_state": ([vp, I, dp, dp, dp, dp, dp], I),
         "dmpcb200_last_timing": ([vp, dp, C.POINTER(C.c_int64)], I),
+        "dmpcb200_last_host_timing": ([vp, dp], I),
         "dmpcb200_device_ptr": ([vp, I], vp),
         "dmpcb200_swap_horizons": ([vp], I),
         "dmpcb200_config": ([vp, ip], I),
@@ -125,7 +126,8 @@ EXPORTS = [
     "dmpcb200_model_mats", "dmpcb200_create", "dmpcb200_destroy", "dmpcb200_set_bounds", "dmpcb200_set_goals",
     "dmpcb200_init_horizons", "dmpcb200_step", "dmpcb200_step_dev", "dmpcb200_goal_dev", "dmpcb200_reached_goal", "dmpcb200_run",
     "dmpcb200_get_state", "dmpcb200_set_state", "dmpcb200_solve_agent", "dmpcb200_check_coll",
-    "dmpcb200_coll_constr", "dmpcb200_prop_state", "dmpcb200_last_timing", "dmpcb200_device_ptr",
+    "dmpcb200_coll_constr", "dmpcb200_prop_state", "dmpcb200_last_timing", "dmpcb200_last_host_timing",
+    "dmpcb200_device_ptr",
     "dmpcb200_swap_horizons", "dmpcb200_config",
 ]
 

@@ -6,6 +6,7 @@
 #include <algorithm>
 #include <cstdio>
 #include <cstdlib>
+#include <chrono>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -52,6 +53,12 @@ struct dmpcb200_handle {
     cudaStream_t stream = nullptr;
     // resident state
     double* d_tab = nullptr;
+    // resident state lives in ONE arena so that the host step moves it with one copy per direction:
+    //   side b: [ l (Npad*3K) | pk | vk | ak ]   then   [ status | diag | first_fail ]
+    unsigned char* d_arena = nullptr;
+    size_t side_bytes = 0, tailblk_bytes = 0;
+    unsigned char* h_stage = nullptr;  // pinned + mapped: one input side + one output side + tail block
+    unsigned char* d_stage = nullptr;  // device alias of h_stage (the QP kernel writes the outputs of a host step there)
     double* d_l[2] = {nullptr, nullptr};
     double* d_st[2][3] = {{nullptr, nullptr, nullptr}, {nullptr, nullptr, nullptr}};  // pk, vk, ak ping-pong
     double* d_pf = nullptr;
@@ -88,6 +95,7 @@ struct dmpcb200_handle {
     // timing
     std::vector<cudaEvent_t> ev;
     double t_ms[3] = {0, 0, 0};
+    double t_host_us[4] = {0, 0, 0, 0};  // host step: pack, submit, wait, unpack
     int64_t launches = 0;
     bool have_bounds = false, have_goals = false, have_init = false;
 };
@@ -225,6 +233,9 @@ TailArgs make_tail(dmpcb200_t* h, const double* p, int ld, const int* status, co
     T.fail_out = h->d_fail;
     T.rescue_next = h->d_rescue_next;
     T.ctrl = ctrl;
+    T.copy_src = nullptr;
+    T.copy_dst = nullptr;
+    T.copy_bytes = 0;
     return T;
 }
 
@@ -402,17 +413,35 @@ int dmpcb200_create(const dmpcb200_params* p, int N, int n0, int n1, int device,
     if ((e = dalloc(&h->d_tab, tab.size())) != cudaSuccess) return bail(e, "tables");
     if ((e = cudaMemcpy(h->d_tab, tab.data(), tab.size() * sizeof(double), cudaMemcpyHostToDevice)) != cudaSuccess)
         return bail(e, "tables copy");
-    const size_t lN = (size_t)h->Npad * n3;
-    for (int b = 0; b < 2; ++b) {
-        if ((e = dalloc(&h->d_l[b], lN)) != cudaSuccess) return bail(e, "horizons");
-        for (int s = 0; s < 3; ++s)
-            if ((e = dalloc(&h->d_st[b][s], 3 * (size_t)N)) != cudaSuccess) return bail(e, "state");
+    {
+        const size_t lB = align_up((size_t)h->Npad * n3 * sizeof(double), 256);
+        const size_t sB = align_up(3 * (size_t)N * sizeof(double), 256);
+        h->side_bytes = lB + 3 * sB;
+        const size_t stB = align_up((size_t)N * sizeof(int), 256), dgB = align_up((size_t)N * sizeof(AgentDiag), 256);
+        h->tailblk_bytes = stB + dgB + 256;
+        const size_t total = 2 * h->side_bytes + h->tailblk_bytes;
+        if ((e = cudaMalloc((void**)&h->d_arena, total)) != cudaSuccess) return bail(e, "state arena");
+        if ((e = cudaMemset(h->d_arena, 0, total)) != cudaSuccess) return bail(e, "state arena");
+        unsigned char* s0 = h->d_arena;
+        unsigned char* s1 = h->d_arena + h->side_bytes;
+        unsigned char* tb = h->d_arena + 2 * h->side_bytes;
+        unsigned char* sides[2] = {s0, s1};
+        for (int b = 0; b < 2; ++b) {
+            h->d_l[b] = reinterpret_cast<double*>(sides[b]);
+            for (int q = 0; q < 3; ++q) h->d_st[b][q] = reinterpret_cast<double*>(sides[b] + lB + q * sB);
+        }
+        h->d_status = reinterpret_cast<int*>(tb);
+        h->d_diag = reinterpret_cast<AgentDiag*>(tb + stB);
+        h->d_fail = reinterpret_cast<int*>(tb + stB + dgB);
+        if ((e = cudaHostAlloc((void**)&h->h_stage, 2 * h->side_bytes + h->tailblk_bytes, cudaHostAllocMapped)) !=
+            cudaSuccess)
+            return bail(e, "pinned staging");
+        if ((e = cudaHostGetDevicePointer((void**)&h->d_stage, h->h_stage, 0)) != cudaSuccess)
+            return bail(e, "pinned staging (device alias)");
     }
     if ((e = dalloc(&h->d_pf, 3 * (size_t)N)) != cudaSuccess) return bail(e, "goals");
     if ((e = dalloc(&h->d_vhor, (size_t)N * n3)) != cudaSuccess) return bail(e, "v_hor");
     if ((e = dalloc(&h->d_ahor, (size_t)N * n3)) != cudaSuccess) return bail(e, "a_hor");
-    if ((e = dalloc(&h->d_status, (size_t)N)) != cudaSuccess) return bail(e, "status");
-    if ((e = dalloc(&h->d_diag, (size_t)N)) != cudaSuccess) return bail(e, "diag");
     const size_t NL = h->NL;
     if ((e = dalloc(&h->d_nearmask, NL * h->Npad)) != cudaSuccess) return bail(e, "nearmask");
     if ((e = dalloc(&h->d_scan, NL)) != cudaSuccess) return bail(e, "scan");
@@ -426,7 +455,6 @@ int dmpcb200_create(const dmpcb200_params* p, int N, int n0, int n1, int device,
     if ((e = dalloc(&h->d_done, 1)) != cudaSuccess) return bail(e, "done counter");
     if ((e = dalloc(&h->d_ctrl, 1)) != cudaSuccess) return bail(e, "ctrl");
     if ((e = dalloc(&h->d_goal, 2)) != cudaSuccess) return bail(e, "goal");
-    if ((e = dalloc(&h->d_fail, 1)) != cudaSuccess) return bail(e, "fail");
     if ((e = dalloc(&h->d_u8, 2 * (size_t)N)) != cudaSuccess) return bail(e, "u8");
     if ((e = dalloc(&h->d_small, 64)) != cudaSuccess) return bail(e, "small");
     if ((e = dalloc(&h->d_ismall, 16)) != cudaSuccess) return bail(e, "ismall");
@@ -441,14 +469,12 @@ void dmpcb200_destroy(dmpcb200_t* h) {
     drop_graph(h);
     for (auto e : h->ev) cudaEventDestroy(e);
     cudaFree(h->d_tab);
-    for (int b = 0; b < 2; ++b) {
-        cudaFree(h->d_l[b]);
-        for (int s = 0; s < 3; ++s) cudaFree(h->d_st[b][s]);
-    }
-    cudaFree(h->d_pf); cudaFree(h->d_vhor); cudaFree(h->d_ahor); cudaFree(h->d_status); cudaFree(h->d_diag);
+    cudaFree(h->d_arena);
+    if (h->h_stage) cudaFreeHost(h->h_stage);
+    cudaFree(h->d_pf); cudaFree(h->d_vhor); cudaFree(h->d_ahor);
     cudaFree(h->d_nearmask); cudaFree(h->d_scan); cudaFree(h->d_grow); cudaFree(h->d_gkc); cudaFree(h->d_gidx);
     cudaFree(h->d_gscr_d); cudaFree(h->d_gscr_i); cudaFree(h->d_rescue); cudaFree(h->d_rescue_next);
-    cudaFree(h->d_done); cudaFree(h->d_ctrl); cudaFree(h->d_goal); cudaFree(h->d_fail); cudaFree(h->d_u8); cudaFree(h->d_small);
+    cudaFree(h->d_done); cudaFree(h->d_ctrl); cudaFree(h->d_goal); cudaFree(h->d_u8); cudaFree(h->d_small);
     cudaFree(h->d_ismall);
     for (int s = 0; s < 3; ++s) cudaFree(h->d_traj[s]);
     cudaFree(h->d_hist);
@@ -566,15 +592,33 @@ int dmpcb200_step(dmpcb200_t* h, const double* pk, const double* vk, const doubl
     cudaStream_t s = h->stream;
     const size_t sN = 3 * (size_t)N * sizeof(double), lB = (size_t)N * n3 * sizeof(double);
     const int c = 0, nx = 1;
-    CK(cudaMemcpyAsync(h->d_st[c][0], pk, sN, cudaMemcpyHostToDevice, s));
-    CK(cudaMemcpyAsync(h->d_st[c][1], vk, sN, cudaMemcpyHostToDevice, s));
-    CK(cudaMemcpyAsync(h->d_st[c][2], ak, sN, cudaMemcpyHostToDevice, s));
-    CK(cudaMemcpyAsync(h->d_l[c], l_prev, lB, cudaMemcpyHostToDevice, s));
+    // inputs: packed into the pinned staging block in the arena's layout, ONE host-to-device copy
+    unsigned char* hs_in = h->h_stage;
+    unsigned char* hs_out = h->h_stage + h->side_bytes;  // side 1 followed by the tail block, like the arena
+    const size_t off_st[3] = {(size_t)((unsigned char*)h->d_st[c][0] - (unsigned char*)h->d_l[c]),
+                              (size_t)((unsigned char*)h->d_st[c][1] - (unsigned char*)h->d_l[c]),
+                              (size_t)((unsigned char*)h->d_st[c][2] - (unsigned char*)h->d_l[c])};
+    const auto tp0 = std::chrono::steady_clock::now();
+    std::memcpy(hs_in, l_prev, lB);
+    std::memcpy(hs_in + off_st[0], pk, sN);
+    std::memcpy(hs_in + off_st[1], vk, sN);
+    std::memcpy(hs_in + off_st[2], ak, sN);
+    const auto tp1 = std::chrono::steady_clock::now();
+    CK(cudaMemcpyAsync(h->d_l[c], hs_in, h->side_bytes, cudaMemcpyHostToDevice, s));
     if (int rc = ensure_events(h, 4)) return rc;
-    StepArgs A = make_args(h, h->n0, h->n1, h->d_st[c][0], h->d_st[c][1], h->d_st[c][2], h->d_l[c], h->d_l[nx],
-                           h->d_st[nx][0], h->d_st[nx][1], h->d_st[nx][2], (v_hor ? h->d_vhor : nullptr),
-                           (a_hor ? h->d_ahor : nullptr), h->d_status, h->d_diag, true, nullptr);
+    // outputs: the QP kernel writes the new horizons and states STRAIGHT into the mapped pinned block (posted
+    // writes over PCIe as each agent finishes, overlapped with the rest of the kernel); the last CTA adds
+    // status | diag | first_fail after the tail.  No device-to-host copy is queued at all.
+    unsigned char* ds_out = h->d_stage + h->side_bytes;
+    StepArgs A = make_args(h, h->n0, h->n1, h->d_st[c][0], h->d_st[c][1], h->d_st[c][2], h->d_l[c],
+                           reinterpret_cast<double*>(ds_out), reinterpret_cast<double*>(ds_out + off_st[0]),
+                           reinterpret_cast<double*>(ds_out + off_st[1]), reinterpret_cast<double*>(ds_out + off_st[2]),
+                           (v_hor ? h->d_vhor : nullptr), (a_hor ? h->d_ahor : nullptr), h->d_status, h->d_diag, true,
+                           nullptr);
     A.T = make_tail(h, nullptr, 3, h->d_status, nullptr, nullptr, nullptr, false, nullptr);
+    A.T.copy_src = reinterpret_cast<const unsigned char*>(h->d_status);
+    A.T.copy_dst = ds_out + h->side_bytes;
+    A.T.copy_bytes = h->tailblk_bytes;
     A.fuse_tail = 1;  // first failing agent + rescue-slot reset in the last CTA of the QP kernel
     CK(cudaEventRecord(h->ev[0], s));
     CK(launch_scan(h, A, s));
@@ -582,21 +626,33 @@ int dmpcb200_step(dmpcb200_t* h, const double* pk, const double* vk, const doubl
     CK(launch_qp(h, A, s));
     CK(cudaEventRecord(h->ev[2], s));
     CK(cudaEventRecord(h->ev[3], s));
-    // outputs: only the rows of agents n0..n1-1
     const size_t o3 = 3 * (size_t)n0, b3 = 3 * (size_t)NL * sizeof(double);
     const size_t oL = (size_t)n0 * n3, bL = (size_t)NL * n3 * sizeof(double);
-    if (l_new) CK(cudaMemcpyAsync(l_new + oL, h->d_l[nx] + oL, bL, cudaMemcpyDeviceToHost, s));
-    if (p1) CK(cudaMemcpyAsync(p1 + o3, h->d_st[nx][0] + o3, b3, cudaMemcpyDeviceToHost, s));
-    if (v1) CK(cudaMemcpyAsync(v1 + o3, h->d_st[nx][1] + o3, b3, cudaMemcpyDeviceToHost, s));
-    if (a1) CK(cudaMemcpyAsync(a1 + o3, h->d_st[nx][2] + o3, b3, cudaMemcpyDeviceToHost, s));
     if (v_hor) CK(cudaMemcpyAsync(v_hor + oL, h->d_vhor + oL, bL, cudaMemcpyDeviceToHost, s));
     if (a_hor) CK(cudaMemcpyAsync(a_hor + oL, h->d_ahor + oL, bL, cudaMemcpyDeviceToHost, s));
-    if (status) CK(cudaMemcpyAsync(status + n0, h->d_status + n0, (size_t)NL * sizeof(int), cudaMemcpyDeviceToHost, s));
-    if (diag) CK(cudaMemcpyAsync(diag + n0, h->d_diag + n0, (size_t)NL * sizeof(AgentDiag), cudaMemcpyDeviceToHost, s));
-    int ff = -1;
-    CK(cudaMemcpyAsync(&ff, h->d_fail, sizeof(int), cudaMemcpyDeviceToHost, s));
+    const auto tp2 = std::chrono::steady_clock::now();
     CK(cudaStreamSynchronize(s));
-    if (first_fail) *first_fail = ff;
+    const auto tp3 = std::chrono::steady_clock::now();
+    {
+        const unsigned char* tb = hs_out + h->side_bytes;
+        const size_t stB = (size_t)((unsigned char*)h->d_diag - (unsigned char*)h->d_status);
+        const size_t dgB = (size_t)((unsigned char*)h->d_fail - (unsigned char*)h->d_diag);
+        if (l_new) std::memcpy(l_new + oL, reinterpret_cast<const double*>(hs_out) + oL, bL);
+        if (p1) std::memcpy(p1 + o3, reinterpret_cast<const double*>(hs_out + off_st[0]) + o3, b3);
+        if (v1) std::memcpy(v1 + o3, reinterpret_cast<const double*>(hs_out + off_st[1]) + o3, b3);
+        if (a1) std::memcpy(a1 + o3, reinterpret_cast<const double*>(hs_out + off_st[2]) + o3, b3);
+        if (status) std::memcpy(status + n0, reinterpret_cast<const int*>(tb) + n0, (size_t)NL * sizeof(int));
+        if (diag) std::memcpy(diag + n0, reinterpret_cast<const AgentDiag*>(tb + stB) + n0, (size_t)NL * sizeof(AgentDiag));
+        if (first_fail) *first_fail = *reinterpret_cast<const int*>(tb + stB + dgB);
+    }
+    {
+        const auto tp4 = std::chrono::steady_clock::now();
+        auto us = [](auto a, auto b) { return std::chrono::duration<double, std::micro>(b - a).count(); };
+        h->t_host_us[0] = us(tp0, tp1);
+        h->t_host_us[1] = us(tp1, tp2);
+        h->t_host_us[2] = us(tp2, tp3);
+        h->t_host_us[3] = us(tp3, tp4);
+    }
     float a = 0, b = 0, w = 0;
     cudaEventElapsedTime(&a, h->ev[0], h->ev[1]);
     cudaEventElapsedTime(&b, h->ev[1], h->ev[2]);
@@ -891,6 +947,13 @@ int dmpcb200_prop_state(dmpcb200_t* h, int B, const double* po, const double* vo
     CK(cudaFreeAsync(d, s));
     CK(cudaStreamSynchronize(s));
     h->launches = 1;
+    return 0;
+}
+
+/* host-side phases of the last dmpcb200_step in microseconds: pack, submit, wait, unpack */
+int dmpcb200_last_host_timing(dmpcb200_t* h, double* us4) {
+    if (!h || !us4) return fail(DMPCB200_ERR_ARG, "last_host_timing: null argument");
+    for (int i = 0; i < 4; ++i) us4[i] = h->t_host_us[i];
     return 0;
 }
 

@@ -57,6 +57,10 @@ struct TailArgs {
     int* fail_out;     // first failing agent or -1
     int* rescue_next;
     Ctrl* ctrl;  // optional
+    // optional: after the tail, copy a block (status | diag | first_fail) to mapped host memory
+    const unsigned char* copy_src;
+    unsigned char* copy_dst;
+    size_t copy_bytes;  // multiple of 16
 };
 
 struct StepArgs {
@@ -371,6 +375,12 @@ __device__ __forceinline__ void tail_body(const TailArgs& T) {
             if (ff != 0x7fffffff && c->stop_on_fail) c->done = 1;
             if (step + 1 >= c->max_steps) c->done = 1;
         }
+    }
+    if (T.copy_bytes) {
+        __syncthreads();  // first_fail is written
+        const int4* src = reinterpret_cast<const int4*>(T.copy_src);
+        int4* dst = reinterpret_cast<int4*>(T.copy_dst);
+        for (size_t i = tid; i < T.copy_bytes / 16; i += NT) dst[i] = __ldcg(src + i);
     }
 }
 

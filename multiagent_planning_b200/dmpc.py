@@ -34,6 +34,9 @@ _u8p = C.POINTER(C.c_uint8)
 
 
 def _f(a, shape=None):
+    if (isinstance(a, np.ndarray) and a.dtype == np.float64 and a.flags.f_contiguous
+            and (shape is None or a.shape == shape)):
+        return a  # already in the library's layout: no copy, no new object
     a = np.asfortranarray(np.asarray(a, dtype=np.float64))
     if shape is not None:
         a = np.asfortranarray(a.reshape(shape, order="F"))
@@ -133,6 +136,30 @@ class Solver:
         out["first_fail"] = int(ff.value)
         return out
 
+    def bind_step(self, pk, vk, ak, l_prev, out):
+        """Pre-marshal one set of caller-owned HOST arrays (float64, column-major; `out` as returned by
+        `step`) and return a zero-argument callable that runs `dmpcb200_step` on them -- what a tight
+        closed loop over preallocated (pinned) buffers uses instead of re-deriving the pointers every step.
+        Returns first_fail."""
+        N, K = self.N, self.K
+        for a, shp in ((pk, (3, N)), (vk, (3, N)), (ak, (3, N)), (l_prev, (3, K, N)), (out["l_new"], (3, K, N)),
+                       (out["p1"], (3, N)), (out["v1"], (3, N)), (out["a1"], (3, N))):
+            if not (isinstance(a, np.ndarray) and a.dtype == np.float64 and a.flags.f_contiguous and a.shape == shp):
+                raise DmpcError("bind_step: arrays must be float64, column-major, of the documented shapes")
+        ff = C.c_int32(-1)
+        args = (self.h, _p(pk), _p(vk), _p(ak), _p(l_prev), _p(out["l_new"]), _p(out["p1"]), _p(out["v1"]),
+                _p(out["a1"]), _p(out.get("v_hor")), _p(out.get("a_hor")), out["status"].ctypes.data_as(_ip),
+                out["diag"].ctypes.data_as(C.POINTER(Diag)), C.byref(ff))
+        fn, chk = self.L.dmpcb200_step, _lib.check
+        keep = (pk, vk, ak, l_prev, out)  # the arrays stay alive as long as the binding does
+
+        def call(_keep=keep):
+            rc = fn(*args)
+            if rc:
+                chk(rc, "step")
+            return ff.value
+        return call
+
     def step_dev(self, d_pk, d_vk, d_ak, d_l_prev, d_l_new, d_p1, d_v1, d_a1, d_status, stream=0,
                  d_v_hor=0, d_a_hor=0, d_diag=0):
         """Same step on raw DEVICE pointers (ints), asynchronous on `stream` (cudaStream_t as int)."""
@@ -176,6 +203,12 @@ class Solver:
         if hist is not None:
             res["status_hist"] = hist[:s]
         return res
+
+    def last_host_timing(self):
+        """host-side phases of the last `step` in microseconds"""
+        us = (C.c_double * 4)()
+        _lib.check(self.L.dmpcb200_last_host_timing(self.h, us), "last_host_timing")
+        return dict(pack_us=us[0], submit_us=us[1], wait_us=us[2], unpack_us=us[3])
 
     def get_state(self):
         N, K = self.N, self.K
