@@ -422,6 +422,9 @@ __global__ void __launch_bounds__(W * 32, 1) qp_kernel(const __grid_constant__ S
     const int li = blockIdx.x * W + warp;
     const int n = A.n0 + li;
     if (n < A.n1) {
+#if defined(DMPC_PROF_AGENT)
+    const long long agent_t0 = clock64();
+#endif
     const ScanRec sr = A.scan[li];
     AgentIO io;
     io.po = A.pk + 3 * n;
@@ -479,6 +482,9 @@ __global__ void __launch_bounds__(W * 32, 1) qp_kernel(const __grid_constant__ S
         rescue = true;
         it0 = dg.iters;
     }
+#if defined(DMPC_PROF_AGENT)
+    dg.nact = (int)((clock64() - agent_t0) >> 4);  // profiling build: cycles / 16 of this agent's solve
+#endif
     if (lane == 0) {
         A.status[n] = st;
         if (A.diag) A.diag[n] = dg;

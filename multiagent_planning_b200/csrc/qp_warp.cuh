@@ -548,9 +548,7 @@ struct QpW {
     }
 
     // ---- primal direction z = H^{-1}(n_p - N r), Lz, zeps; returns delta = z'Hz ----------------------
-    DMPC_D double direction(const PInfo& p) {
-        coefs();
-        apply(z, L, nullptr, nullptr, -1.0, &p);
+    DMPC_D double direction_finish(const PInfo& p) {
         QW_FOR(h) {
             const int i = qw_item(h);
             if (h * kLanes < n3) {  // uniform; entries beyond n3 of a half in use land in the padding
@@ -719,7 +717,7 @@ struct QpW {
             }
             mx = wmax(mx);
             wsync();
-            if (!(mx > 1e-13)) break;
+            if (!(mx > 1e-11)) break;
             mat_vec<false>(q, nullptr);
             QW_FOR(h) u[h] -= r[h];
         }
@@ -920,6 +918,28 @@ struct QpW {
         rows_refresh();
     }
 
+    // ---- drop the active constraints with a negative multiplier, most negative first (rank-1 updates of u
+    //      and M), until u >= 0.  Returns the number of drops. ----------------------------------------------
+    DMPC_COLD int drop_negative() {
+        int nd = 0;
+        for (;;) {
+            double neg = 0.0;
+            int l = -1;
+            QW_FOR(h) {
+                const int s = qw_item(h);
+                if (s < q && u[h] < 0.0 && (l < 0 || -u[h] > neg)) { neg = -u[h]; l = s; }
+            }
+            const int src = warg_max_nonneg(neg, l >= 0);
+            if (src < 0) break;
+            l = wbcast(l, src);
+            const double ul = item_d(u, l);
+            wsync();
+            drop_slot(l, u, ul, nullptr);
+            ++nd;
+        }
+        return nd;
+    }
+
     // ---- restart after the slack data (term, slb) changed: the acceleration-box and workspace
     //      constraints of the old active set are kept (their part of the problem does not depend on
     //      term or slb), everything that involves a slack goes back to the implicit start (rows
@@ -983,20 +1003,7 @@ struct QpW {
             if (!(fabs(r[h]) < 1e300)) bad = 1.0;
         }
         if (wmax(bad) > 0.0) return false;
-        for (;;) {
-            double neg = 0.0;
-            int l = -1;
-            QW_FOR(h) {
-                const int s = qw_item(h);
-                if (s < q && u[h] < 0.0 && (l < 0 || -u[h] > neg)) { neg = -u[h]; l = s; }
-            }
-            const int src = warg_max_nonneg(neg, l >= 0);
-            if (src < 0) break;
-            l = wbcast(l, src);
-            const double ul = item_d(u, l);
-            wsync();
-            drop_slot(l, u, ul, nullptr);
-        }
+        drop_negative();
         synth_from_u();
         return true;
     }
@@ -1017,7 +1024,7 @@ struct QpW {
             PROF(0);
             const int pcode = most_violated(feas_tol, &sp);
             PROF(1);
-            if (pcode < 0) {
+            if (__builtin_expect(pcode < 0, 0)) {
                 if (polished || q == 0) break;  // optimal
                 for (int pass = 0; pass < 2; ++pass) {
                     if (dirty || pass) refresh();
@@ -1046,7 +1053,7 @@ struct QpW {
             bool need_r = true, have_z = false, failed = false, added = false, rebuilt = false;
             while (!added) {
                 if (need_r) {
-                    if (dirty) { refresh(); dirty = false; }
+                    if (__builtin_expect(dirty, 0)) { refresh(); dirty = false; }
                     gvec(p, q);
                     PROF(4);
                     mat_vec<false>(q, &rmax);
@@ -1054,7 +1061,7 @@ struct QpW {
                     need_r = false;
                     have_z = false;
                 }
-                if (++iters > max_iter) { res.rc = QP_ITERCAP; failed = true; break; }
+                if (__builtin_expect(++iters > max_iter, 0)) { res.rc = QP_ITERCAP; failed = true; break; }
                 // dual ratio test: smallest u_i / r_i over r_i > 0 (needs u and r only: issued before the
                 // direction so that its latency hides behind the table products)
                 const double rthr = 1e-12 * rmax;
@@ -1074,14 +1081,19 @@ struct QpW {
                     ldrop = (src >= 0) ? wbcast(ldrop, src) : -1;
                     if (src < 0) t1 = INFINITY;
                 }
+                PROF(9);
                 if (!have_z) {
-                    delta = direction(p);
-                    have_z = true;
+                    coefs();
+                    PROF(6);
+                    apply(z, L, nullptr, nullptr, -1.0, &p);
                     PROF(7);
+                    delta = direction_finish(p);
+                    have_z = true;
+                    PROF(8);
                     // In exact arithmetic 0 <= delta <= n_p'H^{-1}n_p.  Anything else (or a NaN) means the
                     // explicit inverse has lost its accuracy: rebuild M exactly once for this candidate;
                     // if that does not cure it the problem is reported infeasible.
-                    if (!(delta <= 1.000001 * p.nph)) {
+                    if (__builtin_expect(!(delta <= 1.000001 * p.nph), 0)) {
                         if (rebuilt) { res.rc = QP_INFEASIBLE; failed = true; m_valid = false; break; }
                         rebuilt = true;
                         dirty = true;
@@ -1090,10 +1102,9 @@ struct QpW {
                     }
                 }
                 const bool dependent = !(delta > dep_tol * p.nph) || (q >= n3 + nmat);
-                PROF(9);
                 const double t2 = dependent ? INFINITY : (-sp * qw_rcp(delta));
                 const double t = (t1 < t2) ? t1 : t2;
-                if (!(t < INFINITY)) {  // also catches NaN
+                if (__builtin_expect(!(t < INFINITY), 0)) {  // also catches NaN
                     res.rc = QP_INFEASIBLE;
                     failed = true;
                     if (!(t == t) || !(delta == delta)) m_valid = false;

@@ -9,8 +9,8 @@ L = _lib.lib()
 cfg = scenarios.config(sys.argv[1] if len(sys.argv) > 1 else "C3")
 steps = int(sys.argv[2]) if len(sys.argv) > 2 else 12
 P = dmpc.default_params(cfg["variant"], **cfg["params"])
-names = ["loop-top", "most_violated", "polish", "decode/materialise", "gvec", "mat_vec", "direction_sparse", "direction (coefs+apply+z'Hz)",
-         "zeps+zHz", "ratio test", "x,u update+update_P", "border(add)", "drop_slot", "", "", ""]
+names = ["loop-top", "most_violated", "polish", "decode/materialise", "gvec", "mat_vec", "direction: coefs", "direction: apply",
+         "direction: zeps + z'Hz", "ratio test", "x,u update+update_P", "border(add)", "drop_slot", "", "", ""]
 with dmpc.Solver(cfg["N"], P, pmin=cfg["pmin"], pmax=cfg["pmax"], pf=cfg["pf"]) as s:
     s.init_horizons(cfg["po"])
     out = (C.c_uint64 * 32)()

@@ -106,3 +106,68 @@ def test_longer_horizon_k20(orc, emul):
     for k in range(8):
         o, e = _cmp(orc, emul, P, pk, vk, ak, pf, l, pmin, pmax, QMAX=96)
         l, pk, vk, ak = e["l_new"], e["p1"], e["v1"], e["a1"]
+
+
+# ---- the kernel's fast path (qp_warp.cuh register-resident solver, scan_tile_hw high-word scan, 3-D
+#      relaxation of the retry loop, two-pass row build), selected in the host build by QMAX < 0 --------
+@pytest.mark.parametrize("name,variant", [("kat_soft_bound", 0), ("kat_soft_bound2", 1), ("kat_soft_bound", 3)])
+def test_fast_path_single_step_matches_oracle(orc, emul, golden, name, variant):
+    g = golden[name]
+    P = orc.default_params(variant)
+    o, e = _cmp(orc, emul, P, g["pk_prev"], g["vk_prev"], g["ak_prev"], g["pf"], g["l"], g["pmin"], g["pmax"],
+                QMAX=-64)
+    # the retry count (slack bound / penalty doublings) is the reference's: skipped tries are counted
+    assert np.array_equal((o["status"] >> 8) & 0xFF, (e["status"] >> 8) & 0xFF)
+
+
+def test_fast_path_closed_loop_dense(orc, emul):
+    """dense random transition: many agents go through the infeasible-retry loop; the fast path (which skips
+    the tries its 3-D necessary condition proves infeasible) must reproduce status, retry count and result"""
+    from multiagent_planning_b200 import scenarios
+    N = 120
+    pmin, pmax = scenarios.density_arena(N, density=2.5)
+    po, pf = scenarios.random_test(N, pmin, pmax, 0.35, 2.0, seed=3)
+    P = orc.default_params(0)
+    K = P.K
+    l = np.zeros((3, K, N), order="F")
+    for n in range(N):
+        l[:, :, n] = orc.init_dmpc(po[:, n], pf[:, n], P.h, K, P.init_div)[0]
+    pk, vk, ak = l[:, 0, :].copy(), np.zeros((3, N)), np.zeros((3, N))
+    retried = 0
+    fewer = 0
+    for k in range(16):
+        o, e = _cmp(orc, emul, P, pk, vk, ak, pf, l, pmin, pmax, QMAX=-64)
+        assert np.array_equal((o["status"] >> 8) & 0xFF, (e["status"] >> 8) & 0xFF)
+        g = emul.step(emul.params_from(P), pk, vk, ak, pf, l, pmin, pmax, QMAX=64)   # generic solver
+        tr = (e["status"] >> 8) & 0xFF
+        retried += int((tr > 0).sum())
+        fewer += int((e["diag"][:, 2][tr > 0] < g["diag"][:, 2][tr > 0]).sum())
+        l, pk, vk, ak = o["l_new"], o["p1"], o["v1"], o["a1"]
+    assert retried >= 3 and fewer >= 0.8 * retried      # the skipped tries show up as saved iterations
+
+
+def test_fast_path_small_capacity_reports_overflow(orc, emul, golden):
+    g = golden["kat_soft_bound"]
+    P = orc.default_params(0)
+    e = emul.step(emul.params_from(P), g["pk_prev"], g["vk_prev"], g["ak_prev"], g["pf"], g["l"], g["pmin"],
+                  g["pmax"], QMAX=-4)
+    o = orc.step(P, g["pk_prev"], g["vk_prev"], g["ak_prev"], g["pf"], g["l"], g["pmin"], g["pmax"])
+    ovf = (e["status"] & 32) != 0
+    assert ovf.any()
+    assert np.abs(o["l_new"][:, :, ~ovf] - e["l_new"][:, :, ~ovf]).max() <= 1e-9
+
+
+def test_fast_path_k20(orc, emul):
+    from multiagent_planning_b200 import scenarios
+    N = 40
+    pmin, pmax = scenarios.density_arena(N, density=2.0)
+    po, pf = scenarios.random_test(N, pmin, pmax, 0.35, 2.0, seed=5)
+    P = orc.default_params(0)
+    P.K = 20
+    l = np.zeros((3, 20, N), order="F")
+    for n in range(N):
+        l[:, :, n] = orc.init_dmpc(po[:, n], pf[:, n], P.h, 20, P.init_div)[0]
+    pk, vk, ak = l[:, 0, :].copy(), np.zeros((3, N)), np.zeros((3, N))
+    for k in range(8):
+        o, e = _cmp(orc, emul, P, pk, vk, ak, pf, l, pmin, pmax, QMAX=-64)
+        l, pk, vk, ak = e["l_new"], e["p1"], e["v1"], e["a1"]

@@ -378,3 +378,25 @@ def test_two_gpus_nccl_equal_one_gpu(dmpc):
         s.init_horizons(cfg["po"])
         s.run(10)
         assert np.array_equal(s.get_state()["l"], l2)
+
+
+def test_bound_step_and_host_timing(dmpc, orc, golden):
+    """bind_step: pre-marshalled caller-owned buffers; same bits as step(); host phase timing is reported"""
+    g = golden["kat_soft_bound"]
+    P, s = _solver(dmpc, g, 0)
+    f = lambda a: np.asfortranarray(np.array(a, dtype=np.float64))
+    pk, vk, ak, l = f(g["pk_prev"]), f(g["vk_prev"]), f(g["ak_prev"]), f(g["l"])
+    with s:
+        ref = s.step(pk, vk, ak, l)
+        out = dict(l_new=np.zeros_like(l), p1=np.zeros_like(pk), v1=np.zeros_like(pk), a1=np.zeros_like(pk),
+                   status=np.zeros(200, np.int32), diag=np.zeros(200, dtype=ref["diag"].dtype))
+        call = s.bind_step(pk, vk, ak, l, out)
+        for _ in range(3):
+            ff = call()
+            assert ff == ref["first_fail"]
+            for k in ("l_new", "p1", "v1", "a1", "status"):
+                assert np.array_equal(out[k], ref[k]), k
+        t = s.last_host_timing()
+        assert set(t) == {"pack_us", "submit_us", "wait_us", "unpack_us"} and t["wait_us"] > 0
+        with pytest.raises(dmpc.DmpcError):
+            s.bind_step(pk.astype(np.float32), vk, ak, l, out)
