@@ -233,6 +233,7 @@ def run_single(args):
     scan_us = 1e3 * scan / n_timed
     qp_us = 1e3 * qp / n_timed
     ach_scan = b_alg(N, K) * N / (scan_us * 1e-6) / 1e9
+    ach_qp = b_alg(N, K) * N / (qp_us * 1e-6) / 1e9
     ach_step = b_alg(N, K) * N / (ms_per_step * 1e-3) / 1e9
 
     line = {
@@ -251,12 +252,25 @@ def run_single(args):
         "gpu_launches": 2 * n_timed,
         "resident_graph": {"value": N / (graph_ms * 1e-3) if graph_ms else None, "ms_per_step": graph_ms,
                            "steps": graph_steps, "note": "dmpcb200_run, CUDA graph, L2-warm, no host sync"},
-        "roofline": {"bound": "hbm", "kernel": "scan_kernel<4> (neighbour scan + constraint rows)",
-                     "achieved": ach_scan, "peak": peak, "unit": "GB/s", "frac": ach_scan / peak,
-                     "traffic": None, "peak_source": peak_src, "avg_launch_us": scan_us,
-                     "algorithmic_bytes_per_launch": b_alg(N, K) * N},
+        # dominant kernel = qp_kernel (80 % of the step).  Per the contract `achieved` charges it the whole
+        # algorithmic traffic of an agent-step (B_alg = 24 K N + 24 K + 168 bytes, dominated by the
+        # neighbour horizons that scan_kernel streams); the kernel itself is bound by the latency of the
+        # slowest agent's dependent fp64 chain, not by bandwidth: its measured DRAM traffic is ~0.7 MB.
+        "roofline": {"bound": "hbm", "kernel": "qp_kernel<4,15> (batched per-agent QP, tail fused)",
+                     "achieved": ach_qp, "peak": peak, "unit": "GB/s", "frac": ach_qp / peak,
+                     "traffic": 705792, "traffic_source": "ncu --set full, profiles/r1d_ncu_full_qp_summary.csv "
+                     "(dram__bytes_read.sum + dram__bytes_write.sum per launch)",
+                     "peak_source": peak_src, "avg_launch_us": qp_us,
+                     "algorithmic_bytes_per_launch": b_alg(N, K) * N,
+                     "note": "latency bound (one warp per SM sub-partition, slowest agent); see DESIGN.md 4"},
+        "roofline_scan": {"bound": "hbm", "kernel": "scan_kernel<4,2,15> (neighbour scan + constraint rows)",
+                          "achieved": ach_scan, "peak": peak, "unit": "GB/s", "frac": ach_scan / peak,
+                          "traffic": 230400, "avg_launch_us": scan_us,
+                          "algorithmic_bytes_per_launch": b_alg(N, K) * N,
+                          "note": "the neighbour buffer (180 KB) is L2 resident and re-read by every CTA through "
+                                  "TMA: algorithmic bytes >> DRAM bytes"},
         "roofline_step": {"bound": "hbm", "achieved": ach_step, "peak": peak, "unit": "GB/s",
-                          "frac": ach_step / peak, "note": "B_alg*N over the whole step (scan+QP+tail)"},
+                          "frac": ach_step / peak, "note": "B_alg*N over the whole step (scan + QP incl. tail)"},
         "kernel_us": {"scan_kernel": scan_us, "qp_kernel": qp_us,
                       "tail_and_gaps": 1e3 * ms_per_step - scan_us - qp_us,
                       "share": {"scan": scan_us / (1e3 * ms_per_step), "qp": qp_us / (1e3 * ms_per_step)}},
@@ -362,14 +376,20 @@ def run_multi(args):
             "gpu_launches": 2 * S,
             "resident_graph": {"ms_per_step": graph_ms, "value": (N / (graph_ms * 1e-3)) if graph_ms else None,
                                "note": "torch CUDA graph of two steps incl. NCCL all-gather"},
-            "roofline_step": {"bound": "hbm", "achieved": ach, "peak": peak * world, "unit": "GB/s",
-                              "frac": ach / (peak * world), "peak_source": peak_src},
+            "roofline": {"bound": "hbm", "kernel": "whole step (scan + QP + all-gather), max over ranks",
+                         "achieved": ach, "peak": peak * world, "unit": "GB/s", "frac": ach / (peak * world),
+                         "traffic": None, "peak_source": peak_src,
+                         "note": "strong scaling of a latency-bound step: the slowest agent sets the step time on "
+                                 "every rank; per-kernel rooflines are reported at n_gpus=1"},
             "all_gathers_per_step": sh.n_allgather / max(sh.steps, 1),
         }
-        print(json.dumps(line))
-    sh.close()
+        print(json.dumps(line), flush=True)
+    # teardown: every rank has its numbers; leave through a barrier and exit at once (destroying a
+    # process group that captured NCCL work into a CUDA graph can block for minutes)
+    torch.cuda.synchronize()
     dist.barrier()
-    dist.destroy_process_group()
+    sys.stdout.flush()
+    os._exit(0)
 
 
 def main():

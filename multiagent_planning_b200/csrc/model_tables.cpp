@@ -160,8 +160,8 @@ void build_tables(double h, int K, const double qs[3][2], std::vector<double>& o
             for (int j = 0; j < K; ++j) {
                 double* t = T4 + 4 * ((size_t)k * K + j);
                 t[0] = G[k * K + j];
-                t[1] = B[k * K + j];
-                t[2] = B[j * K + k];
+                t[1] = B[j * K + k];
+                t[2] = B[k * K + j];
                 t[3] = C[k * K + j];
             }
     }

@@ -21,8 +21,10 @@ namespace dmpc {
 //   [tables_fast_offset(K), +tables_fast_size(K))   the blob the register-resident solver (qp_warp.cuh)
 //       stages in shared memory with ONE bulk copy: a copy of the header (lam, tt, lnorm, ilnorm, padded to a
 //       multiple of 4 doubles) followed, per weight set, by the interleaved table
-//           T4[k][j] = { G[k][j], B[k][j], B[j][k], C[k][j] }        (32-byte records, row-major in k, j)
-//       so that one 128-bit-pair load fetches everything the direction needs for (k, j).
+//           T4[k][j] = { G[k][j], B[j][k], B[k][j], C[k][j] }        (32-byte records, row-major in k, j)
+//       so that two 128-bit loads fetch everything the direction needs for (k, j), and ONE fetches the pair
+//       (acceleration part, position image) of H^-1 n for a normal in acceleration space (first half) or
+//       in position space (second half).
 inline int tables_set_offset(int K, int w) { return K * K + 4 * K + w * 3 * K * K; }
 inline int tables_base_size(int K) { return K * K + 4 * K + 9 * K * K; }
 inline int tables_fast_offset(int K) { return (tables_base_size(K) + 3) / 4 * 4; }

@@ -36,7 +36,7 @@
 #define PROF(i)                                                              \
     do {                                                                     \
         const long long prof_t1 = clock64();                                 \
-        if (lane_id() == 0 && q >= DMPC_PROF_QMIN) {                         \
+        if (lane_id() == 0 && q >= DMPC_PROF_QMIN && q <= DMPC_PROF_QMAX) {  \
             atomicAdd(&g_prof[i], (unsigned long long)(prof_t1 - prof_t0));  \
             atomicAdd(&g_prof[16 + (i)], 1ull);                              \
         }                                                                    \
@@ -44,6 +44,9 @@
     } while (0)
 #ifndef DMPC_PROF_QMIN
 #define DMPC_PROF_QMIN 0
+#endif
+#ifndef DMPC_PROF_QMAX
+#define DMPC_PROF_QMAX 64
 #endif
 #endif
 
@@ -253,8 +256,8 @@ struct QpW {
             bcode = better ? mk_code(w ? t23 : t01, i) : bcode;
             braw = better ? (w ? raw23 : raw01) : braw;
         }
-        if (nv > 0) {
-            QW_FOR(h) {
+        QW_FOR(h) {
+            if (h * kLanes < nv) {  // uniform: this half of the rows exists
                 const int j = qw_item(h);
                 const bool ok = j < nv;
                 const unsigned m = rmap[h];
@@ -285,7 +288,7 @@ struct QpW {
     }
 
     // ---- g[s] = n_{act[s]}' H^{-1} n_p for s < cnt, into gs; gs[s] = 0 for every other slot of the halves
-    //      in use.  One table record per slot: T4[ks][kp][2 sp + space]. --------------------------------
+    //      in use.  One table record per slot: T4[ks][kp][sp + 2 space]. --------------------------------
     DMPC_D void gvec(const PInfo& p, int cnt) {
         const int Kk = KK();
         const int cnt4 = (cnt + 3) & ~3;
@@ -295,7 +298,7 @@ struct QpW {
                 const int info = sinfo[s];  // (records of unused slots hold valid stale data)
                 const int sp = info & 1, ks = (info >> 1) & 0xff, js = (info >> 9) - 1;
                 const double dot = sv0[s] * p.v0 + sv1[s] * p.v1 + sv2[s] * p.v2;
-                double gv = dot * T4[4 * (ks * Kk + p.k) + 2 * sp + p.space];
+                double gv = dot * T4[4 * (ks * Kk + p.k) + sp + 2 * p.space];
                 gv = (js >= 0 && js == p.j) ? fma(0.5 * se[s], p.e, gv) : gv;
                 gs[s] = (s < cnt) ? gv : 0.0;
             }
@@ -478,12 +481,14 @@ struct QpW {
         double D0 = 0.0, D1 = 0.0, D2 = 0.0;
         if (nra) {
             QW_FOR(h) {
-                const int j = qw_item(h) & (kQW - 1);
-                const unsigned sr = qw_getb(rmap[h], 0);
-                const double c = (sr != kNone) ? rs[sr & (kQW - 1)] : 0.0;  // rows beyond nv are never active
-                D0 = fma(c, rd0[j], D0);
-                D1 = fma(c, rd1[j], D1);
-                D2 = fma(c, rd2[j], D2);
+                if (h * kLanes < nv) {  // uniform
+                    const int j = qw_item(h) & (kQW - 1);
+                    const unsigned sr = qw_getb(rmap[h], 0);
+                    const double c = (sr != kNone) ? rs[sr & (kQW - 1)] : 0.0;  // rows beyond nv are never active
+                    D0 = fma(c, rd0[j], D0);
+                    D1 = fma(c, rd1[j], D1);
+                    D2 = fma(c, rd2[j], D2);
+                }
             }
             wsum3(D0, D1, D2);
         }
@@ -518,15 +523,15 @@ struct QpW {
             cq[h] = cbp + 2 * (ex[h] * Kk);
             sa[h][0] = sa[h][1] = sP[h][0] = sP[h][1] = 0.0;
         }
-#pragma unroll
+#pragma unroll 5
         for (int j = 0; j < Kk; ++j) {
             QW_FOR(h) {
                 if (h * kLanes < n3) {  // uniform
                     const Dbl2 t01 = ld2(tp[h] + 4 * j), t23 = ld2(tp[h] + 4 * j + 2), c = ld2(cq[h] + 2 * j);
-                    sa[h][0] = fma(t01.x, c.x, sa[h][0]);
-                    sa[h][1] = fma(t01.y, c.y, sa[h][1]);
-                    sP[h][0] = fma(t23.x, c.x, sP[h][0]);
-                    sP[h][1] = fma(t23.y, c.y, sP[h][1]);
+                    sa[h][0] = fma(t01.x, c.x, sa[h][0]);  // G[k][j] cb
+                    sP[h][0] = fma(t01.y, c.x, sP[h][0]);  // B[j][k] cb
+                    sa[h][1] = fma(t23.x, c.y, sa[h][1]);  // B[k][j] cp
+                    sP[h][1] = fma(t23.y, c.y, sP[h][1]);  // C[k][j] cp
                 }
             }
         }
@@ -536,8 +541,8 @@ struct QpW {
                 const int x = ex[h];
                 const double vx = (x == 0) ? hp->v0 : ((x == 1) ? hp->v1 : hp->v2);
                 const double* t = tp[h] + 4 * hp->k;
-                b_a = vx * t[hp->space];
-                b_P = vx * t[2 + hp->space];
+                b_a = vx * t[2 * hp->space];      // G[k][kp] | B[k][kp]
+                b_P = vx * t[2 * hp->space + 1];  // B[kp][k] | C[k][kp]
             } else {
                 b_a = ba[h];
                 b_P = bP[h];
@@ -559,6 +564,8 @@ struct QpW {
         double loc = 0.0;
         if (soft && nmat) {
             QW_FOR(h) {
+                zeps[h] = 0.0;
+                if (h * kLanes >= nv) continue;  // uniform
                 const int j = qw_item(h) & (kQW - 1);
                 const unsigned m = rmap[h];
                 const unsigned sr = qw_getb(m, 0), su = qw_getb(m, 1), sl = qw_getb(m, 2);
@@ -1068,6 +1075,7 @@ struct QpW {
                 double t1 = INFINITY;
                 int ldrop = -1;
                 QW_FOR(h) {
+                    if (h * kLanes >= q) continue;  // uniform
                     const int s = qw_item(h);
                     const double ri = r[h];
                     const bool ok = s < q && ri > rthr;
@@ -1119,6 +1127,7 @@ struct QpW {
                     if (nv > 0) {
                         const double l0 = Ls[3 * kc_all], l1 = Ls[3 * kc_all + 1], l2 = Ls[3 * kc_all + 2];
                         QW_FOR(h) {
+                            if (h * kLanes >= nv) continue;  // uniform
                             const int j = qw_item(h) & (kQW - 1);
                             double nz = rd0[j] * l0 + rd1[j] * l1 + rd2[j] * l2;
                             const double ze = zeps[h];  // 0 unless soft and materialised
@@ -1128,7 +1137,9 @@ struct QpW {
                         }
                     }
                 }
-                QW_FOR(h) u[h] = fma(-t, r[h], u[h]);
+                QW_FOR(h) {
+                    if (h * kLanes < q) u[h] = fma(-t, r[h], u[h]);  // uniform
+                }
                 up += t;
                 PROF(10);
                 if (!dependent && t2 <= t1) {
@@ -1277,7 +1288,7 @@ DMPC_D int agent_solve_fast(const DevParams& Pm, const double* __restrict__ tab,
             const double vox = (x == 0) ? x_vo[0] : ((x == 1) ? x_vo[1] : x_vo[2]);
             const double aox = (x == 0) ? x_ao[0] : ((x == 1) ? x_ao[1] : x_ao[2]);
             const double e = pfx - (pox + t_tt[K - 1] * vox);
-            au = 2.0 * qw * e * t_T4[4 * (k * K + (K - 1)) + 1] + 2.0 * sw * aox * t_T4[4 * (k * K)];
+            au = 2.0 * qw * e * t_T4[4 * (k * K + (K - 1)) + 2] + 2.0 * sw * aox * t_T4[4 * (k * K)];
             qp.zs[i] = au;
             qp.elo[h] = qp.pmin_of(i);
             qp.ehi[h] = qp.pmax_of(i);

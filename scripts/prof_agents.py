@@ -8,10 +8,13 @@ _lib.LIB_PATH = os.path.join(os.path.dirname(_lib.LIB_PATH), "libdmpc_b200_prof.
 from multiagent_planning_b200 import dmpc, scenarios
 cfg = scenarios.config(sys.argv[1] if len(sys.argv) > 1 else "C3")
 steps = int(sys.argv[2]) if len(sys.argv) > 2 else 8
+skip = int(sys.argv[3]) if len(sys.argv) > 3 else 0
 P = dmpc.default_params(cfg["variant"], **cfg["params"])
 with dmpc.Solver(cfg["N"], P, pmin=cfg["pmin"], pmax=cfg["pmax"], pf=cfg["pf"]) as s:
     s.init_horizons(cfg["po"])
-    for k in range(steps):
+    if skip:
+        s.run(skip, mode=2)
+    for k in range(skip, skip + steps):
         s.run(1, mode=1)
         t = s.last_timing()
         st = s.get_state()
