@@ -40,7 +40,10 @@ def main():
     raw = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--print-source", "sass"],
                          capture_output=True, text=True).stdout
     blocks = raw.split('"Kernel Name"')[1:]
-    rows = list(csv.reader(io.StringIO('"Kernel Name"' + blocks[launch])))
+    # launches of OTHER kernels are in the report too: keep the blocks whose instruction count matches
+    parsed = [list(csv.reader(io.StringIO('"Kernel Name"' + b))) for b in blocks]
+    same = [r for r in parsed if len(r) - 2 == len(lines)]
+    rows = same[launch] if same else parsed[launch]
     hdr = rows[1]
     i_s, i_e = hdr.index("# Samples"), hdr.index("Instructions Executed")
     body = rows[2:]
