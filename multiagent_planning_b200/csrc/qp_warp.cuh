@@ -56,6 +56,7 @@ constexpr int kQW = 64;             // capacity: entries, rows, slots
 constexpr int kMS = 66;             // row stride of M in doubles
 constexpr int kEPL = kQW / kLanes;  // items per lane: 2 on the device, 64 in the host build
 constexpr unsigned kNone = 0xffu;
+constexpr int kPolishSkip = 12;  // plain adds after which the final re-synthesis of x is skipped
 
 #if defined(__CUDA_ARCH__)
 #define QW_FOR(h) _Pragma("unroll") for (int h = 0; h < kEPL; ++h)
@@ -575,27 +576,21 @@ struct QpW {
                 ze += (su != kNone) ? 0.5 * c1 : 0.0;
                 ze -= (sl != kNone) ? 0.5 * c2 : 0.0;
                 ze = qw_getb(m, 3) ? ze : 0.0;  // not materialised: eps is held at 0 by its implicit bound
-                loc = fma(ze, ze, loc);
                 zeps[h] = ze;
             }
         } else {
             QW_FOR(h) zeps[h] = 0.0;
         }
         wsync();
-        // z'Hz, H_K = 2 (q lamK lamK' + s Delta'Delta + I): a sum of squares (no cancellation)
-        QW_FOR(h) {
-            const int i = qw_item(h);
-            const bool ok = i < n3;
-            const double zi = ok ? z[h] : 0.0;
-            const double zp = (ok && i >= 3) ? zs[(i - 3) & (kQW - 1)] : 0.0;
-            const double dz = zi - zp;
-            loc = fma(zi, zi, loc);
-            loc = fma(sw * dz, dz, loc);
-        }
-        loc = wsum(loc);
-        const int Kk = KK();
-        const double t0 = Ls[3 * (Kk - 1)], t1 = Ls[3 * (Kk - 1) + 1], t2 = Ls[3 * (Kk - 1) + 2];
-        return 2.0 * (loc + qw * (t0 * t0 + t1 * t1 + t2 * t2));
+        // delta = z'Hz = n_p'z: the candidate's own normal picks it out of the published direction -- one or
+        // three shared-memory reads (and one shuffle for a slack component) instead of a warp reduction
+        (void)loc;
+        if (p.type <= T_BOXU) return ((p.type == T_BOXL) ? zs[p.idx] : -zs[p.idx]);
+        if (p.type <= T_WSU) return ((p.type == T_WSL) ? Ls[p.idx] : -Ls[p.idx]);
+        const double zj = (soft && nmat) ? item_d(zeps, p.j) : 0.0;
+        double d = p.e * zj;
+        if (p.type == T_ROW) d += p.v0 * Ls[3 * p.k] + p.v1 * Ls[3 * p.k + 1] + p.v2 * Ls[3 * p.k + 2];
+        return d;
     }
 
     // ---- x (a, eps, P) re-synthesised from the multipliers: x = x_unc + H^{-1} N u; residuals of the
@@ -1022,6 +1017,8 @@ struct QpW {
         const double dep_tol = 1e-9;   // on delta = z'Hz relative to n_p'H^{-1}n_p
         const double ill_tol = 1e-5;   // adds below this mark M for an exact rebuild
         int iters = 0, npolish = 0;
+        int nsteps = 0;          // primal steps since x was last synthesised from the multipliers
+        bool rough = false;      // a drop, a rebuild or an ill-conditioned add happened since then
         bool polished = false, dirty = false, m_valid = true;
         QpResult res;
         res.rc = QP_OK;
@@ -1033,12 +1030,17 @@ struct QpW {
             PROF(1);
             if (__builtin_expect(pcode < 0, 0)) {
                 if (polished || q == 0) break;  // optimal
+                // a short run of plain adds carries no drift worth removing (each step is one fused
+                // multiply-add per entry on top of a synthesised x): accept it as it is
+                if (nsteps <= kPolishSkip && !rough && !dirty) break;
                 for (int pass = 0; pass < 2; ++pass) {
                     if (dirty || pass) refresh();
                     dirty = false;
                     if (!(polish() > 1e-9)) break;
                 }
                 polished = true;
+                nsteps = 0;
+                rough = false;
                 PROF(2);
                 if (++npolish > 8) { res.rc = QP_ITERCAP; break; }
                 continue;
@@ -1104,6 +1106,7 @@ struct QpW {
                     if (__builtin_expect(!(delta <= 1.000001 * p.nph), 0)) {
                         if (rebuilt) { res.rc = QP_INFEASIBLE; failed = true; m_valid = false; break; }
                         rebuilt = true;
+                        rough = true;
                         dirty = true;
                         need_r = true;
                         continue;
@@ -1155,12 +1158,14 @@ struct QpW {
                     wsync();
                     ++q;
                     added = true;
-                    if (delta < ill_tol * p.nph) dirty = true;
+                    ++nsteps;
+                    if (delta < ill_tol * p.nph) { dirty = true; rough = true; }
                     PROF(11);
                 } else {
                     const double rl = rs[ldrop], mll = M[(size_t)ldrop * kMS + ldrop];
                     wsync();
                     drop_slot(ldrop, r, rl, u);
+                    rough = true;
                     if (dirty) {
                         need_r = true;  // rebuild M, then r from scratch
                     } else {
