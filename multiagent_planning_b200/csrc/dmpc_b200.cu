@@ -149,6 +149,7 @@ StepArgs make_args(dmpcb200_t* h, int n0, int n1, const double* pk, const double
     A.ctrl = ctrl;
     A.fuse_tail = 0;
     A.done_cnt = h->d_done;
+    A.work_cnt = h->d_done + 1;
     return A;
 }
 
@@ -177,7 +178,16 @@ cudaError_t launch_qp_w(const StepArgs& A, int nl, size_t smem, cudaStream_t s) 
         if (e != cudaSuccess) return e;
         attr_smem = smem;
     }
-    qp_kernel<W, KT><<<(nl + W - 1) / W, W * 32, smem, s>>>(A);
+    // one CTA per SM at most (shared memory): larger swarms run a persistent grid with an agent queue
+    static int n_sm = 0;
+    if (!n_sm) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
+        if (n_sm < 1) n_sm = 148;
+    }
+    const int ctas = std::min((nl + W - 1) / W, n_sm);
+    qp_kernel<W, KT><<<ctas, W * 32, smem, s>>>(A);
     return cudaGetLastError();
 }
 
@@ -188,13 +198,11 @@ cudaError_t launch_scan(dmpcb200_t* h, const StepArgs& A, cudaStream_t s) {
     const int nl = A.n1 - A.n0, K = h->K, N = h->N;
     if (nl <= 4 * 148 || scan_stages(K, N, 8, A.RMAX) < 2) {
         if (scan_stages(K, N, 4, A.RMAX) < 1) return launch_scan_w<1, 2, 0>(A, nl, K, s);
-        static const int variant = getenv("DMPCB200_SCAN") ? atoi(getenv("DMPCB200_SCAN")) : 0;  // tuning hook
-        if (variant == 1) return launch_scan_w<8, 2, 0>(A, nl, K, s);
-        if (variant == 2) return launch_scan_w<4, 4, 0>(A, nl, K, s);
         if (K == 15) return launch_scan_w<4, 2, 15>(A, nl, K, s);
         if (K == 20) return launch_scan_w<4, 2, 20>(A, nl, K, s);
         return launch_scan_w<4, 4, 0>(A, nl, K, s);
     }
+    if (K == 15) return launch_scan_w<8, 1, 15>(A, nl, K, s);  // measured at N=2000: 123 us vs 151 (<8,2,0>) / 145 (<4,2,15>)
     if (K == 20) return launch_scan_w<8, 1, 20>(A, nl, K, s);
     return launch_scan_w<8, 2, 0>(A, nl, K, s);
 }
@@ -452,7 +460,7 @@ int dmpcb200_create(const dmpcb200_params* p, int N, int n0, int n1, int device,
     if ((e = dalloc(&h->d_gscr_i, NL * 4 * h->RMAX)) != cudaSuccess) return bail(e, "row scratch");
     if ((e = dalloc(&h->d_rescue, h->rescue_bytes * h->n_rescue)) != cudaSuccess) return bail(e, "rescue");
     if ((e = dalloc(&h->d_rescue_next, 1)) != cudaSuccess) return bail(e, "rescue counter");
-    if ((e = dalloc(&h->d_done, 1)) != cudaSuccess) return bail(e, "done counter");
+    if ((e = dalloc(&h->d_done, 2)) != cudaSuccess) return bail(e, "done / work counters");
     if ((e = dalloc(&h->d_ctrl, 1)) != cudaSuccess) return bail(e, "ctrl");
     if ((e = dalloc(&h->d_goal, 2)) != cudaSuccess) return bail(e, "goal");
     if ((e = dalloc(&h->d_u8, 2 * (size_t)N)) != cudaSuccess) return bail(e, "u8");

@@ -91,7 +91,8 @@ struct StepArgs {
     Ctrl* ctrl;        // optional
     // K3 fused into K2: the last CTA of the QP kernel to finish runs the step's tail (optional)
     int fuse_tail;
-    unsigned* done_cnt;
+    unsigned* done_cnt;  // CTAs that finished (reset by the last one)
+    unsigned* work_cnt;  // agent queue of the persistent QP grid (reset by the last CTA)
     TailArgs T;
 };
 
@@ -419,9 +420,16 @@ __global__ void __launch_bounds__(W * 32, 1) qp_kernel(const __grid_constant__ S
         tma_bulk_g2s(tab_s, A.tab + tab_fast_offset(K), (uint32_t)qp_table_bytes(K), bar);
     }
     __syncthreads();
-    const int li = blockIdx.x * W + warp;
+    // one agent per warp while the grid covers the swarm; beyond that the CTAs are persistent (one per SM:
+    // the per-agent workspace fills shared memory) and every warp takes its next agent from a device
+    // counter as soon as it is done -- the solve times differ by 50x, a static assignment would leave
+    // three warps of a CTA idle behind its slowest agent
+    const int nl = A.n1 - A.n0;
+    const bool queued = (int)gridDim.x * W < nl;
+    int li = blockIdx.x * W + warp;
+    while (li < nl) {
     const int n = A.n0 + li;
-    if (n < A.n1) {
+    {
 #if defined(DMPC_PROF_AGENT)
     const long long agent_t0 = clock64();
 #endif
@@ -489,9 +497,15 @@ __global__ void __launch_bounds__(W * 32, 1) qp_kernel(const __grid_constant__ S
         A.status[n] = st;
         if (A.diag) A.diag[n] = dg;
     }
-    }  // n < A.n1
-    if (A.fuse_tail) {
-        // the last CTA to arrive has every agent's result behind it: it runs the tail of the step
+    }
+    if (!queued) break;
+    if (lane == 0) li = (int)gridDim.x * W + (int)atomicAdd(A.work_cnt, 1u);
+    li = __shfl_sync(0xffffffffu, li, 0);
+    __syncwarp();
+    }  // agents of this warp
+    {
+        // the last CTA to arrive has every agent's result behind it: it resets the counters and, in the
+        // resident loop and the host step, runs the tail of the step
         __shared__ int s_last;
         __threadfence();
         __syncthreads();
@@ -499,8 +513,11 @@ __global__ void __launch_bounds__(W * 32, 1) qp_kernel(const __grid_constant__ S
         __syncthreads();
         if (s_last) {
             __threadfence();
-            tail_body<W * 32>(A.T);
-            if (threadIdx.x == 0) *A.done_cnt = 0;
+            if (A.fuse_tail) tail_body<W * 32>(A.T);
+            if (threadIdx.x == 0) {
+                *A.done_cnt = 0;
+                *A.work_cnt = 0;
+            }
         }
     }
 }
