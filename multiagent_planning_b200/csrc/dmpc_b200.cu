@@ -9,6 +9,7 @@
 #include <chrono>
 #include <cstring>
 #include <string>
+#include <utility>
 #include <vector>
 
 #include "../../include/dmpc_b200.h"
@@ -51,6 +52,8 @@ struct dmpcb200_handle {
     int RMAX = 0, QMAX = 0, RCAP = 0, QBIG = 0, W = 4, n_rescue = 0;
     size_t rescue_bytes = 0;
     cudaStream_t stream = nullptr;
+    cudaStream_t stream2 = nullptr;  // host step: the small state copies run beside the horizon copy + scan
+    cudaEvent_t ev_in = nullptr;
     // resident state
     double* d_tab = nullptr;
     // resident state lives in ONE arena so that the host step moves it with one copy per direction:
@@ -59,6 +62,9 @@ struct dmpcb200_handle {
     size_t side_bytes = 0, tailblk_bytes = 0;
     unsigned char* h_stage = nullptr;  // pinned + mapped: one input side + one output side + tail block
     unsigned char* d_stage = nullptr;  // device alias of h_stage (the QP kernel writes the outputs of a host step there)
+    // caller-owned host arrays that turned out to be pinned (page-locked + mapped): host pointer -> device alias
+    // (nullptr: pageable).  The QP kernel then writes a host step's outputs straight into the caller's arrays.
+    std::vector<std::pair<const void*, void*>> pinned_cache;
     double* d_l[2] = {nullptr, nullptr};
     double* d_st[2][3] = {{nullptr, nullptr, nullptr}, {nullptr, nullptr, nullptr}};  // pk, vk, ak ping-pong
     double* d_pf = nullptr;
@@ -283,6 +289,22 @@ int ensure_pin(dmpcb200_t* h, size_t n) {
     return 0;
 }
 
+// device alias of a caller-owned host pointer if it is pinned and mapped, else nullptr (cached per pointer)
+void* pinned_alias(dmpcb200_t* h, const void* p) {
+    if (!p) return nullptr;
+    for (auto& e : h->pinned_cache)
+        if (e.first == p) return e.second;
+    void* dev = nullptr;
+    cudaPointerAttributes at;
+    if (cudaPointerGetAttributes(&at, p) == cudaSuccess && at.type == cudaMemoryTypeHost && at.devicePointer)
+        dev = at.devicePointer;
+    else
+        cudaGetLastError();
+    if (h->pinned_cache.size() >= 64) h->pinned_cache.clear();
+    h->pinned_cache.emplace_back(p, dev);
+    return dev;
+}
+
 void drop_graph(dmpcb200_t* h) {
     if (h->graph) cudaGraphExecDestroy(h->graph);
     h->graph = nullptr;
@@ -414,6 +436,8 @@ int dmpcb200_create(const dmpcb200_params* p, int N, int n0, int n1, int device,
     };
     cudaError_t e;
     if ((e = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking)) != cudaSuccess) return bail(e, "stream");
+    if ((e = cudaStreamCreateWithFlags(&h->stream2, cudaStreamNonBlocking)) != cudaSuccess) return bail(e, "stream");
+    if ((e = cudaEventCreateWithFlags(&h->ev_in, cudaEventDisableTiming)) != cudaSuccess) return bail(e, "event");
     // tables
     std::vector<double> tab;
     const double qs[3][2] = {{p->Q_far, p->S_free}, {p->Q_near, p->S_free}, {p->Q1, p->S1}};
@@ -487,6 +511,8 @@ void dmpcb200_destroy(dmpcb200_t* h) {
     for (int s = 0; s < 3; ++s) cudaFree(h->d_traj[s]);
     cudaFree(h->d_hist);
     if (h->h_pin) cudaFreeHost(h->h_pin);
+    if (h->ev_in) cudaEventDestroy(h->ev_in);
+    if (h->stream2) cudaStreamDestroy(h->stream2);
     if (h->stream) cudaStreamDestroy(h->stream);
     delete h;
 }
@@ -607,20 +633,40 @@ int dmpcb200_step(dmpcb200_t* h, const double* pk, const double* vk, const doubl
                               (size_t)((unsigned char*)h->d_st[c][1] - (unsigned char*)h->d_l[c]),
                               (size_t)((unsigned char*)h->d_st[c][2] - (unsigned char*)h->d_l[c])};
     const auto tp0 = std::chrono::steady_clock::now();
-    std::memcpy(hs_in, l_prev, lB);
-    std::memcpy(hs_in + off_st[0], pk, sN);
-    std::memcpy(hs_in + off_st[1], vk, sN);
-    std::memcpy(hs_in + off_st[2], ak, sN);
+    const bool in_pinned = pinned_alias(h, l_prev) && pinned_alias(h, pk) && pinned_alias(h, vk) && pinned_alias(h, ak);
+    if (!in_pinned) {
+        std::memcpy(hs_in, l_prev, lB);
+        std::memcpy(hs_in + off_st[0], pk, sN);
+        std::memcpy(hs_in + off_st[1], vk, sN);
+        std::memcpy(hs_in + off_st[2], ak, sN);
+    }
     const auto tp1 = std::chrono::steady_clock::now();
-    CK(cudaMemcpyAsync(h->d_l[c], hs_in, h->side_bytes, cudaMemcpyHostToDevice, s));
+    if (in_pinned) {
+        // pinned caller arrays: DMA straight from them (the horizons first: the scan kernel needs only those)
+        CK(cudaMemcpyAsync(h->d_l[c], l_prev, lB, cudaMemcpyHostToDevice, s));
+        CK(cudaMemcpyAsync(h->d_st[c][0], pk, sN, cudaMemcpyHostToDevice, h->stream2));
+        CK(cudaMemcpyAsync(h->d_st[c][1], vk, sN, cudaMemcpyHostToDevice, h->stream2));
+        CK(cudaMemcpyAsync(h->d_st[c][2], ak, sN, cudaMemcpyHostToDevice, h->stream2));
+        CK(cudaEventRecord(h->ev_in, h->stream2));
+    } else {
+        CK(cudaMemcpyAsync(h->d_l[c], hs_in, h->side_bytes, cudaMemcpyHostToDevice, s));
+    }
     if (int rc = ensure_events(h, 4)) return rc;
     // outputs: the QP kernel writes the new horizons and states STRAIGHT into the mapped pinned block (posted
     // writes over PCIe as each agent finishes, overlapped with the rest of the kernel); the last CTA adds
     // status | diag | first_fail after the tail.  No device-to-host copy is queued at all.
     unsigned char* ds_out = h->d_stage + h->side_bytes;
+    // caller arrays that are pinned are written by the kernel directly (no staging, nothing to hand over)
+    double* w_l = static_cast<double*>(pinned_alias(h, l_new));
+    double* w_p = static_cast<double*>(pinned_alias(h, p1));
+    double* w_v = static_cast<double*>(pinned_alias(h, v1));
+    double* w_a = static_cast<double*>(pinned_alias(h, a1));
+    const bool direct = w_l && w_p && w_v && w_a;
     StepArgs A = make_args(h, h->n0, h->n1, h->d_st[c][0], h->d_st[c][1], h->d_st[c][2], h->d_l[c],
-                           reinterpret_cast<double*>(ds_out), reinterpret_cast<double*>(ds_out + off_st[0]),
-                           reinterpret_cast<double*>(ds_out + off_st[1]), reinterpret_cast<double*>(ds_out + off_st[2]),
+                           direct ? w_l : reinterpret_cast<double*>(ds_out),
+                           direct ? w_p : reinterpret_cast<double*>(ds_out + off_st[0]),
+                           direct ? w_v : reinterpret_cast<double*>(ds_out + off_st[1]),
+                           direct ? w_a : reinterpret_cast<double*>(ds_out + off_st[2]),
                            (v_hor ? h->d_vhor : nullptr), (a_hor ? h->d_ahor : nullptr), h->d_status, h->d_diag, true,
                            nullptr);
     A.T = make_tail(h, nullptr, 3, h->d_status, nullptr, nullptr, nullptr, false, nullptr);
@@ -631,6 +677,7 @@ int dmpcb200_step(dmpcb200_t* h, const double* pk, const double* vk, const doubl
     CK(cudaEventRecord(h->ev[0], s));
     CK(launch_scan(h, A, s));
     CK(cudaEventRecord(h->ev[1], s));
+    if (in_pinned) CK(cudaStreamWaitEvent(s, h->ev_in, 0));  // the states have arrived
     CK(launch_qp(h, A, s));
     CK(cudaEventRecord(h->ev[2], s));
     CK(cudaEventRecord(h->ev[3], s));
@@ -645,10 +692,12 @@ int dmpcb200_step(dmpcb200_t* h, const double* pk, const double* vk, const doubl
         const unsigned char* tb = hs_out + h->side_bytes;
         const size_t stB = (size_t)((unsigned char*)h->d_diag - (unsigned char*)h->d_status);
         const size_t dgB = (size_t)((unsigned char*)h->d_fail - (unsigned char*)h->d_diag);
-        if (l_new) std::memcpy(l_new + oL, reinterpret_cast<const double*>(hs_out) + oL, bL);
-        if (p1) std::memcpy(p1 + o3, reinterpret_cast<const double*>(hs_out + off_st[0]) + o3, b3);
-        if (v1) std::memcpy(v1 + o3, reinterpret_cast<const double*>(hs_out + off_st[1]) + o3, b3);
-        if (a1) std::memcpy(a1 + o3, reinterpret_cast<const double*>(hs_out + off_st[2]) + o3, b3);
+        if (!direct) {
+            if (l_new) std::memcpy(l_new + oL, reinterpret_cast<const double*>(hs_out) + oL, bL);
+            if (p1) std::memcpy(p1 + o3, reinterpret_cast<const double*>(hs_out + off_st[0]) + o3, b3);
+            if (v1) std::memcpy(v1 + o3, reinterpret_cast<const double*>(hs_out + off_st[1]) + o3, b3);
+            if (a1) std::memcpy(a1 + o3, reinterpret_cast<const double*>(hs_out + off_st[2]) + o3, b3);
+        }
         if (status) std::memcpy(status + n0, reinterpret_cast<const int*>(tb) + n0, (size_t)NL * sizeof(int));
         if (diag) std::memcpy(diag + n0, reinterpret_cast<const AgentDiag*>(tb + stB) + n0, (size_t)NL * sizeof(AgentDiag));
         if (first_fail) *first_fail = *reinterpret_cast<const int*>(tb + stB + dgB);

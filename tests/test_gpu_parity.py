@@ -400,3 +400,13 @@ def test_bound_step_and_host_timing(dmpc, orc, golden):
         assert set(t) == {"pack_us", "submit_us", "wait_us", "unpack_us"} and t["wait_us"] > 0
         with pytest.raises(dmpc.DmpcError):
             s.bind_step(pk.astype(np.float32), vk, ak, l, out)
+        # pinned caller arrays: the kernel writes the outputs straight into them (no staging copy)
+        import torch
+        pin = lambda shape: torch.zeros(shape, dtype=torch.float64).pin_memory().numpy()
+        out2 = dict(l_new=pin((200, 15, 3)).transpose(2, 1, 0), p1=pin((200, 3)).T, v1=pin((200, 3)).T,
+                    a1=pin((200, 3)).T, status=np.zeros(200, np.int32), diag=np.zeros(200, dtype=ref["diag"].dtype))
+        call2 = s.bind_step(pk, vk, ak, l, out2)
+        for _ in range(2):
+            assert call2() == ref["first_fail"]
+            for k in ("l_new", "p1", "v1", "a1", "status"):
+                assert np.array_equal(out2[k], ref[k]), k
