@@ -318,25 +318,55 @@ __device__ __forceinline__ void tail_body(const TailArgs& T) {
     const int step = T.ctrl ? T.ctrl->step : 0;
     double md = 0.0;
     int ff = 0x7fffffff;
-    for (int n = tid; n < T.N; n += NT) {
-        if (T.p) {
-            // ReachedGoal.m:4-5
-            const double dx = __ldcg(T.p + (size_t)T.ld * n) - T.pf[3 * n];
-            const double dy = __ldcg(T.p + (size_t)T.ld * n + 1) - T.pf[3 * n + 1];
-            const double dz = __ldcg(T.p + (size_t)T.ld * n + 2) - T.pf[3 * n + 2];
-            md = fmax(md, sqrt(dx * dx + dy * dy + dz * dz));
+    // four agents per thread and pass: all loads of a pass are issued before anything is stored, so their
+    // L2 round trips overlap (the last CTA is alone on the chip here: this is pure latency)
+    constexpr int U = 4;
+    const bool rec = T.traj_p && step < T.S;
+    for (int base = tid; base < T.N; base += NT * U) {
+        double pp[U][3], gg[U][3], r1[U][3], r2[U][3], r3[U][3];
+        int stv[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const int n = base + u * NT;
+            stv[u] = ST_SOLVED;
+            if (n < T.N) {
+#pragma unroll
+                for (int x = 0; x < 3; ++x) {
+                    if (T.p) {
+                        pp[u][x] = __ldcg(T.p + (size_t)T.ld * n + x);
+                        gg[u][x] = T.pf[3 * n + x];
+                    }
+                    if (rec) {
+                        r1[u][x] = __ldcg(T.p1 + 3 * n + x);
+                        r2[u][x] = __ldcg(T.v1 + 3 * n + x);
+                        r3[u][x] = __ldcg(T.a1 + 3 * n + x);
+                    }
+                }
+                if (T.status && n >= T.n0 && n < T.n1) stv[u] = __ldcg(T.status + n);
+            }
         }
-        if (T.status && n >= T.n0 && n < T.n1) {
-            const int st = __ldcg(T.status + n);
-            if ((!(st & ST_SOLVED) || (st & ST_OUTBOUND)) && n < ff) ff = n;
-            if (T.status_hist && step < T.S) T.status_hist[(size_t)step * T.N + n] = st;
-        }
-        if (T.traj_p && step < T.S) {
-            const size_t o = 3 * ((size_t)(step + 1) + (size_t)(T.S + 1) * n);
-            for (int x = 0; x < 3; ++x) {
-                T.traj_p[o + x] = __ldcg(T.p1 + 3 * n + x);
-                T.traj_v[o + x] = __ldcg(T.v1 + 3 * n + x);
-                T.traj_a[o + x] = __ldcg(T.a1 + 3 * n + x);
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const int n = base + u * NT;
+            if (n >= T.N) continue;
+            if (T.p) {
+                // ReachedGoal.m:4-5
+                const double dx = pp[u][0] - gg[u][0], dy = pp[u][1] - gg[u][1], dz = pp[u][2] - gg[u][2];
+                md = fmax(md, sqrt(dx * dx + dy * dy + dz * dz));
+            }
+            if (T.status && n >= T.n0 && n < T.n1) {
+                const int st = stv[u];
+                if ((!(st & ST_SOLVED) || (st & ST_OUTBOUND)) && n < ff) ff = n;
+                if (T.status_hist && step < T.S) T.status_hist[(size_t)step * T.N + n] = st;
+            }
+            if (rec) {
+                const size_t o = 3 * ((size_t)(step + 1) + (size_t)(T.S + 1) * n);
+#pragma unroll
+                for (int x = 0; x < 3; ++x) {
+                    T.traj_p[o + x] = r1[u][x];
+                    T.traj_v[o + x] = r2[u][x];
+                    T.traj_a[o + x] = r3[u][x];
+                }
             }
         }
     }
