@@ -858,10 +858,14 @@ struct QpW {
                     if (i < qa) uA[i] = fma(-t, r3[i], uA[i]);
                 up += t;
                 if (!dependent && t2 <= t1) {
-                    nA[qa][0] = np[0]; nA[qa][1] = np[1]; nA[qa][2] = np[2];
-                    bA[qa] = bp;
-                    uA[qa] = up;
-                    cA[qa] = pc;
+#pragma unroll
+                    for (int i = 0; i < 3; ++i)  // (compile-time indices: the arrays stay in registers)
+                        if (i == qa) {
+                            nA[i][0] = np[0]; nA[i][1] = np[1]; nA[i][2] = np[2];
+                            bA[i] = bp;
+                            uA[i] = up;
+                            cA[i] = pc;
+                        }
                     ++qa;
                     break;
                 }
