@@ -410,3 +410,22 @@ def test_bound_step_and_host_timing(dmpc, orc, golden):
             assert call2() == ref["first_fail"]
             for k in ("l_new", "p1", "v1", "a1", "status"):
                 assert np.array_equal(out2[k], ref[k]), k
+
+
+def test_large_swarm_persistent_grid_vs_oracle(dmpc, orc):
+    """N > 4 x (number of SMs): the QP kernel runs as a persistent grid with an agent queue and the scan
+    kernel in its 8-agents-per-CTA layout with tile refill; teacher-forced against the oracle"""
+    from multiagent_planning_b200 import scenarios
+    N = 700
+    pmin, pmax = scenarios.density_arena(N)
+    po, pf = scenarios.random_test(N, pmin, pmax, 0.35, 2.0, seed=77)
+    P = dmpc.default_params(0)
+    with dmpc.Solver(N, P, pmin=pmin, pmax=pmax, pf=pf) as s:
+        l, pk, vk, ak = s.init_horizons(po)
+        for _ in range(3):
+            g, _ = _cmp_step(orc, P, s, pk, vk, ak, pf, l, pmin, pmax)
+            l, pk, vk, ak = g["l_new"], g["p1"], g["v1"], g["a1"]
+        # and the resident loop gives the same bits as the host-stepped one
+        s.init_horizons(po)
+        r = s.run(3, record=True)
+        assert np.array_equal(r["pk"][:, 3, :], pk)
