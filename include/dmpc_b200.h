@@ -130,6 +130,14 @@ int dmpcb200_step(dmpcb200_t* h, const double* pk, const double* vk, const doubl
                   double* v_hor, double* a_hor, int32_t* status, dmpcb200_diag* diag,
                   int32_t* first_fail);
 
+/* The same call with the argument list bound once (a tight closed loop over preallocated, ideally pinned,
+ * caller arrays: MATLAB would hold them in the MEX gateway's persistent state).  bind returns a slot (0..63),
+ * step_bound runs dmpcb200_step on the arrays bound to it.  The arrays stay owned by the caller. */
+int dmpcb200_bind_step(dmpcb200_t* h, const double* pk, const double* vk, const double* ak,
+                       const double* l_prev, double* l_new, double* p1, double* v1, double* a1,
+                       double* v_hor, double* a_hor, int32_t* status, dmpcb200_diag* diag, int32_t* slot);
+int dmpcb200_step_bound(dmpcb200_t* h, int32_t slot, int32_t* first_fail);
+
 /* Same step on DEVICE pointers, asynchronous on `stream` (a cudaStream_t passed as void*).
  * State arrays are 3 x N, horizons 3 x K x N, on the handle's device.  No host sync. */
 int dmpcb200_step_dev(dmpcb200_t* h, const double* d_pk, const double* d_vk, const double* d_ak,

@@ -96,6 +96,8 @@ def lib():
         "dmpcb200_set_goals": ([vp, dp], I),
         "dmpcb200_init_horizons": ([vp, dp, dp, dp, dp, dp], I),
         "dmpcb200_step": ([vp, dp, dp, dp, dp, dp, dp, dp, dp, dp, dp, ip, DP, ip], I),
+        "dmpcb200_bind_step": ([vp, dp, dp, dp, dp, dp, dp, dp, dp, dp, dp, ip, DP, ip], I),
+        "dmpcb200_step_bound": ([vp, C.c_int32, ip], I),
         "dmpcb200_step_dev": ([vp] + [vp] * 12 + [vp], I),
         "dmpcb200_goal_dev": ([vp, vp, I, vp, vp], I),
         "dmpcb200_reached_goal": ([vp, dp, dp, D, dp, ip], I),
@@ -124,7 +126,7 @@ def lib():
 EXPORTS = [
     "dmpcb200_abi_version", "dmpcb200_last_error", "dmpcb200_device_count", "dmpcb200_default_params",
     "dmpcb200_model_mats", "dmpcb200_create", "dmpcb200_destroy", "dmpcb200_set_bounds", "dmpcb200_set_goals",
-    "dmpcb200_init_horizons", "dmpcb200_step", "dmpcb200_step_dev", "dmpcb200_goal_dev", "dmpcb200_reached_goal", "dmpcb200_run",
+    "dmpcb200_init_horizons", "dmpcb200_step", "dmpcb200_bind_step", "dmpcb200_step_bound", "dmpcb200_step_dev", "dmpcb200_goal_dev", "dmpcb200_reached_goal", "dmpcb200_run",
     "dmpcb200_get_state", "dmpcb200_set_state", "dmpcb200_solve_agent", "dmpcb200_check_coll",
     "dmpcb200_coll_constr", "dmpcb200_prop_state", "dmpcb200_last_timing", "dmpcb200_last_host_timing",
     "dmpcb200_device_ptr",

@@ -65,6 +65,13 @@ struct dmpcb200_handle {
     // caller-owned host arrays that turned out to be pinned (page-locked + mapped): host pointer -> device alias
     // (nullptr: pageable).  The QP kernel then writes a host step's outputs straight into the caller's arrays.
     std::vector<std::pair<const void*, void*>> pinned_cache;
+    struct Bound {
+        const double *pk, *vk, *ak, *l_prev;
+        double *l_new, *p1, *v1, *a1, *v_hor, *a_hor;
+        int32_t* status;
+        dmpcb200_diag* diag;
+    };
+    std::vector<Bound> bound;  // dmpcb200_bind_step slots
     double* d_l[2] = {nullptr, nullptr};
     double* d_st[2][3] = {{nullptr, nullptr, nullptr}, {nullptr, nullptr, nullptr}};  // pk, vk, ak ping-pong
     double* d_pf = nullptr;
@@ -720,6 +727,23 @@ int dmpcb200_step(dmpcb200_t* h, const double* pk, const double* vk, const doubl
     h->launches = 2;
     h->cur = 0;
     return 0;
+}
+
+int dmpcb200_bind_step(dmpcb200_t* h, const double* pk, const double* vk, const double* ak, const double* l_prev,
+                       double* l_new, double* p1, double* v1, double* a1, double* v_hor, double* a_hor,
+                       int32_t* status, dmpcb200_diag* diag, int32_t* slot) {
+    if (!h || !pk || !vk || !ak || !l_prev || !slot) return fail(DMPCB200_ERR_ARG, "bind_step: null argument");
+    if (h->bound.size() >= 64) return fail(DMPCB200_ERR_STATE, "bind_step: too many bindings on this handle (64)");
+    h->bound.push_back({pk, vk, ak, l_prev, l_new, p1, v1, a1, v_hor, a_hor, status, diag});
+    *slot = (int32_t)h->bound.size() - 1;
+    return 0;
+}
+
+int dmpcb200_step_bound(dmpcb200_t* h, int32_t slot, int32_t* first_fail) {
+    if (!h || slot < 0 || (size_t)slot >= h->bound.size()) return fail(DMPCB200_ERR_ARG, "step_bound: bad slot");
+    const auto& b = h->bound[slot];
+    return dmpcb200_step(h, b.pk, b.vk, b.ak, b.l_prev, b.l_new, b.p1, b.v1, b.a1, b.v_hor, b.a_hor, b.status, b.diag,
+                         first_fail);
 }
 
 int dmpcb200_run(dmpcb200_t* h, int max_steps, int stop_on_fail, int mode, double* traj_p, double* traj_v,

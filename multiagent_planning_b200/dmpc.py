@@ -146,15 +146,16 @@ class Solver:
                        (out["p1"], (3, N)), (out["v1"], (3, N)), (out["a1"], (3, N))):
             if not (isinstance(a, np.ndarray) and a.dtype == np.float64 and a.flags.f_contiguous and a.shape == shp):
                 raise DmpcError("bind_step: arrays must be float64, column-major, of the documented shapes")
-        ff = C.c_int32(-1)
-        args = (self.h, _p(pk), _p(vk), _p(ak), _p(l_prev), _p(out["l_new"]), _p(out["p1"]), _p(out["v1"]),
-                _p(out["a1"]), _p(out.get("v_hor")), _p(out.get("a_hor")), out["status"].ctypes.data_as(_ip),
-                out["diag"].ctypes.data_as(C.POINTER(Diag)), C.byref(ff))
-        fn, chk = self.L.dmpcb200_step, _lib.check
+        slot, ff = C.c_int32(-1), C.c_int32(-1)
+        _lib.check(self.L.dmpcb200_bind_step(
+            self.h, _p(pk), _p(vk), _p(ak), _p(l_prev), _p(out["l_new"]), _p(out["p1"]), _p(out["v1"]),
+            _p(out["a1"]), _p(out.get("v_hor")), _p(out.get("a_hor")), out["status"].ctypes.data_as(_ip),
+            out["diag"].ctypes.data_as(C.POINTER(Diag)), C.byref(slot)), "bind_step")
+        fn, chk, h, sl, pff = self.L.dmpcb200_step_bound, _lib.check, self.h, slot.value, C.byref(ff)
         keep = (pk, vk, ak, l_prev, out)  # the arrays stay alive as long as the binding does
 
         def call(_keep=keep):
-            rc = fn(*args)
+            rc = fn(h, sl, pff)
             if rc:
                 chk(rc, "step")
             return ff.value
