@@ -80,7 +80,6 @@ struct dmpcb200_handle {
     AgentDiag* d_diag = nullptr;
     int cur = 0;  // index of the current l / state
     // scratch
-    unsigned* d_nearmask = nullptr;
     ScanRec* d_scan = nullptr;
     double *d_grow = nullptr, *d_gscr_d = nullptr;
     int *d_gkc = nullptr, *d_gidx = nullptr, *d_gscr_i = nullptr;
@@ -148,8 +147,6 @@ StepArgs make_args(dmpcb200_t* h, int n0, int n1, const double* pk, const double
     A.status = status;
     A.diag = diag;
     A.tab = h->d_tab;
-    A.nearmask = h->d_nearmask;
-    A.nm_stride = (size_t)h->Npad;
     A.scan = h->d_scan;
     A.grow = h->d_grow;
     A.gkc = h->d_gkc;
@@ -482,7 +479,6 @@ int dmpcb200_create(const dmpcb200_params* p, int N, int n0, int n1, int device,
     if ((e = dalloc(&h->d_vhor, (size_t)N * n3)) != cudaSuccess) return bail(e, "v_hor");
     if ((e = dalloc(&h->d_ahor, (size_t)N * n3)) != cudaSuccess) return bail(e, "a_hor");
     const size_t NL = h->NL;
-    if ((e = dalloc(&h->d_nearmask, NL * h->Npad)) != cudaSuccess) return bail(e, "nearmask");
     if ((e = dalloc(&h->d_scan, NL)) != cudaSuccess) return bail(e, "scan");
     if ((e = dalloc(&h->d_grow, NL * 5 * h->RMAX)) != cudaSuccess) return bail(e, "rows");
     if ((e = dalloc(&h->d_gkc, NL * h->RMAX)) != cudaSuccess) return bail(e, "rows kc");
@@ -511,7 +507,7 @@ void dmpcb200_destroy(dmpcb200_t* h) {
     cudaFree(h->d_arena);
     if (h->h_stage) cudaFreeHost(h->h_stage);
     cudaFree(h->d_pf); cudaFree(h->d_vhor); cudaFree(h->d_ahor);
-    cudaFree(h->d_nearmask); cudaFree(h->d_scan); cudaFree(h->d_grow); cudaFree(h->d_gkc); cudaFree(h->d_gidx);
+    cudaFree(h->d_scan); cudaFree(h->d_grow); cudaFree(h->d_gkc); cudaFree(h->d_gidx);
     cudaFree(h->d_gscr_d); cudaFree(h->d_gscr_i); cudaFree(h->d_rescue); cudaFree(h->d_rescue_next);
     cudaFree(h->d_done); cudaFree(h->d_ctrl); cudaFree(h->d_goal); cudaFree(h->d_u8); cudaFree(h->d_small);
     cudaFree(h->d_ismall);

@@ -77,8 +77,6 @@ struct StepArgs {
     int* status;
     AgentDiag* diag;  // optional
     const double* tab;
-    unsigned* nearmask;  // (n1-n0) x nm_stride
-    size_t nm_stride;
     ScanRec* scan;  // per local agent
     double* grow;   // per local agent 5*RMAX
     int* gkc;       // per local agent RMAX

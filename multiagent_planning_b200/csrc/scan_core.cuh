@@ -65,9 +65,6 @@ struct ScanThr {
     double T_viol;       // dist < rmin
     double T_coll;       // dist < rmin - coll_tol   (k = 1 only, solveSoftDMPCbound.m:25)
     double T_near[32];   // dist < neigh_thr(k)
-    // two-sided bands around the thresholds for decisions taken on the FMA estimate of s
-    double Tv_lo, Tv_hi, Tc_lo, Tc_hi;
-    double Tn_lo[32], Tn_hi[32];
     double inv_c;
     // high 32 bits of the exact thresholds, minus 1: decisions on the high word of the estimate
     // (scan_tile_hw).  he - h*_m (unsigned):  negative -> surely below;  0,1,2 -> ambiguous;  else surely above
@@ -93,17 +90,10 @@ inline double sq_threshold(double r) {
 
 inline ScanThr make_scan_thr(const DevParams& P) {
     ScanThr T;
-    const double lo = 1.0 - 1e-12, hi = 1.0 + 1e-12;  // the estimate is good to a few ulp
     T.T_viol = sq_threshold(P.rmin);
     T.T_coll = sq_threshold(P.rmin - P.coll_tol);
-    T.Tv_lo = T.T_viol * lo;
-    T.Tv_hi = T.T_viol * hi;
-    T.Tc_lo = T.T_coll * lo;
-    T.Tc_hi = T.T_coll * hi;
     for (int k = 0; k < 32; ++k) {
         T.T_near[k] = (k < P.K) ? sq_threshold(neigh_thr(P, k + 1)) : 0.0;
-        T.Tn_lo[k] = T.T_near[k] * lo;
-        T.Tn_hi[k] = T.T_near[k] * hi;
     }
     T.inv_c = 1.0 / P.c;
     T.hv_m = hi_word(T.T_viol) - 1u;
@@ -117,61 +107,9 @@ struct ScanAcc {
     unsigned coll0;  // per lane: some neighbour is closer than rmin - coll_tol at step 1
 };
 
-// Accumulate `cnt` neighbours starting at global index ibase whose horizons lie at tile
-// (cnt x K x 3 doubles, same layout as l).  own = this agent's previous horizon (3K doubles).
-// nearmask[i] (i global) receives the K-bit near mask.  thr: ScanThr (kernel parameter space).
-// Branch-free: every decision is taken on an FMA estimate of s against the two-sided bands; only an
-// estimate that falls INSIDE a band (relative width 2e-12 -- practically never) sends the pair through
-// the reference's exact rounding sequence (division included), so all decisions stay bit-identical.
-DMPC_D void scan_tile(const DevParams& P, const ScanThr* __restrict__ thr, const double* __restrict__ own, int n,
-                      const double* __restrict__ tile, int ibase, int cnt, unsigned* nearmask,
-                      ScanAcc& acc) {
-    const int K = P.K;
-    const double inv_c = thr->inv_c, Tv_lo = thr->Tv_lo, Tv_hi = thr->Tv_hi;
-    for (int m = lane_id(); m < cnt; m += kLanes) {
-        const int i = ibase + m;
-        unsigned nm = 0;
-        if (i != n) {
-            const double* pj = tile + (size_t)m * 3 * K;
-            unsigned vm = 0, amb = 0;
-#pragma unroll 5
-            for (int k = 0; k < K; ++k) {
-                const double dx = own[3 * k] - pj[3 * k];
-                const double dy = own[3 * k + 1] - pj[3 * k + 1];
-                const double dz = own[3 * k + 2] - pj[3 * k + 2];
-                const double ez = dz * inv_c;
-                const double est = fma(ez, ez, fma(dy, dy, dx * dx));  // estimate of s, good to a few ulp
-                const double Tnl = thr->Tn_lo[k], Tnh = thr->Tn_hi[k];
-                vm |= (est < Tv_lo ? 1u : 0u) << k;
-                nm |= (est < Tnl ? 1u : 0u) << k;
-                amb |= ((est >= Tv_lo && est < Tv_hi) || (est >= Tnl && est < Tnh)) ? 1u : 0u;
-            }
-            {   // k = 0 again for the rmin - coll_tol test (solveSoftDMPCbound.m:25)
-                const double dx = own[0] - pj[0], dy = own[1] - pj[1], dz = own[2] - pj[2];
-                const double ez = dz * inv_c;
-                const double est = fma(ez, ez, fma(dy, dy, dx * dx));
-                if (est < thr->Tc_lo) acc.coll0 = 1u;
-                amb |= (est >= thr->Tc_lo && est < thr->Tc_hi) ? 1u : 0u;
-            }
-            if (amb) {
-                // some estimate sits within 1e-12 of a threshold: redo this neighbour exactly
-                vm = 0;
-                nm = 0;
-                for (int k = 0; k < K; ++k) {
-                    const double s = ell_sq(own[3 * k] - pj[3 * k], own[3 * k + 1] - pj[3 * k + 1],
-                                            own[3 * k + 2] - pj[3 * k + 2], P.c);
-                    if (s < thr->T_viol) vm |= 1u << k;
-                    if (s < thr->T_near[k]) nm |= 1u << k;
-                    if (k == 0 && s < thr->T_coll) acc.coll0 = 1u;
-                }
-            }
-            acc.vmask |= vm;
-        }
-        nearmask[i] = nm;
-    }
-}
-
-// Same contract as scan_tile for ONE neighbour per lane (cnt <= kLanes), decisions taken on the HIGH WORD
+// Accumulate ONE neighbour per lane (cnt <= kLanes) starting at global index ibase whose horizons lie at
+// `tile` (cnt x K x 3 doubles, same layout as l).  own = this agent's previous horizon (3K doubles).
+// nearmask[i] (i global) receives the K-bit near mask.  Decisions are taken on the HIGH WORD
 // of the FMA estimate of s with integer compares: for positive doubles  s < T  <=>  hi(s) < hi(T)  unless
 // the high words are within 1 of each other -- only then (relative distance to a threshold < 2^-19, and
 // the estimate is good to a few ulp) the pair goes through the reference's exact rounding sequence.  The

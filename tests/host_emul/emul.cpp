@@ -52,11 +52,8 @@ extern "C" int emul_step(const dmpcb200_params* p, int N, int n0, int n1, const 
         ScanAcc acc;
         acc.vmask = 0;
         acc.coll0 = 0;
-        if (fast)  // the kernel's tile function: one neighbour per lane, decisions on the high word
-            for (int i = 0; i < N; ++i)
-                scan_tile_hw<0>(D, &thr, own, n, l_prev + (size_t)3 * K * i, i, 1, nearmask.data(), acc);
-        else
-            scan_tile(D, &thr, own, n, l_prev, 0, N, nearmask.data(), acc);
+        for (int i = 0; i < N; ++i)  // the kernel's tile function: one neighbour per lane, high-word decisions
+            scan_tile_hw<0>(D, &thr, own, n, l_prev + (size_t)3 * K * i, i, 1, nearmask.data(), acc);
         ScanOut so = scan_finish(D, own, n, l_prev, nearmask.data(), acc, RMAX, grow.data(), gkc.data(),
                                  gidx.data(), list.data());
         AgentIO io;
