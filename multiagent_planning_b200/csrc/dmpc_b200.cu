@@ -197,7 +197,19 @@ cudaError_t launch_qp_w(const StepArgs& A, int nl, size_t smem, cudaStream_t s) 
         if (n_sm < 1) n_sm = 148;
     }
     const int ctas = std::min((nl + W - 1) / W, n_sm);
-    qp_kernel<W, KT><<<ctas, W * 32, smem, s>>>(A);
+    // programmatic stream serialization: the grid may launch while the scan kernel drains (the kernel
+    // itself waits for the scan's completion before it reads the rows)
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)ctas);
+    cfg.blockDim = dim3(W * 32);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = s;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, qp_kernel<W, KT>, A);
     return cudaGetLastError();
 }
 

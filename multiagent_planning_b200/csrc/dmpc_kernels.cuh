@@ -169,6 +169,9 @@ DMPC_HD size_t scan_smem_bytes(int K, int W, int stages, int Npad, int RMAX) {
 
 template <int W, int S, int KT>
 __global__ void __launch_bounds__(W * S * 32) scan_kernel(const __grid_constant__ StepArgs A, int stages) {
+    // programmatic dependent launch: the QP kernel of this step may start its prologue (barrier, table
+    // TMA) while this grid is still running; it waits (griddepcontrol.wait) before it reads our output
+    asm volatile("griddepcontrol.launch_dependents;");
     if (A.ctrl && A.ctrl->done) return;
 #if defined(DMPC_PROF_SCAN)
     const long long scan_t0 = clock64();
@@ -447,6 +450,8 @@ __global__ void __launch_bounds__(W * 32, 1) qp_kernel(const __grid_constant__ S
         mbar_expect_tx(bar, (uint32_t)qp_table_bytes(K));
         tma_bulk_g2s(tab_s, A.tab + tab_fast_offset(K), (uint32_t)qp_table_bytes(K), bar);
     }
+    // everything above touches constants only; the scan kernel's rows are read below
+    asm volatile("griddepcontrol.wait;" ::: "memory");
     __syncthreads();
     // one agent per warp while the grid covers the swarm; beyond that the CTAs are persistent (one per SM:
     // the per-agent workspace fills shared memory) and every warp takes its next agent from a device
