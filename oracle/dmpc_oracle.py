@@ -415,3 +415,81 @@ def simulate(P: Params, po, pf, pmin, pmax, max_steps, tol=0.01, nthreads=1, rec
         k += 1
     return dict(pk=np.stack(pk, 1), vk=np.stack(vk, 1), ak=np.stack(ak, 1), l=l, steps=k,
                 reached_goal=reached, failed_agent=failed, hist=hist)
+
+
+# ---- post-processing of a finished transition (test/failure_rate.m:134-195) ----------------------------
+def spline_not_a_knot(x, y, xq):
+    """MATLAB `spline(x, y, xq)` for row-wise data y (..., n), n >= 4: cubic spline with not-a-knot end
+    conditions in the slope (Hermite) form of spline.m, evaluated like ppval (right-continuous pieces,
+    the last point in the last piece).  Pure numpy."""
+    x = np.asarray(x, float)
+    y = np.asarray(y, float)
+    n = x.size
+    dx = np.diff(x)
+    dd = np.diff(y, axis=-1) / dx
+    A = np.zeros((n, n))
+    b = np.zeros(y.shape)
+    for i in range(1, n - 1):
+        A[i, i - 1], A[i, i], A[i, i + 1] = dx[i], 2.0 * (dx[i - 1] + dx[i]), dx[i - 1]
+        b[..., i] = 3.0 * (dx[i] * dd[..., i - 1] + dx[i - 1] * dd[..., i])
+    x31, xn = x[2] - x[0], x[-1] - x[-3]
+    A[0, 0], A[0, 1] = dx[1], x31
+    b[..., 0] = ((dx[0] + 2.0 * x31) * dx[1] * dd[..., 0] + dx[0] ** 2 * dd[..., 1]) / x31
+    A[-1, -2], A[-1, -1] = xn, dx[-2]
+    b[..., -1] = (dx[-1] ** 2 * dd[..., -2] + (2.0 * xn + dx[-1]) * dx[-2] * dd[..., -1]) / xn
+    s = np.linalg.solve(A, b.reshape(-1, n).T).T.reshape(y.shape)
+    xq = np.asarray(xq, float)
+    idx = np.clip(np.searchsorted(x, xq, side="right") - 1, 0, n - 2)
+    t = xq - x[idx]
+    hx = dx[idx]
+    y0, y1, s0, s1, d = y[..., idx], y[..., idx + 1], s[..., idx], s[..., idx + 1], dd[..., idx]
+    c2 = (3.0 * d - 2.0 * s0 - s1) / hx
+    c3 = (s0 - 2.0 * d + s1) / hx ** 2
+    return y0 + t * (s0 + t * (c2 + t * c3))
+
+
+def postprocess(pk, vk, ak, pf, h, c=2.0, rmin=0.35, vmax=2.0, amax=1.0, Ts=0.01, coll_tol=0.05,
+                goal_radius=0.05, want_interp=True):
+    """failure_rate.m:134-195 for one finished transition.  pk, vk, ak: (3, S, N) as the loop left them
+    (column k = state after MPC step k).  Returns the time-scaled pk, vk, ak, the 100 Hz interpolation
+    p, v, a (3, nt, N), and the trial's figures: r_factor, h_scaled, T, violation (post-interpolation
+    collision check), min_dist, totdist, time_index (N), traj_time."""
+    pk, vk, ak = (np.array(x, dtype=np.float64, order="F") for x in (pk, vk, ak))
+    S, N = pk.shape[1], pk.shape[2]
+    pf = np.asarray(pf, float).reshape(3, N, order="F")
+    with np.errstate(divide="ignore"):
+        ak_mod = amax / np.sqrt((ak[0] ** 2 + ak[1] ** 2) + ak[2] ** 2)       # :141
+        vk_mod = vmax / np.sqrt((vk[0] ** 2 + vk[1] ** 2) + vk[2] ** 2)       # :142
+    r_factor = min(ak_mod.min(), vk_mod.min())                                 # :144
+    h_scaled = h / np.sqrt(r_factor)                                           # :145
+    T = (S - 1) * h_scaled          # :148  (k - 2) h_scaled with k = S + 1 when the loop ended
+    tk = np.arange(S) * h_scaled    # :149  0:h_scaled:T
+    nt = int(np.floor(T / Ts + 1e-9)) + 1
+    t = np.arange(nt) * Ts          # :151  0:Ts:T
+    hh = h_scaled ** 2 / 2
+    for k in range(S - 1):          # :156-162
+        ak[:, k, :] = ak[:, k, :] * r_factor
+        vk[:, k + 1, :] = vk[:, k, :] + h_scaled * ak[:, k, :]
+        pk[:, k + 1, :] = (pk[:, k, :] + h_scaled * vk[:, k, :]) + hh * ak[:, k, :]
+    out = dict(pk=pk, vk=vk, ak=ak, r_factor=r_factor, h_scaled=h_scaled, T=T, tk=tk, t=t, nt=nt)
+    p = spline_not_a_knot(tk, np.moveaxis(pk, 1, -1), t)      # (3, N, nt)   :164-168
+    if want_interp:
+        out["p"] = np.moveaxis(p, -1, 1)
+        out["v"] = np.moveaxis(spline_not_a_knot(tk, np.moveaxis(vk, 1, -1), t), -1, 1)
+        out["a"] = np.moveaxis(spline_not_a_knot(tk, np.moveaxis(ak, 1, -1), t), -1, 1)
+    # :170-181 pairwise check on the interpolated positions, E1 = diag(1, 1, 1/c)
+    md = np.inf
+    for i in range(N - 1):
+        d = p[:, i + 1:, :] - p[:, i:i + 1, :]
+        dist = np.sqrt((d[0] ** 2 + d[1] ** 2) + (d[2] / c) ** 2)
+        md = min(md, dist.min())
+    out["min_dist"] = md
+    out["violation"] = int(md < rmin - coll_tol)
+    dp = np.diff(p, axis=-1)
+    out["totdist"] = float(np.sqrt((dp[0] ** 2 + dp[1] ** 2) + dp[2] ** 2).sum())   # :183
+    dg = np.sqrt(((p - pf[:, :, None]) ** 2).sum(0))                           # :185-193
+    far = dg >= goal_radius
+    last = np.where(far.any(1), nt - 1 - np.argmax(far[:, ::-1], axis=1), -1)
+    out["time_index"] = np.where(last >= 0, last + 2, 0).astype(np.int32)      # 1-based hola + 1
+    out["traj_time"] = float(out["time_index"].max() * Ts)
+    return out

@@ -31,7 +31,7 @@ def golden():
     import numpy as np
     d = os.path.join(ROOT, "tests", "golden")
     return {n: np.load(os.path.join(d, n + ".npz")) for n in
-            ("kat_matrices", "kat_soft_bound", "kat_soft_bound2", "ref_transition_n200")}
+            ("kat_matrices", "kat_soft_bound", "kat_soft_bound2", "ref_transition_n200", "postprocess_n200")}
 
 
 @pytest.fixture(scope="session")
@@ -48,3 +48,17 @@ def oracle_params(orc, P):
     for n, _ in O._fields_:
         setattr(O, n, getattr(P, n))
     return O
+
+
+def raw_transition(g):
+    """raw MPC trajectory (pk, vk, ak of the loop, (3, S, N)) of the golden post-processing fixture: v and p
+    follow from the stored raw accelerations and start points by the model recursion"""
+    import numpy as np
+    a, po, h = g["ak_raw"], g["po"], float(g["h"])
+    S = a.shape[1]
+    v, p = np.zeros_like(a), np.zeros_like(a)
+    p[:, 0, :] = po
+    for k in range(1, S):
+        v[:, k, :] = v[:, k - 1, :] + h * a[:, k, :]
+        p[:, k, :] = p[:, k - 1, :] + h * v[:, k - 1, :] + h * h / 2 * a[:, k, :]
+    return p, v, a

@@ -84,6 +84,35 @@ def main():
     )
     print("ref_transition_n200.npz", ak.shape)
 
+    # post-processing of the same finished trial (failure_rate.m:134-195): raw MPC trajectory in, MATLAB's
+    # time-scaled / interpolated trajectories and trial figures out.  The raw trajectory is recovered exactly
+    # (SURVEY 0.8): a_raw = ak / r_factor (all but the last column), v, p by the model with the raw h.
+    h = float(m["h"][0, 0])
+    S = ak.shape[1]
+    a_raw = ak.copy()
+    a_raw[:, :S - 1, :] = ak[:, :S - 1, :] / rf
+    po = np.asarray(m["po"], float).reshape(3, N, order="F")
+    v_raw, p_raw = np.zeros_like(ak), np.zeros_like(ak)
+    p_raw[:, 0, :] = po
+    for k in range(1, S):
+        v_raw[:, k, :] = v_raw[:, k - 1, :] + h * a_raw[:, k, :]
+        p_raw[:, k, :] = p_raw[:, k - 1, :] + h * v_raw[:, k - 1, :] + h * h / 2 * a_raw[:, k, :]
+    sel = np.array([0, 5, 77, 199])
+    np.savez_compressed(
+        os.path.join(OUT, "postprocess_n200.npz"),
+        # (v, p of the raw trajectory follow from ak_raw and po by the recursion above: tests rebuild them)
+        ak_raw=a_raw, po=po, pf=np.asarray(m["pf"], float).reshape(3, N, order="F"),
+        h=h, c=float(m["c"][0, 0]), rmin=float(m["rmin"][0, 0]),
+        r_factor=rf, h_scaled=float(m["h_scaled"][0, 0]), T=float(m["T"][0, 0]), nt=m["t"].size,
+        pk=np.asarray(m["pk"], float)[:, :, sel], vk=np.asarray(m["vk"], float)[:, :, sel],
+        ak=np.asarray(m["ak"], float)[:, :, sel],
+        sel=sel, p=np.asarray(m["p"], float)[:, :, sel], v=np.asarray(m["v"], float)[:, :, sel],
+        a=np.asarray(m["a"], float)[:, :, sel], time_index=np.asarray(m["time_index"], np.int32).ravel(),
+        violation=int(np.asarray(m["violation"])[-1, -1]), totdist=float(np.asarray(m["totdist_dmpc"])[-1, -1]),
+        traj_time=float(np.asarray(m["traj_time"])[-1, -1]), source="data/failure_rate/failure_rate3.mat",
+    )
+    print("postprocess_n200.npz")
+
 
 if __name__ == "__main__":
     main()

@@ -128,3 +128,26 @@ def test_closed_loop_first_steps_vs_reference(orc, golden):
         e = np.abs(a_ref[:, k, :] - r["ak"][:, k, :]).max(0)
         assert np.quantile(e, 0.9) <= 1e-3, (k, np.quantile(e, 0.9))
     assert np.abs(r["ak"]).max() <= P.alim + 1e-9
+
+
+def test_postprocess_matches_matlab_workspace(orc, golden):
+    """failure_rate.m:134-195 on the finished N=200 trial of failure_rate3.mat: time scaling bit-exact,
+    100 Hz not-a-knot splines to 1e-14, the trial's figures (collision flag, trajectory time) identical"""
+    from tests.conftest import raw_transition
+    g = golden["postprocess_n200"]
+    pk, vk, ak = raw_transition(g)
+    o = orc.postprocess(pk, vk, ak, g["pf"], float(g["h"]), c=float(g["c"]), rmin=float(g["rmin"]))
+    assert o["r_factor"] == float(g["r_factor"]) and o["h_scaled"] == float(g["h_scaled"])
+    assert o["nt"] == int(g["nt"]) and abs(o["T"] - float(g["T"])) < 1e-12
+    sel = g["sel"]
+    for k in ("pk", "vk", "ak"):
+        assert np.array_equal(o[k][:, :, sel], g[k]), k
+    for k in ("p", "v", "a"):
+        assert np.abs(o[k][:, :, sel] - g[k]).max() < 1e-14, k
+    assert np.array_equal(o["time_index"], g["time_index"])
+    assert o["traj_time"] == float(g["traj_time"]) and o["violation"] == int(g["violation"]) == 1
+    assert abs(o["totdist"] - float(g["totdist"])) < 1e-9
+    # the spline is MATLAB's: cross-check the pure-numpy implementation against scipy's not-a-knot
+    from scipy.interpolate import CubicSpline
+    ref = CubicSpline(o["tk"], o["pk"][:, :, 3], axis=1, bc_type="not-a-knot")(o["t"])
+    assert np.abs(ref - o["p"][:, :, 3]).max() < 1e-12
