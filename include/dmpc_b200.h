@@ -203,6 +203,27 @@ int dmpcb200_coll_constr(dmpcb200_t* h, const double* p3, const double* po, cons
 int dmpcb200_prop_state(dmpcb200_t* h, int B, const double* po, const double* vo, const double* a,
                         double* p, double* v);
 
+/* Post-processing of a finished transition -- the rest of the reference's t_dmpc, test/failure_rate.m:134-195
+ * (C++: dmpc.cpp:1912-2086): time scaling of the trajectory to the velocity / acceleration limits (:136-162,
+ * r_factor, h_scaled), 100 Hz cubic-spline interpolation (MATLAB `spline`, not-a-knot, :164-168), the O(N^2 T)
+ * pairwise collision check on the interpolated positions (:170-181), travelled distance (:183) and trajectory
+ * time (:185-194).
+ * pk, vk, ak: HOST 3 x S x N as the MPC loop left them (column k = state after step k; S >= 4); they are scaled
+ * IN PLACE like the reference does.  p, v, a: optional HOST outputs 3 x nt_cap x N for the interpolated
+ * trajectories (written only if nt <= nt_cap; pass NULL / 0 to get the figures only -- res->nt tells the size).
+ * time_index: optional int32[N] (failure_rate.m:186-193). */
+typedef struct dmpcb200_post {
+    double r_factor, h_scaled, T;  /* failure_rate.m:144,145,148 */
+    double min_dist;               /* min over pairs and samples of ||E1 (p_i - p_j)||  (:174-175) */
+    double totdist, traj_time;     /* :183, :194 */
+    int32_t nt;                    /* number of 100 Hz samples, length(0:Ts:T) */
+    int32_t violation;             /* min_dist < rmin - coll_tol  (:176-179) */
+    double device_ms;              /* device time of the whole post-processing (CUDA events) */
+} dmpcb200_post;
+int dmpcb200_postprocess(dmpcb200_t* h, int S, double* pk, double* vk, double* ak, double vmax, double amax,
+                         double Ts, double goal_radius, double* p, double* v, double* a, int nt_cap,
+                         int32_t* time_index, dmpcb200_post* res);
+
 /* timing of the last dmpcb200_step / dmpcb200_run, CUDA events on the launch stream:
  * ms[0] = neighbour-scan kernel, ms[1] = QP kernel, ms[2] = whole step (device), averaged over
  * the steps of the call; launches[0] = number of kernels launched. */

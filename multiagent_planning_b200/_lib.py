@@ -15,7 +15,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 _CSRC = os.path.join(_HERE, "csrc")
 LIB_PATH = os.path.join(_HERE, "libdmpc_b200.so")
 SOURCES = ["dmpc_b200.cu", "model_tables.cpp"]
-HEADERS = ["dmpc_kernels.cuh", "scan_core.cuh", "agent_solve.cuh", "qp_core.cuh", "qp_warp.cuh", "model_tables.h",
+HEADERS = ["dmpc_kernels.cuh", "scan_core.cuh", "agent_solve.cuh", "qp_core.cuh", "qp_warp.cuh", "postprocess.cuh", "model_tables.h",
            os.path.join("..", "..", "include", "dmpc_b200.h")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "-shared", "-diag-suppress", "177"]
@@ -42,6 +42,13 @@ class Params(C.Structure):
 
     def as_dict(self):
         return {n: getattr(self, n) for n, _ in self._fields_}
+
+
+class Post(C.Structure):
+    """dmpcb200_post (include/dmpc_b200.h): figures of test/failure_rate.m:134-195"""
+    _fields_ = [("r_factor", C.c_double), ("h_scaled", C.c_double), ("T", C.c_double), ("min_dist", C.c_double),
+                ("totdist", C.c_double), ("traj_time", C.c_double), ("nt", C.c_int32), ("violation", C.c_int32),
+                ("device_ms", C.c_double)]
 
 
 class Diag(C.Structure):
@@ -108,6 +115,7 @@ def lib():
         "dmpcb200_check_coll": ([vp, dp, dp, I, I, u8p, u8p, dp, ip], I),
         "dmpcb200_coll_constr": ([vp, dp, dp, dp, I, I, dp, u8p, I, dp, dp, dp, ip], I),
         "dmpcb200_prop_state": ([vp, I, dp, dp, dp, dp, dp], I),
+        "dmpcb200_postprocess": ([vp, I, dp, dp, dp, D, D, D, D, dp, dp, dp, I, ip, C.POINTER(Post)], I),
         "dmpcb200_last_timing": ([vp, dp, C.POINTER(C.c_int64)], I),
         "dmpcb200_last_host_timing": ([vp, dp], I),
         "dmpcb200_device_ptr": ([vp, I], vp),
@@ -128,7 +136,7 @@ EXPORTS = [
     "dmpcb200_model_mats", "dmpcb200_create", "dmpcb200_destroy", "dmpcb200_set_bounds", "dmpcb200_set_goals",
     "dmpcb200_init_horizons", "dmpcb200_step", "dmpcb200_bind_step", "dmpcb200_step_bound", "dmpcb200_step_dev", "dmpcb200_goal_dev", "dmpcb200_reached_goal", "dmpcb200_run",
     "dmpcb200_get_state", "dmpcb200_set_state", "dmpcb200_solve_agent", "dmpcb200_check_coll",
-    "dmpcb200_coll_constr", "dmpcb200_prop_state", "dmpcb200_last_timing", "dmpcb200_last_host_timing",
+    "dmpcb200_coll_constr", "dmpcb200_prop_state", "dmpcb200_postprocess", "dmpcb200_last_timing", "dmpcb200_last_host_timing",
     "dmpcb200_device_ptr",
     "dmpcb200_swap_horizons", "dmpcb200_config",
 ]

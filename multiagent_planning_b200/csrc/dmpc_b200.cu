@@ -7,6 +7,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <chrono>
+#include <cmath>
 #include <cstring>
 #include <string>
 #include <utility>
@@ -14,6 +15,7 @@
 
 #include "../../include/dmpc_b200.h"
 #include "dmpc_kernels.cuh"
+#include "postprocess.cuh"
 #include "model_tables.h"
 
 using namespace dmpc;
@@ -1036,6 +1038,116 @@ int dmpcb200_prop_state(dmpcb200_t* h, int B, const double* po, const double* vo
     CK(cudaFreeAsync(d, s));
     CK(cudaStreamSynchronize(s));
     h->launches = 1;
+    return 0;
+}
+
+int dmpcb200_postprocess(dmpcb200_t* h, int S, double* pk, double* vk, double* ak, double vmax, double amax,
+                         double Ts, double goal_radius, double* p, double* v, double* a, int nt_cap,
+                         int32_t* time_index, dmpcb200_post* res) {
+    if (!h || !pk || !vk || !ak || !res) return fail(DMPCB200_ERR_ARG, "postprocess: null argument");
+    if (S < 4) return fail(DMPCB200_ERR_ARG, "postprocess: needs at least 4 trajectory columns (not-a-knot spline)");
+    if (!(vmax > 0) || !(amax > 0) || !(Ts > 0)) return fail(DMPCB200_ERR_ARG, "postprocess: vmax, amax, Ts must be positive");
+    if (!h->have_goals) return fail(DMPCB200_ERR_STATE, "postprocess: set_goals first");
+    if (int rc = ensure_device(h)) return rc;
+    const int N = h->N;
+    cudaStream_t s = h->stream;
+    const size_t nS = (size_t)N * S * 3, bS = nS * sizeof(double);
+    const bool want_all = p && v && a;
+    const int nq = want_all ? 3 : 1;  // positions only unless the caller wants v and a as well
+    double *d_tr = nullptr, *d_sl = nullptr, *d_out = nullptr, *d_dist = nullptr;
+    int* d_tidx = nullptr;
+    unsigned long long* d_bits = nullptr;
+    auto cleanup = [&]() {
+        cudaFree(d_tr); cudaFree(d_sl); cudaFree(d_out); cudaFree(d_dist); cudaFree(d_tidx); cudaFree(d_bits);
+    };
+    auto bail = [&](cudaError_t e, const char* what) {
+        cleanup();
+        return fail(DMPCB200_ERR_CUDA, std::string("postprocess: ") + what + ": " + cudaGetErrorString(e));
+    };
+    cudaError_t e;
+    if ((e = cudaMalloc((void**)&d_tr, 3 * bS)) != cudaSuccess) return bail(e, "trajectory");
+    if ((e = cudaMalloc((void**)&d_sl, 2 * (size_t)nq * nS * sizeof(double))) != cudaSuccess) return bail(e, "slopes");
+    if ((e = cudaMalloc((void**)&d_dist, (size_t)N * sizeof(double))) != cudaSuccess) return bail(e, "dist");
+    if ((e = cudaMalloc((void**)&d_tidx, (size_t)N * sizeof(int))) != cudaSuccess) return bail(e, "time index");
+    if ((e = cudaMalloc((void**)&d_bits, 2 * sizeof(unsigned long long))) != cudaSuccess) return bail(e, "reductions");
+    double *d_pk = d_tr, *d_vk = d_tr + nS, *d_ak = d_tr + 2 * nS;
+    if (int rc = ensure_events(h, 4)) { cleanup(); return rc; }
+    if ((e = cudaMemcpyAsync(d_pk, pk, bS, cudaMemcpyHostToDevice, s)) != cudaSuccess) return bail(e, "copy");
+    if ((e = cudaMemcpyAsync(d_vk, vk, bS, cudaMemcpyHostToDevice, s)) != cudaSuccess) return bail(e, "copy");
+    if ((e = cudaMemcpyAsync(d_ak, ak, bS, cudaMemcpyHostToDevice, s)) != cudaSuccess) return bail(e, "copy");
+    if ((e = cudaMemsetAsync(d_bits, 0x7f, 2 * sizeof(unsigned long long), s)) != cudaSuccess) return bail(e, "memset");
+    cudaEventRecord(h->ev[0], s);
+    // 1. r_factor  (failure_rate.m:141-144)
+    pp_rfactor_kernel<<<std::min((N * S + 255) / 256, 592), 256, 0, s>>>(N * S, d_vk, d_ak, vmax, amax, d_bits);
+    unsigned long long bits = 0;
+    if ((e = cudaMemcpyAsync(&bits, d_bits, sizeof(bits), cudaMemcpyDeviceToHost, s)) != cudaSuccess) return bail(e, "copy");
+    if ((e = cudaStreamSynchronize(s)) != cudaSuccess) return bail(e, "r_factor");
+    double r_factor;
+    std::memcpy(&r_factor, &bits, sizeof(double));
+    if (!(r_factor > 0) || !std::isfinite(r_factor)) {
+        cleanup();
+        return fail(DMPCB200_ERR_ARG, "postprocess: the trajectory has no motion (r_factor is not finite)");
+    }
+    const double hs = h->prm.h / std::sqrt(r_factor);  // :145
+    const double T = (double)(S - 1) * hs;             // :148
+    const int nt = (int)std::floor(T / Ts + 1e-9) + 1; // length(0:Ts:T)
+    // 2. time scaling (:156-162)
+    pp_rescale_kernel<<<(3 * N + 127) / 128, 128, 0, s>>>(N, S, r_factor, hs, d_pk, d_vk, d_ak);
+    // 3. spline slopes and 100 Hz evaluation (:164-168)
+    if ((e = cudaMalloc((void**)&d_out, (size_t)nq * N * nt * 3 * sizeof(double))) != cudaSuccess) return bail(e, "interpolation");
+    double* d_p = d_out;
+    double* d_v = want_all ? d_out + (size_t)N * nt * 3 : nullptr;
+    double* d_a = want_all ? d_out + 2 * (size_t)N * nt * 3 : nullptr;
+    pp_slopes_kernel<<<(nq * 3 * N + 63) / 64, 64, 0, s>>>(N, S, nq, hs, d_pk, d_vk, d_ak, d_sl, d_sl + (size_t)nq * nS);
+    {
+        const long long tot = (long long)nq * N * nt;
+        pp_eval_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, s>>>(N, S, nt, nq, hs, Ts, d_pk, d_vk, d_ak, d_sl, d_p, d_v, d_a);
+    }
+    // 4. pairwise check (:170-181), distance and trajectory time (:183-194)
+    {
+        const int tiles = (N + kPairTile - 1) / kPairTile;
+        pp_pairs_kernel<<<dim3(tiles, tiles), dim3(kPairTile, kPairTile), 0, s>>>(N, nt, h->prm.c, d_p, d_bits + 1);
+        pp_stats_kernel<<<(N + 3) / 4, 128, 0, s>>>(N, nt, goal_radius, d_p, h->d_pf, d_dist, d_tidx);
+    }
+    cudaEventRecord(h->ev[1], s);
+    if ((e = cudaGetLastError()) != cudaSuccess) return bail(e, "launch");
+    std::vector<double> dist(N);
+    std::vector<int> tidx(N);
+    if ((e = cudaMemcpyAsync(pk, d_pk, bS, cudaMemcpyDeviceToHost, s)) != cudaSuccess) return bail(e, "copy");
+    if ((e = cudaMemcpyAsync(vk, d_vk, bS, cudaMemcpyDeviceToHost, s)) != cudaSuccess) return bail(e, "copy");
+    if ((e = cudaMemcpyAsync(ak, d_ak, bS, cudaMemcpyDeviceToHost, s)) != cudaSuccess) return bail(e, "copy");
+    if ((e = cudaMemcpyAsync(dist.data(), d_dist, (size_t)N * sizeof(double), cudaMemcpyDeviceToHost, s)) != cudaSuccess) return bail(e, "copy");
+    if ((e = cudaMemcpyAsync(tidx.data(), d_tidx, (size_t)N * sizeof(int), cudaMemcpyDeviceToHost, s)) != cudaSuccess) return bail(e, "copy");
+    if ((e = cudaMemcpyAsync(&bits, d_bits + 1, sizeof(bits), cudaMemcpyDeviceToHost, s)) != cudaSuccess) return bail(e, "copy");
+    const size_t bO = (size_t)N * nt * 3 * sizeof(double);
+    if (nt <= nt_cap) {
+        if (p && (e = cudaMemcpyAsync(p, d_p, bO, cudaMemcpyDeviceToHost, s)) != cudaSuccess) return bail(e, "copy");
+        if (want_all && (e = cudaMemcpyAsync(v, d_v, bO, cudaMemcpyDeviceToHost, s)) != cudaSuccess) return bail(e, "copy");
+        if (want_all && (e = cudaMemcpyAsync(a, d_a, bO, cudaMemcpyDeviceToHost, s)) != cudaSuccess) return bail(e, "copy");
+    }
+    if ((e = cudaStreamSynchronize(s)) != cudaSuccess) return bail(e, "sync");
+    double min_sq;
+    std::memcpy(&min_sq, &bits, sizeof(double));
+    float ms = 0;
+    cudaEventElapsedTime(&ms, h->ev[0], h->ev[1]);
+    res->r_factor = r_factor;
+    res->h_scaled = hs;
+    res->T = T;
+    res->nt = nt;
+    res->min_dist = N > 1 ? std::sqrt(min_sq) : INFINITY;
+    res->violation = res->min_dist < h->prm.rmin - h->prm.coll_tol ? 1 : 0;
+    double tot = 0.0;
+    int tmax = 0;
+    for (int n = 0; n < N; ++n) {
+        tot += dist[n];
+        tmax = std::max(tmax, tidx[n]);
+        if (time_index) time_index[n] = tidx[n];
+    }
+    res->totdist = tot;
+    res->traj_time = tmax * Ts;
+    res->device_ms = ms;
+    h->launches = 6;
+    cleanup();
     return 0;
 }
 

@@ -23,7 +23,7 @@ import ctypes as C
 import numpy as np
 
 from . import _lib
-from ._lib import Diag, DmpcError, Params
+from ._lib import Diag, DmpcError, Params, Post
 
 SOFT_BOUND, SOFT_BOUND2, HARD, HARD_ONDEMAND = 0, 1, 2, 3
 ST_SOLVED, ST_COLL, ST_INFEASIBLE, ST_OUTBOUND, ST_QPFAIL, ST_OVERFLOW = 1, 2, 4, 8, 16, 32
@@ -210,6 +210,36 @@ class Solver:
         us = (C.c_double * 4)()
         _lib.check(self.L.dmpcb200_last_host_timing(self.h, us), "last_host_timing")
         return dict(pack_us=us[0], submit_us=us[1], wait_us=us[2], unpack_us=us[3])
+
+    def postprocess(self, pk, vk, ak, vmax=2.0, amax=1.0, Ts=0.01, goal_radius=0.05, want_interp=True):
+        """The rest of the reference's t_dmpc (test/failure_rate.m:134-195) for a finished transition: time
+        scaling to the limits, 100 Hz spline interpolation, pairwise collision check, distance and trajectory
+        time.  pk, vk, ak: (3, S, N) as `run(record=True)` returns them.  Returns a dict with the scaled
+        pk, vk, ak, the figures, and (want_interp) p, v, a of shape (3, nt, N)."""
+        N = self.N
+        pk, vk, ak = (np.array(x, dtype=np.float64, order="F") for x in (pk, vk, ak))
+        S = pk.shape[1]
+        res = Post()
+        tidx = np.zeros(N, np.int32)
+        p = v = a = None
+        cap = 0
+        if want_interp:
+            # size of the 100 Hz grid: T = (S-1) h / sqrt(r_factor); r_factor comes from the same norms
+            with np.errstate(divide="ignore"):
+                rf = min((amax / np.sqrt((ak[0] ** 2 + ak[1] ** 2) + ak[2] ** 2)).min(),
+                         (vmax / np.sqrt((vk[0] ** 2 + vk[1] ** 2) + vk[2] ** 2)).min())
+            cap = int(np.floor((S - 1) * self.P.h / np.sqrt(rf) / Ts + 1e-9)) + 2
+            p, v, a = (np.zeros((3, cap, N), order="F") for _ in range(3))
+        _lib.check(self.L.dmpcb200_postprocess(self.h, S, _p(pk), _p(vk), _p(ak), float(vmax), float(amax), float(Ts),
+                                               float(goal_radius), _p(p), _p(v), _p(a), cap,
+                                               tidx.ctypes.data_as(_ip), C.byref(res)), "postprocess")
+        out = dict(pk=pk, vk=vk, ak=ak, time_index=tidx, **{k: getattr(res, k) for k, _ in Post._fields_})
+        if want_interp:
+            nt = res.nt
+            # the library wrote (3, nt, N) contiguously at the start of the (3, cap, N) buffers
+            out.update({k: np.asfortranarray(b.ravel(order="F")[: 3 * nt * N].reshape((3, nt, N), order="F"))
+                        for k, b in (("p", p), ("v", v), ("a", a))})
+        return out
 
     def get_state(self):
         N, K = self.N, self.K

@@ -429,3 +429,49 @@ def test_large_swarm_persistent_grid_vs_oracle(dmpc, orc):
         s.init_horizons(po)
         r = s.run(3, record=True)
         assert np.array_equal(r["pk"][:, 3, :], pk)
+
+
+def test_postprocess_vs_oracle_and_matlab(dmpc, orc, golden):
+    """dmpcb200_postprocess (failure_rate.m:134-195) on the finished N=200 trial of failure_rate3.mat:
+    against the oracle and against MATLAB's own workspace (time scaling bit-exact, splines 1e-12)"""
+    from tests.conftest import raw_transition
+    g = golden["postprocess_n200"]
+    pk, vk, ak = raw_transition(g)
+    N = pk.shape[2]
+    P = dmpc.default_params(0, c=float(g["c"]), rmin=float(g["rmin"]), h=float(g["h"]))
+    with dmpc.Solver(N, P, pf=g["pf"]) as s:
+        r = s.postprocess(pk, vk, ak)
+        o = orc.postprocess(pk, vk, ak, g["pf"], float(g["h"]), c=float(g["c"]), rmin=float(g["rmin"]))
+        assert r["r_factor"] == o["r_factor"] == float(g["r_factor"]) and r["h_scaled"] == float(g["h_scaled"])
+        assert r["nt"] == o["nt"] == int(g["nt"])
+        for k in ("pk", "vk", "ak"):
+            assert np.array_equal(r[k], o[k]), k                       # bit-exact time scaling
+        sel = g["sel"]
+        for k in ("p", "v", "a"):
+            assert np.abs(r[k] - o[k]).max() < 1e-12, k
+            assert np.abs(r[k][:, :, sel] - g[k]).max() < 1e-12, k     # MATLAB's spline
+        assert np.array_equal(r["time_index"], g["time_index"]) and r["traj_time"] == float(g["traj_time"])
+        assert r["violation"] == int(g["violation"]) == 1 and abs(r["min_dist"] - o["min_dist"]) < 1e-12
+        assert abs(r["totdist"] - float(g["totdist"])) < 1e-8
+        # figures only (no interpolated output requested)
+        r2 = s.postprocess(pk, vk, ak, want_interp=False)
+        assert r2["nt"] == r["nt"] and r2["min_dist"] == r["min_dist"] and r2["traj_time"] == r["traj_time"]
+        with pytest.raises(dmpc.DmpcError):
+            s.postprocess(pk[:, :3], vk[:, :3], ak[:, :3])            # too short for a not-a-knot spline
+
+
+def test_postprocess_of_device_run(dmpc, orc):
+    """whole pipeline: device-resident transition (N=100) -> post-processing, against the oracle's"""
+    from multiagent_planning_b200 import scenarios
+    cfg = scenarios.config("N100")
+    P = dmpc.default_params(cfg["variant"])
+    with dmpc.Solver(100, P, pmin=cfg["pmin"], pmax=cfg["pmax"], pf=cfg["pf"]) as s:
+        s.init_horizons(cfg["po"])
+        run = s.run(149, record=True)
+        assert run["reached"]
+        r = s.postprocess(run["pk"], run["vk"], run["ak"])
+        o = orc.postprocess(run["pk"], run["vk"], run["ak"], cfg["pf"], P.h, c=P.c, rmin=P.rmin)
+        assert r["r_factor"] == o["r_factor"] and r["nt"] == o["nt"] and r["violation"] == o["violation"]
+        assert np.array_equal(r["pk"], o["pk"]) and np.abs(r["p"] - o["p"]).max() < 1e-12
+        assert np.array_equal(r["time_index"], o["time_index"]) and abs(r["totdist"] - o["totdist"]) < 1e-8
+        assert abs(r["min_dist"] - o["min_dist"]) < 1e-12
