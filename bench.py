@@ -282,6 +282,29 @@ def run_single(args):
                             "sample": f"steps {W + 1}..{W + done} of the same transition ({done} MPC steps x {N} "
                                       f"agents, {secs:.1f} s), oracle/liboracle.so with {threads} threads; the "
                                       "reference's MATLAB / C++ cannot run on this box"}
+    # ---- next row of the path: post-processing of the finished transition (failure_rate.m:
+    # 134-195, the rest of the reference's t_dmpc), reported beside the headline, not inside it ------------
+    try:
+        from oracle import dmpc_oracle as orc
+        s.init_horizons(cfg["po"])
+        tr = s.run(cfg["max_steps"], record=True)
+        t0 = time.perf_counter()
+        pp = s.postprocess(tr["pk"], tr["vk"], tr["ak"], want_interp=False)
+        t_api = time.perf_counter() - t0
+        t0 = time.perf_counter()
+        po_ = orc.postprocess(tr["pk"], tr["vk"], tr["ak"], cfg["pf"], P.h, c=P.c, rmin=P.rmin, want_interp=False)
+        t_cpu = time.perf_counter() - t0
+        pairs = N * (N - 1) // 2 * pp["nt"]
+        line["postprocess"] = {
+            "what": "time scaling + 100 Hz not-a-knot splines + O(N^2 T) pairwise check + distance / trajectory time "
+                    f"of the {tr['steps']}-step transition (nt = {pp['nt']} samples)",
+            "device_ms": pp["device_ms"], "api_ms_host_arrays": 1e3 * t_api, "cpu_port_ms": 1e3 * t_cpu,
+            "pair_samples_per_s": pairs / (pp["device_ms"] * 1e-3),
+            "parity": {"r_factor_equal": bool(pp["r_factor"] == po_["r_factor"]),
+                       "min_dist_abs_diff": abs(pp["min_dist"] - po_["min_dist"]),
+                       "time_index_equal": bool(np.array_equal(pp["time_index"], po_["time_index"]))}}
+    except Exception as ex:  # the headline numbers stand on their own
+        line["postprocess"] = {"error": repr(ex)[:200]}
     s.close()
     print(json.dumps(line))
 

@@ -16,6 +16,7 @@
 //   [viol,min_dist,violc]   = dmpc_b200_mex('check', P, p, l, n, k)
 //   [Ain,bin,prev_dist]     = dmpc_b200_mex('constr',P, p, po, vo, n, k, l, mask)
 //   [p,v]                   = dmpc_b200_mex('prop',  P, po, vo, a)
+//   [pk,vk,ak,p,v,a,info]   = dmpc_b200_mex('post',  P, pk, vk, ak)            % failure_rate.m:134-195
 //   [A,Av,A0,Delta]         = dmpc_b200_mex('mats',  h, K)
 //   dmpc_b200_mex('close')
 // P is a struct with the fields of dmpcb200_params (missing fields = reference defaults) plus N.
@@ -161,6 +162,26 @@ void mexFunction(int nlhs, mxArray* plhs[], int nrhs, const mxArray* prhs[]) {
         plhs[0] = mat(3 * K, B); plhs[1] = mat(3 * K, B);
         check(dmpcb200_prop_state(g_h, B, mxGetDoubles(prhs[2]), mxGetDoubles(prhs[3]), mxGetDoubles(prhs[4]),
                                   mxGetDoubles(plhs[0]), mxGetDoubles(plhs[1])), "prop_state");
+    } else if (c == "post") {
+        // [pk,vk,ak,p,v,a,info] = dmpc_b200_mex('post', P, pk, vk, ak)   % failure_rate.m:134-195
+        const int S = (int)(mxGetNumberOfElements(prhs[2]) / (3 * (size_t)N));
+        plhs[0] = mxDuplicateArray(prhs[2]); plhs[1] = mxDuplicateArray(prhs[3]); plhs[2] = mxDuplicateArray(prhs[4]);
+        dmpcb200_post res;
+        // first pass for the size of the 100 Hz grid, second with the outputs allocated
+        mxArray* tmp[3] = {mxDuplicateArray(prhs[2]), mxDuplicateArray(prhs[3]), mxDuplicateArray(prhs[4])};
+        check(dmpcb200_postprocess(g_h, S, mxGetDoubles(tmp[0]), mxGetDoubles(tmp[1]), mxGetDoubles(tmp[2]), 2.0, 1.0,
+                                   0.01, 0.05, nullptr, nullptr, nullptr, 0, nullptr, &res), "postprocess");
+        for (auto* t : tmp) mxDestroyArray(t);
+        plhs[3] = cube(3, res.nt, N); plhs[4] = cube(3, res.nt, N); plhs[5] = cube(3, res.nt, N);
+        check(dmpcb200_postprocess(g_h, S, mxGetDoubles(plhs[0]), mxGetDoubles(plhs[1]), mxGetDoubles(plhs[2]), 2.0,
+                                   1.0, 0.01, 0.05, mxGetDoubles(plhs[3]), mxGetDoubles(plhs[4]),
+                                   mxGetDoubles(plhs[5]), res.nt, nullptr, &res), "postprocess");
+        if (nlhs > 6) {
+            plhs[6] = mat(1, 7);
+            double* o = mxGetDoubles(plhs[6]);  // r_factor, h_scaled, T, violation, min_dist, totdist, traj_time
+            o[0] = res.r_factor; o[1] = res.h_scaled; o[2] = res.T; o[3] = res.violation; o[4] = res.min_dist;
+            o[5] = res.totdist; o[6] = res.traj_time;
+        }
     } else {
         mexErrMsgIdAndTxt("dmpcb200:arg", "unknown command %s", cmd);
     }
