@@ -1106,7 +1106,14 @@ int dmpcb200_postprocess(dmpcb200_t* h, int S, double* pk, double* vk, double* a
     // 4. pairwise check (:170-181), distance and trajectory time (:183-194)
     {
         const int tiles = (N + kPairTile - 1) / kPairTile;
-        pp_pairs_kernel<<<dim3(tiles, tiles), dim3(kPairTile, kPairTile), 0, s>>>(N, nt, h->prm.c, d_p, d_bits + 1);
+        int ex = 0;
+        const bool pow2 = std::frexp(h->prm.c, &ex) == 0.5;  // dz / c is then an exact scaling
+        if (pow2)
+            pp_pairs_kernel<true><<<dim3(tiles, tiles), dim3(kPairTile, kPairTile), 0, s>>>(N, nt, h->prm.c, 1.0 / h->prm.c,
+                                                                                            d_p, d_bits + 1);
+        else
+            pp_pairs_kernel<false><<<dim3(tiles, tiles), dim3(kPairTile, kPairTile), 0, s>>>(N, nt, h->prm.c, 1.0 / h->prm.c,
+                                                                                             d_p, d_bits + 1);
         pp_stats_kernel<<<(N + 3) / 4, 128, 0, s>>>(N, nt, goal_radius, d_p, h->d_pf, d_dist, d_tidx);
     }
     cudaEventRecord(h->ev[1], s);
