@@ -124,7 +124,10 @@ int dmpcb200_init_horizons(dmpcb200_t* h, const double* po, double* l, double* p
  * Outputs (rows of agents n0..n1-1 written, others untouched; any may be NULL):
  *   l_new 3 x K x N, p1,v1,a1 3 x N (first columns), v_hor,a_hor 3 x K x N (full v,a horizons),
  *   status[N], diag[N].  Agents that are not SOLVED keep l_new(:,:,n) = l_prev(:,:,n).
- * first_fail: lowest agent index without SOLVED or with OUTBOUND, -1 if none. */
+ * first_fail: lowest agent index without SOLVED or with OUTBOUND, -1 if none.
+ * Caller arrays that are page-locked (cudaHostAlloc / cudaHostRegister, MATLAB: none) are used in place: DMA
+ * straight from the inputs, kernel writes straight into l_new / p1 / v1 / a1; pageable arrays go through the
+ * handle's pinned staging block (one copy in, none out).  The call returns when the results are in the arrays. */
 int dmpcb200_step(dmpcb200_t* h, const double* pk, const double* vk, const double* ak,
                   const double* l_prev, double* l_new, double* p1, double* v1, double* a1,
                   double* v_hor, double* a_hor, int32_t* status, dmpcb200_diag* diag,
