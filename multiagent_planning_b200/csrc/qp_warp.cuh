@@ -57,7 +57,7 @@ constexpr int kMS = 66;             // row stride of M in doubles
 constexpr int kEPL = kQW / kLanes;  // items per lane: 2 on the device, 64 in the host build
 constexpr unsigned kNone = 0xffu;
 constexpr double kBoundWeight = 0.125;  // see most_violated
-constexpr int kPolishSkip = 12;  // plain adds after which the final re-synthesis of x is skipped
+constexpr int kPolishSkip = 64;  // plain adds after which the final re-synthesis of x is skipped
 
 #if defined(__CUDA_ARCH__)
 #define QW_FOR(h) _Pragma("unroll") for (int h = 0; h < kEPL; ++h)
