@@ -532,7 +532,7 @@ struct QpW {
             sa[h][0] = sa[h][1] = sP[h][0] = sP[h][1] = 0.0;
         }
 #pragma unroll 5
-        for (int j = 0; j < Kk; ++j) {
+        for (int j = 0; j < (q > 0 ? Kk : 0); ++j) {  // empty active set: the coefficient vectors are zero
             QW_FOR(h) {
                 if (h * kLanes < n3) {  // uniform
                     const Dbl2 t01 = ld2(tp[h] + 4 * j), t23 = ld2(tp[h] + 4 * j + 2), c = ld2(cq[h] + 2 * j);
@@ -1104,7 +1104,7 @@ struct QpW {
                 }
                 PROF(9);
                 if (!have_z) {
-                    coefs();
+                    if (q > 0) coefs();
                     PROF(6);
                     apply(z, L, nullptr, nullptr, -1.0, &p);
                     PROF(7);
