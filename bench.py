@@ -282,6 +282,26 @@ def run_single(args):
                             "sample": f"steps {W + 1}..{W + done} of the same transition ({done} MPC steps x {N} "
                                       f"agents, {secs:.1f} s), oracle/liboracle.so with {threads} threads; the "
                                       "reference's MATLAB / C++ cannot run on this box"}
+    # ---- the second half of BASELINE's metric: max position error vs the reference (here: the fp64 oracle,
+    # teacher-forced on the dense first steps of the same workload; tolerance 1e-6 m) ------------
+    try:
+        from oracle import dmpc_oracle as orc
+        O = orc.default_params(cfg["variant"])
+        for kk, vv in cfg["params"].items():
+            setattr(O, kk, vv)
+        l_, pk_, vk_, ak_ = s.init_horizons(cfg["po"])
+        worst, same = 0.0, True
+        for _ in range(6):
+            g_ = s.step(pk_, vk_, ak_, l_)
+            o_ = orc.step(O, pk_, vk_, ak_, cfg["pf"], l_, cfg["pmin"], cfg["pmax"], nthreads=threads)
+            worst = max(worst, float(np.abs(g_["l_new"] - o_["l_new"]).max()))
+            same = same and bool(np.array_equal(g_["status"] & 0xFF, o_["status"] & 0xFF))
+            l_, pk_, vk_, ak_ = o_["l_new"], o_["p1"], o_["v1"], o_["a1"]
+        line["max_pos_err_vs_ref"] = {"value": worst, "unit": "m", "tolerance": 1e-6, "status_flags_equal": same,
+                                      "reference": "oracle/liboracle.so (fp64 port pinned on the reference's MATLAB "
+                                                   "workspaces), 6 teacher-forced steps of the same workload"}
+    except Exception as ex:
+        line["max_pos_err_vs_ref"] = {"error": repr(ex)[:200]}
     # ---- next row of the path: post-processing of the finished transition (failure_rate.m:
     # 134-195, the rest of the reference's t_dmpc), reported beside the headline, not inside it ------------
     try:
