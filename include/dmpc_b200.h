@@ -197,7 +197,9 @@ int dmpcb200_check_coll(dmpcb200_t* h, const double* p3, const double* l, int n,
 /* CollConstrSoftDMPC.m / CollConstrSoftDMPC2.m / CollConstrHardDMPC.m / ...OnDemand.m
  * (C++ build_collconstraintv2 dmpc.cpp:496-546): dense rows like the reference.
  * Ain: cap x 3K column-major (leading dimension cap), bin, prev_dist: cap.  mask = viol_constr
- * (N bytes; ignored for the HARD variant).  *nrows rows written, neighbour order ascending. */
+ * (N bytes; ignored for the HARD variant).  *nrows rows written, neighbour order ascending.
+ * n = -1: no own agent, every column of l is an obstacle (dec-iSCP/CollConstr.m:1-23 with the SOFT_BOUND2
+ * variant: rows on block k-1, right-hand side without the velocity term when vo = 0). */
 int dmpcb200_coll_constr(dmpcb200_t* h, const double* p3, const double* po, const double* vo,
                          int n, int k, const double* l, const uint8_t* mask, int cap, double* Ain,
                          double* bin, double* prev_dist, int32_t* nrows);

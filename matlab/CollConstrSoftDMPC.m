@@ -1,5 +1,5 @@
 function [Ainr,binr,prev_dist] = CollConstrSoftDMPC(p,po,vo,n,k,l,rmin,Ain,A_initp,E1,E2,order,violation)
-% Drop-in for dmpc/matlab/CollConstrSoftDMPC.m (also the dec-iSCP name CollConstr listed in BASELINE).
+% Drop-in for dmpc/matlab/CollConstrSoftDMPC.m:1-32 (k_ctr = k).  The dec-iSCP name CollConstr has its own wrapper (CollConstr.m).
 if order ~= 2, error('dmpcb200:order','only order = 2 is implemented'); end
 P = struct('N',size(l,3),'K',size(l,2),'rmin',rmin,'c',1/E1(3,3),'h',A_initp(1,4));
 [Ainr,binr,prev_dist] = dmpc_b200_mex('constr',P,p(:),po(:),vo(:),n,k,l,logical(violation(:)));

@@ -15,6 +15,7 @@
 //   [p,v,a,status]          = dmpc_b200_mex('solve', P, po, pf, vo, ao, n, l, pmin, pmax)
 //   [viol,min_dist,violc]   = dmpc_b200_mex('check', P, p, l, n, k)
 //   [Ain,bin,prev_dist]     = dmpc_b200_mex('constr',P, p, po, vo, n, k, l, mask)
+//   [pass,max_dist]         = dmpc_b200_mex('goal',  P, pk, pf, tol)            % ReachedGoal.m
 //   [p,v]                   = dmpc_b200_mex('prop',  P, po, vo, a)
 //   [pk,vk,ak,p,v,a,info]   = dmpc_b200_mex('post',  P, pk, vk, ak)            % failure_rate.m:134-195
 //   [A,Av,A0,Delta]         = dmpc_b200_mex('mats',  h, K)
@@ -143,7 +144,8 @@ void mexFunction(int nlhs, mxArray* plhs[], int nrhs, const mxArray* prhs[]) {
                                   (uint8_t*)mxGetLogicals(plhs[2]), &md, &any), "check_coll");
         plhs[1] = mxCreateDoubleScalar(md);
     } else if (c == "constr") {
-        const int cap = N > 1 ? N - 1 : 1;
+        // rows: at most N-1 neighbours; n = 0 (no own agent, dec-iSCP CollConstr.m) allows N; optional 10th argument
+        const int cap = nrhs > 9 ? (int)mxGetScalar(prhs[9]) : (N > 1 ? N - 1 : 1);
         mxArray* A = mat(cap, 3 * K); mxArray* b = mat(cap, 1); mxArray* pd = mat(cap, 1);
         int32_t nr = 0;
         const uint8_t* mask = (nrhs > 8 && !mxIsEmpty(prhs[8])) ? (const uint8_t*)mxGetLogicals(prhs[8]) : nullptr;
@@ -157,6 +159,13 @@ void mexFunction(int nlhs, mxArray* plhs[], int nrhs, const mxArray* prhs[]) {
         std::memcpy(mxGetDoubles(plhs[1]), mxGetDoubles(b), nr * sizeof(double));
         std::memcpy(mxGetDoubles(plhs[2]), mxGetDoubles(pd), nr * sizeof(double));
         mxDestroyArray(A); mxDestroyArray(b); mxDestroyArray(pd);
+    } else if (c == "goal") {
+        // [pass,max_dist] = dmpc_b200_mex('goal', P, pk, pf, tol)      % ReachedGoal.m:1-11, pk / pf are 3 x N
+        double md = 0; int32_t pass = 0;
+        check(dmpcb200_reached_goal(g_h, mxGetDoubles(prhs[2]), mxGetDoubles(prhs[3]), mxGetScalar(prhs[4]), &md, &pass),
+              "reached_goal");
+        plhs[0] = mxCreateDoubleScalar(pass);
+        if (nlhs > 1) plhs[1] = mxCreateDoubleScalar(md);
     } else if (c == "prop") {
         const int B = (int)(mxGetNumberOfElements(prhs[4]) / (3 * K));
         plhs[0] = mat(3 * K, B); plhs[1] = mat(3 * K, B);

@@ -3,5 +3,5 @@ function [p,v,a,success,outbound,coll] = solveSoftDMPCbound2(po,pf,vo,ao,n,h,l,K
 if order ~= 2, error('dmpcb200:order','only order = 2 is implemented'); end
 P = struct('N',size(l,3),'K',K,'variant',1,'h',h,'rmin',rmin,'c',1/E1(3,3),'alim',alim,'Q1',Q1,'S1',S1,'term',term);
 [p,v,a,st] = dmpc_b200_mex('solve',P,po(:),pf(:),vo(:),ao(:),n,l,pmin(:),pmax(:));
-[p,v,a,success,outbound,coll] = dmpc_b200_flags(p,v,a,st);
+[p,v,a,success,outbound,coll] = dmpc_b200_flags(p,v,a,st,P.variant);
 end

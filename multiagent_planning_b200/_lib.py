@@ -7,6 +7,7 @@ is present, compute calls raise.
 from __future__ import annotations
 
 import ctypes as C
+import hashlib
 import os
 import shutil
 import subprocess
@@ -14,11 +15,12 @@ import subprocess
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _CSRC = os.path.join(_HERE, "csrc")
 LIB_PATH = os.path.join(_HERE, "libdmpc_b200.so")
-SOURCES = ["dmpc_b200.cu", "model_tables.cpp"]
-HEADERS = ["dmpc_kernels.cuh", "scan_core.cuh", "agent_solve.cuh", "qp_core.cuh", "qp_warp.cuh", "postprocess.cuh", "model_tables.h",
-           os.path.join("..", "..", "include", "dmpc_b200.h")]
+SOURCES = ["dmpc_b200.cu", "k_qp15.cu", "k_qp20.cu", "k_qpgen.cu", "k_scan.cu", "model_tables.cpp"]
+HEADERS = ["dmpc_kernels.cuh", "small_kernels.cuh", "launch.cuh", "scan_core.cuh", "agent_solve.cuh", "qp_core.cuh",
+           "qp_warp.cuh", "postprocess.cuh", "model_tables.h", os.path.join("..", "..", "include", "dmpc_b200.h")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
-              "-Xcompiler", "-fPIC", "-shared", "-diag-suppress", "177"]
+              "-Xcompiler", "-fPIC", "-diag-suppress", "177"]
+HASH_PATH = LIB_PATH + ".srchash"
 
 _LIB = None
 
@@ -62,20 +64,57 @@ def _nvcc():
     raise DmpcError("nvcc not found: cannot build libdmpc_b200.so")
 
 
+def source_hash() -> str:
+    """sha256 over every source, header and compiler flag of the library.  The built .so carries it in a
+    side file: `build()` rebuilds whenever the tree and the binary disagree (mtimes are not trusted: a
+    binary that travelled to another box, or a checkout, has arbitrary times)."""
+    hh = hashlib.sha256()
+    hh.update(" ".join(NVCC_FLAGS).encode())
+    for f in SOURCES + HEADERS:
+        path = os.path.join(_CSRC, f)
+        hh.update(f.encode())
+        with open(path, "rb") as fh:
+            hh.update(fh.read())
+    return hh.hexdigest()
+
+
+def built_hash() -> str | None:
+    try:
+        with open(HASH_PATH) as fh:
+            return fh.read().strip()
+    except OSError:
+        return None
+
+
 def is_stale() -> bool:
-    if not os.path.exists(LIB_PATH):
-        return True
-    t = os.path.getmtime(LIB_PATH)
-    deps = [os.path.join(_CSRC, s) for s in SOURCES + HEADERS]
-    return any(os.path.exists(d) and os.path.getmtime(d) > t for d in deps)
+    return not os.path.exists(LIB_PATH) or built_hash() != source_hash()
 
 
 def build(force: bool = False, verbose: bool = False) -> str:
-    """nvcc -gencode arch=compute_100a,code=sm_100a -lineinfo ... -> multiagent_planning_b200/libdmpc_b200.so"""
+    """nvcc -gencode arch=compute_100a,code=sm_100a -lineinfo ... -> multiagent_planning_b200/libdmpc_b200.so
+    (one object per translation unit, compiled in parallel, then linked)."""
     if not force and not is_stale():
         return LIB_PATH
-    cmd = [_nvcc()] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB_PATH] + SOURCES
-    subprocess.check_call(cmd, cwd=_CSRC)
+    nvcc = _nvcc()
+    want = source_hash()
+    objdir = os.path.join(_HERE, "build")
+    os.makedirs(objdir, exist_ok=True)
+    procs = []
+    for src in SOURCES:
+        obj = os.path.join(objdir, os.path.splitext(src)[0] + ".o")
+        cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-c", "-o", obj, src]
+        procs.append((src, obj, subprocess.Popen(cmd, cwd=_CSRC)))
+    objs = []
+    for src, obj, pr in procs:
+        if pr.wait() != 0:
+            raise DmpcError(f"nvcc failed on {src}")
+        objs.append(obj)
+    if os.path.exists(HASH_PATH):
+        os.remove(HASH_PATH)
+    subprocess.check_call([nvcc, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", LIB_PATH] + objs,
+                          cwd=_CSRC)
+    with open(HASH_PATH, "w") as fh:
+        fh.write(want + "\n")
     return LIB_PATH
 
 

@@ -14,7 +14,14 @@
 #include <vector>
 
 #include "../../include/dmpc_b200.h"
-#include "dmpc_kernels.cuh"
+#if defined(DMPC_SINGLE_TU)  // profiling build: one translation unit (one copy of the cycle counters)
+#include "k_qp15.cu"
+#include "k_qp20.cu"
+#include "k_qpgen.cu"
+#include "k_scan.cu"
+#endif
+#include "launch.cuh"
+#include "small_kernels.cuh"
 #include "postprocess.cuh"
 #include "model_tables.h"
 
@@ -64,14 +71,15 @@ struct dmpcb200_handle {
     size_t side_bytes = 0, tailblk_bytes = 0;
     unsigned char* h_stage = nullptr;  // pinned + mapped: one input side + one output side + tail block
     unsigned char* d_stage = nullptr;  // device alias of h_stage (the QP kernel writes the outputs of a host step there)
-    // caller-owned host arrays that turned out to be pinned (page-locked + mapped): host pointer -> device alias
-    // (nullptr: pageable).  The QP kernel then writes a host step's outputs straight into the caller's arrays.
-    std::vector<std::pair<const void*, void*>> pinned_cache;
+    // caller-owned host arrays that are pinned (page-locked + mapped) are used in place: DMA straight from the
+    // inputs, and the QP kernel writes a host step's outputs straight into the device alias of the outputs.
     struct Bound {
         const double *pk, *vk, *ak, *l_prev;
         double *l_new, *p1, *v1, *a1, *v_hor, *a_hor;
         int32_t* status;
         dmpcb200_diag* diag;
+        bool in_pinned;          // resolved once at bind time (the arrays' lifetime is the caller's contract)
+        double *w_l, *w_p, *w_v, *w_a;  // device aliases of l_new, p1, v1, a1 (all four or none)
     };
     std::vector<Bound> bound;  // dmpcb200_bind_step slots
     double* d_l[2] = {nullptr, nullptr};
@@ -91,6 +99,9 @@ struct dmpcb200_handle {
     Ctrl* d_ctrl = nullptr;
     double* d_goal = nullptr;  // 2 doubles
     int* d_fail = nullptr;
+    // scratch of the per-agent drop-ins (solve_agent / check_coll / coll_constr): they never touch the
+    // resident loop state.  [ l_in | l_out | pk vk ak | p1 v1 a1 | pf ], allocated at first use
+    double* d_scr = nullptr;
     // helper scratch
     unsigned char* d_u8 = nullptr;  // 2N
     double* d_small = nullptr;      // misc
@@ -165,81 +176,31 @@ StepArgs make_args(dmpcb200_t* h, int n0, int n1, const double* pk, const double
     return A;
 }
 
-template <int W, int S, int KT>
-cudaError_t launch_scan_w(const StepArgs& A, int nl, int K, cudaStream_t s) {
-    const int Npad = round_up(A.P.N, kTile);
-    int stages = scan_stages(K, A.P.N, W, A.RMAX);
-    if (stages < 1) return cudaErrorInvalidConfiguration;
-    if (stages > S) stages = stages / S * S;  // rounds of S tiles map onto distinct stages
-    const size_t smem = scan_smem_bytes(K, W, stages, Npad, A.RMAX);
-    static size_t attr_smem = 0;
-    if (attr_smem < smem) {
-        cudaError_t e = cudaFuncSetAttribute(scan_kernel<W, S, KT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return e;
-        attr_smem = smem;
-    }
-    scan_kernel<W, S, KT><<<(nl + W - 1) / W, W * S * 32, smem, s>>>(A, stages);
-    return cudaGetLastError();
-}
-template <int W, int KT>
-cudaError_t launch_qp_w(const StepArgs& A, int nl, size_t smem, cudaStream_t s) {
-    static size_t attr_smem = 0;
-    if (attr_smem < smem) {  // (the kernel also has a few hundred bytes of static shared memory)
-        cudaError_t e =
-            cudaFuncSetAttribute(qp_kernel<W, KT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return e;
-        attr_smem = smem;
-    }
-    // one CTA per SM at most (shared memory): larger swarms run a persistent grid with an agent queue
-    static int n_sm = 0;
-    if (!n_sm) {
-        int dev = 0;
-        cudaGetDevice(&dev);
-        cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
-        if (n_sm < 1) n_sm = 148;
-    }
-    const int ctas = std::min((nl + W - 1) / W, n_sm);
-    // programmatic stream serialization: the grid may launch while the scan kernel drains (the kernel
-    // itself waits for the scan's completion before it reads the rows)
-    cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3((unsigned)ctas);
-    cfg.blockDim = dim3(W * 32);
-    cfg.dynamicSmemBytes = smem;
-    cfg.stream = s;
-    cudaLaunchAttribute at[1];
-    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-    at[0].val.programmaticStreamSerializationAllowed = 1;
-    cfg.attrs = at;
-    cfg.numAttrs = 1;
-    return cudaLaunchKernelEx(&cfg, qp_kernel<W, KT>, A);
-    return cudaGetLastError();
-}
-
 // 4 agents x 2 warps per CTA while one wave of CTAs covers the swarm, 8 agents beyond (or fewer when the
 // per-agent near masks of a very large swarm do not fit next to a tile); the reference's horizons
 // (15, 20) are compiled with the horizon as a constant (the own horizon then lives in registers)
 cudaError_t launch_scan(dmpcb200_t* h, const StepArgs& A, cudaStream_t s) {
     const int nl = A.n1 - A.n0, K = h->K, N = h->N;
     if (nl <= 4 * 148 || scan_stages(K, N, 8, A.RMAX) < 2) {
-        if (scan_stages(K, N, 4, A.RMAX) < 1) return launch_scan_w<1, 2, 0>(A, nl, K, s);
-        if (K == 15) return launch_scan_w<4, 2, 15>(A, nl, K, s);
-        if (K == 20) return launch_scan_w<4, 2, 20>(A, nl, K, s);
-        return launch_scan_w<4, 4, 0>(A, nl, K, s);
+        if (scan_stages(K, N, 4, A.RMAX) < 1) return launch_scan_layout(SCAN_1_2_0, A, nl, K, s);
+        if (K == 15) return launch_scan_layout(SCAN_4_2_15, A, nl, K, s);
+        if (K == 20) return launch_scan_layout(SCAN_4_2_20, A, nl, K, s);
+        return launch_scan_layout(SCAN_4_4_0, A, nl, K, s);
     }
-    if (K == 15) return launch_scan_w<8, 1, 15>(A, nl, K, s);  // measured at N=2000: 123 us vs 151 (<8,2,0>) / 145 (<4,2,15>)
-    if (K == 20) return launch_scan_w<8, 1, 20>(A, nl, K, s);
-    return launch_scan_w<8, 2, 0>(A, nl, K, s);
+    if (K == 15) return launch_scan_layout(SCAN_8_1_15, A, nl, K, s);  // measured at N=2000: 123 us vs 151 (<8,2,0>) / 145 (<4,2,15>)
+    if (K == 20) return launch_scan_layout(SCAN_8_1_20, A, nl, K, s);
+    return launch_scan_layout(SCAN_8_2_0, A, nl, K, s);
 }
 // horizon lengths 15 and 20 (the reference's configurations) are compiled with the horizon as a
 // compile-time constant (fully unrolled table products); anything else takes the generic kernel
 cudaError_t launch_qp(dmpcb200_t* h, const StepArgs& A, cudaStream_t s) {
     const int nl = A.n1 - A.n0;
     const size_t smem = qp_smem_bytes(h->K, h->W, h->QMAX, h->RCAP);
-    if (h->K == 15 && h->W == 4) return launch_qp_w<4, 15>(A, nl, smem, s);
-    if (h->K == 20 && h->W == 4) return launch_qp_w<4, 20>(A, nl, smem, s);
+    if (h->K == 15 && h->W == 4) return launch_qp_4_15(A, nl, smem, s);
+    if (h->K == 20 && h->W == 4) return launch_qp_4_20(A, nl, smem, s);
     // W = 4 for every horizon up to 21, 3 beyond (the tables grow with K^2)
-    if (h->W == 4) return launch_qp_w<4, 0>(A, nl, smem, s);
-    return launch_qp_w<3, 0>(A, nl, smem, s);
+    if (h->W == 4) return launch_qp_4_0(A, nl, smem, s);
+    return launch_qp_3_0(A, nl, smem, s);
 }
 
 TailArgs make_tail(dmpcb200_t* h, const double* p, int ld, const int* status, const double* p1, const double* v1,
@@ -307,20 +268,45 @@ int ensure_pin(dmpcb200_t* h, size_t n) {
     return 0;
 }
 
-// device alias of a caller-owned host pointer if it is pinned and mapped, else nullptr (cached per pointer)
-void* pinned_alias(dmpcb200_t* h, const void* p) {
-    if (!p) return nullptr;
-    for (auto& e : h->pinned_cache)
-        if (e.first == p) return e.second;
-    void* dev = nullptr;
-    cudaPointerAttributes at;
-    if (cudaPointerGetAttributes(&at, p) == cudaSuccess && at.type == cudaMemoryTypeHost && at.devicePointer)
-        dev = at.devicePointer;
-    else
+// device alias of a caller-owned host array if ALL of it is pinned and mapped, else nullptr.  Queried on every
+// call (a cached answer would go stale when the caller frees the buffer and the address is reused by a
+// pageable allocation); only dmpcb200_bind_step keeps the answer, where the arrays' lifetime is the caller's
+// contract.  First and last byte must belong to the same mapping.
+void* pinned_alias(const void* p, size_t bytes) {
+    if (!p || !bytes) return nullptr;
+    cudaPointerAttributes a0, a1;
+    if (cudaPointerGetAttributes(&a0, p) != cudaSuccess || a0.type != cudaMemoryTypeHost || !a0.devicePointer) {
         cudaGetLastError();
-    if (h->pinned_cache.size() >= 64) h->pinned_cache.clear();
-    h->pinned_cache.emplace_back(p, dev);
-    return dev;
+        return nullptr;
+    }
+    const char* last = static_cast<const char*>(p) + bytes - 1;
+    if (cudaPointerGetAttributes(&a1, last) != cudaSuccess || a1.type != cudaMemoryTypeHost || !a1.devicePointer ||
+        static_cast<char*>(a1.devicePointer) - static_cast<char*>(a0.devicePointer) != (ptrdiff_t)(bytes - 1)) {
+        cudaGetLastError();
+        return nullptr;
+    }
+    return a0.devicePointer;
+}
+
+// scratch of the per-agent drop-ins: pointers into h->d_scr
+struct Scratch {
+    double *l_in, *l_out, *st_in[3], *st_out[3], *pf;
+    int* status;
+    AgentDiag* diag;
+};
+int get_scratch(dmpcb200_t* h, Scratch* S) {
+    const size_t nl = (size_t)h->Npad * 3 * h->K, ns = 3 * (size_t)round_up(h->N, 2);
+    const size_t nst = ((size_t)h->N + 1) / 2 + 1, ndg = 2 * (size_t)h->N;  // int[N], AgentDiag[N] in doubles
+    if (!h->d_scr) CK(dalloc(&h->d_scr, 2 * nl + 7 * ns + nst + ndg));
+    double* d = h->d_scr;
+    S->l_in = d; d += nl;
+    S->l_out = d; d += nl;
+    for (int q = 0; q < 3; ++q) { S->st_in[q] = d; d += ns; }
+    for (int q = 0; q < 3; ++q) { S->st_out[q] = d; d += ns; }
+    S->pf = d; d += ns;
+    S->diag = reinterpret_cast<AgentDiag*>(d); d += ndg;
+    S->status = reinterpret_cast<int*>(d);
+    return 0;
 }
 
 void drop_graph(dmpcb200_t* h) {
@@ -389,7 +375,9 @@ int dmpcb200_create(const dmpcb200_params* p, int N, int n0, int n1, int device,
     if (!p || !out) return fail(DMPCB200_ERR_ARG, "create: null argument");
     *out = nullptr;
     if (p->K < 1 || p->K > 32) return fail(DMPCB200_ERR_ARG, "create: horizon K must be in 1..32");
-    if (N < 1 || n0 < 0 || n1 > N || n0 >= n1) return fail(DMPCB200_ERR_ARG, "create: bad agent range");
+    // n0 == n1 is a valid (empty) block: a rank of a sharded run whose block is empty still owns a replica of
+    // the horizon buffer and takes part in the exchange
+    if (N < 1 || n0 < 0 || n1 > N || n0 > n1) return fail(DMPCB200_ERR_ARG, "create: bad agent range");
     if (p->variant < 0 || p->variant > 3) return fail(DMPCB200_ERR_ARG, "create: unknown variant");
     if (!(p->h > 0) || !(p->rmin > 0) || !(p->c > 0) || !(p->alim > 0))
         return fail(DMPCB200_ERR_ARG, "create: h, rmin, c, alim must be positive");
@@ -525,6 +513,7 @@ void dmpcb200_destroy(dmpcb200_t* h) {
     cudaFree(h->d_gscr_d); cudaFree(h->d_gscr_i); cudaFree(h->d_rescue); cudaFree(h->d_rescue_next);
     cudaFree(h->d_done); cudaFree(h->d_ctrl); cudaFree(h->d_goal); cudaFree(h->d_u8); cudaFree(h->d_small);
     cudaFree(h->d_ismall);
+    cudaFree(h->d_scr);
     for (int s = 0; s < 3; ++s) cudaFree(h->d_traj[s]);
     cudaFree(h->d_hist);
     if (h->h_pin) cudaFreeHost(h->h_pin);
@@ -589,6 +578,10 @@ int dmpcb200_step_dev(dmpcb200_t* h, const double* d_pk, const double* d_vk, con
     const bool padded = (d_l_prev == h->d_l[0] || d_l_prev == h->d_l[1]);
     StepArgs A = make_args(h, h->n0, h->n1, d_pk, d_vk, d_ak, d_l_prev, d_l_new, d_p1, d_v1, d_a1, d_v_hor, d_a_hor,
                            d_status, reinterpret_cast<AgentDiag*>(d_diag), padded, nullptr);
+    if (h->NL == 0) {  // empty block: nothing to solve
+        h->launches = 0;
+        return 0;
+    }
     CK(cudaMemsetAsync(h->d_rescue_next, 0, sizeof(int), s));
     CK(launch_scan(h, A, s));
     CK(launch_qp(h, A, s));
@@ -633,11 +626,31 @@ int dmpcb200_reached_goal(dmpcb200_t* h, const double* p, const double* pf, doub
     return 0;
 }
 
-int dmpcb200_step(dmpcb200_t* h, const double* pk, const double* vk, const double* ak, const double* l_prev,
-                  double* l_new, double* p1, double* v1, double* a1, double* v_hor, double* a_hor,
-                  int32_t* status, dmpcb200_diag* diag, int32_t* first_fail) {
+}  // extern "C"
+
+namespace {
+// pinned-ness of a host step's arrays: inputs all pinned? device aliases of the four outputs (all or none)
+void resolve_pinned(dmpcb200_t* h, dmpcb200_handle::Bound& b) {
+    const size_t sN = 3 * (size_t)h->N * sizeof(double), lB = (size_t)h->N * 3 * h->K * sizeof(double);
+    b.in_pinned = pinned_alias(b.l_prev, lB) && pinned_alias(b.pk, sN) && pinned_alias(b.vk, sN) && pinned_alias(b.ak, sN);
+    b.w_l = static_cast<double*>(pinned_alias(b.l_new, lB));
+    b.w_p = b.w_l ? static_cast<double*>(pinned_alias(b.p1, sN)) : nullptr;
+    b.w_v = b.w_p ? static_cast<double*>(pinned_alias(b.v1, sN)) : nullptr;
+    b.w_a = b.w_v ? static_cast<double*>(pinned_alias(b.a1, sN)) : nullptr;
+    if (!b.w_a) b.w_l = b.w_p = b.w_v = nullptr;
+}
+
+int step_impl(dmpcb200_t* h, const dmpcb200_handle::Bound& B, int32_t* first_fail) {
+    const double *pk = B.pk, *vk = B.vk, *ak = B.ak, *l_prev = B.l_prev;
+    double *l_new = B.l_new, *p1 = B.p1, *v1 = B.v1, *a1 = B.a1, *v_hor = B.v_hor, *a_hor = B.a_hor;
+    int32_t* status = B.status;
+    dmpcb200_diag* diag = B.diag;
     if (!h || !pk || !vk || !ak || !l_prev) return fail(DMPCB200_ERR_ARG, "step: null input");
     if (!h->have_goals || !h->have_bounds) return fail(DMPCB200_ERR_STATE, "step: set_goals and set_bounds first");
+    if (h->NL == 0) {
+        if (first_fail) *first_fail = -1;
+        return 0;
+    }
     if (int rc = ensure_device(h)) return rc;
     const int N = h->N, K = h->K, n3 = 3 * K, n0 = h->n0, NL = h->NL;
     cudaStream_t s = h->stream;
@@ -650,7 +663,7 @@ int dmpcb200_step(dmpcb200_t* h, const double* pk, const double* vk, const doubl
                               (size_t)((unsigned char*)h->d_st[c][1] - (unsigned char*)h->d_l[c]),
                               (size_t)((unsigned char*)h->d_st[c][2] - (unsigned char*)h->d_l[c])};
     const auto tp0 = std::chrono::steady_clock::now();
-    const bool in_pinned = pinned_alias(h, l_prev) && pinned_alias(h, pk) && pinned_alias(h, vk) && pinned_alias(h, ak);
+    const bool in_pinned = B.in_pinned;
     if (!in_pinned) {
         std::memcpy(hs_in, l_prev, lB);
         std::memcpy(hs_in + off_st[0], pk, sN);
@@ -674,10 +687,7 @@ int dmpcb200_step(dmpcb200_t* h, const double* pk, const double* vk, const doubl
     // status | diag | first_fail after the tail.  No device-to-host copy is queued at all.
     unsigned char* ds_out = h->d_stage + h->side_bytes;
     // caller arrays that are pinned are written by the kernel directly (no staging, nothing to hand over)
-    double* w_l = static_cast<double*>(pinned_alias(h, l_new));
-    double* w_p = static_cast<double*>(pinned_alias(h, p1));
-    double* w_v = static_cast<double*>(pinned_alias(h, v1));
-    double* w_a = static_cast<double*>(pinned_alias(h, a1));
+    double *w_l = B.w_l, *w_p = B.w_p, *w_v = B.w_v, *w_a = B.w_a;
     const bool direct = w_l && w_p && w_v && w_a;
     StepArgs A = make_args(h, h->n0, h->n1, h->d_st[c][0], h->d_st[c][1], h->d_st[c][2], h->d_l[c],
                            direct ? w_l : reinterpret_cast<double*>(ds_out),
@@ -738,22 +748,37 @@ int dmpcb200_step(dmpcb200_t* h, const double* pk, const double* vk, const doubl
     h->cur = 0;
     return 0;
 }
+}  // namespace
+
+extern "C" {
+
+int dmpcb200_step(dmpcb200_t* h, const double* pk, const double* vk, const double* ak, const double* l_prev,
+                  double* l_new, double* p1, double* v1, double* a1, double* v_hor, double* a_hor,
+                  int32_t* status, dmpcb200_diag* diag, int32_t* first_fail) {
+    if (!h || !pk || !vk || !ak || !l_prev) return fail(DMPCB200_ERR_ARG, "step: null input");
+    dmpcb200_handle::Bound b = {pk, vk, ak, l_prev, l_new, p1, v1, a1, v_hor, a_hor, status, diag,
+                                false, nullptr, nullptr, nullptr, nullptr};
+    resolve_pinned(h, b);  // queried afresh on every call: nothing about the caller's arrays is remembered
+    return step_impl(h, b, first_fail);
+}
 
 int dmpcb200_bind_step(dmpcb200_t* h, const double* pk, const double* vk, const double* ak, const double* l_prev,
                        double* l_new, double* p1, double* v1, double* a1, double* v_hor, double* a_hor,
                        int32_t* status, dmpcb200_diag* diag, int32_t* slot) {
     if (!h || !pk || !vk || !ak || !l_prev || !slot) return fail(DMPCB200_ERR_ARG, "bind_step: null argument");
     if (h->bound.size() >= 64) return fail(DMPCB200_ERR_STATE, "bind_step: too many bindings on this handle (64)");
-    h->bound.push_back({pk, vk, ak, l_prev, l_new, p1, v1, a1, v_hor, a_hor, status, diag});
+    dmpcb200_handle::Bound b = {pk, vk, ak, l_prev, l_new, p1, v1, a1, v_hor, a_hor, status, diag,
+                                false, nullptr, nullptr, nullptr, nullptr};
+    if (int rc = ensure_device(h)) return rc;
+    resolve_pinned(h, b);
+    h->bound.push_back(b);
     *slot = (int32_t)h->bound.size() - 1;
     return 0;
 }
 
 int dmpcb200_step_bound(dmpcb200_t* h, int32_t slot, int32_t* first_fail) {
     if (!h || slot < 0 || (size_t)slot >= h->bound.size()) return fail(DMPCB200_ERR_ARG, "step_bound: bad slot");
-    const auto& b = h->bound[slot];
-    return dmpcb200_step(h, b.pk, b.vk, b.ak, b.l_prev, b.l_new, b.p1, b.v1, b.a1, b.v_hor, b.a_hor, b.status, b.diag,
-                         first_fail);
+    return step_impl(h, h->bound[slot], first_fail);
 }
 
 int dmpcb200_run(dmpcb200_t* h, int max_steps, int stop_on_fail, int mode, double* traj_p, double* traj_v,
@@ -933,27 +958,30 @@ int dmpcb200_solve_agent(dmpcb200_t* h, const double* po, const double* pf, cons
     const int N = h->N, K = h->K, n3 = 3 * K;
     cudaStream_t s = h->stream;
     const size_t b3 = 3 * sizeof(double);
-    CK(cudaMemcpyAsync(h->d_st[0][0] + 3 * n, po, b3, cudaMemcpyHostToDevice, s));
-    CK(cudaMemcpyAsync(h->d_st[0][1] + 3 * n, vo, b3, cudaMemcpyHostToDevice, s));
-    CK(cudaMemcpyAsync(h->d_st[0][2] + 3 * n, ao, b3, cudaMemcpyHostToDevice, s));
-    CK(cudaMemcpyAsync(h->d_pf + 3 * n, pf, b3, cudaMemcpyHostToDevice, s));
-    CK(cudaMemcpyAsync(h->d_l[0], l, (size_t)N * n3 * sizeof(double), cudaMemcpyHostToDevice, s));
+    // a batch of one on the handle's drop-in scratch: the resident loop state (l, pk, vk, ak, goals) of
+    // dmpcb200_run / dmpcb200_step is not touched
+    Scratch S;
+    if (int rc = get_scratch(h, &S)) return rc;
+    CK(cudaMemcpyAsync(S.st_in[0] + 3 * n, po, b3, cudaMemcpyHostToDevice, s));
+    CK(cudaMemcpyAsync(S.st_in[1] + 3 * n, vo, b3, cudaMemcpyHostToDevice, s));
+    CK(cudaMemcpyAsync(S.st_in[2] + 3 * n, ao, b3, cudaMemcpyHostToDevice, s));
+    CK(cudaMemcpyAsync(S.pf + 3 * n, pf, b3, cudaMemcpyHostToDevice, s));
+    CK(cudaMemcpyAsync(S.l_in, l, (size_t)N * n3 * sizeof(double), cudaMemcpyHostToDevice, s));
     CK(cudaMemsetAsync(h->d_rescue_next, 0, sizeof(int), s));
-    // a batch of one: scratch slot 0 (local index = n - n0 with n0 = n)
-    StepArgs A = make_args(h, n, n + 1, h->d_st[0][0], h->d_st[0][1], h->d_st[0][2], h->d_l[0], h->d_l[1],
-                           h->d_st[1][0], h->d_st[1][1], h->d_st[1][2], h->d_vhor, h->d_ahor, h->d_status,
-                           h->d_diag, true, nullptr);
+    // scratch slot 0 of the row buffers (local index = n - n0 with n0 = n)
+    StepArgs A = make_args(h, n, n + 1, S.st_in[0], S.st_in[1], S.st_in[2], S.l_in, S.l_out, S.st_out[0],
+                           S.st_out[1], S.st_out[2], h->d_vhor, h->d_ahor, S.status, S.diag, true, nullptr);
+    A.pf = S.pf;
     CK(launch_scan(h, A, s));
     CK(launch_qp(h, A, s));
     int st = 0;
-    CK(cudaMemcpyAsync(&st, h->d_status + n, sizeof(int), cudaMemcpyDeviceToHost, s));
-    if (p) CK(cudaMemcpyAsync(p, h->d_l[1] + (size_t)n * n3, n3 * sizeof(double), cudaMemcpyDeviceToHost, s));
+    CK(cudaMemcpyAsync(&st, S.status + n, sizeof(int), cudaMemcpyDeviceToHost, s));
+    if (p) CK(cudaMemcpyAsync(p, S.l_out + (size_t)n * n3, n3 * sizeof(double), cudaMemcpyDeviceToHost, s));
     if (v) CK(cudaMemcpyAsync(v, h->d_vhor + (size_t)n * n3, n3 * sizeof(double), cudaMemcpyDeviceToHost, s));
     if (a) CK(cudaMemcpyAsync(a, h->d_ahor + (size_t)n * n3, n3 * sizeof(double), cudaMemcpyDeviceToHost, s));
-    if (diag) CK(cudaMemcpyAsync(diag, h->d_diag + n, sizeof(AgentDiag), cudaMemcpyDeviceToHost, s));
+    if (diag) CK(cudaMemcpyAsync(diag, S.diag + n, sizeof(AgentDiag), cudaMemcpyDeviceToHost, s));
     CK(cudaStreamSynchronize(s));
     if (status) *status = st;
-    h->have_goals = true;
     h->launches = 2;
     return 0;
 }
@@ -965,8 +993,10 @@ int dmpcb200_check_coll(dmpcb200_t* h, const double* p3, const double* l, int n,
     if (int rc = ensure_device(h)) return rc;
     const int N = h->N, n3 = 3 * h->K;
     cudaStream_t s = h->stream;
-    CK(cudaMemcpyAsync(h->d_l[0], l, (size_t)N * n3 * sizeof(double), cudaMemcpyHostToDevice, s));
-    check_coll_kernel<<<1, 256, 0, s>>>(h->dp, p3[0], p3[1], p3[2], h->d_l[0], n, k, h->d_u8, h->d_u8 + N,
+    Scratch S;
+    if (int rc = get_scratch(h, &S)) return rc;
+    CK(cudaMemcpyAsync(S.l_in, l, (size_t)N * n3 * sizeof(double), cudaMemcpyHostToDevice, s));
+    check_coll_kernel<<<1, 256, 0, s>>>(h->dp, p3[0], p3[1], p3[2], S.l_in, n, k, h->d_u8, h->d_u8 + N,
                                         h->d_small, h->d_ismall);
     CK(cudaGetLastError());
     double md = 0;
@@ -986,7 +1016,8 @@ int dmpcb200_coll_constr(dmpcb200_t* h, const double* p3, const double* po, cons
                          const double* l, const uint8_t* mask, int cap, double* Ain, double* bin,
                          double* prev_dist, int32_t* nrows) {
     if (!h || !p3 || !po || !vo || !l || !nrows) return fail(DMPCB200_ERR_ARG, "coll_constr: null argument");
-    if (k < 1 || k > h->K || n < 0 || n >= h->N || cap < 1)
+    // n = -1: no own agent (dec-iSCP/CollConstr.m:1-23, where l holds the obstacles only)
+    if (k < 1 || k > h->K || n < -1 || n >= h->N || cap < 1)
         return fail(DMPCB200_ERR_ARG, "coll_constr: k, n or cap out of range");
     if (h->prm.variant != DMPCB200_HARD && !mask)
         return fail(DMPCB200_ERR_ARG, "coll_constr: mask required for this variant");
@@ -996,13 +1027,15 @@ int dmpcb200_coll_constr(dmpcb200_t* h, const double* p3, const double* po, cons
     const int N = h->N, n3 = 3 * h->K;
     cudaStream_t s = h->stream;
     double *d_A = nullptr, *d_b = nullptr;
-    CK(cudaMemcpyAsync(h->d_l[0], l, (size_t)N * n3 * sizeof(double), cudaMemcpyHostToDevice, s));
+    Scratch S;
+    if (int rc = get_scratch(h, &S)) return rc;
+    CK(cudaMemcpyAsync(S.l_in, l, (size_t)N * n3 * sizeof(double), cudaMemcpyHostToDevice, s));
     if (mask) CK(cudaMemcpyAsync(h->d_u8, mask, N, cudaMemcpyHostToDevice, s));
     CK(cudaMallocAsync((void**)&d_A, (size_t)cap * n3 * sizeof(double), s));
     CK(cudaMallocAsync((void**)&d_b, 2 * (size_t)cap * sizeof(double), s));
     CK(cudaMemsetAsync(d_A, 0, (size_t)cap * n3 * sizeof(double), s));
     coll_constr_kernel<<<1, 32, 0, s>>>(h->dp, h->d_tab, p3[0], p3[1], p3[2], po[0], po[1], po[2], vo[0], vo[1],
-                                        vo[2], n, k, h->d_l[0], h->d_u8, cap, d_A, d_b, d_b + cap, h->d_ismall);
+                                        vo[2], n, k, S.l_in, h->d_u8, cap, d_A, d_b, d_b + cap, h->d_ismall);
     CK(cudaGetLastError());
     int nr = 0;
     CK(cudaMemcpyAsync(&nr, h->d_ismall, sizeof(int), cudaMemcpyDeviceToHost, s));
@@ -1075,7 +1108,10 @@ int dmpcb200_postprocess(dmpcb200_t* h, int S, double* pk, double* vk, double* a
     if ((e = cudaMemcpyAsync(d_pk, pk, bS, cudaMemcpyHostToDevice, s)) != cudaSuccess) return bail(e, "copy");
     if ((e = cudaMemcpyAsync(d_vk, vk, bS, cudaMemcpyHostToDevice, s)) != cudaSuccess) return bail(e, "copy");
     if ((e = cudaMemcpyAsync(d_ak, ak, bS, cudaMemcpyHostToDevice, s)) != cudaSuccess) return bail(e, "copy");
-    if ((e = cudaMemsetAsync(d_bits, 0x7f, 2 * sizeof(unsigned long long), s)) != cudaSuccess) return bail(e, "memset");
+    // the two atomicMin reductions run on the bit patterns of non-negative doubles: seed with +inf, so that a
+    // trajectory without motion (all v = a = 0) leaves r_factor = inf and is reported as such
+    static const unsigned long long kInfBits[2] = {0x7ff0000000000000ull, 0x7ff0000000000000ull};
+    if ((e = cudaMemcpyAsync(d_bits, kInfBits, sizeof(kInfBits), cudaMemcpyHostToDevice, s)) != cudaSuccess) return bail(e, "seed");
     cudaEventRecord(h->ev[0], s);
     // 1. r_factor  (failure_rate.m:141-144)
     pp_rfactor_kernel<<<std::min((N * S + 255) / 256, 592), 256, 0, s>>>(N * S, d_vk, d_ak, vmax, amax, d_bits);

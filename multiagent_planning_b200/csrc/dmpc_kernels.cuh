@@ -416,11 +416,6 @@ __device__ __forceinline__ void tail_body(const TailArgs& T) {
     }
 }
 
-__global__ void __launch_bounds__(256) tail_kernel(const __grid_constant__ TailArgs T) {
-    if (T.ctrl && T.ctrl->done) return;
-    tail_body<256>(T);
-}
-
 // ---- K2 -------------------------------------------------------------------------------------
 // shared-memory tables of K2: the blob of the register-resident solver (multiple of 32 bytes)
 DMPC_HD size_t qp_table_bytes(int K) { return (size_t)tab_fast_size(K) * sizeof(double); }
@@ -553,138 +548,6 @@ __global__ void __launch_bounds__(W * 32, 1) qp_kernel(const __grid_constant__ S
             }
         }
     }
-}
-
-// ---- K3 -------------------------------------------------------------------------------------
-// ---- initDMPC.m:1-13 for all agents -------------------------------------------------------------
-__global__ void init_kernel(int N, int K, double h, double init_div, const double* __restrict__ po,
-                            const double* __restrict__ pf, double* l, double* pk, double* vk, double* ak) {
-    const int n = blockIdx.x * blockDim.x + threadIdx.x;
-    if (n >= N) return;
-    for (int x = 0; x < 3; ++x) {
-        const double o = po[3 * n + x];
-        const double d = pf[3 * n + x] - o;
-        for (int k = 0; k < K; ++k) {
-            // t = 0:h:(K-1)*h ; p(:,i) = po + 1*t(i)*diff/10
-            const double t = (double)k * h;
-            l[(size_t)n * 3 * K + 3 * k + x] = o + __ddiv_rn(__dmul_rn(t, d), init_div);
-        }
-        pk[3 * n + x] = o;
-        vk[3 * n + x] = 0.0;
-        ak[3 * n + x] = 0.0;
-    }
-}
-
-// ---- CheckCollSoftDMPC.m:1-17 for one agent and one horizon step (helper drop-in) ---------------
-// out_d[0] = min distance, out_i[0] = any(violation)
-__global__ void __launch_bounds__(256) check_coll_kernel(DevParams P, double px, double py, double pz, const double* l,
-                                                         int n, int k1, unsigned char* violation,
-                                                         unsigned char* viol_constr, double* out_d, int* out_i) {
-    __shared__ double s_md[8];
-    __shared__ int s_any[8];
-    const int tid = threadIdx.x;
-    const double thr = neigh_thr(P, k1);
-    double md = INFINITY;
-    int any = 0;
-    for (int i = tid; i < P.N; i += 256) {
-        unsigned char v = 0, vc = 0;
-        if (i != n) {
-            const double* pj = l + 3 * ((size_t)(k1 - 1) + (size_t)P.K * i);
-            const double dist = ell_dist(px - pj[0], py - pj[1], pz - pj[2], P.c);
-            v = dist < P.rmin;
-            vc = dist < thr;
-            md = fmin(md, dist);
-            any |= v;
-        }
-        violation[i] = v;
-        viol_constr[i] = vc;
-    }
-    for (int o = 16; o; o >>= 1) {
-        md = fmin(md, __shfl_xor_sync(0xffffffffu, md, o));
-        any |= __shfl_xor_sync(0xffffffffu, any, o);
-    }
-    if ((tid & 31) == 0) {
-        s_md[tid >> 5] = md;
-        s_any[tid >> 5] = any;
-    }
-    __syncthreads();
-    if (tid == 0) {
-        for (int w = 1; w < 8; ++w) {
-            md = fmin(md, s_md[w]);
-            any |= s_any[w];
-        }
-        out_d[0] = md;
-        out_i[0] = any;
-    }
-}
-
-// ---- CollConstr*DMPC.m for one agent and one horizon step: dense rows like the reference -------
-// one warp; rows in ascending neighbour order.  Ain cap x 3K column-major.
-__global__ void __launch_bounds__(32) coll_constr_kernel(DevParams P, const double* __restrict__ tab, double px,
-                                                         double py, double pz, double po0, double po1, double po2,
-                                                         double vo0, double vo1, double vo2, int n, int k1,
-                                                         const double* l, const unsigned char* mask, int cap,
-                                                         double* Ain, double* bin, double* prev_dist, int* nrows) {
-    const int K = P.K, N = P.N, lane = threadIdx.x;
-    const bool hard = (P.variant == VAR_HARD);
-    const int kc1 = (P.variant == VAR_SOFT_BOUND2) ? k1 - 1 : k1;  // CollConstrSoftDMPC2.m:8
-    const double* lam = tab;
-    const double* tt = tab + K * K;
-    const double c2 = P.c * P.c;
-    int nv = 0;
-    for (int base = 0; base < N; base += 32) {
-        const int i = base + lane;
-        bool hit = false;
-        double dx = 0, dy = 0, dz = 0, dist = 0;
-        if (i < N && i != n && (hard || mask[i])) {
-            const double* pj = l + 3 * ((size_t)(k1 - 1) + (size_t)K * i);
-            dx = px - pj[0];
-            dy = py - pj[1];
-            dz = pz - pj[2];
-            dist = ell_dist(dx, dy, dz, P.c);
-            hit = hard ? (dist < P.hard_radius) : true;
-        }
-        const unsigned bal = __ballot_sync(0xffffffffu, hit);
-        if (hit) {
-            const int slot = nv + __popc(bal & ((1u << lane) - 1u));
-            if (slot < cap) {
-                const double d0 = dx, d1 = dy, d2 = dz / c2;
-                const double dp = d0 * px + d1 * py + d2 * pz;
-                const double tk = (kc1 >= 1) ? tt[kc1 - 1] : 0.0;
-                const double dq = d0 * (po0 + tk * vo0) + d1 * (po1 + tk * vo1) + d2 * (po2 + tk * vo2);
-                const double r = dist * ((P.rmin - dist) + dp / dist) - dq;
-                for (int j = 0; j < K; ++j) {
-                    const double lj = (kc1 >= 1) ? lam[(kc1 - 1) * K + j] : 0.0;
-                    Ain[slot + (size_t)cap * (3 * j + 0)] = -d0 * lj;
-                    Ain[slot + (size_t)cap * (3 * j + 1)] = -d1 * lj;
-                    Ain[slot + (size_t)cap * (3 * j + 2)] = -d2 * lj;
-                }
-                bin[slot] = -r;
-                prev_dist[slot] = dist;
-            }
-        }
-        nv += __popc(bal);
-    }
-    if (lane == 0) *nrows = nv;
-}
-
-// ---- propStatedmpc.m:1-8 for a batch: a 3K x B -> p, v 3K x B -----------------------------------
-__global__ void prop_state_kernel(int B, int K, const double* __restrict__ tab, double h, const double* po,
-                                  const double* vo, const double* a, double* p, double* v) {
-    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
-    const int n3 = 3 * K;
-    if (idx >= B * n3) return;
-    const int b = idx / n3, i = idx - b * n3, k = i / 3, x = i - 3 * k;
-    const double* lam = tab;
-    const double* tt = tab + K * K;
-    double sp = 0.0, sv = 0.0;
-    for (int j = 0; j <= k; ++j) {
-        const double aj = a[(size_t)b * n3 + 3 * j + x];
-        sp = fma(lam[k * K + j], aj, sp);
-        sv += h * aj;
-    }
-    p[idx] = sp + (po[3 * b + x] + tt[k] * vo[3 * b + x]);
-    v[idx] = sv + vo[3 * b + x];
 }
 
 }  // namespace dmpc

@@ -441,18 +441,49 @@ def CollConstrSoftDMPC2(p, po, vo, n, k, l, rmin, Ain, A_initp, E1, E2, order, v
 
 
 def CollConstrHardDMPCOnDemand(p, po, vo, n, k, l, rmin, Ain, A_initp, E1, E2, order, violation):
-    """CollConstrHardDMPCOnDemand.m:1-32."""
-    return _coll_constr(HARD_ONDEMAND, p, po, vo, n, k, l, rmin, A_initp, E1, order, violation)
+    """CollConstrHardDMPCOnDemand.m:1-32 -> Ain_total, bin_total (two outputs, like the reference)."""
+    A, b, _ = _coll_constr(HARD_ONDEMAND, p, po, vo, n, k, l, rmin, A_initp, E1, order, violation)
+    return A, b
 
 
 def CollConstrHardDMPC(p, po, vo, n, k, l, rmin, Ain, A_initp, E1, E2, order):
-    """CollConstrHardDMPC.m:1-34: rows of all neighbours with dist < 1 (the reference's vacuous
-    all-zero rows for the other agents are not returned)."""
-    return _coll_constr(HARD, p, po, vo, n, k, l, rmin, A_initp, E1, order, None)
+    """CollConstrHardDMPC.m:1-34 -> Ain_total (N-1, 3K), bin_total (N-1,): one row per neighbour with
+    dist < 1 (:19), packed first in ascending neighbour order, and all-zero rows for the rest (:3-5) --
+    the reference's exact shape (solveHardDMPC.m:18-22 stacks K of these blocks).  The device returns the
+    non-trivial rows; the zero rows are padding added here."""
+    A, b, _ = _coll_constr(HARD, p, po, vo, n, k, l, rmin, A_initp, E1, order, None)
+    N, K = np.asarray(l).shape[2], np.asarray(l).shape[1]
+    Ain_total, bin_total = np.zeros((max(N - 1, 0), 3 * K)), np.zeros(max(N - 1, 0))
+    Ain_total[:A.shape[0]] = A
+    bin_total[:A.shape[0]] = b
+    return Ain_total, bin_total
 
 
-CollConstr = CollConstrSoftDMPC   # dec-iSCP/CollConstr.m name kept as an alias (BASELINE north_star)
-propState = propStatedmpc         # dec-iSCP/propState.m
+def CollConstr(p, po, k, l, Ain, rmin, E1, E2, order):
+    """The dec-iSCP helper name (dec-iSCP/CollConstr.m:1-23) on the device path -> Ain_total (N_obs, 3K),
+    bin_total (N_obs,).  Its rows are the DMPC rows of CollConstrSoftDMPC2 with vo = 0 and no own agent: every
+    column of l is an obstacle, the row acts on block k-1 (:17), r = dist (rmin - dist + diff p / dist) -
+    diff po' (:14).  Ain must be getPosMat(h, K) (dec-iSCP/singleiSCP.m:9); h is read from it."""
+    _order2(order)
+    if int(k) < 2:
+        raise DmpcError("CollConstr needs k >= 2 (the row acts on block k-1)")
+    l = _f(l)
+    K, N = l.shape[1], l.shape[2]
+    h = float(np.sqrt(2.0 * np.asarray(Ain)[0, 0]))
+    s = _solver_for(N, K, h, rmin, _c_from_E1(E1), 1.0, 1000.0, 100.0, -5e4, SOFT_BOUND2)
+    A, b, _ = s.coll_constr(p, po, np.zeros(3), -1, int(k), l, mask=np.ones(N, np.uint8), cap=N)
+    return A, b
+
+
+def propState(po, a, A_p, A_v, K):
+    """The dec-iSCP helper name (dec-iSCP/propState.m:1-10) on the device path: K trajectory points from rest,
+    p = [po; A_p a + po], v = [0; A_v a] with A_p, A_v the first 3(K-1) rows of the kinematic maps
+    (dec-iSCP/decSCP.m:55-71), i.e. the first K-1 rows of propStatedmpc.m with vo = 0."""
+    K = int(K)
+    h = float(np.asarray(A_v)[0, 0])
+    pp, vv = propStatedmpc(po, np.zeros(3), a, h=h)
+    po = _f(po).ravel()
+    return np.r_[po, pp[:3 * (K - 1)]], np.r_[np.zeros(3), vv[:3 * (K - 1)]]
 
 
 def is_inbounds(p, pmin, pmax, tol=50e-3):
@@ -471,16 +502,32 @@ def ReachedGoal(p, pf, length_t, error_tol, N):
     return s.reached_goal(pk, pf, error_tol)[0]
 
 
+def status_flags(st: int, variant: int):
+    """status word -> (solved, success/feasible, outbound, coll) exactly as the reference function of the
+    variant returns them.  solveSoftDMPCbound.m keeps `feasible = 1` on the k == 1 collision exit (:29-30)
+    and when the first position is out of bounds (:125-128 only sets `outbound`); solveSoftDMPCbound2.m
+    (:14,26,123-126), solveHardDMPC.m (:14,76-79) and solveHardDMPCOnDemand.m (:14,81-84) start from
+    `success = 0`, leave it 0 on the collision exit and reset it to 0 when out of bounds.  The library's
+    internal failures (iteration cap, capacity overflow) count as not feasible for every variant."""
+    st = int(st)
+    solved = bool(st & ST_SOLVED)
+    outbound = 1 if (st & ST_OUTBOUND) else 0
+    coll = 1 if (st & ST_COLL) else 0
+    hard_fail = bool(st & (ST_INFEASIBLE | ST_QPFAIL | ST_OVERFLOW))
+    if int(variant) == SOFT_BOUND:
+        success = 0 if hard_fail else 1
+    else:
+        success = 1 if (solved and not outbound and not coll and not hard_fail) else 0
+    return solved, success, outbound, coll
+
+
 def _solve(variant, po, pf, vo, ao, n, h, l, K, rmin, pmin, pmax, alim, Q1, S1, E1, order, term):
     _order2(order)
     l = _f(l)
     N = l.shape[2]
     s = _solver_for(N, K, h, rmin, _c_from_E1(E1), alim, Q1, S1, term, variant, pmin, pmax)
     p, v, a, st, dg = s.solve_agent(po, pf, vo, ao, int(n) - 1, l)
-    solved = bool(st & ST_SOLVED)
-    feasible = 0 if (st & (ST_INFEASIBLE | ST_QPFAIL)) else 1
-    outbound = 1 if (st & ST_OUTBOUND) else 0
-    coll = 1 if (st & ST_COLL) else 0
+    solved, feasible, outbound, coll = status_flags(st, variant)
     if not solved:
         e = np.zeros((0, 0))
         return e, e, e, feasible, outbound, coll

@@ -26,7 +26,11 @@ from . import dmpc
 
 
 def partition(N: int, world: int):
-    """Contiguous blocks of ceil(N/world) agents (dmpc.cpp:1600-1625)."""
+    """Contiguous blocks of ceil(N/world) agents (dmpc.cpp:1600-1625).  Trailing blocks may be short or EMPTY
+    (N = 17 on 8 ranks: blocks of 3, ranks 6 and 7 own nothing): an empty rank still holds a replica of the
+    horizon buffer and takes part in the exchange, it just solves no agent (the library accepts n0 == n1)."""
+    if N < 1 or world < 1:
+        raise ValueError("partition: need N >= 1 and world >= 1")
     blk = -(-N // world)
     return blk, [(min(r * blk, N), min((r + 1) * blk, N)) for r in range(world)]
 
@@ -48,7 +52,8 @@ class CudaBackend:
         self.solver = dmpc.Solver(N, params, n0=n0, n1=n1, device=device, pmin=pmin, pmax=pmax, pf=pf)
         s = self.solver
         npad = -(-N // 32) * 32
-        assert rows <= npad, "world size must divide 32 (1, 2, 4, 8)"
+        if rows > npad:
+            raise dmpc.DmpcError("world size must divide 32 (1, 2, 4, 8)")
         view = lambda which, shape, ts="<f8": torch.as_tensor(_DevArray(s.device_ptr(which), shape, ts),
                                                               device=self.device)
         self.l = [view(0, (npad, self.K, 3)), view(1, (npad, self.K, 3))]
@@ -81,9 +86,12 @@ class ShardedDMPC:
         self.rank = dist.get_rank(group) if rank is None else rank
         self.world = dist.get_world_size(group) if world is None else world
         self.N, self.K, self.P = int(N), int(params.K), params
-        if self.N < self.world:
-            raise dmpc.DmpcError("need at least one agent per rank")
+        # every rank computes the same partition from (N, world): a bad configuration raises on ALL ranks
+        # before any backend exists, never on one rank while the others wait in the all-gather
         self.blk, parts = partition(self.N, self.world)
+        if self.blk * self.world > -(-self.N // 32) * 32:
+            raise dmpc.DmpcError(f"{self.world} blocks of {self.blk} agents exceed the padded horizon buffer "
+                                 f"({-(-self.N // 32) * 32} rows): use a world size of 1, 2, 4 or 8")
         self.n0, self.n1 = parts[self.rank]
         self.rows = self.blk * self.world  # agent rows in the gathered buffer (>= N, tail rows inert)
         self.pf = np.asarray(pf, float).reshape(3, N, order="F")
@@ -105,9 +113,15 @@ class ShardedDMPC:
         if self.world > 1:
             out = be.l[nx][: self.rows]
             send = out[self.rank * self.blk:(self.rank + 1) * self.blk]
-            if not self._inplace:
-                send = send.clone()
-            dist.all_gather_into_tensor(out.view(-1), send.reshape(-1), group=self.group)
+            if self._inplace:
+                dist.all_gather_into_tensor(out.view(-1), send.reshape(-1), group=self.group)
+            elif out.is_cuda:
+                # test configuration (gloo with device buffers: two ranks on one GPU): stage through the host
+                got = torch.empty(out.shape, dtype=out.dtype)
+                dist.all_gather_into_tensor(got.view(-1), send.reshape(-1).cpu(), group=self.group)
+                out.copy_(got)
+            else:
+                dist.all_gather_into_tensor(out.view(-1), send.clone().reshape(-1), group=self.group)
             self.n_allgather += 1
         self.cur = nx
         self.steps += 1

@@ -104,3 +104,20 @@ def test_mex_gateway_syntax_against_the_header():
                         "-I", os.path.join(ROOT, "include"), os.path.join(ROOT, "matlab", "dmpc_b200_mex.cpp")],
                        capture_output=True, text=True)
     assert r.returncode == 0, r.stderr
+
+
+def test_status_to_reference_flags():
+    """status word -> [success/feasible, outbound, coll] per variant (solveSoftDMPCbound.m:17-19,29-30,125-128;
+    solveSoftDMPCbound2.m:14,26,123-126; solveHardDMPC.m:14,76-79)"""
+    from multiagent_planning_b200 import dmpc as d
+    f = d.status_flags
+    assert f(d.ST_SOLVED, 0) == (True, 1, 0, 0)
+    assert f(d.ST_SOLVED | d.ST_OUTBOUND, 0) == (True, 1, 1, 0)      # bound: feasible stays 1
+    assert f(d.ST_COLL, 0) == (False, 1, 0, 1)                       # bound: coll = 1, feasible = 1
+    assert f(d.ST_INFEASIBLE | (30 << 8), 0) == (False, 0, 0, 0)
+    assert f(d.ST_QPFAIL | d.ST_OVERFLOW, 0) == (False, 0, 0, 0)
+    for v in (1, 2, 3):
+        assert f(d.ST_SOLVED, v) == (True, 1, 0, 0)
+        assert f(d.ST_SOLVED | d.ST_OUTBOUND, v) == (True, 0, 1, 0)  # success = 0; outbound = 1
+        assert f(d.ST_COLL, v) == (False, 0, 0, 1)                   # success stays 0 on the collision exit
+        assert f(d.ST_INFEASIBLE, v) == (False, 0, 0, 0)

@@ -52,7 +52,7 @@ def _worker(rank, world, port, N, steps, q):
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("N", [31, 48])
+@pytest.mark.parametrize("N", [1, 31, 48])   # N = 1: the second rank owns an EMPTY block
 def test_two_ranks_equal_one_rank(emul, N):
     steps = 6
     ctx = mp.get_context("spawn")
@@ -89,3 +89,22 @@ def test_partition():
     assert partition(100, 1) == (100, [(0, 100)])
     blk, parts = partition(9, 4)
     assert blk == 3 and parts[-1] == (9, 9)
+    blk, parts = partition(17, 8)          # two empty trailing ranks: valid, they only take part in the exchange
+    assert blk == 3 and parts[5] == (15, 17) and parts[6] == parts[7] == (17, 17)
+    with pytest.raises(ValueError):
+        partition(0, 2)
+
+
+def test_bad_world_size_raises_identically_on_every_rank():
+    """a partition that does not fit the padded buffer must raise before any backend is created (so that no
+    rank is left waiting in the all-gather): same exception for every rank index"""
+    from multiagent_planning_b200 import _lib, dmpc, sharded
+    pmin, pmax, po, pf = _scenario(64)
+    P = _lib.Params()
+    _lib.lib().dmpcb200_default_params(P, 0)
+    made = []
+    for rank in range(3):   # 3 blocks of 22 = 66 rows > 64 padded rows
+        with pytest.raises(dmpc.DmpcError, match="exceed the padded"):
+            sharded.ShardedDMPC(64, P, pmin, pmax, po, pf, rank=rank, world=3,
+                                backend_factory=lambda **kw: made.append(kw))
+    assert not made
