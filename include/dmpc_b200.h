@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define DMPCB200_ABI_VERSION 1
+#define DMPCB200_ABI_VERSION 2
 
 /* solver variants (which reference function the step reproduces) */
 enum {
@@ -103,9 +103,14 @@ void dmpcb200_default_params(dmpcb200_params* p, int variant);
 int dmpcb200_model_mats(double h, int K, double* A_p, double* A_v, double* A_initp, double* Delta);
 
 /* Create a solver for N agents (whole swarm) of which this handle solves agents [n0, n1)
- * on CUDA device `device` (one handle per GPU/process; dmpc.cpp:1600-1625 clusters).
+ * on CUDA device `device` (one handle per GPU/process; dmpc.cpp:1600-1625 clusters).  n0 == n1 (an empty
+ * block) is valid: such a handle only holds a replica of the horizon buffer.
+ * n_scenarios >= 1: number of INDEPENDENT swarms of N agents solved side by side by every kernel launch --
+ * the trial loops of test/failure_rate.m:61-68 (50 random trials per swarm size) as one batch.  Scenarios
+ * never interact (own horizons, own workspace box, own loop control); they are sharded WHOLE across GPUs
+ * (one handle with n0 = 0, n1 = N per GPU, no collective).  n_scenarios = 1 is the single swarm.
  * max_rows: capacity of the per-agent constraint-row buffer, 0 = automatic. */
-int dmpcb200_create(const dmpcb200_params* p, int N, int n0, int n1, int device, int max_rows,
+int dmpcb200_create(const dmpcb200_params* p, int N, int n0, int n1, int n_scenarios, int device, int max_rows,
                     dmpcb200_t** out);
 void dmpcb200_destroy(dmpcb200_t* h);
 
@@ -171,6 +176,30 @@ int dmpcb200_reached_goal(dmpcb200_t* h, const double* p, const double* pf, doub
 int dmpcb200_run(dmpcb200_t* h, int max_steps, int stop_on_fail, int mode, double* traj_p,
                  double* traj_v, double* traj_a, int32_t* status_hist, int32_t* steps_done,
                  int32_t* reached, int32_t* first_fail_step, int32_t* first_fail_agent);
+
+/* ---- scenario batching (n_scenarios of dmpcb200_create) --------------------------------------------
+ * set_scenario: start points po, goals pf (3 x N), workspace box of scenario s, and initDMPC.m:1-13 for its
+ * agents (the scenario's loop state is reset).  On a single-scenario handle (s = 0) it is
+ * set_bounds + set_goals + init_horizons in one call. */
+int dmpcb200_set_scenario(dmpcb200_t* h, int s, const double* po, const double* pf, const double* pmin,
+                          const double* pmax);
+/* The closed loop of EVERY scenario, test/failure_rate.m:99-133 per trial: at most max_steps MPC steps; a
+ * scenario stops at its goal (ReachedGoal.m) and, if stop_on_fail, at its first failing agent (the reference
+ * `break`s the trial, failure_rate.m:112-123); the others go on.  Three launches per step for the whole batch
+ * (scan, QP, per-scenario tail), CUDA graph of two steps, no host synchronisation inside the loop.
+ * mode: 0 = CUDA graph, non-zero = plain launches.
+ * Per-scenario outputs (any may be NULL): steps_done, reached, first_fail_step (-1 none), first_fail_agent,
+ * goal_dist (max_n ||p - pf|| after the last step): n_scenarios entries each.
+ * traj_p/v/a: optional, n_scenarios blocks of 3 x (max_steps+1) x N (column 0 = initial state). */
+int dmpcb200_run_batch(dmpcb200_t* h, int max_steps, int stop_on_fail, int mode, double* traj_p, double* traj_v,
+                       double* traj_a, int32_t* steps_done, int32_t* reached, int32_t* first_fail_step,
+                       int32_t* first_fail_agent, double* goal_dist);
+/* loop state of scenario s (any output may be NULL): l 3 x K x N, pk,vk,ak 3 x N, status / diag of its agents */
+int dmpcb200_get_scenario(dmpcb200_t* h, int s, double* l, double* pk, double* vk, double* ak, int32_t* status,
+                          dmpcb200_diag* diag);
+/* device time (CUDA events) of the last dmpcb200_run_batch and the agent-steps it solved (sum over the
+ * scenarios of steps_done x N) */
+int dmpcb200_last_batch_timing(dmpcb200_t* h, double* total_ms, int64_t* agent_steps);
 
 /* read / overwrite the device-resident loop state (any output may be NULL):
  * l 3 x K x N, pk,vk,ak 3 x N, status / diag of the last step. */

@@ -67,7 +67,7 @@ static void ensure_handle(const mxArray* s) {
     get_params(s, &p, &N);
     if (g_h && N == g_N && std::memcmp(&p, &g_p, sizeof(p)) == 0) return;
     close_handle();
-    check(dmpcb200_create(&p, N, 0, N, (int)field(s, "device", 0), 0, &g_h), "create");
+    check(dmpcb200_create(&p, N, 0, N, /*n_scenarios*/ 1, (int)field(s, "device", 0), 0, &g_h), "create");
     g_p = p;
     g_N = N;
     if (!mexIsLocked()) {

@@ -59,6 +59,7 @@ struct AgentIO {
     double *out_p, *out_v, *out_a;
     double *p1, *v1, *a1;  // 3 each
     const double* l_prev_n;  // previous horizon of this agent (copied to out_p when unsolved)
+    const double* bounds = nullptr;  // workspace box of the agent's scenario: pmin[3], pmax[3]; null = P.pmin / P.pmax
 };
 
 // All lanes of the warp call this with identical arguments.  Returns the status word.
@@ -127,8 +128,8 @@ DMPC_D int agent_solve(const DevParams& P, const double* __restrict__ tab, unsig
             s_x0[3 + x] = io.pf[x];
             s_x0[6 + x] = io.vo[x];
             s_x0[9 + x] = io.ao[x];
-            s_bnd[x] = P.pmin[x];
-            s_bnd[3 + x] = P.pmax[x];
+            s_bnd[x] = io.bounds ? io.bounds[x] : P.pmin[x];
+            s_bnd[3 + x] = io.bounds ? io.bounds[3 + x] : P.pmax[x];
         }
         wsync();
         const double *x_po = s_x0, *x_pf = s_x0 + 3, *x_vo = s_x0 + 6, *x_ao = s_x0 + 9;

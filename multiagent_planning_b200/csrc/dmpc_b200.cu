@@ -58,6 +58,10 @@ struct dmpcb200_handle {
     dmpcb200_params prm;
     DevParams dp;
     int N = 0, n0 = 0, n1 = 0, NL = 0, Npad = 0, K = 0, device = 0;
+    int S = 1;                   // scenarios batched in this handle (independent swarms of N agents)
+    double* d_bounds = nullptr;  // S x 6: pmin, pmax of every scenario (dmpcb200_set_scenario)
+    bool per_scen_bounds = false;
+    std::vector<char> scen_set;  // which scenarios have been set
     int RMAX = 0, QMAX = 0, RCAP = 0, QBIG = 0, W = 4, n_rescue = 0;
     size_t rescue_bytes = 0;
     cudaStream_t stream = nullptr;
@@ -109,11 +113,13 @@ struct dmpcb200_handle {
     // trajectory record of dmpcb200_run
     double *d_traj[3] = {nullptr, nullptr, nullptr};
     int* d_hist = nullptr;
-    int traj_S = 0;
+    int traj_S = 0, traj_scen = 1;
     bool hist_on = false;
+    double batch_ms = 0;            // dmpcb200_run_batch: device time of the whole call
+    long long batch_agent_steps = 0;  //   and the agent-steps it solved
     // closed-loop graph (two steps: even -> odd -> even)
     cudaGraphExec_t graph = nullptr;
-    bool graph_record = false;
+    bool graph_record = false, graph_batch = false;
     // pinned host staging
     double* h_pin = nullptr;
     size_t h_pin_n = 0;
@@ -140,6 +146,9 @@ StepArgs make_args(dmpcb200_t* h, int n0, int n1, const double* pk, const double
     A.thr = make_scan_thr(h->dp);
     A.n0 = n0;
     A.n1 = n1;
+    A.n_scen = 1;
+    A.lstride = 0;
+    A.bounds = nullptr;
     A.RMAX = h->RMAX;
     A.QMAX = h->QMAX;
     A.RCAP = h->RCAP;
@@ -180,7 +189,7 @@ StepArgs make_args(dmpcb200_t* h, int n0, int n1, const double* pk, const double
 // per-agent near masks of a very large swarm do not fit next to a tile); the reference's horizons
 // (15, 20) are compiled with the horizon as a constant (the own horizon then lives in registers)
 cudaError_t launch_scan(dmpcb200_t* h, const StepArgs& A, cudaStream_t s) {
-    const int nl = A.n1 - A.n0, K = h->K, N = h->N;
+    const int nl = A.n1 - A.n0, K = h->K, N = h->N;  // (per scenario)
     if (nl <= 4 * 148 || scan_stages(K, N, 8, A.RMAX) < 2) {
         if (scan_stages(K, N, 4, A.RMAX) < 1) return launch_scan_layout(SCAN_1_2_0, A, nl, K, s);
         if (K == 15) return launch_scan_layout(SCAN_4_2_15, A, nl, K, s);
@@ -371,13 +380,17 @@ int dmpcb200_model_mats(double h, int K, double* A_p, double* A_v, double* A_ini
     return 0;
 }
 
-int dmpcb200_create(const dmpcb200_params* p, int N, int n0, int n1, int device, int max_rows, dmpcb200_t** out) {
+int dmpcb200_create(const dmpcb200_params* p, int N, int n0, int n1, int n_scenarios, int device, int max_rows,
+                    dmpcb200_t** out) {
     if (!p || !out) return fail(DMPCB200_ERR_ARG, "create: null argument");
     *out = nullptr;
     if (p->K < 1 || p->K > 32) return fail(DMPCB200_ERR_ARG, "create: horizon K must be in 1..32");
     // n0 == n1 is a valid (empty) block: a rank of a sharded run whose block is empty still owns a replica of
     // the horizon buffer and takes part in the exchange
     if (N < 1 || n0 < 0 || n1 > N || n0 > n1) return fail(DMPCB200_ERR_ARG, "create: bad agent range");
+    if (n_scenarios < 1) return fail(DMPCB200_ERR_ARG, "create: n_scenarios must be >= 1");
+    if (n_scenarios > 1 && (n0 != 0 || n1 != N))
+        return fail(DMPCB200_ERR_ARG, "create: batched scenarios are sharded whole (n0 = 0, n1 = N)");
     if (p->variant < 0 || p->variant > 3) return fail(DMPCB200_ERR_ARG, "create: unknown variant");
     if (!(p->h > 0) || !(p->rmin > 0) || !(p->c > 0) || !(p->alim > 0))
         return fail(DMPCB200_ERR_ARG, "create: h, rmin, c, alim must be positive");
@@ -399,6 +412,8 @@ int dmpcb200_create(const dmpcb200_params* p, int N, int n0, int n1, int device,
     h->K = p->K;
     h->device = device;
     h->Npad = round_up(N, kTile);
+    h->S = n_scenarios;
+    h->scen_set.assign(n_scenarios, 0);
     DevParams& D = h->dp;
     D.K = p->K; D.variant = p->variant; D.max_tries = p->max_tries; D.neigh_mode = p->neigh_mode; D.N = N;
     D.h = p->h; D.rmin = p->rmin; D.c = p->c; D.alim = p->alim; D.Q1 = p->Q1; D.S1 = p->S1; D.term = p->term;
@@ -452,11 +467,12 @@ int dmpcb200_create(const dmpcb200_params* p, int N, int n0, int n1, int device,
     if ((e = cudaMemcpy(h->d_tab, tab.data(), tab.size() * sizeof(double), cudaMemcpyHostToDevice)) != cudaSuccess)
         return bail(e, "tables copy");
     {
-        const size_t lB = align_up((size_t)h->Npad * n3 * sizeof(double), 256);
-        const size_t sB = align_up(3 * (size_t)N * sizeof(double), 256);
+        const size_t nS = (size_t)h->S;
+        const size_t lB = align_up(nS * h->Npad * n3 * sizeof(double), 256);
+        const size_t sB = align_up(3 * nS * N * sizeof(double), 256);
         h->side_bytes = lB + 3 * sB;
-        const size_t stB = align_up((size_t)N * sizeof(int), 256), dgB = align_up((size_t)N * sizeof(AgentDiag), 256);
-        h->tailblk_bytes = stB + dgB + 256;
+        const size_t stB = align_up(nS * N * sizeof(int), 256), dgB = align_up(nS * N * sizeof(AgentDiag), 256);
+        h->tailblk_bytes = stB + dgB + align_up(nS * sizeof(int), 256);
         const size_t total = 2 * h->side_bytes + h->tailblk_bytes;
         if ((e = cudaMalloc((void**)&h->d_arena, total)) != cudaSuccess) return bail(e, "state arena");
         if ((e = cudaMemset(h->d_arena, 0, total)) != cudaSuccess) return bail(e, "state arena");
@@ -477,10 +493,12 @@ int dmpcb200_create(const dmpcb200_params* p, int N, int n0, int n1, int device,
         if ((e = cudaHostGetDevicePointer((void**)&h->d_stage, h->h_stage, 0)) != cudaSuccess)
             return bail(e, "pinned staging (device alias)");
     }
-    if ((e = dalloc(&h->d_pf, 3 * (size_t)N)) != cudaSuccess) return bail(e, "goals");
-    if ((e = dalloc(&h->d_vhor, (size_t)N * n3)) != cudaSuccess) return bail(e, "v_hor");
-    if ((e = dalloc(&h->d_ahor, (size_t)N * n3)) != cudaSuccess) return bail(e, "a_hor");
-    const size_t NL = h->NL;
+    const size_t nS = (size_t)h->S;
+    if ((e = dalloc(&h->d_pf, 3 * nS * N)) != cudaSuccess) return bail(e, "goals");
+    if ((e = dalloc(&h->d_bounds, 6 * nS)) != cudaSuccess) return bail(e, "bounds");
+    if ((e = dalloc(&h->d_vhor, nS * N * n3)) != cudaSuccess) return bail(e, "v_hor");
+    if ((e = dalloc(&h->d_ahor, nS * N * n3)) != cudaSuccess) return bail(e, "a_hor");
+    const size_t NL = (size_t)h->NL * nS;
     if ((e = dalloc(&h->d_scan, NL)) != cudaSuccess) return bail(e, "scan");
     if ((e = dalloc(&h->d_grow, NL * 5 * h->RMAX)) != cudaSuccess) return bail(e, "rows");
     if ((e = dalloc(&h->d_gkc, NL * h->RMAX)) != cudaSuccess) return bail(e, "rows kc");
@@ -490,8 +508,8 @@ int dmpcb200_create(const dmpcb200_params* p, int N, int n0, int n1, int device,
     if ((e = dalloc(&h->d_rescue, h->rescue_bytes * h->n_rescue)) != cudaSuccess) return bail(e, "rescue");
     if ((e = dalloc(&h->d_rescue_next, 1)) != cudaSuccess) return bail(e, "rescue counter");
     if ((e = dalloc(&h->d_done, 2)) != cudaSuccess) return bail(e, "done / work counters");
-    if ((e = dalloc(&h->d_ctrl, 1)) != cudaSuccess) return bail(e, "ctrl");
-    if ((e = dalloc(&h->d_goal, 2)) != cudaSuccess) return bail(e, "goal");
+    if ((e = dalloc(&h->d_ctrl, nS)) != cudaSuccess) return bail(e, "ctrl");
+    if ((e = dalloc(&h->d_goal, 2 * nS)) != cudaSuccess) return bail(e, "goal");
     if ((e = dalloc(&h->d_u8, 2 * (size_t)N)) != cudaSuccess) return bail(e, "u8");
     if ((e = dalloc(&h->d_small, 64)) != cudaSuccess) return bail(e, "small");
     if ((e = dalloc(&h->d_ismall, 16)) != cudaSuccess) return bail(e, "ismall");
@@ -508,7 +526,7 @@ void dmpcb200_destroy(dmpcb200_t* h) {
     cudaFree(h->d_tab);
     cudaFree(h->d_arena);
     if (h->h_stage) cudaFreeHost(h->h_stage);
-    cudaFree(h->d_pf); cudaFree(h->d_vhor); cudaFree(h->d_ahor);
+    cudaFree(h->d_pf); cudaFree(h->d_bounds); cudaFree(h->d_vhor); cudaFree(h->d_ahor);
     cudaFree(h->d_scan); cudaFree(h->d_grow); cudaFree(h->d_gkc); cudaFree(h->d_gidx);
     cudaFree(h->d_gscr_d); cudaFree(h->d_gscr_i); cudaFree(h->d_rescue); cudaFree(h->d_rescue_next);
     cudaFree(h->d_done); cudaFree(h->d_ctrl); cudaFree(h->d_goal); cudaFree(h->d_u8); cudaFree(h->d_small);
@@ -537,6 +555,7 @@ int dmpcb200_set_bounds(dmpcb200_t* h, const double* pmin, const double* pmax) {
 
 int dmpcb200_set_goals(dmpcb200_t* h, const double* pf) {
     if (!h || !pf) return fail(DMPCB200_ERR_ARG, "set_goals: null argument");
+    if (h->S != 1) return fail(DMPCB200_ERR_STATE, "set_goals: single-scenario entry point on a batched handle (use set_scenario / run_batch / get_scenario)");
     if (int rc = ensure_device(h)) return rc;
     CK(cudaMemcpyAsync(h->d_pf, pf, 3 * (size_t)h->N * sizeof(double), cudaMemcpyHostToDevice, h->stream));
     CK(cudaStreamSynchronize(h->stream));
@@ -546,6 +565,7 @@ int dmpcb200_set_goals(dmpcb200_t* h, const double* pf) {
 
 int dmpcb200_init_horizons(dmpcb200_t* h, const double* po, double* l, double* p1, double* v1, double* a1) {
     if (!h || !po) return fail(DMPCB200_ERR_ARG, "init_horizons: null argument");
+    if (h->S != 1) return fail(DMPCB200_ERR_STATE, "init_horizons: single-scenario entry point on a batched handle (use set_scenario / run_batch / get_scenario)");
     if (!h->have_goals) return fail(DMPCB200_ERR_STATE, "init_horizons: call dmpcb200_set_goals first");
     if (int rc = ensure_device(h)) return rc;
     const int N = h->N, K = h->K;
@@ -570,6 +590,7 @@ int dmpcb200_step_dev(dmpcb200_t* h, const double* d_pk, const double* d_vk, con
                       double* d_v_hor, double* d_a_hor, int32_t* d_status, dmpcb200_diag* d_diag, void* stream) {
     if (!h || !d_pk || !d_vk || !d_ak || !d_l_prev || !d_l_new || !d_p1 || !d_v1 || !d_a1 || !d_status)
         return fail(DMPCB200_ERR_ARG, "step_dev: null argument");
+    if (h->S != 1) return fail(DMPCB200_ERR_STATE, "step_dev: single-scenario entry point on a batched handle (use set_scenario / run_batch / get_scenario)");
     if (!h->have_goals || !h->have_bounds)
         return fail(DMPCB200_ERR_STATE, "step_dev: set_goals and set_bounds first");
     if (((uintptr_t)d_l_prev & 15) != 0) return fail(DMPCB200_ERR_ARG, "step_dev: l_prev must be 16-byte aligned");
@@ -646,6 +667,7 @@ int step_impl(dmpcb200_t* h, const dmpcb200_handle::Bound& B, int32_t* first_fai
     int32_t* status = B.status;
     dmpcb200_diag* diag = B.diag;
     if (!h || !pk || !vk || !ak || !l_prev) return fail(DMPCB200_ERR_ARG, "step: null input");
+    if (h->S != 1) return fail(DMPCB200_ERR_STATE, "step: single-scenario entry point on a batched handle (use set_scenario / run_batch / get_scenario)");
     if (!h->have_goals || !h->have_bounds) return fail(DMPCB200_ERR_STATE, "step: set_goals and set_bounds first");
     if (h->NL == 0) {
         if (first_fail) *first_fail = -1;
@@ -785,6 +807,7 @@ int dmpcb200_run(dmpcb200_t* h, int max_steps, int stop_on_fail, int mode, doubl
                  double* traj_a, int32_t* status_hist, int32_t* steps_done, int32_t* reached,
                  int32_t* first_fail_step, int32_t* first_fail_agent) {
     if (!h || max_steps < 1) return fail(DMPCB200_ERR_ARG, "run: bad argument");
+    if (h->S != 1) return fail(DMPCB200_ERR_STATE, "run: single-scenario entry point on a batched handle (use set_scenario / run_batch / get_scenario)");
     if (h->n0 != 0 || h->n1 != h->N) return fail(DMPCB200_ERR_STATE, "run: needs a handle that owns all agents");
     if (!h->have_init || !h->have_bounds) return fail(DMPCB200_ERR_STATE, "run: set_bounds and init_horizons first");
     if (int rc = ensure_device(h)) return rc;
@@ -826,8 +849,9 @@ int dmpcb200_run(dmpcb200_t* h, int max_steps, int stop_on_fail, int mode, doubl
     const int start_cur = h->cur;
     int issued = 0;
     if (!timed && !no_graph) {
-        if (!h->graph || h->graph_record != record) {
+        if (!h->graph || h->graph_record != record || h->graph_batch) {
             drop_graph(h);
+            h->graph_batch = false;
             cudaGraph_t g;
             CK(cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal));
             int rc = launch_resident_step(h, 0, record, h->d_ctrl, s, nullptr);
@@ -914,9 +938,222 @@ int dmpcb200_run(dmpcb200_t* h, int max_steps, int stop_on_fail, int mode, doubl
     return 0;
 }
 
+/* ---- scenario batching: test/failure_rate.m:61-133 (trial loops) as one launch per kernel ------------- */
+
+int dmpcb200_set_scenario(dmpcb200_t* h, int s, const double* po, const double* pf, const double* pmin,
+                          const double* pmax) {
+    if (!h || !po || !pf || !pmin || !pmax) return fail(DMPCB200_ERR_ARG, "set_scenario: null argument");
+    if (s < 0 || s >= h->S) return fail(DMPCB200_ERR_ARG, "set_scenario: scenario index out of range");
+    for (int x = 0; x < 3; ++x)
+        if (!(pmin[x] < pmax[x])) return fail(DMPCB200_ERR_ARG, "set_scenario: need pmin < pmax");
+    if (int rc = ensure_device(h)) return rc;
+    const int N = h->N, K = h->K;
+    cudaStream_t st = h->stream;
+    const size_t o3 = 3 * (size_t)s * N, b3 = 3 * (size_t)N * sizeof(double);
+    double bb[6] = {pmin[0], pmin[1], pmin[2], pmax[0], pmax[1], pmax[2]};
+    CK(cudaMemcpyAsync(h->d_bounds + 6 * s, bb, sizeof(bb), cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(h->d_pf + o3, pf, b3, cudaMemcpyHostToDevice, st));
+    double* d_po = h->d_st[1][0] + o3;  // staging: the other side's position block of this scenario
+    CK(cudaMemcpyAsync(d_po, po, b3, cudaMemcpyHostToDevice, st));
+    // initDMPC.m for the scenario's agents into side 0
+    init_kernel<<<(N + 127) / 128, 128, 0, st>>>(N, K, h->prm.h, h->prm.init_div, d_po, h->d_pf + o3,
+                                                 h->d_l[0] + (size_t)s * h->Npad * 3 * K, h->d_st[0][0] + o3,
+                                                 h->d_st[0][1] + o3, h->d_st[0][2] + o3);
+    CK(cudaGetLastError());
+    CK(cudaStreamSynchronize(st));
+    if (h->S == 1) {  // the single-swarm entry points see the same scenario
+        for (int x = 0; x < 3; ++x) { h->dp.pmin[x] = pmin[x]; h->dp.pmax[x] = pmax[x]; }
+        h->have_bounds = h->have_goals = h->have_init = true;
+        drop_graph(h);
+    }
+    h->per_scen_bounds = true;
+    h->scen_set[s] = 1;
+    h->cur = 0;
+    return 0;
+}
+
+int dmpcb200_run_batch(dmpcb200_t* h, int max_steps, int stop_on_fail, int mode, double* traj_p, double* traj_v,
+                       double* traj_a, int32_t* steps_done, int32_t* reached, int32_t* first_fail_step,
+                       int32_t* first_fail_agent, double* goal_dist) {
+    if (!h || max_steps < 1) return fail(DMPCB200_ERR_ARG, "run_batch: bad argument");
+    for (int s = 0; s < h->S; ++s)
+        if (!h->scen_set[s]) return fail(DMPCB200_ERR_STATE, "run_batch: dmpcb200_set_scenario every scenario first");
+    if (int rc = ensure_device(h)) return rc;
+    const int N = h->N, S = h->S;
+    cudaStream_t st = h->stream;
+    const bool record = traj_p || traj_v || traj_a;
+    const bool no_graph = (mode & 3) != 0;
+    const bool timed = (mode & 1) != 0;  // per-kernel CUDA events (plain launches)
+    if (record) {
+        if (h->traj_S < max_steps || h->traj_scen < S) {
+            drop_graph(h);
+            for (int i = 0; i < 3; ++i) { cudaFree(h->d_traj[i]); h->d_traj[i] = nullptr; }
+            h->traj_S = max_steps;
+            h->traj_scen = S;
+            for (int i = 0; i < 3; ++i) CK(dalloc(&h->d_traj[i], 3 * (size_t)(max_steps + 1) * N * S));
+        }
+        // column 0 = current state of every agent of every scenario (agents are contiguous: S*N of them)
+        for (int i = 0; i < 3; ++i)
+            CK(cudaMemcpy2DAsync(h->d_traj[i], 3 * (size_t)(h->traj_S + 1) * sizeof(double), h->d_st[h->cur][i],
+                                 3 * sizeof(double), 3 * sizeof(double), (size_t)N * S, cudaMemcpyDeviceToDevice, st));
+    }
+    std::vector<Ctrl> hc(S);
+    for (auto& c : hc) {
+        std::memset(&c, 0, sizeof(c));
+        c.fail_step = -1;
+        c.fail_agent = -1;
+        c.stop_on_fail = stop_on_fail;
+        c.max_steps = max_steps;
+    }
+    CK(cudaMemcpyAsync(h->d_ctrl, hc.data(), S * sizeof(Ctrl), cudaMemcpyHostToDevice, st));
+    CK(cudaMemsetAsync(h->d_rescue_next, 0, sizeof(int), st));
+    if (int rc = ensure_events(h, timed ? 4 * (size_t)max_steps + 6 : 2)) return rc;
+    int ev_step = 0;
+    auto launch_step = [&](int cur) -> int {
+        const int nx = cur ^ 1;
+        cudaEvent_t* evs = timed ? &h->ev[2 + 4 * (size_t)ev_step++] : nullptr;
+        StepArgs A = make_args(h, 0, N, h->d_st[cur][0], h->d_st[cur][1], h->d_st[cur][2], h->d_l[cur], h->d_l[nx],
+                               h->d_st[nx][0], h->d_st[nx][1], h->d_st[nx][2], nullptr, nullptr, h->d_status,
+                               h->d_diag, true, h->d_ctrl);
+        A.n_scen = S;
+        A.lstride = (size_t)h->Npad * 3 * h->K;
+        A.bounds = h->d_bounds;
+        if (evs) CK(cudaEventRecord(evs[0], st));
+        CK(launch_scan(h, A, st));
+        if (evs) CK(cudaEventRecord(evs[1], st));
+        CK(launch_qp(h, A, st));
+        if (evs) CK(cudaEventRecord(evs[2], st));
+        TailArgs T = make_tail(h, h->d_st[nx][0], 3, h->d_status, h->d_st[nx][0], h->d_st[nx][1], h->d_st[nx][2],
+                               record, h->d_ctrl);
+        T.n0 = 0;
+        T.n1 = N;
+        T.status_hist = nullptr;
+        tail_batch_kernel<<<S, 128, 0, st>>>(T);
+        CK(cudaGetLastError());
+        if (evs) CK(cudaEventRecord(evs[3], st));
+        return 0;
+    };
+    const int start_cur = h->cur;
+    if (!no_graph && (!h->graph || h->graph_record != record || !h->graph_batch)) {
+        drop_graph(h);
+        cudaGraph_t g;
+        CK(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
+        int rc = launch_step(0);
+        if (!rc) rc = launch_step(1);
+        cudaError_t e = cudaStreamEndCapture(st, &g);
+        if (rc) return rc;
+        CK(e);
+        CK(cudaGraphInstantiate(&h->graph, g, 0));
+        cudaGraphDestroy(g);
+        h->graph_record = record;
+        h->graph_batch = true;
+    }
+    CK(cudaEventRecord(h->ev[0], st));
+    int issued = 0, cur = start_cur;
+    auto all_done = [&]() -> int {
+        CK(cudaMemcpyAsync(hc.data(), h->d_ctrl, S * sizeof(Ctrl), cudaMemcpyDeviceToHost, st));
+        CK(cudaStreamSynchronize(st));
+        for (const auto& c : hc)
+            if (!c.done) return 0;
+        return 1;
+    };
+    while (issued < max_steps) {
+        if (!no_graph && cur == 0) {
+            CK(cudaGraphLaunch(h->graph, st));
+            issued += 2;
+        } else {
+            if (int rc = launch_step(cur)) return rc;
+            cur ^= 1;
+            issued += 1;
+        }
+        if ((issued & 15) == 0 && issued < max_steps) {
+            const int d = all_done();
+            if (d < 0) return d;
+            if (d) break;
+        }
+    }
+    CK(cudaEventRecord(h->ev[1], st));
+    {
+        const int d = all_done();
+        if (d < 0) return d;
+    }
+    // every scenario that is still running has done `issued` steps (capped by max_steps through its own control
+    // word); the buffers have been swapped `issued` times
+    h->cur = start_cur ^ (issued & 1);
+    float whole = 0;
+    cudaEventElapsedTime(&whole, h->ev[0], h->ev[1]);
+    long long agent_steps = 0;
+    int max_s = 0;
+    for (int s = 0; s < S; ++s) {
+        agent_steps += (long long)hc[s].step * N;
+        max_s = std::max(max_s, hc[s].step);
+        if (steps_done) steps_done[s] = hc[s].step;
+        if (reached) reached[s] = hc[s].reached;
+        if (first_fail_step) first_fail_step[s] = hc[s].fail_step;
+        if (first_fail_agent) first_fail_agent[s] = hc[s].fail_agent;
+        if (goal_dist) goal_dist[s] = hc[s].goal_dist;
+    }
+    h->t_ms[0] = h->t_ms[1] = 0;
+    h->t_ms[2] = issued ? whole / issued : 0;
+    if (timed && ev_step) {
+        double a = 0, b = 0;
+        for (int i = 0; i < ev_step; ++i) {
+            float x;
+            cudaEvent_t* evs = &h->ev[2 + 4 * (size_t)i];
+            cudaEventElapsedTime(&x, evs[0], evs[1]);
+            a += x;
+            cudaEventElapsedTime(&x, evs[1], evs[2]);
+            b += x;
+        }
+        h->t_ms[0] = a / ev_step;
+        h->t_ms[1] = b / ev_step;
+    }
+    h->batch_ms = whole;
+    h->batch_agent_steps = agent_steps;
+    h->launches = 3 * (int64_t)issued;
+    if (record) {
+        // device: per scenario 3 x (traj_S+1) x N  ->  host: per scenario 3 x (max_steps+1) x N
+        const size_t cols = (size_t)std::min(max_s, max_steps) + 1;
+        double* outs[3] = {traj_p, traj_v, traj_a};
+        for (int i = 0; i < 3; ++i)
+            if (outs[i])
+                CK(cudaMemcpy2DAsync(outs[i], 3 * (size_t)(max_steps + 1) * sizeof(double), h->d_traj[i],
+                                     3 * (size_t)(h->traj_S + 1) * sizeof(double), 3 * cols * sizeof(double),
+                                     (size_t)N * S, cudaMemcpyDeviceToHost, st));
+        CK(cudaStreamSynchronize(st));
+    }
+    return 0;
+}
+
+int dmpcb200_get_scenario(dmpcb200_t* h, int s, double* l, double* pk, double* vk, double* ak, int32_t* status,
+                          dmpcb200_diag* diag) {
+    if (!h) return fail(DMPCB200_ERR_ARG, "get_scenario: null handle");
+    if (s < 0 || s >= h->S) return fail(DMPCB200_ERR_ARG, "get_scenario: scenario index out of range");
+    if (int rc = ensure_device(h)) return rc;
+    const int N = h->N, n3 = 3 * h->K, c = h->cur;
+    cudaStream_t st = h->stream;
+    const size_t o3 = 3 * (size_t)s * N, b3 = 3 * (size_t)N * sizeof(double);
+    if (l) CK(cudaMemcpyAsync(l, h->d_l[c] + (size_t)s * h->Npad * n3, (size_t)N * n3 * sizeof(double), cudaMemcpyDeviceToHost, st));
+    if (pk) CK(cudaMemcpyAsync(pk, h->d_st[c][0] + o3, b3, cudaMemcpyDeviceToHost, st));
+    if (vk) CK(cudaMemcpyAsync(vk, h->d_st[c][1] + o3, b3, cudaMemcpyDeviceToHost, st));
+    if (ak) CK(cudaMemcpyAsync(ak, h->d_st[c][2] + o3, b3, cudaMemcpyDeviceToHost, st));
+    if (status) CK(cudaMemcpyAsync(status, h->d_status + (size_t)s * N, (size_t)N * sizeof(int), cudaMemcpyDeviceToHost, st));
+    if (diag) CK(cudaMemcpyAsync(diag, h->d_diag + (size_t)s * N, (size_t)N * sizeof(AgentDiag), cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    return 0;
+}
+
+int dmpcb200_last_batch_timing(dmpcb200_t* h, double* total_ms, int64_t* agent_steps) {
+    if (!h) return fail(DMPCB200_ERR_ARG, "last_batch_timing: null handle");
+    if (total_ms) *total_ms = h->batch_ms;
+    if (agent_steps) *agent_steps = h->batch_agent_steps;
+    return 0;
+}
+
 int dmpcb200_get_state(dmpcb200_t* h, double* l, double* pk, double* vk, double* ak, int32_t* status,
                        dmpcb200_diag* diag) {
     if (!h) return fail(DMPCB200_ERR_ARG, "get_state: null handle");
+    if (h->S != 1) return fail(DMPCB200_ERR_STATE, "get_state: single-scenario entry point on a batched handle (use set_scenario / run_batch / get_scenario)");
     if (int rc = ensure_device(h)) return rc;
     const int N = h->N, n3 = 3 * h->K;
     cudaStream_t s = h->stream;
@@ -933,6 +1170,7 @@ int dmpcb200_get_state(dmpcb200_t* h, double* l, double* pk, double* vk, double*
 
 int dmpcb200_set_state(dmpcb200_t* h, const double* l, const double* pk, const double* vk, const double* ak) {
     if (!h || !l || !pk || !vk || !ak) return fail(DMPCB200_ERR_ARG, "set_state: null argument");
+    if (h->S != 1) return fail(DMPCB200_ERR_STATE, "set_state: single-scenario entry point on a batched handle (use set_scenario / run_batch / get_scenario)");
     if (!h->have_goals) return fail(DMPCB200_ERR_STATE, "set_state: call dmpcb200_set_goals first");
     if (int rc = ensure_device(h)) return rc;
     const int N = h->N, n3 = 3 * h->K;

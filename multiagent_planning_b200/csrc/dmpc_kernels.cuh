@@ -66,7 +66,14 @@ struct TailArgs {
 struct StepArgs {
     DevParams P;
     ScanThr thr;  // exact squared distance thresholds (scan_core.cuh)
-    int n0, n1;  // agents solved by this launch
+    int n0, n1;  // agents solved by this launch (of every scenario)
+    // scenario batching (test/failure_rate.m trial loops as ONE launch): n_scen independent swarms of P.N agents.
+    // Scenario s keeps its horizons at l + s * lstride (doubles; a whole number of 32-agent tiles) and the
+    // per-agent arrays (states, goals, status, first columns, v/a horizons) at agent index s * P.N + n.
+    // n_scen = 1, lstride = 0 is the single-swarm layout.
+    int n_scen;
+    size_t lstride;
+    const double* bounds;  // optional: per scenario pmin[3], pmax[3] (null: P.pmin / P.pmax for all)
     int RMAX, QMAX, RCAP, QBIG, n_rescue;
     int tile_padded;  // l_prev is readable up to a multiple of kTile agents
     const double* l_prev;
@@ -172,7 +179,13 @@ __global__ void __launch_bounds__(W * S * 32) scan_kernel(const __grid_constant_
     // programmatic dependent launch: the QP kernel of this step may start its prologue (barrier, table
     // TMA) while this grid is still running; it waits (griddepcontrol.wait) before it reads our output
     asm volatile("griddepcontrol.launch_dependents;");
-    if (A.ctrl && A.ctrl->done) return;
+    // CTA -> (scenario, block of W agents of it): the W agents of a CTA share the scenario's tiles
+    const int nl_s = A.n1 - A.n0;
+    const int cps = (nl_s + W - 1) / W;
+    const int scen = (A.n_scen > 1) ? (int)blockIdx.x / cps : 0;
+    const int blk = (int)blockIdx.x - scen * cps;
+    if (A.ctrl && A.ctrl[scen].done) return;
+    const double* const l_prev = A.l_prev + (size_t)scen * A.lstride;
 #if defined(DMPC_PROF_SCAN)
     const long long scan_t0 = clock64();
     long long scan_wait = 0;
@@ -190,14 +203,15 @@ __global__ void __launch_bounds__(W * S * 32) scan_kernel(const __grid_constant_
     int* list_all = reinterpret_cast<int*>(nm_all + (size_t)W * Npad);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int ag = warp / S, sub = warp - ag * S;
-    const int li = blockIdx.x * W + ag;
-    const int n = A.n0 + li;
+    const int li_s = blk * W + ag;                  // local index within the scenario's block of agents
+    const int n = A.n0 + li_s;
     const bool valid = n < A.n1;
+    const int li = scen * nl_s + li_s;              // index into the per-agent scratch (scan records, rows)
     double* own = own_all + ag * n3p;
 
     const int ntma = A.tile_padded ? (N + kTile - 1) / kTile : N / kTile;
     // every CTA walks the tiles in its own rotation: the CTAs do not all pull the same L2 lines at once
-    const int rot = ntma ? (int)(blockIdx.x % (unsigned)ntma) : 0;
+    const int rot = ntma ? (int)((unsigned)blk % (unsigned)ntma) : 0;
     if (threadIdx.x == 0) {
         for (int b = 0; b < stages; ++b) mbar_init(&bars[b], 1);
         mbar_fence_init();
@@ -205,11 +219,11 @@ __global__ void __launch_bounds__(W * S * 32) scan_kernel(const __grid_constant_
             int tau = t + rot;
             tau -= (tau >= ntma) ? ntma : 0;
             mbar_expect_tx(&bars[t], tile_bytes);
-            tma_bulk_g2s(tiles + (size_t)t * tile_d, A.l_prev + (size_t)tau * tile_d, tile_bytes, &bars[t]);
+            tma_bulk_g2s(tiles + (size_t)t * tile_d, l_prev + (size_t)tau * tile_d, tile_bytes, &bars[t]);
         }
     }
     if (valid && sub == 0)
-        for (int i = lane; i < n3; i += 32) own[i] = A.l_prev[(size_t)n * n3 + i];
+        for (int i = lane; i < n3; i += 32) own[i] = l_prev[(size_t)n * n3 + i];
     __syncthreads();  // barrier init + own horizons visible
     SCAN_PROF(0);
 
@@ -252,7 +266,7 @@ __global__ void __launch_bounds__(W * S * 32) scan_kernel(const __grid_constant_
                         int tau = tt + stages + rot;
                         tau -= (tau >= ntma) ? ntma : 0;
                         mbar_expect_tx(&bars[b], tile_bytes);
-                        tma_bulk_g2s(tiles + (size_t)b * tile_d, A.l_prev + (size_t)tau * tile_d, tile_bytes,
+                        tma_bulk_g2s(tiles + (size_t)b * tile_d, l_prev + (size_t)tau * tile_d, tile_bytes,
                                      &bars[b]);
                     }
                 }
@@ -272,7 +286,7 @@ __global__ void __launch_bounds__(W * S * 32) scan_kernel(const __grid_constant_
         // caller-owned buffer without tile padding: the ragged last tile is loaded by the threads
         const int cnt = N - rem_base;
         __syncthreads();
-        for (int i = threadIdx.x; i < cnt * n3; i += W * S * 32) tiles[i] = A.l_prev[(size_t)rem_base * n3 + i];
+        for (int i = threadIdx.x; i < cnt * n3; i += W * S * 32) tiles[i] = l_prev[(size_t)rem_base * n3 + i];
         __syncthreads();
         if (valid && sub == 0) scan_tile_hw<KT>(A.P, &A.thr, ownp, n, tiles, rem_base, cnt, nm, acc);
     }
@@ -294,7 +308,7 @@ __global__ void __launch_bounds__(W * S * 32) scan_kernel(const __grid_constant_
     }
     // neighbour positions from the resident tiles when the whole buffer is in shared memory
     const bool resident = !refill && rem_base >= N;
-    const ScanOut so = scan_finish(A.P, own, n, A.l_prev, nm, acc, A.RMAX, A.grow + (size_t)li * 5 * A.RMAX,
+    const ScanOut so = scan_finish(A.P, own, n, l_prev, nm, acc, A.RMAX, A.grow + (size_t)li * 5 * A.RMAX,
                                    A.gkc + (size_t)li * A.RMAX, A.gidx ? A.gidx + (size_t)li * A.RMAX : nullptr,
                                    list_all + (size_t)ag * A.RMAX, resident ? tiles : nullptr, rot, ntma);
     if (lane == 0) {
@@ -430,7 +444,7 @@ DMPC_HD size_t qp_smem_bytes(int K, int W, int QMAX, int RCAP) {
 
 template <int W, int KT>
 __global__ void __launch_bounds__(W * 32, 1) qp_kernel(const __grid_constant__ StepArgs A) {
-    if (A.ctrl && A.ctrl->done) return;
+    if (A.ctrl && A.n_scen == 1 && A.ctrl->done) return;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const int K = KT ? KT : A.P.K, n3 = 3 * K;
     const size_t tab_bytes = align_up(qp_table_bytes(K), 16);
@@ -452,21 +466,34 @@ __global__ void __launch_bounds__(W * 32, 1) qp_kernel(const __grid_constant__ S
     // the per-agent workspace fills shared memory) and every warp takes its next agent from a device
     // counter as soon as it is done -- the solve times differ by 50x, a static assignment would leave
     // three warps of a CTA idle behind its slowest agent
-    const int nl = A.n1 - A.n0;
+    const int nl_s = A.n1 - A.n0, nl = nl_s * A.n_scen;  // agents per scenario / of this launch
     const bool queued = (int)gridDim.x * W < nl;
     int li = blockIdx.x * W + warp;
     while (li < nl) {
-    const int n = A.n0 + li;
-    {
+    const int scen = (A.n_scen > 1) ? li / nl_s : 0;
+    const int n = A.n0 + (li - scen * nl_s);               // agent index within its scenario
+    const int ng = scen * A.P.N + n;                        // index into the per-agent arrays
+    const double* const l_prev = A.l_prev + (size_t)scen * A.lstride;
+    double* const l_new = A.l_new + (size_t)scen * A.lstride;
+    if (A.n_scen > 1 && A.ctrl && A.ctrl[scen].done) {
+        // this scenario's loop has ended (goal reached / failed): its state is carried over unchanged
+        for (int i = lane; i < n3; i += 32) l_new[(size_t)n * n3 + i] = l_prev[(size_t)n * n3 + i];
+        if (lane < 3) {
+            A.p1[3 * ng + lane] = A.pk[3 * ng + lane];
+            A.v1[3 * ng + lane] = A.vk[3 * ng + lane];
+            A.a1[3 * ng + lane] = A.ak[3 * ng + lane];
+        }
+    } else {
 #if defined(DMPC_PROF_AGENT)
     const long long agent_t0 = clock64();
 #endif
     const ScanRec sr = A.scan[li];
     AgentIO io;
-    io.po = A.pk + 3 * n;
-    io.pf = A.pf + 3 * n;
-    io.vo = A.vk + 3 * n;
-    io.ao = A.ak + 3 * n;
+    io.po = A.pk + 3 * ng;
+    io.pf = A.pf + 3 * ng;
+    io.vo = A.vk + 3 * ng;
+    io.ao = A.ak + 3 * ng;
+    io.bounds = A.bounds ? A.bounds + 6 * scen : nullptr;
     io.kstar = sr.kstar;
     io.nv = sr.nv;
     io.scanflag = sr.flag;
@@ -475,13 +502,13 @@ __global__ void __launch_bounds__(W * 32, 1) qp_kernel(const __grid_constant__ S
     io.gkc = A.gkc + (size_t)li * A.RMAX;
     io.gscr_d = A.gscr_d + (size_t)li * 4 * A.RMAX;
     io.gscr_i = A.gscr_i + (size_t)li * 4 * A.RMAX;
-    io.out_p = A.l_new + (size_t)n * n3;
-    io.out_v = A.v_hor ? A.v_hor + (size_t)n * n3 : nullptr;
-    io.out_a = A.a_hor ? A.a_hor + (size_t)n * n3 : nullptr;
-    io.p1 = A.p1 + 3 * n;
-    io.v1 = A.v1 + 3 * n;
-    io.a1 = A.a1 + 3 * n;
-    io.l_prev_n = A.l_prev + (size_t)n * n3;
+    io.out_p = l_new + (size_t)n * n3;
+    io.out_v = A.v_hor ? A.v_hor + (size_t)ng * n3 : nullptr;
+    io.out_a = A.a_hor ? A.a_hor + (size_t)ng * n3 : nullptr;
+    io.p1 = A.p1 + 3 * ng;
+    io.v1 = A.v1 + 3 * ng;
+    io.a1 = A.a1 + 3 * ng;
+    io.l_prev_n = l_prev + (size_t)n * n3;
 
     mbar_wait(bar, 0);  // tables have landed
     AgentDiag dg;
@@ -522,8 +549,8 @@ __global__ void __launch_bounds__(W * 32, 1) qp_kernel(const __grid_constant__ S
     dg.nact = (int)((clock64() - agent_t0) >> 4);  // profiling build: cycles / 16 of this agent's solve
 #endif
     if (lane == 0) {
-        A.status[n] = st;
-        if (A.diag) A.diag[n] = dg;
+        A.status[ng] = st;
+        if (A.diag) A.diag[ng] = dg;
     }
     }
     if (!queued) break;

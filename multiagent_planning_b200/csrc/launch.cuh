@@ -50,7 +50,7 @@ cudaError_t launch_scan_w(const StepArgs& A, int nl, int K, cudaStream_t s) {
         if (e != cudaSuccess) return e;
         attr_smem[dev] = smem;
     }
-    scan_kernel<W, S, KT><<<(nl + W - 1) / W, W * S * 32, smem, s>>>(A, stages);
+    scan_kernel<W, S, KT><<<(nl + W - 1) / W * A.n_scen, W * S * 32, smem, s>>>(A, stages);
     return cudaGetLastError();
 }
 template <int W, int KT>
@@ -64,7 +64,7 @@ cudaError_t launch_qp_w(const StepArgs& A, int nl, size_t smem, cudaStream_t s) 
         attr_smem[dev] = smem;
     }
     // one CTA per SM at most (shared memory): larger swarms run a persistent grid with an agent queue
-    const int ctas = std::min((nl + W - 1) / W, sm_count(dev));
+    const int ctas = std::min((nl * A.n_scen + W - 1) / W, sm_count(dev));
     // programmatic stream serialization: the grid may launch while the scan kernel drains (the kernel
     // itself waits for the scan's completion before it reads the rows)
     cudaLaunchConfig_t cfg = {};

@@ -1248,8 +1248,8 @@ DMPC_D int agent_solve_fast(const DevParams& Pm, const double* __restrict__ tab,
         x_pf[x] = io.pf[x];
         x_vo[x] = io.vo[x];
         x_ao[x] = io.ao[x];
-        qp.bnd6[x] = Pm.pmin[x];
-        qp.bnd6[3 + x] = Pm.pmax[x];
+        qp.bnd6[x] = io.bounds ? io.bounds[x] : Pm.pmin[x];
+        qp.bnd6[3 + x] = io.bounds ? io.bounds[3 + x] : Pm.pmax[x];
     }
     // ---- weights (solveSoftDMPCbound.m:43-58) -------------------------------------------------------
     const double dgx = x_po[0] - x_pf[0], dgy = x_po[1] - x_pf[1], dgz = x_po[2] - x_pf[2];

@@ -10,6 +10,35 @@ __global__ void __launch_bounds__(256) tail_kernel(const __grid_constant__ TailA
     tail_body<256>(T);
 }
 
+// per-scenario tail of a batched step (n_scen > 1): one CTA per scenario runs ReachedGoal.m, the lowest
+// failing agent, the trajectory record and the scenario's own loop control word
+__global__ void __launch_bounds__(128) tail_batch_kernel(const __grid_constant__ TailArgs T0) {
+    const int s = blockIdx.x;
+    if (s == 0 && threadIdx.x == 0 && T0.rescue_next) *T0.rescue_next = 0;
+    TailArgs T = T0;
+    const size_t o3 = 3 * (size_t)s * T.N;
+    T.ctrl = T0.ctrl + s;
+    if (T.ctrl->done) return;  // this scenario's loop has ended
+    T.p = T0.p + o3;
+    T.pf = T0.pf + o3;
+    T.status = T0.status + (size_t)s * T.N;
+    T.p1 = T0.p1 + o3;
+    T.v1 = T0.v1 + o3;
+    T.a1 = T0.a1 + o3;
+    if (T0.traj_p) {
+        const size_t ot = 3 * (size_t)(T.S + 1) * T.N * s;
+        T.traj_p = T0.traj_p + ot;
+        T.traj_v = T0.traj_v + ot;
+        T.traj_a = T0.traj_a + ot;
+    }
+    if (T0.status_hist) T.status_hist = T0.status_hist + (size_t)s * T.S * T.N;
+    T.goal_out = T0.goal_out + 2 * s;
+    T.fail_out = T0.fail_out + s;
+    T.rescue_next = nullptr;
+    T.copy_bytes = 0;
+    tail_body<128>(T);
+}
+
 // ---- initDMPC.m:1-13 for all agents -------------------------------------------------------------
 __global__ void init_kernel(int N, int K, double h, double init_div, const double* __restrict__ po,
                             const double* __restrict__ pf, double* l, double* pk, double* vk, double* ak) {

@@ -66,14 +66,15 @@ class Solver:
     """One library handle: N agents, this handle solves agents [n0, n1) on CUDA device `device`."""
 
     def __init__(self, N: int, params: Params | None = None, n0: int = 0, n1: int | None = None,
-                 device: int = 0, max_rows: int = 0, pmin=None, pmax=None, pf=None):
+                 device: int = 0, max_rows: int = 0, pmin=None, pmax=None, pf=None, n_scenarios: int = 1):
         self.L = _lib.lib()
         self.P = params if params is not None else default_params()
         self.N, self.K = int(N), int(self.P.K)
         self.n0, self.n1 = int(n0), int(N if n1 is None else n1)
         self.device = int(device)
+        self.S = int(n_scenarios)
         h = C.c_void_p()
-        _lib.check(self.L.dmpcb200_create(C.byref(self.P), self.N, self.n0, self.n1, self.device,
+        _lib.check(self.L.dmpcb200_create(C.byref(self.P), self.N, self.n0, self.n1, self.S, self.device,
                                           int(max_rows), C.byref(h)), "dmpcb200_create")
         self.h = h
         if pmin is not None:
@@ -115,6 +116,49 @@ class Solver:
         p1, v1, a1 = (np.zeros((3, self.N), order="F") for _ in range(3))
         _lib.check(self.L.dmpcb200_init_horizons(self.h, _p(po), _p(l), _p(p1), _p(v1), _p(a1)), "init_horizons")
         return l, p1, v1, a1
+
+    # -- scenario batching (test/failure_rate.m trial loops as one batch) ------------------------------
+    def set_scenario(self, s, po, pf, pmin, pmax):
+        """start points, goals (3,N) and workspace box of scenario s; runs initDMPC.m for its agents"""
+        po, pf = _f(po, (3, self.N)), _f(pf, (3, self.N))
+        pmin, pmax = _f(pmin).ravel(), _f(pmax).ravel()
+        _lib.check(self.L.dmpcb200_set_scenario(self.h, int(s), _p(po), _p(pf), _p(pmin), _p(pmax)), "set_scenario")
+
+    def run_batch(self, max_steps, stop_on_fail=True, mode=0, record=False):
+        """the closed loop of every scenario (failure_rate.m:99-133 per trial).  Returns per-scenario arrays
+        steps, reached, first_fail_step, first_fail_agent, goal_dist (+ pk, vk, ak of shape (S, 3, T, N) in
+        column-major blocks when record) and the device time / agent-steps of the call."""
+        S, N = self.S, self.N
+        steps, reached, fs, fa = (np.zeros(S, np.int32) for _ in range(4))
+        gd = np.zeros(S)
+        tp = tv = ta = None
+        if record:
+            tp, tv, ta = (np.zeros(3 * (max_steps + 1) * N * S) for _ in range(3))
+        _lib.check(self.L.dmpcb200_run_batch(self.h, int(max_steps), int(bool(stop_on_fail)), int(mode), _p(tp), _p(tv),
+                                             _p(ta), steps.ctypes.data_as(_ip), reached.ctypes.data_as(_ip),
+                                             fs.ctypes.data_as(_ip), fa.ctypes.data_as(_ip), _p(gd)), "run_batch")
+        ms, ast = C.c_double(0), C.c_int64(0)
+        _lib.check(self.L.dmpcb200_last_batch_timing(self.h, C.byref(ms), C.byref(ast)), "last_batch_timing")
+        res = dict(steps=steps, reached=reached.astype(bool), first_fail_step=fs, first_fail_agent=fa, goal_dist=gd,
+                   device_ms=float(ms.value), agent_steps=int(ast.value))
+        if record:
+            shp = (3, max_steps + 1, N)
+            blk = 3 * (max_steps + 1) * N
+            for k, b in (("pk", tp), ("vk", tv), ("ak", ta)):
+                res[k] = [np.asfortranarray(b[s * blk:(s + 1) * blk].reshape(shp, order="F"))[:, :steps[s] + 1, :]
+                          for s in range(S)]
+        return res
+
+    def get_scenario(self, s):
+        N, K = self.N, self.K
+        l = np.zeros((3, K, N), order="F")
+        pk, vk, ak = (np.zeros((3, N), order="F") for _ in range(3))
+        status = np.zeros(N, np.int32)
+        diag = np.zeros(N, dtype=_DIAG_DT)
+        _lib.check(self.L.dmpcb200_get_scenario(self.h, int(s), _p(l), _p(pk), _p(vk), _p(ak),
+                                                status.ctypes.data_as(_ip), diag.ctypes.data_as(C.POINTER(Diag))),
+                   "get_scenario")
+        return dict(l=l, pk=pk, vk=vk, ak=ak, status=status, diag=diag)
 
     # -- one Jacobi step, host buffers ---------------------------------------------------------------
     def step(self, pk, vk, ak, l_prev, want_horizons=False, out=None):

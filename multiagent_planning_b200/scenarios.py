@@ -64,4 +64,12 @@ def config(name: str):
         po, pf = random_test(2000, pmin, pmax, 0.35, 2.0, 1004)
         return dict(N=2000, K=20, variant=dmpc.SOFT_BOUND, pmin=pmin, pmax=pmax, po=po, pf=pf, params=dict(K=20),
                     max_steps=149)
+    if name == "C5":
+        # 100 Monte-Carlo trials x N = 200 (test/failure_rate.m:61-68 shape, 1 agent/m^3 arena), seeds 2000..2099:
+        # po / pf are lists, one (3, N) pair per scenario; batched by Solver(n_scenarios=100)
+        N, S = 200, 100
+        pmin, pmax = density_arena(N)
+        pairs = [random_test(N, pmin, pmax, 0.35, 2.0, 2000 + s) for s in range(S)]
+        return dict(N=N, K=15, S=S, variant=dmpc.SOFT_BOUND, pmin=pmin, pmax=pmax, po=[p[0] for p in pairs],
+                    pf=[p[1] for p in pairs], params=dict(), max_steps=149)
     raise KeyError(name)

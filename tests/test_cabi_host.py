@@ -24,7 +24,7 @@ def test_library_exports_every_declared_symbol():
     for n in names:
         assert hasattr(L, n), f"{n} declared in include/dmpc_b200.h but not exported"
     assert sorted(_lib.EXPORTS) == names          # ctypes prototypes cover the whole header
-    assert L.dmpcb200_abi_version() == 1
+    assert L.dmpcb200_abi_version() == 2
 
 
 def test_default_params_are_the_reference_values():

@@ -543,6 +543,48 @@ def test_sharded_two_ranks_on_one_gpu_equal_whole(dmpc):
         assert np.array_equal(st["l"], l2) and np.array_equal(st["status"], st2)
 
 
+def test_scenario_batch_equals_single_runs(dmpc):
+    """n_scenarios independent swarms in ONE handle (failure_rate.m trial loops as a batch): trajectories, steps,
+    goal / failure outcome of every scenario bit-equal to its own single-scenario run (which is oracle-gated
+    above).  N = 50 is not a multiple of the 32-agent tile; the arenas differ per scenario; one scenario fails
+    (two agents start inside each other) and stops at once while the others go on."""
+    from multiagent_planning_b200 import scenarios
+    N, S, steps = 50, 5, 130
+    P = dmpc.default_params(0)
+    scen = []
+    for s in range(S):
+        pmin, pmax = scenarios.density_arena(N, density=0.6 + 0.3 * s)
+        po, pf = scenarios.random_test(N, pmin, pmax, 0.35, 2.0, seed=300 + s)
+        scen.append((po, pf, pmin, pmax))
+    scen[3][0][:, 7] = scen[3][0][:, 6] + np.array([0.05, 0.0, 0.0])       # a collision at k = 1 in scenario 3
+    with dmpc.Solver(N, P, n_scenarios=S) as b:
+        for s, c in enumerate(scen):
+            b.set_scenario(s, *c)
+        rb = b.run_batch(steps, stop_on_fail=True, record=True)
+        last = [b.get_scenario(s) for s in range(S)]
+        with pytest.raises(dmpc.DmpcError):
+            b.run(3)                         # single-swarm entry point on a batched handle
+        # again from the start, plain launches: same bits
+        for s, c in enumerate(scen):
+            b.set_scenario(s, *c)
+        rb2 = b.run_batch(steps, stop_on_fail=True, mode=2, record=True)
+    assert rb["first_fail_step"][3] == 0 and rb["first_fail_agent"][3] == 6 and rb["steps"][3] == 1
+    assert rb["agent_steps"] == int(rb["steps"].sum()) * N
+    for s, (po, pf, pmin, pmax) in enumerate(scen):
+        with dmpc.Solver(N, P, pmin=pmin, pmax=pmax, pf=pf) as one:
+            one.init_horizons(po)
+            r = one.run(steps, stop_on_fail=True, record=True)
+            st = one.get_state()
+        assert r["steps"] == rb["steps"][s] == rb2["steps"][s] and r["reached"] == rb["reached"][s]
+        assert r["first_fail_step"] == rb["first_fail_step"][s] and r["first_fail_agent"] == rb["first_fail_agent"][s]
+        for k in ("pk", "vk", "ak"):
+            assert np.array_equal(r[k], rb[k][s]), (s, k)
+            assert np.array_equal(r[k], rb2[k][s]), (s, k)
+        assert np.array_equal(st["l"], last[s]["l"]) and np.array_equal(st["pk"], last[s]["pk"])
+        assert np.array_equal(st["status"], last[s]["status"])
+    assert rb["reached"].sum() >= 3
+
+
 def _nccl_worker(rank, world, port, q):
     import torch
     import torch.distributed as dist
