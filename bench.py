@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """bench.py -- agent-MPC-steps/s of the DMPC per-agent QP hot path on B200 (BASELINE.json metric).
 
-Workload (config C3 of SURVEY.md section 8d = the configuration the metric is quoted on):
+Default workload = config C3 of SURVEY.md section 8d (the configuration the metric is quoted on):
 N = 500 agents, horizon K = 15, soft-constraint DMPC (solveSoftDMPCbound), random point-to-point
 transition in the 1 agent/m^3 arena of test/failure_rate.m:63-64, seed 1003, synthetic.
 A "step" is one MPC time step = one solve of all N per-agent QPs (scan + constraint build + QP +
@@ -10,15 +10,20 @@ initDMPC, so the mix of easy and hard (dense) steps is the workload's own.
 
 Timing: every timed step is bracketed by CUDA events on the launching stream; between steps the L2
 is flushed by writing a 512 MiB buffer (the step's working set is ~0.2 MB, so without the flush
-every step would run out of L2).  value = N * K / sum(step times).  The extra key
-`resident_graph` is the same loop run device-resident through a CUDA graph (no flush, no host
-sync) -- the deployment mode -- reported beside it, not instead of it.
+every step would run out of L2).  value = N * K / sum(step times).  `resident_graph` is the same
+loop run device-resident through a CUDA graph (no flush, no host sync) -- the deployment mode --
+reported beside it, not instead of it.  `e2e` is the same steps through dmpcb200_step with HOST
+buffers (pinned), copies inside the timed region; `e2e_pageable` the same with pageable arrays (what a
+MATLAB mxArray is).
 
-python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--workload C3|N100|N2000|C4]
+python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--workload C1|C2|C3|N100|N2000|C4|C5]
 Under torchrun (N > 1) the agents are sharded in contiguous blocks with one NCCL all-gather of the
-predicted horizons per step ("strong" scaling: the swarm is fixed).
+predicted horizons per step ("strong" scaling: the swarm is fixed); the batched workload C5 (100
+Monte-Carlo scenarios x N = 200, test/failure_rate.m shape) shards whole scenarios, no collective.
 """
 import argparse
+import csv
+import glob
 import json
 import os
 import subprocess
@@ -30,6 +35,20 @@ import numpy as np
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
+
+VARIANT_NAMES = {0: "soft-constraint DMPC (solveSoftDMPCbound)", 1: "soft-constraint DMPC (solveSoftDMPCbound2)",
+                 2: "hard-constraint DMPC (solveHardDMPC)", 3: "hard-constraint DMPC (solveHardDMPCOnDemand)"}
+ARENAS = {"C1": "4-agent corner swap (dmpc_soft_bound.m:43-54)", "C2": "10x10x3 m arena, seed 1002",
+          "C3": "1 agent/m^3 arena, seed 1003", "N100": "1 agent/m^3 arena, seed 1003",
+          "N500": "1 agent/m^3 arena, seed 1003", "N2000": "1 agent/m^3 arena, seed 1003",
+          "C4": "2 agents/m^3 arena (dense), seed 1004",
+          "C5": "100 Monte-Carlo scenarios (test/failure_rate.m shape), 1 agent/m^3 arena, seeds 2000..2099"}
+
+
+def workload_label(name, cfg, K):
+    tail = "whole transitions, every scenario until its goal / first failure" if name == "C5" else \
+        "closed-loop steps W+1..W+K"
+    return f"{name}: N={cfg['N']} K={K} {VARIANT_NAMES[int(cfg['variant'])]}, {ARENAS.get(name, '')}, {tail}"
 
 
 def b_alg(N, K):
@@ -44,6 +63,47 @@ def peaks():
             return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
     except Exception:
         return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+def ncu_profile(kernel_prefix):
+    """per-launch figures of a kernel from the newest tracked `ncu --set full` summary under profiles/
+    (written by scripts/ncu_summary.py): DRAM traffic (bytes), issue-active %, fp64 pipe %, warps active %.
+    Returns (dict, path) or (None, None) when no tracked summary lists the kernel."""
+    best = None
+    for path in sorted(glob.glob(os.path.join(ROOT, "profiles", "r*_ncu_full*summary*.csv"))):
+        try:
+            rows = list(csv.reader(open(path)))
+        except OSError:
+            continue
+        if len(rows) < 3:
+            continue
+        hdr, units = rows[0], rows[1]
+        col = {k: i for i, k in enumerate(hdr)}
+        need = ("Kernel Name", "dram__bytes_read.sum", "dram__bytes_write.sum")
+        if any(k not in col for k in need):
+            continue
+
+        def to_bytes(v, u):
+            scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}.get(u, 1.0)
+            return float(v) * scale
+        acc, n = {}, 0
+        for r in rows[2:]:
+            if not r or kernel_prefix not in r[col["Kernel Name"]]:
+                continue
+            n += 1
+            tr = to_bytes(r[col["dram__bytes_read.sum"]], units[col["dram__bytes_read.sum"]]) + \
+                to_bytes(r[col["dram__bytes_write.sum"]], units[col["dram__bytes_write.sum"]])
+            acc["traffic"] = acc.get("traffic", 0.0) + tr
+            for key, name in (("issue_active_pct", "smsp__issue_active.avg.pct_of_peak_sustained_active"),
+                              ("fp64_pipe_pct", "sm__inst_executed_pipe_fp64.avg.pct_of_peak_sustained_active"),
+                              ("warps_active_pct", "sm__warps_active.avg.pct_of_peak_sustained_active"),
+                              ("lsu_shared_wavefronts", "l1tex__data_pipe_lsu_wavefronts_mem_shared.sum"),
+                              ("cycles_elapsed", "sm__cycles_elapsed.max")):
+                if name in col and r[col[name]]:
+                    acc[key] = acc.get(key, 0.0) + float(r[col[name]])
+        if n:
+            best = ({k: v / n for k, v in acc.items()} | {"launches_averaged": n}, os.path.relpath(path, ROOT))
+    return best if best else (None, None)
 
 
 class ClockSampler:
@@ -88,27 +148,49 @@ class ClockSampler:
 
 def workload(name):
     from multiagent_planning_b200 import scenarios
-    cfg = scenarios.config(name)
-    return cfg
+    return scenarios.config(name)
 
 
-def cpu_port_run(cfg, warmup, steps, threads, budget_s=None):
-    """the CPU oracle (port of the reference algorithm) on the same workload: steps W+1..W+K of the
-    transition.  Returns (agent_steps_per_s, steps_done, seconds)."""
+def oracle_params(cfg):
     from oracle import dmpc_oracle as orc
     P = orc.default_params(cfg["variant"])
     for k, v in cfg["params"].items():
         setattr(P, k, v)
+    return P
+
+
+def _init_state(cfg, P, po, pf):
+    from oracle import dmpc_oracle as orc
     N, K = cfg["N"], P.K
-    po, pf = cfg["po"], cfg["pf"]
     l = np.zeros((3, K, N), order="F")
     for n in range(N):
         l[:, :, n] = orc.init_dmpc(po[:, n], pf[:, n], P.h, K, P.init_div)[0]
-    pk, vk, ak = l[:, 0, :].copy(), np.zeros((3, N)), np.zeros((3, N))
+    return l, l[:, 0, :].copy(), np.zeros((3, N)), np.zeros((3, N))
+
+
+def cpu_port_run(cfg, warmup, steps, threads, budget_s=None, structured=False, scenario=0):
+    """CPU legs on the same workload: steps W+1..W+K of the transition (scenario `scenario` of a batch).
+    structured=False: oracle/liboracle.so, the dense restatement of the reference algorithm (it assembles the
+    (3K+nv)-variable QP like solveSoftDMPCbound.m:60-98 does), `threads` host threads in contiguous agent
+    clusters like dmpc.cpp:1600-1625.  structured=True: the test-suite's host build of the device algorithm
+    (Kronecker / rank-1 structure exploited, one thread) -- what a tuned CPU port would do.
+    Returns (agent_steps_per_s, steps_done, seconds)."""
+    from oracle import dmpc_oracle as orc
+    P = oracle_params(cfg)
+    N = cfg["N"]
+    po, pf = (cfg["po"][scenario], cfg["pf"][scenario]) if isinstance(cfg["po"], list) else (cfg["po"], cfg["pf"])
+    l, pk, vk, ak = _init_state(cfg, P, po, pf)
+    if structured:
+        from tests.host_emul import emul
+        emul.build()
+        EP = emul.params_from(P)
     t_total, done = 0.0, 0
     for k in range(warmup + steps):
         t0 = time.perf_counter()
-        o = orc.step(P, pk, vk, ak, pf, l, cfg["pmin"], cfg["pmax"], nthreads=threads)
+        if structured:
+            o = emul.step(EP, pk, vk, ak, pf, l, cfg["pmin"], cfg["pmax"], QMAX=-64)
+        else:
+            o = orc.step(P, pk, vk, ak, pf, l, cfg["pmin"], cfg["pmax"], nthreads=threads)
         dt = time.perf_counter() - t0
         l, pk, vk, ak = o["l_new"], o["p1"], o["v1"], o["a1"]
         if k >= warmup:
@@ -119,29 +201,55 @@ def cpu_port_run(cfg, warmup, steps, threads, budget_s=None):
     return N * done / t_total, done, t_total
 
 
+REF_NOTE = "the reference's MATLAB / C++ cannot run on this box (no MATLAB/Octave; dmpc/cpp needs Eigen, OOQP, CPLEX)"
+
+
 def run_reference(args):
     """--impl reference: the reference's MATLAB / C++ implementations cannot run on this box (no
     MATLAB/Octave; dmpc/cpp needs Eigen, eigen-quadprog, OOQP, CPLEX, Boost).  The CPU arm is the
-    oracle port of the same algorithm with all host threads."""
+    oracle port of the same algorithm (dense, like the reference) with all host threads."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     cfg = workload(args.workload)
     threads = os.cpu_count() or 1
-    v, done, secs = cpu_port_run(cfg, args.warmup, args.steps, threads)
-    P_K = cfg["params"].get("K", 15)
+    steps = args.steps
+    if args.workload == "C5":
+        steps = min(steps, 30)  # one scenario of the batch, bounded
+    v, done, secs = cpu_port_run(cfg, args.warmup, steps, threads, budget_s=120.0)
+    K = cfg["params"].get("K", 15)
     line = {
         "impl": "reference", "metric": "agent-MPC-steps/sec", "value": v, "unit": "agent-steps/s",
         "n_gpus": args.gpus, "steps": done, "warmup": args.warmup, "ms_per_step": 1e3 * secs / max(done, 1),
         "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": f"{args.workload}: N={cfg['N']} K={P_K} soft-constraint DMPC (solveSoftDMPCbound), "
-                               "1 agent/m^3 arena, seed 1003, closed-loop steps W+1..W+K"},
+        "config": {"workload": workload_label(args.workload, cfg, K)},
         "cpu_baseline": {"value": v, "unit": "agent-steps/s", "cores": threads, "kind": "port",
-                         "sample": f"{done} MPC steps x {cfg['N']} agents, oracle/liboracle.so, {threads} threads"},
+                         "sample": f"{done} MPC steps x {cfg['N']} agents, oracle/liboracle.so (dense restatement of "
+                                   f"the reference algorithm), {threads} threads; {REF_NOTE}"},
         "e2e": {"value": v, "unit": "agent-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
     print(json.dumps(line))
+
+
+def parity_leg(s, cfg, threads, nsteps=6):
+    """max position error vs the reference (here: the fp64 oracle, teacher-forced on the dense first steps
+    of the same workload; tolerance 1e-6 m); status flags AND retry counts (bits 0..15) compared"""
+    from oracle import dmpc_oracle as orc
+    O = oracle_params(cfg)
+    l_, pk_, vk_, ak_ = s.init_horizons(cfg["po"])
+    worst, same, retried = 0.0, True, 0
+    for _ in range(nsteps):
+        g_ = s.step(pk_, vk_, ak_, l_)
+        o_ = orc.step(O, pk_, vk_, ak_, cfg["pf"], l_, cfg["pmin"], cfg["pmax"], nthreads=threads)
+        worst = max(worst, float(np.abs(g_["l_new"] - o_["l_new"]).max()))
+        same = same and bool(np.array_equal(g_["status"] & 0xFFFF, o_["status"] & 0xFFFF))
+        retried += int((((o_["status"] >> 8) & 0xFF) > 0).sum())
+        l_, pk_, vk_, ak_ = o_["l_new"], o_["p1"], o_["v1"], o_["a1"]
+    return {"value": worst, "unit": "m", "tolerance": 1e-6, "status_flags_and_retry_counts_equal": same,
+            "retried_agent_steps": retried,
+            "reference": f"oracle/liboracle.so (fp64 port pinned on the reference's MATLAB workspaces), {nsteps} "
+                         "teacher-forced steps of the same workload"}
 
 
 def run_single(args):
@@ -158,10 +266,11 @@ def run_single(args):
     conf = s.config()
 
     # ---- device-resident timing with L2 flush between steps (the `value`) ----------------------
-    def flushed_pass():
+    def flushed_pass(want_iters=False):
         s.init_horizons(cfg["po"])
         tot = scan = qp = 0.0
         n = 0
+        it_max = []
         for k in range(W + S):
             flush.zero_()
             torch.cuda.synchronize()
@@ -174,12 +283,15 @@ def run_single(args):
                 scan += t["scan_ms"]
                 qp += t["qp_ms"]
                 n += 1
-        return tot, scan, qp, n
+                if want_iters:  # (a device-to-host read between the timed steps, outside the events)
+                    it_max.append(int(s.get_state()["diag"]["iters"].max()))
+        return tot, scan, qp, n, it_max
 
     flushed_pass()  # whole-pass warm-up (module load, attribute sets, allocator)
     clk = ClockSampler(0)
     clk.start()
-    tot, scan, qp, n_timed = flushed_pass()
+    tot, scan, qp, n_timed, _ = flushed_pass()
+    _, _, _, _, it_max = flushed_pass(want_iters=True)  # same steps again for the iteration counts
     # ---- the same loop as one device-resident CUDA-graph run (no flush, no host sync) -----------
     s.init_horizons(cfg["po"])
     s.run(W, mode=0) if W else None
@@ -187,42 +299,51 @@ def run_single(args):
     graph_ms = s.last_timing()["step_ms"]
     graph_steps = r["steps"]
 
-    # ---- end to end through the C-ABI with HOST buffers (pinned), copies inside the timed region
-    s.init_horizons(cfg["po"])
-    pin = lambda shape, dt=torch.float64: torch.empty(shape, dtype=dt).pin_memory().numpy()
-    l_a = pin((N, K, 3)).transpose(2, 1, 0)
-    l_b = pin((N, K, 3)).transpose(2, 1, 0)
-    st = [[pin((N, 3)).T for _ in range(3)] for _ in range(2)]
-    out = dict(status=pin((N,), torch.int32), diag=np.zeros(N, dtype=[("kstar", "i4"), ("nv", "i4"), ("iters", "i4"),
-                                                                     ("nact", "i4")]))
-    l0, p0, v0, a0 = s.init_horizons(cfg["po"])
-    l_a[...] = l0
-    st[0][0][...], st[0][1][...], st[0][2][...] = p0, v0, a0
-    cur, t_e2e = 0, 0.0
-    host_us = dict(pack_us=0.0, submit_us=0.0, wait_us=0.0, unpack_us=0.0)
-    # the caller's buffers are preallocated and pinned: the two ping-pong argument sets are bound once
-    outs = [dict(out, l_new=l_b, p1=st[1][0], v1=st[1][1], a1=st[1][2]),
-            dict(out, l_new=l_a, p1=st[0][0], v1=st[0][1], a1=st[0][2])]
-    calls = [s.bind_step(st[0][0], st[0][1], st[0][2], l_a, outs[0]),
-             s.bind_step(st[1][0], st[1][1], st[1][2], l_b, outs[1])]
-    for k in range(W + S):
-        o = outs[cur]
-        lp = l_a if cur == 0 else l_b
-        t0 = time.perf_counter()
-        calls[cur]()
-        dt = time.perf_counter() - t0
-        if k >= W:
-            t_e2e += dt
-            ht = s.last_host_timing()
-            for kk in host_us:
-                host_us[kk] += ht[kk]
-        # agents that failed keep their horizon (the library leaves their rows untouched)
-        bad = (o["status"] & 1) == 0
-        if bad.any():
-            o["l_new"][:, :, bad] = lp[:, :, bad]
-            for i in range(3):
-                st[cur ^ 1][i][:, bad] = st[cur][i][:, bad]
-        cur ^= 1
+    # ---- end to end through the C-ABI with HOST buffers, copies inside the timed region ------------
+    def e2e_pass(pinned):
+        s.init_horizons(cfg["po"])
+        if pinned:
+            mk = lambda shape, dt=torch.float64: torch.empty(shape, dtype=dt).pin_memory().numpy()
+        else:
+            mk = lambda shape, dt=torch.float64: np.empty(shape, dtype=np.float64 if dt == torch.float64 else np.int32)
+        l_a = mk((N, K, 3)).transpose(2, 1, 0)
+        l_b = mk((N, K, 3)).transpose(2, 1, 0)
+        st = [[mk((N, 3)).T for _ in range(3)] for _ in range(2)]
+        out = dict(status=mk((N,), torch.int32), diag=np.zeros(N, dtype=[("kstar", "i4"), ("nv", "i4"),
+                                                                       ("iters", "i4"), ("nact", "i4")]))
+        l0, p0, v0, a0 = s.init_horizons(cfg["po"])
+        l_a[...] = l0
+        st[0][0][...], st[0][1][...], st[0][2][...] = p0, v0, a0
+        cur, t_e2e = 0, 0.0
+        host_us = dict(pack_us=0.0, submit_us=0.0, wait_us=0.0, unpack_us=0.0)
+        # the caller's buffers are preallocated: the two ping-pong argument sets are bound once
+        outs = [dict(out, l_new=l_b, p1=st[1][0], v1=st[1][1], a1=st[1][2]),
+                dict(out, l_new=l_a, p1=st[0][0], v1=st[0][1], a1=st[0][2])]
+        calls = [s.bind_step(st[0][0], st[0][1], st[0][2], l_a, outs[0]),
+                 s.bind_step(st[1][0], st[1][1], st[1][2], l_b, outs[1])]
+        for k in range(W + S):
+            o = outs[cur]
+            lp = l_a if cur == 0 else l_b
+            t0 = time.perf_counter()
+            calls[cur]()
+            dt = time.perf_counter() - t0
+            if k >= W:
+                t_e2e += dt
+                ht = s.last_host_timing()
+                for kk in host_us:
+                    host_us[kk] += ht[kk]
+            # agents that failed keep their horizon (the library leaves their rows untouched)
+            bad = (o["status"] & 1) == 0
+            if bad.any():
+                o["l_new"][:, :, bad] = lp[:, :, bad]
+                for i in range(3):
+                    st[cur ^ 1][i][:, bad] = st[cur][i][:, bad]
+            cur ^= 1
+        return t_e2e, {k: v / S for k, v in host_us.items()}
+
+    e2e_pass(True)
+    t_e2e, host_us = e2e_pass(True)
+    t_e2e_pg, host_us_pg = e2e_pass(False)
     clocks = clk.stop()
     h2d = (9 * N + 3 * K * N) * 8
     d2h = (3 * K * N + 9 * N) * 8 + 4 * N + 16 * N + 4
@@ -235,71 +356,96 @@ def run_single(args):
     ach_scan = b_alg(N, K) * N / (scan_us * 1e-6) / 1e9
     ach_qp = b_alg(N, K) * N / (qp_us * 1e-6) / 1e9
     ach_step = b_alg(N, K) * N / (ms_per_step * 1e-3) / 1e9
+    qp_name = f"qp_kernel<{conf['agents_per_qp_block']}, {K if K in (15, 20) else 0}>"
+    prof_qp, prof_qp_path = ncu_profile("qp_kernel")
+    prof_sc, prof_sc_path = ncu_profile("scan_kernel")
+    sm_mhz = (clocks or {}).get("sm_mhz") or 1965.0
+    slow_it = float(np.mean(it_max)) if it_max else None
+    compulsory = 24 * K * N + (24 * K + 168) * N  # every horizon once from DRAM + per-agent state and outputs
 
     line = {
         "metric": "agent-MPC-steps/sec", "value": value, "unit": "agent-steps/s", "n_gpus": 1, "steps": n_timed,
         "warmup": W, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": f"{args.workload}: N={N} K={K} soft-constraint DMPC (solveSoftDMPCbound), "
-                               "1 agent/m^3 arena, seed 1003, closed-loop steps W+1..W+K",
+        "config": {"workload": workload_label(args.workload, cfg, K),
                    "l2": "flushed between timed steps (512 MiB write); per-step CUDA events on the launch stream",
                    "launch": conf},
         "clocks": clocks,
         "e2e": {"value": N * S / t_e2e, "unit": "agent-steps/s", "h2d_bytes_per_step": h2d,
                 "d2h_bytes_per_step": d2h, "ms_per_step": 1e3 * t_e2e / S,
-                "api": "dmpcb200_step (host buffers, pinned)",
-                "host_phases_us": {k: v / S for k, v in host_us.items()}},
+                "api": "dmpcb200_step (host buffers, pinned: DMA from / kernel writes into the caller's arrays)",
+                "host_phases_us": host_us},
+        "e2e_pageable": {"value": N * S / t_e2e_pg, "unit": "agent-steps/s", "ms_per_step": 1e3 * t_e2e_pg / S,
+                         "api": "dmpcb200_step (host buffers, PAGEABLE like a MATLAB mxArray: staged through the "
+                                "handle's pinned block, one copy in, one out)", "host_phases_us": host_us_pg},
         "gpu_launches": 2 * n_timed,
         "resident_graph": {"value": N / (graph_ms * 1e-3) if graph_ms else None, "ms_per_step": graph_ms,
                            "steps": graph_steps, "note": "dmpcb200_run, CUDA graph, L2-warm, no host sync"},
-        # dominant kernel = qp_kernel (80 % of the step).  Per the contract `achieved` charges it the whole
-        # algorithmic traffic of an agent-step (B_alg = 24 K N + 24 K + 168 bytes, dominated by the
-        # neighbour horizons that scan_kernel streams); the kernel itself is bound by the latency of the
-        # slowest agent's dependent fp64 chain, not by bandwidth: its measured DRAM traffic is ~0.7 MB.
-        "roofline": {"bound": "hbm", "kernel": "qp_kernel<4,15> (batched per-agent QP, tail fused)",
+        # dominant kernel = qp_kernel.  By the contract `achieved` charges it the whole algorithmic traffic of
+        # an agent-step (B_alg = 24 K N + 24 K + 168 bytes, dominated by the neighbour horizons that
+        # scan_kernel streams) -- but that is not what bounds it: its DRAM traffic is < 1 MB per launch and the
+        # launch lasts as long as its SLOWEST agent's dependent chain of dual active-set iterations.
+        "roofline": {"bound": "latency", "contract_bound": "hbm",
+                     "kernel": f"{qp_name} (batched per-agent QP, tail fused)",
                      "achieved": ach_qp, "peak": peak, "unit": "GB/s", "frac": ach_qp / peak,
-                     "traffic": 705792, "traffic_source": "ncu --set full, profiles/r1d_ncu_full_qp_summary.csv "
-                     "(dram__bytes_read.sum + dram__bytes_write.sum per launch)",
+                     "traffic": prof_qp["traffic"] if prof_qp else None,
+                     "traffic_source": (f"ncu --set full, {prof_qp_path} (dram__bytes_read.sum + dram__bytes_write.sum, "
+                                        f"mean of {prof_qp['launches_averaged']} launches)") if prof_qp else
+                     "no tracked ncu summary lists this kernel",
                      "peak_source": peak_src, "avg_launch_us": qp_us,
                      "algorithmic_bytes_per_launch": b_alg(N, K) * N,
-                     "note": "latency bound (one warp per SM sub-partition, slowest agent); see DESIGN.md 4"},
-        "roofline_scan": {"bound": "hbm", "kernel": "scan_kernel<4,2,15> (neighbour scan + constraint rows)",
+                     "latency": {"slowest_agent_iters": slow_it,
+                                 "us_per_iter": (qp_us / slow_it) if slow_it else None,
+                                 "cycles_per_iter": (qp_us * sm_mhz / slow_it) if slow_it else None,
+                                 "issue_active_pct": prof_qp.get("issue_active_pct") if prof_qp else None,
+                                 "fp64_pipe_pct": prof_qp.get("fp64_pipe_pct") if prof_qp else None,
+                                 "warps_active_pct": prof_qp.get("warps_active_pct") if prof_qp else None,
+                                 "note": "launch time = iterations of the slowest agent x time per iteration (+ "
+                                         "set-up); one warp per SM sub-partition; see DESIGN.md section 4"}},
+        "roofline_scan": {"bound": "shared-memory bandwidth / fp64 issue", "contract_bound": "hbm",
+                          "kernel": "scan_kernel (neighbour scan + constraint rows)",
                           "achieved": ach_scan, "peak": peak, "unit": "GB/s", "frac": ach_scan / peak,
-                          "traffic": 230400, "avg_launch_us": scan_us,
+                          "traffic": prof_sc["traffic"] if prof_sc else None,
+                          "traffic_source": prof_sc_path, "avg_launch_us": scan_us,
                           "algorithmic_bytes_per_launch": b_alg(N, K) * N,
-                          "note": "the neighbour buffer (180 KB) is L2 resident and re-read by every CTA through "
-                                  "TMA: algorithmic bytes >> DRAM bytes"},
-        "roofline_step": {"bound": "hbm", "achieved": ach_step, "peak": peak, "unit": "GB/s",
+                          "compulsory_dram_bytes_per_launch": compulsory,
+                          "compulsory_dram_frac_of_peak": compulsory / (scan_us * 1e-6) / 1e9 / peak,
+                          "smem_bytes_per_launch": (prof_sc["lsu_shared_wavefronts"] * 128) if prof_sc and
+                          "lsu_shared_wavefronts" in prof_sc else None,
+                          "issue_active_pct": prof_sc.get("issue_active_pct") if prof_sc else None,
+                          "fp64_pipe_pct": prof_sc.get("fp64_pipe_pct") if prof_sc else None,
+                          "note": "every CTA streams the whole neighbour buffer through shared memory by TMA: the "
+                                  "buffer is L2 resident, so the contract's byte model (algorithmic bytes >> DRAM "
+                                  "bytes) may exceed the DRAM peak; the kernel's own limit is the shared-memory / "
+                                  "fp64 work of the distance loop"},
+        "roofline_step": {"bound": "hbm (contract accounting)", "achieved": ach_step, "peak": peak, "unit": "GB/s",
                           "frac": ach_step / peak, "note": "B_alg*N over the whole step (scan + QP incl. tail)"},
         "kernel_us": {"scan_kernel": scan_us, "qp_kernel": qp_us,
                       "tail_and_gaps": 1e3 * ms_per_step - scan_us - qp_us,
                       "share": {"scan": scan_us / (1e3 * ms_per_step), "qp": qp_us / (1e3 * ms_per_step)}},
     }
-    # ---- CPU baseline: oracle port on a bounded sample of the same workload -----------------------
+    # ---- CPU baselines: bounded samples of the same workload ----------------------------------------
     threads = os.cpu_count() or 1
-    v, done, secs = cpu_port_run(cfg, W, S, threads, budget_s=15.0)
+    v, done, secs = cpu_port_run(cfg, W, S, threads, budget_s=12.0)
     line["cpu_baseline"] = {"value": v, "unit": "agent-steps/s", "cores": threads, "kind": "port",
                             "sample": f"steps {W + 1}..{W + done} of the same transition ({done} MPC steps x {N} "
-                                      f"agents, {secs:.1f} s), oracle/liboracle.so with {threads} threads; the "
-                                      "reference's MATLAB / C++ cannot run on this box"}
-    # ---- the second half of BASELINE's metric: max position error vs the reference (here: the fp64 oracle,
-    # teacher-forced on the dense first steps of the same workload; tolerance 1e-6 m) ------------
+                                      f"agents, {secs:.1f} s), oracle/liboracle.so (dense QP assembly like the "
+                                      f"reference, exact dual active-set solve) with {threads} threads; {REF_NOTE}"}
     try:
-        from oracle import dmpc_oracle as orc
-        O = orc.default_params(cfg["variant"])
-        for kk, vv in cfg["params"].items():
-            setattr(O, kk, vv)
-        l_, pk_, vk_, ak_ = s.init_horizons(cfg["po"])
-        worst, same = 0.0, True
-        for _ in range(6):
-            g_ = s.step(pk_, vk_, ak_, l_)
-            o_ = orc.step(O, pk_, vk_, ak_, cfg["pf"], l_, cfg["pmin"], cfg["pmax"], nthreads=threads)
-            worst = max(worst, float(np.abs(g_["l_new"] - o_["l_new"]).max()))
-            same = same and bool(np.array_equal(g_["status"] & 0xFF, o_["status"] & 0xFF))
-            l_, pk_, vk_, ak_ = o_["l_new"], o_["p1"], o_["v1"], o_["a1"]
-        line["max_pos_err_vs_ref"] = {"value": worst, "unit": "m", "tolerance": 1e-6, "status_flags_equal": same,
-                                      "reference": "oracle/liboracle.so (fp64 port pinned on the reference's MATLAB "
-                                                   "workspaces), 6 teacher-forced steps of the same workload"}
+        v1, d1, s1 = cpu_port_run(cfg, W, S, 1, budget_s=6.0)
+        line["cpu_baseline_1thread"] = {"value": v1, "unit": "agent-steps/s", "cores": 1, "kind": "port",
+                                        "sample": f"{d1} MPC steps, same code, one thread (the serial `for n = 1:N` of "
+                                                  f"the MATLAB scripts), {s1:.1f} s"}
+        v2, d2, s2 = cpu_port_run(cfg, W, S, 1, budget_s=6.0, structured=True)
+        line["cpu_baseline_structured_1thread"] = {
+            "value": v2, "unit": "agent-steps/s", "cores": 1, "kind": "port",
+            "sample": f"{d2} MPC steps, {s2:.1f} s: host build of the device algorithm (tests/host_emul: Kronecker / "
+                      "rank-1 structure exploited, no dense H, no per-step allocation), one thread -- the tuned-CPU "
+                      "reading of the same path"}
+    except Exception as ex:
+        line["cpu_baseline_1thread"] = {"error": repr(ex)[:200]}
+    try:
+        line["max_pos_err_vs_ref"] = parity_leg(s, cfg, threads)
     except Exception as ex:
         line["max_pos_err_vs_ref"] = {"error": repr(ex)[:200]}
     # ---- next row of the path: post-processing of the finished transition (failure_rate.m:
@@ -308,6 +454,7 @@ def run_single(args):
         from oracle import dmpc_oracle as orc
         s.init_horizons(cfg["po"])
         tr = s.run(cfg["max_steps"], record=True)
+        s.postprocess(tr["pk"], tr["vk"], tr["ak"], want_interp=False)   # warm-up (first-use allocations)
         t0 = time.perf_counter()
         pp = s.postprocess(tr["pk"], tr["vk"], tr["ak"], want_interp=False)
         t_api = time.perf_counter() - t0
@@ -327,6 +474,139 @@ def run_single(args):
         line["postprocess"] = {"error": repr(ex)[:200]}
     s.close()
     print(json.dumps(line))
+
+
+def batch_outcomes(cfg, r, S):
+    """reference-style outcome statistics of a Monte-Carlo batch (test/failure_rate.m:253-258) beside the
+    reference's published curve (data/failure_rate/failure_rate3.mat: success 0.28 at N = 200, 50 trials)"""
+    reached = np.asarray(r["reached"], bool)
+    failed = np.asarray(r["first_fail_step"]) >= 0
+    steps = np.asarray(r["steps"])
+    out = {"scenarios": int(S), "reached_goal": int(reached.sum()), "failed_agent": int(failed.sum()),
+           "neither_by_max_steps": int((~reached & ~failed).sum()),
+           "success_rate": float((reached & ~failed).mean()),
+           "steps_to_goal_mean": float(steps[reached].mean()) if reached.any() else None,
+           "steps_to_goal_max": int(steps[reached].max()) if reached.any() else None,
+           "reference_published": {"source": "data/failure_rate/failure_rate3.mat (success_dmpc, N = 200, 50 trials; "
+                                             "MATLAB quadprog, success also needs the 100 Hz post-check)",
+                                   "success_rate": 0.28, "steps_to_goal_last_trial": 90}}
+    return out
+
+
+def run_batch(args):
+    """C5: Monte-Carlo scenarios batched in one handle per GPU; whole scenarios per rank, no collective."""
+    import torch
+    from multiagent_planning_b200 import dmpc
+    rank, world = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", rank))
+    multi = world > 1
+    torch.cuda.set_device(local)
+    if multi:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    cfg = workload(args.workload)
+    N, S_all = cfg["N"], cfg["S"]
+    P = dmpc.default_params(cfg["variant"], **cfg["params"])
+    K = P.K
+    mine = list(range(rank, S_all, world))       # whole scenarios, round robin
+    S = len(mine)
+    max_steps = cfg["max_steps"]
+    b = dmpc.Solver(N, P, n_scenarios=S, device=local)
+
+    def load():
+        for i, sc in enumerate(mine):
+            b.set_scenario(i, cfg["po"][sc], cfg["pf"][sc], cfg["pmin"], cfg["pmax"])
+
+    # a "step" of this workload = one pass over the whole batch = every scenario's complete transition
+    W, R = max(args.warmup, 3), max(1, min(args.steps, 20))
+    for _ in range(W):
+        load()
+        b.run_batch(max_steps, stop_on_fail=True)
+    clk = ClockSampler(local)
+    if rank == 0:
+        clk.start()
+    if multi:
+        dist.barrier()
+    torch.cuda.synchronize()
+    dev_ms, agent_steps, wall = 0.0, 0, 0.0
+    for _ in range(R):
+        load()
+        t0 = time.perf_counter()
+        r = b.run_batch(max_steps, stop_on_fail=True)
+        wall += time.perf_counter() - t0
+        dev_ms += r["device_ms"]
+        agent_steps += r["agent_steps"]
+    torch.cuda.synchronize()
+    # per-kernel split and e2e (scenario upload + whole batch + outcome read-back through the C-ABI)
+    load()
+    rk = b.run_batch(30, stop_on_fail=False, mode=1)
+    tk = b.last_timing()
+    t0 = time.perf_counter()
+    load()
+    r2 = b.run_batch(max_steps, stop_on_fail=True)
+    t_e2e = time.perf_counter() - t0
+    clocks = clk.stop() if rank == 0 else None
+    if multi:
+        t = torch.tensor([dev_ms, float(agent_steps), t_e2e, float(r2["agent_steps"])], dtype=torch.float64,
+                         device="cuda")
+        tmax = t.clone()
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        dev_ms, agent_steps = float(tmax[0]), int(t[1])
+        t_e2e, e2e_steps = float(tmax[2]), int(t[3])
+        outs = [None] * world
+        dist.all_gather_object(outs, {k: np.asarray(r[k]).tolist() for k in ("reached", "first_fail_step", "steps")})
+        allr = {k: sum((o[k] for o in outs), []) for k in ("reached", "first_fail_step", "steps")}
+    else:
+        e2e_steps = r2["agent_steps"]
+        allr = r
+    if rank == 0:
+        peak, peak_src = peaks()
+        value = agent_steps / (dev_ms * 1e-3)
+        ach = b_alg(N, K) * value / 1e9
+        dense_us = 1e3 * tk["step_ms"]
+        line = {
+            "metric": "agent-MPC-steps/sec", "value": value, "unit": "agent-steps/s", "n_gpus": world, "steps": R,
+            "warmup": W, "ms_per_step": dev_ms / R, "higher_is_better": True, "scaling": "strong",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": workload_label(args.workload, cfg, K),
+                       "step": f"one pass over the batch: {S_all} complete transitions (<= {max_steps} MPC steps each, "
+                               "a scenario stops at its goal or first failing agent like failure_rate.m:112-125)",
+                       "parallelism": f"{S_all} scenarios sharded whole over {world} GPU(s), no collective",
+                       "l2": f"inputs larger than L2 are not needed: every pass re-uploads the scenarios; the batch "
+                             f"state ({S * N * 3 * K * 8 * 2 / 1e6:.1f} MB per GPU) is device resident by design",
+                       "launch": b.config()},
+            "clocks": clocks,
+            "e2e": {"value": e2e_steps / t_e2e, "unit": "agent-steps/s",
+                    "h2d_bytes_per_step": S_all * (6 * N + 6) * 8, "d2h_bytes_per_step": S_all * (4 * 4 + 8),
+                    "ms_per_step": 1e3 * t_e2e,
+                    "api": "dmpcb200_set_scenario x S (pageable host arrays) + dmpcb200_run_batch, outcomes read back"},
+            "gpu_launches": 3 * int(np.max(allr["steps"])) * R,
+            "roofline": {"bound": "hbm", "kernel": "whole batched step (scan_kernel + qp_kernel + per-scenario tail)",
+                         "achieved": ach, "peak": peak * world, "unit": "GB/s", "frac": ach / (peak * world),
+                         "traffic": None, "peak_source": peak_src,
+                         "algorithmic_bytes_per_agent_step": b_alg(N, K),
+                         "note": "contract accounting over the whole run (B_alg x agent-steps / device time); the "
+                                 "neighbour buffers are L2 resident"},
+            "kernel_us": {"dense_first_30_steps": {"scan_kernel": 1e3 * tk["scan_ms"], "qp_kernel": 1e3 * tk["qp_ms"],
+                                                   "step": dense_us,
+                                                   "agent_steps_per_s": rk["agent_steps"] / (rk["device_ms"] * 1e-3)}},
+            "outcomes": batch_outcomes(cfg, allr, S_all),
+        }
+        if not multi:
+            threads = os.cpu_count() or 1
+            v, done, secs = cpu_port_run(cfg, 4, 20, threads, budget_s=12.0)
+            line["cpu_baseline"] = {"value": v, "unit": "agent-steps/s", "cores": threads, "kind": "port",
+                                    "sample": f"scenario 0 of the batch, steps 5..{4 + done} ({done} MPC steps x {N} "
+                                              f"agents, {secs:.1f} s), oracle/liboracle.so, {threads} threads; "
+                                              f"{REF_NOTE}"}
+        print(json.dumps(line), flush=True)
+    b.close()
+    if multi:
+        torch.cuda.synchronize()
+        dist.barrier()
+        sys.stdout.flush()
+        os._exit(0)
 
 
 def run_multi(args):
@@ -395,10 +675,46 @@ def run_multi(args):
         tg = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device="cuda")
         dist.all_reduce(tg, op=dist.ReduceOp.MAX)
         graph_ms = float(tg.item()) / (2 * (S // 2))
-    except Exception as ex:  # graph capture of NCCL is an optimisation, not the measured path
+    except Exception:  # graph capture of NCCL is an optimisation, not the measured path
         graph_ms = None
-        graph_err = repr(ex)[:200]
     clocks = clk.stop() if rank == 0 else None
+    # ---- parity of the SHARDED path: a few steps from the start, the gathered horizons of every step against
+    # one oracle step on the previous gathered horizons (teacher-forced on the GPU trajectory) ---------------
+    parity = None
+    try:
+        sh.be.init(cfg["po"])
+        sh.cur = 0
+        torch.cuda.synchronize()
+        worst, same = 0.0, True
+        if rank == 0:
+            from oracle import dmpc_oracle as orc
+            O = oracle_params(cfg)
+        l_prev = sh.horizons()
+        st_prev = [x.cpu().numpy().T.copy() for x in sh.be.st[sh.cur]]  # rank-local blocks are valid only
+        for _ in range(4):
+            # the states of all agents: gather the blocks (test-only traffic, outside any timed region)
+            full = []
+            for q in range(3):
+                loc = torch.zeros(sh.blk, 3, dtype=torch.float64, device="cuda")
+                loc[: sh.n1 - sh.n0] = sh.be.st[sh.cur][q][sh.n0:sh.n1]
+                out = torch.zeros(sh.rows, 3, dtype=torch.float64, device="cuda")
+                dist.all_gather_into_tensor(out, loc)
+                full.append(np.asfortranarray(out[:N].cpu().numpy().T))
+            sh.step()
+            torch.cuda.synchronize()
+            st = sh.gather_status()
+            l_new = sh.horizons()
+            if rank == 0:
+                o = orc.step(O, full[0], full[1], full[2], cfg["pf"], l_prev, cfg["pmin"], cfg["pmax"],
+                             nthreads=os.cpu_count() or 1)
+                worst = max(worst, float(np.abs(l_new - o["l_new"]).max()))
+                same = same and bool(np.array_equal(st & 0xFFFF, o["status"] & 0xFFFF))
+            l_prev = l_new
+        parity = {"value": worst, "unit": "m", "tolerance": 1e-6, "status_flags_and_retry_counts_equal": same,
+                  "reference": "oracle/liboracle.so, 4 teacher-forced steps of the sharded run (all-gathered horizons "
+                               "of every step against one oracle step on the previous ones)"}
+    except Exception as ex:
+        parity = {"error": repr(ex)[:300]}
     if rank == 0:
         ms = tot / S
         peak, peak_src = peaks()
@@ -407,24 +723,26 @@ def run_multi(args):
             "metric": "agent-MPC-steps/sec", "value": N * S / (tot * 1e-3), "unit": "agent-steps/s", "n_gpus": world,
             "steps": S, "warmup": W, "ms_per_step": ms, "higher_is_better": True, "scaling": "strong",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": f"{args.workload}: N={N} K={K} soft-constraint DMPC (solveSoftDMPCbound), "
-                                   "1 agent/m^3 arena, seed 1003, closed-loop steps W+1..W+K",
+            "config": {"workload": workload_label(args.workload, cfg, K),
                        "parallelism": f"agents sharded in {world} contiguous blocks of {sh.blk}, one NCCL all-gather "
                                       f"of {sh.blk * 3 * K * 8} B per rank per step",
                        "l2": "flushed between timed steps (512 MiB write); per-step CUDA events, max over ranks"},
             "clocks": clocks,
             "e2e": {"value": N * S / (tot * 1e-3), "unit": "agent-steps/s", "h2d_bytes_per_step": 0,
-                    "d2h_bytes_per_step": 0,
-                    "note": "multi-GPU loop is device resident; the host-buffer e2e is measured at n_gpus=1"},
+                    "d2h_bytes_per_step": 0, "copies_declared": False,
+                    "note": "the multi-GPU loop is device resident (no host copies per step): this repeats `value`; "
+                            "the host-buffer e2e is measured at n_gpus=1"},
             "gpu_launches": 2 * S,
             "resident_graph": {"ms_per_step": graph_ms, "value": (N / (graph_ms * 1e-3)) if graph_ms else None,
                                "note": "torch CUDA graph of two steps incl. NCCL all-gather"},
-            "roofline": {"bound": "hbm", "kernel": "whole step (scan + QP + all-gather), max over ranks",
+            "roofline": {"bound": "latency", "contract_bound": "hbm",
+                         "kernel": "whole step (scan + QP + all-gather), max over ranks",
                          "achieved": ach, "peak": peak * world, "unit": "GB/s", "frac": ach / (peak * world),
                          "traffic": None, "peak_source": peak_src,
                          "note": "strong scaling of a latency-bound step: the slowest agent sets the step time on "
                                  "every rank; per-kernel rooflines are reported at n_gpus=1"},
             "all_gathers_per_step": sh.n_allgather / max(sh.steps, 1),
+            "max_pos_err_vs_ref": parity,
         }
         print(json.dumps(line), flush=True)
     # teardown: every rank has its numbers; leave through a barrier and exit at once (destroying a
@@ -446,6 +764,8 @@ def main():
     args.warmup = max(args.warmup, 0)
     if args.impl == "reference":
         return run_reference(args)
+    if args.workload == "C5":
+        return run_batch(args)
     if int(os.environ.get("WORLD_SIZE", "1")) > 1:
         return run_multi(args)
     return run_single(args)
