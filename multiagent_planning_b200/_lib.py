@@ -15,7 +15,8 @@ import subprocess
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _CSRC = os.path.join(_HERE, "csrc")
 LIB_PATH = os.path.join(_HERE, "libdmpc_b200.so")
-SOURCES = ["dmpc_b200.cu", "k_qp15.cu", "k_qp20.cu", "k_qpgen.cu", "k_scan.cu", "model_tables.cpp"]
+SOURCES = ["dmpc_b200.cu", "k_qp15.cu", "k_qp20.cu", "k_qpgen.cu", "k_scan.cu",
+           "model_tables.cpp"]
 HEADERS = ["dmpc_kernels.cuh", "small_kernels.cuh", "launch.cuh", "scan_core.cuh", "agent_solve.cuh", "qp_core.cuh",
            "qp_warp.cuh", "postprocess.cuh", "model_tables.h", os.path.join("..", "..", "include", "dmpc_b200.h")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",

@@ -100,6 +100,10 @@ struct dmpcb200_handle {
     unsigned char* d_rescue = nullptr;
     int* d_rescue_next = nullptr;
     unsigned* d_done = nullptr;  // CTA arrival counter of the fused tail
+    // throughput layout of the QP kernel (launches of more than one wave of agents)
+    RouteQ* d_rq = nullptr;
+    int *d_qlight = nullptr, *d_qheavy = nullptr;
+    int layout = 1;  // 1 classic persistent kernel (default), 0 two-role throughput kernel (DMPCB200_LAYOUT=throughput)
     Ctrl* d_ctrl = nullptr;
     double* d_goal = nullptr;  // 2 doubles
     int* d_fail = nullptr;
@@ -182,7 +186,19 @@ StepArgs make_args(dmpcb200_t* h, int n0, int n1, const double* pk, const double
     A.fuse_tail = 0;
     A.done_cnt = h->d_done;
     A.work_cnt = h->d_done + 1;
+    A.rq = nullptr;
+    A.q_light = h->d_qlight;
+    A.q_heavy = h->d_qheavy;
     return A;
+}
+
+// throughput layout: more agents than one wave of the one-agent-per-sub-partition layout, reference horizon,
+// variant with a fast path.  Decided per launch (a per-agent drop-in on the same handle is a batch of one).
+bool use_throughput_layout(const dmpcb200_t* h, const StepArgs& A) {
+    if (h->layout == 1 || !h->d_rq || h->W != 4) return false;
+    if (h->K != 15 && h->K != 20) return false;
+    if (A.diag != h->d_diag) return false;  // the route prediction reads the handle's own record of the last step
+    return (long long)(A.n1 - A.n0) * A.n_scen > 4LL * sm_count(current_device());
 }
 
 // 4 agents x 2 warps per CTA while one wave of CTAs covers the swarm, 8 agents beyond (or fewer when the
@@ -190,6 +206,16 @@ StepArgs make_args(dmpcb200_t* h, int n0, int n1, const double* pk, const double
 // (15, 20) are compiled with the horizon as a constant (the own horizon then lives in registers)
 cudaError_t launch_scan(dmpcb200_t* h, const StepArgs& A, cudaStream_t s) {
     const int nl = A.n1 - A.n0, K = h->K, N = h->N;  // (per scenario)
+    if (const char* e = getenv("DMPCB200_SCAN_LAYOUT")) {  // experiment hook
+        const int id = atoi(e);
+        if (id >= 0 && id <= 6) return launch_scan_layout((ScanLayout)id, A, nl, K, s);
+    }
+    // throughput mode (batched scenarios / more than one wave of agents) with every tile of a scenario resident:
+    // 8 agents x 2 warps per CTA with the own horizon in shared memory (occupancy beats the register-resident
+    // horizon: C5 scan 247 -> 150 us per step)
+    if ((A.rq || A.n_scen > 1 || (long long)nl * A.n_scen > 4LL * sm_count(current_device())) &&
+        scan_stages(K, N, 8, A.RMAX) >= (N + kTile - 1) / kTile)
+        return launch_scan_layout(SCAN_8_2_0, A, nl, K, s);
     if (nl <= 4 * 148 || scan_stages(K, N, 8, A.RMAX) < 2) {
         if (scan_stages(K, N, 4, A.RMAX) < 1) return launch_scan_layout(SCAN_1_2_0, A, nl, K, s);
         if (K == 15) return launch_scan_layout(SCAN_4_2_15, A, nl, K, s);
@@ -204,6 +230,7 @@ cudaError_t launch_scan(dmpcb200_t* h, const StepArgs& A, cudaStream_t s) {
 // compile-time constant (fully unrolled table products); anything else takes the generic kernel
 cudaError_t launch_qp(dmpcb200_t* h, const StepArgs& A, cudaStream_t s) {
     const int nl = A.n1 - A.n0;
+    if (A.rq) return h->K == 15 ? launch_qp2_15(A, nl, s) : launch_qp2_20(A, nl, s);
     const size_t smem = qp_smem_bytes(h->K, h->W, h->QMAX, h->RCAP);
     if (h->K == 15 && h->W == 4) return launch_qp_4_15(A, nl, smem, s);
     if (h->K == 20 && h->W == 4) return launch_qp_4_20(A, nl, smem, s);
@@ -250,6 +277,7 @@ int launch_resident_step(dmpcb200_t* h, int cur, bool record, Ctrl* ctrl, cudaSt
     A.T = make_tail(h, h->d_st[nx][0], 3, h->d_status, h->d_st[nx][0], h->d_st[nx][1], h->d_st[nx][2], record, ctrl);
     A.fuse_tail = 1;
     if (evs) CK(cudaEventRecord(evs[0], s));
+    if (use_throughput_layout(h, A)) A.rq = h->d_rq;
     CK(launch_scan(h, A, s));
     if (evs) CK(cudaEventRecord(evs[1], s));
     CK(launch_qp(h, A, s));  // the tail of the step runs in the last CTA of the QP kernel
@@ -508,6 +536,23 @@ int dmpcb200_create(const dmpcb200_params* p, int N, int n0, int n1, int n_scena
     if ((e = dalloc(&h->d_rescue, h->rescue_bytes * h->n_rescue)) != cudaSuccess) return bail(e, "rescue");
     if ((e = dalloc(&h->d_rescue_next, 1)) != cudaSuccess) return bail(e, "rescue counter");
     if ((e = dalloc(&h->d_done, 2)) != cudaSuccess) return bail(e, "done / work counters");
+    {
+        const char* lay = getenv("DMPCB200_LAYOUT");
+        // The two-role kernel (8 agents per SM, light agents with a 32-capacity active set) is an OPT-IN experiment:
+        // measured on one B200 it wins where light agents dominate (C5 late steps: QP 159 -> 123 us per step) and
+        // loses where heavy agents do (C5 first 30 steps 711 -> 864 us, N = 2000 286 -> 466 us): net zero to
+        // negative, so the classic persistent kernel stays the default.
+        h->layout = (lay && std::string(lay) == "throughput") ? 0 : 1;
+        int n_sm = 148;
+        cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, device);
+        if (NL > 4 * (size_t)n_sm && h->layout == 0) {
+            const size_t cap = NL + 2 * (size_t)kLightW * n_sm + 64;  // + the indices the draining warps overshoot by
+            if ((e = dalloc(&h->d_rq, 1)) != cudaSuccess) return bail(e, "route queues");
+            if ((e = dalloc(&h->d_qlight, NL)) != cudaSuccess) return bail(e, "route queues");
+            if ((e = cudaMalloc((void**)&h->d_qheavy, cap * sizeof(int))) != cudaSuccess) return bail(e, "route queues");
+            if ((e = cudaMemset(h->d_qheavy, 0xff, cap * sizeof(int))) != cudaSuccess) return bail(e, "route queues");
+        }
+    }
     if ((e = dalloc(&h->d_ctrl, nS)) != cudaSuccess) return bail(e, "ctrl");
     if ((e = dalloc(&h->d_goal, 2 * nS)) != cudaSuccess) return bail(e, "goal");
     if ((e = dalloc(&h->d_u8, 2 * (size_t)N)) != cudaSuccess) return bail(e, "u8");
@@ -529,6 +574,7 @@ void dmpcb200_destroy(dmpcb200_t* h) {
     cudaFree(h->d_pf); cudaFree(h->d_bounds); cudaFree(h->d_vhor); cudaFree(h->d_ahor);
     cudaFree(h->d_scan); cudaFree(h->d_grow); cudaFree(h->d_gkc); cudaFree(h->d_gidx);
     cudaFree(h->d_gscr_d); cudaFree(h->d_gscr_i); cudaFree(h->d_rescue); cudaFree(h->d_rescue_next);
+    cudaFree(h->d_rq); cudaFree(h->d_qlight); cudaFree(h->d_qheavy);
     cudaFree(h->d_done); cudaFree(h->d_ctrl); cudaFree(h->d_goal); cudaFree(h->d_u8); cudaFree(h->d_small);
     cudaFree(h->d_ismall);
     cudaFree(h->d_scr);
@@ -598,12 +644,13 @@ int dmpcb200_step_dev(dmpcb200_t* h, const double* d_pk, const double* d_vk, con
     cudaStream_t s = (cudaStream_t)stream;
     const bool padded = (d_l_prev == h->d_l[0] || d_l_prev == h->d_l[1]);
     StepArgs A = make_args(h, h->n0, h->n1, d_pk, d_vk, d_ak, d_l_prev, d_l_new, d_p1, d_v1, d_a1, d_v_hor, d_a_hor,
-                           d_status, reinterpret_cast<AgentDiag*>(d_diag), padded, nullptr);
+                           d_status, d_diag ? reinterpret_cast<AgentDiag*>(d_diag) : h->d_diag, padded, nullptr);
     if (h->NL == 0) {  // empty block: nothing to solve
         h->launches = 0;
         return 0;
     }
     CK(cudaMemsetAsync(h->d_rescue_next, 0, sizeof(int), s));
+    if (use_throughput_layout(h, A)) A.rq = h->d_rq;
     CK(launch_scan(h, A, s));
     CK(launch_qp(h, A, s));
     h->launches = 2;
@@ -724,6 +771,7 @@ int step_impl(dmpcb200_t* h, const dmpcb200_handle::Bound& B, int32_t* first_fai
     A.T.copy_bytes = h->tailblk_bytes;
     A.fuse_tail = 1;  // first failing agent + rescue-slot reset in the last CTA of the QP kernel
     CK(cudaEventRecord(h->ev[0], s));
+    if (use_throughput_layout(h, A)) A.rq = h->d_rq;
     CK(launch_scan(h, A, s));
     CK(cudaEventRecord(h->ev[1], s));
     if (in_pinned) CK(cudaStreamWaitEvent(s, h->ev_in, 0));  // the states have arrived
@@ -1019,6 +1067,7 @@ int dmpcb200_run_batch(dmpcb200_t* h, int max_steps, int stop_on_fail, int mode,
         A.lstride = (size_t)h->Npad * 3 * h->K;
         A.bounds = h->d_bounds;
         if (evs) CK(cudaEventRecord(evs[0], st));
+        if (use_throughput_layout(h, A)) A.rq = h->d_rq;
         CK(launch_scan(h, A, st));
         if (evs) CK(cudaEventRecord(evs[1], st));
         CK(launch_qp(h, A, st));

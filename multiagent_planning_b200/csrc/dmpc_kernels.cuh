@@ -25,6 +25,10 @@
 namespace dmpc {
 
 constexpr int kTile = 32;  // neighbours per shared-memory tile (= one per lane)
+// throughput layout of K2 (qp2_kernel, below): agents per SM in the light / heavy phases, and the size of last
+// step's active set from which the scan kernel queues an agent as heavy
+constexpr int kLightW = 8, kHeavyW = 2, kHeavyMax = 4;
+constexpr int kRouteNact = 28;
 
 struct ScanRec {
     int kstar, nv, flag, pad;
@@ -63,6 +67,15 @@ struct TailArgs {
     size_t copy_bytes;  // multiple of 16
 };
 
+// route queues of the throughput layout of K2 (qp2_kernel): filled by the scan kernel (and by light agents that
+// outgrow their capacity), consumed and reset by the QP kernel
+struct RouteQ {
+    unsigned n_light, n_heavy;        // entries pushed (n_heavy still grows while the QP kernel runs)
+    unsigned head_light, head_heavy;  // next entry to take
+    unsigned light_done;              // CTAs that have finished their light phase
+    unsigned done_ctas;               // CTAs that have finished (the last one runs the tail and resets the queues)
+};
+
 struct StepArgs {
     DevParams P;
     ScanThr thr;  // exact squared distance thresholds (scan_core.cuh)
@@ -98,6 +111,8 @@ struct StepArgs {
     int fuse_tail;
     unsigned* done_cnt;  // CTAs that finished (reset by the last one)
     unsigned* work_cnt;  // agent queue of the persistent QP grid (reset by the last CTA)
+    RouteQ* rq;          // throughput layout (null: classic layout): route queues
+    int *q_light, *q_heavy;  // agent indices; q_heavy entries are -1 when empty (self-cleaning)
     TailArgs T;
 };
 
@@ -184,7 +199,6 @@ __global__ void __launch_bounds__(W * S * 32) scan_kernel(const __grid_constant_
     const int cps = (nl_s + W - 1) / W;
     const int scen = (A.n_scen > 1) ? (int)blockIdx.x / cps : 0;
     const int blk = (int)blockIdx.x - scen * cps;
-    if (A.ctrl && A.ctrl[scen].done) return;
     const double* const l_prev = A.l_prev + (size_t)scen * A.lstride;
 #if defined(DMPC_PROF_SCAN)
     const long long scan_t0 = clock64();
@@ -207,6 +221,12 @@ __global__ void __launch_bounds__(W * S * 32) scan_kernel(const __grid_constant_
     const int n = A.n0 + li_s;
     const bool valid = n < A.n1;
     const int li = scen * nl_s + li_s;              // index into the per-agent scratch (scan records, rows)
+    if (A.ctrl && A.ctrl[scen].done) {
+        // the scenario's loop has ended: its agents only have their state carried over by the QP kernel
+        // (a single swarm whose loop has ended: the QP kernel returns at once and takes nothing from a queue)
+        if (A.rq && A.n_scen > 1 && valid && sub == 0 && lane == 0) A.q_light[atomicAdd(&A.rq->n_light, 1u)] = li;
+        return;
+    }
     double* own = own_all + ag * n3p;
 
     const int ntma = A.tile_padded ? (N + kTile - 1) / kTile : N / kTile;
@@ -318,6 +338,15 @@ __global__ void __launch_bounds__(W * S * 32) scan_kernel(const __grid_constant_
         r.flag = so.flag;
         r.pad = 0;
         A.scan[li] = r;
+        if (A.rq) {
+            // route of the throughput layout: heavy = needs the 64-capacity workspace for sure (solveHardDMPC,
+            // more than 64 rows) or probably (its active set of the previous MPC step was large)
+            const int ng = scen * N + n;
+            const bool heavy = !so.flag && (A.P.variant == VAR_HARD || so.nv > kQW ||
+                                            (A.diag && A.diag[ng].nact >= kRouteNact));
+            if (heavy) A.q_heavy[atomicAdd(&A.rq->n_heavy, 1u)] = li;
+            else A.q_light[atomicAdd(&A.rq->n_light, 1u)] = li;
+        }
     }
     SCAN_PROF(3);
 }
@@ -442,34 +471,21 @@ DMPC_HD size_t qp_smem_bytes(int K, int W, int QMAX, int RCAP) {
     return align_up(qp_table_bytes(K), 16) + (size_t)W * qp_agent_bytes(K, QMAX, RCAP) + 16;
 }
 
-template <int W, int KT>
-__global__ void __launch_bounds__(W * 32, 1) qp_kernel(const __grid_constant__ StepArgs A) {
-    if (A.ctrl && A.n_scen == 1 && A.ctrl->done) return;
-    extern __shared__ __align__(128) unsigned char smem_raw[];
+// One agent of a QP launch: li = index in [0, n_scen * (n1 - n0)).  MODE 0: the full path -- register-resident
+// solver with QC = 64 where its preconditions hold, generic solver (qp_core.cuh) for solveHardDMPC / more than
+// 64 rows, global-memory rescue slot for an active set beyond the on-chip capacity.  MODE 1 (light agents of the
+// throughput layout): register-resident solver with QC = kLightQ only; returns false when the agent needs the
+// full path instead (nothing useful has been written then).
+constexpr int kLightQ = 32;
+// Inlined into its kernel (a call would cost the hot loop a quarter of its speed): every kernel has exactly ONE
+// call site per MODE, so within a kernel an agent's bits do not depend on how it was scheduled.  Two kernels
+// (classic / throughput layout) carry separately optimised copies whose FMA contraction may differ: across
+// layouts results agree to rounding (~1e-14), not bit for bit.
+template <int KT, int MODE>
+DMPC_D bool qp_agent(const StepArgs& A, int li, const double* tab_s, unsigned char* scratch) {
     const int K = KT ? KT : A.P.K, n3 = 3 * K;
-    const size_t tab_bytes = align_up(qp_table_bytes(K), 16);
-    const size_t per_warp = qp_agent_bytes(K, A.QMAX, A.RCAP);
-    double* tab_s = reinterpret_cast<double*>(smem_raw);
-    uint64_t* bar = reinterpret_cast<uint64_t*>(smem_raw + tab_bytes + (size_t)W * per_warp);
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-
-    if (threadIdx.x == 0) {
-        mbar_init(bar, 1);
-        mbar_fence_init();
-        mbar_expect_tx(bar, (uint32_t)qp_table_bytes(K));
-        tma_bulk_g2s(tab_s, A.tab + tab_fast_offset(K), (uint32_t)qp_table_bytes(K), bar);
-    }
-    // everything above touches constants only; the scan kernel's rows are read below
-    asm volatile("griddepcontrol.wait;" ::: "memory");
-    __syncthreads();
-    // one agent per warp while the grid covers the swarm; beyond that the CTAs are persistent (one per SM:
-    // the per-agent workspace fills shared memory) and every warp takes its next agent from a device
-    // counter as soon as it is done -- the solve times differ by 50x, a static assignment would leave
-    // three warps of a CTA idle behind its slowest agent
-    const int nl_s = A.n1 - A.n0, nl = nl_s * A.n_scen;  // agents per scenario / of this launch
-    const bool queued = (int)gridDim.x * W < nl;
-    int li = blockIdx.x * W + warp;
-    while (li < nl) {
+    const int lane = threadIdx.x & 31;
+    const int nl_s = A.n1 - A.n0;
     const int scen = (A.n_scen > 1) ? li / nl_s : 0;
     const int n = A.n0 + (li - scen * nl_s);               // agent index within its scenario
     const int ng = scen * A.P.N + n;                        // index into the per-agent arrays
@@ -483,7 +499,8 @@ __global__ void __launch_bounds__(W * 32, 1) qp_kernel(const __grid_constant__ S
             A.v1[3 * ng + lane] = A.vk[3 * ng + lane];
             A.a1[3 * ng + lane] = A.ak[3 * ng + lane];
         }
-    } else {
+        return true;
+    }
 #if defined(DMPC_PROF_AGENT)
     const long long agent_t0 = clock64();
 #endif
@@ -510,40 +527,57 @@ __global__ void __launch_bounds__(W * 32, 1) qp_kernel(const __grid_constant__ S
     io.a1 = A.a1 + 3 * ng;
     io.l_prev_n = l_prev + (size_t)n * n3;
 
-    mbar_wait(bar, 0);  // tables have landed
     AgentDiag dg;
     int st = 0, it0 = 0;
-    unsigned char* scratch = smem_raw + tab_bytes + (size_t)warp * per_warp;
     // fast path: the register-resident warp solver (qp_warp.cuh) -- every agent of the soft variants whose
     // rows fit.  The generic solver (qp_core.cuh) takes the rest: solveHardDMPC (rows on many horizon
     // steps), more than 64 rows, and -- in a global-memory rescue slot of capacity QBIG -- agents whose
     // active set outgrew the on-chip capacity.  One call site, so the generic solver exists once.
     const bool fast_ok = (n3 <= kQW) && (sr.nv <= kQW) && (A.P.variant != VAR_HARD) && !sr.flag;
-    bool generic = !fast_ok, rescue = false;
-    int cap = A.QMAX;
-    if (fast_ok) {
-        st = agent_solve_fast<KT>(A.P, tab_s, scratch, A.QMAX, io, &dg);
-        if ((st & ST_OVERFLOW) && A.rescue) {
-            generic = true;
+    if (MODE == 1) {
+        if (sr.flag) {
+            // the scan already decided (predicted collision at the next step / row overflow): the reference
+            // returns empty p, v, a -- the agent keeps its horizon and state
+            st = sr.flag;
+            dg.kstar = sr.kstar; dg.nv = sr.nv; dg.iters = 0; dg.nact = 0;
+            for (int i = lane; i < n3; i += 32) io.out_p[i] = io.l_prev_n[i];
+            if (lane < 3) {
+                io.p1[lane] = io.po[lane];
+                io.v1[lane] = io.vo[lane];
+                io.a1[lane] = io.ao[lane];
+            }
+        } else {
+            if (!fast_ok) return false;
+            st = agent_solve_fast<KT, kLightQ>(A.P, tab_s, scratch, A.QMAX, io, &dg);
+            if (st & ST_OVERFLOW) return false;  // the active set outgrew the light capacity: full path
+        }
+    } else {
+        bool generic = !fast_ok, rescue = false;
+        int cap = A.QMAX;
+        if (fast_ok) {
+            st = agent_solve_fast<KT>(A.P, tab_s, scratch, A.QMAX, io, &dg);
+            if ((st & ST_OVERFLOW) && A.rescue) {
+                generic = true;
+                rescue = true;
+                it0 = dg.iters;
+            }
+        }
+        while (generic) {
+            if (rescue) {
+                int slot = 0;
+                if (lane == 0) slot = atomicAdd(A.rescue_next, 1);
+                slot = __shfl_sync(0xffffffffu, slot, 0);
+                if (slot >= A.n_rescue) break;
+                if (lane == 0 && A.ctrl) atomicAdd(&A.ctrl[scen].rescue_used, 1);
+                scratch = A.rescue + (size_t)slot * A.rescue_bytes;
+                cap = A.QBIG;
+            }
+            st = agent_solve<0>(A.P, A.tab, scratch, cap, A.RCAP, io, &dg);  // tables from global memory (L1/L2)
+            dg.iters += it0;
+            if (rescue || !(st & ST_OVERFLOW) || sr.flag || !A.rescue) break;
             rescue = true;
             it0 = dg.iters;
         }
-    }
-    while (generic) {
-        if (rescue) {
-            int slot = 0;
-            if (lane == 0) slot = atomicAdd(A.rescue_next, 1);
-            slot = __shfl_sync(0xffffffffu, slot, 0);
-            if (slot >= A.n_rescue) break;
-            if (lane == 0 && A.ctrl) atomicAdd(&A.ctrl->rescue_used, 1);
-            scratch = A.rescue + (size_t)slot * A.rescue_bytes;
-            cap = A.QBIG;
-        }
-        st = agent_solve<0>(A.P, A.tab, scratch, cap, A.RCAP, io, &dg);  // tables from global memory (L1/L2)
-        dg.iters += it0;
-        if (rescue || !(st & ST_OVERFLOW) || sr.flag || !A.rescue) break;
-        rescue = true;
-        it0 = dg.iters;
     }
 #if defined(DMPC_PROF_AGENT)
     dg.nact = (int)((clock64() - agent_t0) >> 4);  // profiling build: cycles / 16 of this agent's solve
@@ -552,11 +586,44 @@ __global__ void __launch_bounds__(W * 32, 1) qp_kernel(const __grid_constant__ S
         A.status[ng] = st;
         if (A.diag) A.diag[ng] = dg;
     }
+    return true;
+}
+
+template <int W, int KT>
+__global__ void __launch_bounds__(W * 32, 1) qp_kernel(const __grid_constant__ StepArgs A) {
+    if (A.ctrl && A.n_scen == 1 && A.ctrl->done) return;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    const int K = KT ? KT : A.P.K;
+    const size_t tab_bytes = align_up(qp_table_bytes(K), 16);
+    const size_t per_warp = qp_agent_bytes(K, A.QMAX, A.RCAP);
+    double* tab_s = reinterpret_cast<double*>(smem_raw);
+    uint64_t* bar = reinterpret_cast<uint64_t*>(smem_raw + tab_bytes + (size_t)W * per_warp);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+    if (threadIdx.x == 0) {
+        mbar_init(bar, 1);
+        mbar_fence_init();
+        mbar_expect_tx(bar, (uint32_t)qp_table_bytes(K));
+        tma_bulk_g2s(tab_s, A.tab + tab_fast_offset(K), (uint32_t)qp_table_bytes(K), bar);
     }
-    if (!queued) break;
-    if (lane == 0) li = (int)gridDim.x * W + (int)atomicAdd(A.work_cnt, 1u);
-    li = __shfl_sync(0xffffffffu, li, 0);
-    __syncwarp();
+    // everything above touches constants only; the scan kernel's rows are read below
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    __syncthreads();
+    // one agent per warp while the grid covers the swarm; beyond that the CTAs are persistent (one per SM:
+    // the per-agent workspace fills shared memory) and every warp takes its next agent from a device
+    // counter as soon as it is done -- the solve times differ by 50x, a static assignment would leave
+    // three warps of a CTA idle behind its slowest agent
+    const int nl = (A.n1 - A.n0) * A.n_scen;  // agents of this launch
+    const bool queued = (int)gridDim.x * W < nl;
+    int li = blockIdx.x * W + warp;
+    unsigned char* const scratch = smem_raw + tab_bytes + (size_t)warp * per_warp;
+    while (li < nl) {
+        mbar_wait(bar, 0);  // tables have landed
+        qp_agent<KT, 0>(A, li, tab_s, scratch);
+        if (!queued) break;
+        if (lane == 0) li = (int)gridDim.x * W + (int)atomicAdd(A.work_cnt, 1u);
+        li = __shfl_sync(0xffffffffu, li, 0);
+        __syncwarp();
     }  // agents of this warp
     {
         // the last CTA to arrive has every agent's result behind it: it resets the counters and, in the
@@ -572,6 +639,145 @@ __global__ void __launch_bounds__(W * 32, 1) qp_kernel(const __grid_constant__ S
             if (threadIdx.x == 0) {
                 *A.done_cnt = 0;
                 *A.work_cnt = 0;
+            }
+        }
+    }
+}
+
+// ---- K2, throughput layout (more agents than one wave of the layout above) -----------------------------
+// The solve times of a step differ by 50x and most agents end with a small active set.  Light agents run
+// with an active-set capacity of kLightQ = 32: M shrinks from 34 KB to 8.7 KB, the per-agent workspace to
+// 18 KB.  Heavy agents need the 64-capacity workspace (46 KB).  A CTA (one per SM, persistent) has
+// kHeavyW = 2 warps that own a heavy workspace and kLightW - kHeavyW = 6 warps that own a light one: eight
+// agents are resident per SM (two warps per sub-partition: the solver is a chain of dependent fixed-latency
+// instructions, a second warp fills issue slots the first one leaves empty; shared-memory bandwidth -- ~60 KB
+// of traffic per active-set iteration -- is what stops more).  Who is heavy is PREDICTED by the scan kernel from
+// the size of the agent's active set in the previous MPC step (route queues) and corrected on the fly: a
+// light agent that outgrows its capacity is pushed to the heavy queue.  There are no phases: a heavy-capable
+// warp serves the heavy queue whenever it has an entry and light agents otherwise; when the light queue is
+// empty it drains the heavy queue and leaves once its queue index stays empty after EVERY warp of the grid
+// has left the light queue (nothing can be pushed any more).  The result of an agent does not depend on the
+// route it took (same arithmetic in the same order; only the capacity differs).
+DMPC_HD size_t qp2_light_bytes() { return align_up(qw_smem_bytes(kLightQ), 16); }
+DMPC_HD size_t qp2_smem_bytes(int K, int QMAX, int RCAP) {
+    const size_t a = (size_t)kHeavyW * qp_agent_bytes(K, QMAX, RCAP) + (size_t)(kLightW - kHeavyW) * qp2_light_bytes();
+    const size_t b = (size_t)kHeavyMax * qp_agent_bytes(K, QMAX, RCAP);
+    return align_up(qp_table_bytes(K), 16) + (a > b ? a : b) + 16;
+}
+DMPC_D unsigned ld_volatile_u32(const unsigned* p) { return *reinterpret_cast<const volatile unsigned*>(p); }
+DMPC_D int ld_volatile_i32(const int* p) { return *reinterpret_cast<const volatile int*>(p); }
+
+template <int KT>
+__global__ void __launch_bounds__(kLightW * 32, 1) qp2_kernel(const __grid_constant__ StepArgs A) {
+    if (A.ctrl && A.n_scen == 1 && A.ctrl->done) return;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    const int K = KT ? KT : A.P.K;
+    const size_t tab_bytes = align_up(qp_table_bytes(K), 16);
+    const size_t per_heavy = qp_agent_bytes(K, A.QMAX, A.RCAP), per_light = qp2_light_bytes();
+    double* tab_s = reinterpret_cast<double*>(smem_raw);
+    uint64_t* bar = reinterpret_cast<uint64_t*>(smem_raw + qp2_smem_bytes(K, A.QMAX, A.RCAP) - 16);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    RouteQ* const rq = A.rq;
+
+    if (threadIdx.x == 0) {
+        mbar_init(bar, 1);
+        mbar_fence_init();
+        mbar_expect_tx(bar, (uint32_t)qp_table_bytes(K));
+        tma_bulk_g2s(tab_s, A.tab + tab_fast_offset(K), (uint32_t)qp_table_bytes(K), bar);
+    }
+    asm volatile("griddepcontrol.wait;" ::: "memory");  // the scan kernel's rows and route queues are complete
+    __syncthreads();
+    mbar_wait(bar, 0);  // tables have landed
+    const unsigned nlight = ld_volatile_u32(&rq->n_light), nheavy0 = ld_volatile_u32(&rq->n_heavy);
+    // the mix of this step decides how the SM's shared memory is split (uniform over the grid: every CTA reads
+    // the same counters): many heavy agents -> 4 heavy workspaces and no light-only warps (the classic split;
+    // the heavy agents are the critical path then), else 2 heavy + 6 light workspaces
+    const int n_heavy_ws = (10u * nheavy0 > nlight + nheavy0) ? kHeavyMax : kHeavyW;
+    const int n_ws = (n_heavy_ws == kHeavyMax) ? kHeavyMax : kLightW;  // warps that take agents at all
+    const bool heavy_capable = warp < n_heavy_ws;
+    unsigned char* const scratch =
+        heavy_capable ? smem_raw + tab_bytes + (size_t)warp * per_heavy
+                      : smem_raw + tab_bytes + (size_t)n_heavy_ws * per_heavy + (size_t)(warp - n_heavy_ws) * per_light;
+    const unsigned all_warps = gridDim.x * (unsigned)kLightW;
+    int pending = -1;  // heavy-queue index this warp has taken but not yet served
+    bool light_left = warp < n_ws;
+    if (!light_left && lane == 0) atomicAdd(&rq->light_done, 1u);  // a warp without a workspace pushes nothing
+    bool drain = false;
+    while (warp < n_ws) {
+        // ---- which agent next: a heavy one if one is waiting (heavy-capable warps), else a light one; when the
+        //      light queue is empty, wait for heavy entries until none can come any more -----------------------
+        int li = -1, mode = -1;  // mode 0: full path, 1: light path
+        if (heavy_capable) {
+            int fin = 0;
+            if (lane == 0) {
+                if (pending < 0 && (drain || ld_volatile_u32(&rq->n_heavy) > ld_volatile_u32(&rq->head_heavy)))
+                    pending = (int)atomicAdd(&rq->head_heavy, 1u);
+                while (pending >= 0) {
+                    li = ld_volatile_i32(&A.q_heavy[pending]);
+                    if (li >= 0 || !drain) break;
+                    if (ld_volatile_u32(&rq->light_done) == all_warps) {
+                        __threadfence();
+                        li = ld_volatile_i32(&A.q_heavy[pending]);  // nothing can be pushed any more
+                        fin = li < 0;
+                        break;
+                    }
+                    __nanosleep(256);
+                }
+                if (li >= 0) {
+                    A.q_heavy[pending] = -1;  // the queue cleans itself
+                    pending = -1;
+                }
+            }
+            li = __shfl_sync(0xffffffffu, li, 0);
+            if (__shfl_sync(0xffffffffu, fin, 0)) break;
+            if (li >= 0) mode = 0;
+        }
+        if (mode < 0 && light_left) {
+            unsigned idx = 0;
+            if (lane == 0) idx = atomicAdd(&rq->head_light, 1u);
+            idx = __shfl_sync(0xffffffffu, idx, 0);
+            if (idx < nlight) {
+                li = A.q_light[idx];
+                // (classic split: every agent takes the full path at once -- active sets grow from step to step
+                // in the dense phase, a 32-capacity attempt would often be wasted)
+                mode = (n_heavy_ws == kHeavyMax) ? 0 : 1;
+            } else {
+                light_left = false;  // this warp pushes nothing any more
+                if (lane == 0) {
+                    __threadfence();
+                    atomicAdd(&rq->light_done, 1u);
+                }
+            }
+        }
+        if (mode < 0) {
+            if (light_left) continue;      // (a heavy-capable warp whose pending entry is not there yet)
+            if (!heavy_capable) break;
+            drain = true;
+            continue;
+        }
+        if (mode == 0) {
+            qp_agent<KT, 0>(A, li, tab_s, scratch);
+        } else if (!qp_agent<KT, 1>(A, li, tab_s, scratch)) {
+            if (lane == 0) {
+                const unsigned pos = atomicAdd(&rq->n_heavy, 1u);
+                *reinterpret_cast<volatile int*>(&A.q_heavy[pos]) = li;
+                __threadfence();
+            }
+        }
+        __syncwarp();
+    }
+    {
+        __shared__ int s_last;
+        __threadfence();
+        __syncthreads();
+        if (threadIdx.x == 0) s_last = (atomicAdd(&rq->done_ctas, 1u) == gridDim.x - 1) ? 1 : 0;
+        __syncthreads();
+        if (s_last) {
+            __threadfence();
+            if (A.fuse_tail) tail_body<kLightW * 32>(A.T);
+            if (threadIdx.x == 0) {
+                rq->n_light = 0; rq->n_heavy = 0; rq->head_light = 0; rq->head_heavy = 0;
+                rq->light_done = 0; rq->done_ctas = 0;
             }
         }
     }

@@ -29,6 +29,9 @@ cudaError_t launch_qp_4_15(const StepArgs& A, int nl, size_t smem, cudaStream_t 
 cudaError_t launch_qp_4_20(const StepArgs& A, int nl, size_t smem, cudaStream_t s);
 cudaError_t launch_qp_4_0(const StepArgs& A, int nl, size_t smem, cudaStream_t s);
 cudaError_t launch_qp_3_0(const StepArgs& A, int nl, size_t smem, cudaStream_t s);
+// throughput layout (two-role persistent kernel, 8 light / 4 heavy agents per SM), horizons 15 and 20
+cudaError_t launch_qp2_15(const StepArgs& A, int nl, cudaStream_t s);
+cudaError_t launch_qp2_20(const StepArgs& A, int nl, cudaStream_t s);
 // scan layouts: W agents per CTA x S warps per agent, horizon KT (0: run time)
 enum ScanLayout { SCAN_1_2_0, SCAN_4_2_15, SCAN_4_2_20, SCAN_4_4_0, SCAN_8_1_15, SCAN_8_1_20, SCAN_8_2_0 };
 cudaError_t launch_scan_layout(ScanLayout id, const StepArgs& A, int nl, int K, cudaStream_t s);
@@ -78,6 +81,30 @@ cudaError_t launch_qp_w(const StepArgs& A, int nl, size_t smem, cudaStream_t s) 
     cfg.attrs = at;
     cfg.numAttrs = 1;
     return cudaLaunchKernelEx(&cfg, qp_kernel<W, KT>, A);
+}
+template <int KT>
+cudaError_t launch_qp2_w(const StepArgs& A, int nl, cudaStream_t s) {
+    static size_t attr_smem[kMaxDevices] = {0};
+    const int dev = current_device();
+    const size_t smem = qp2_smem_bytes(KT, A.QMAX, A.RCAP);
+    if (attr_smem[dev] < smem) {
+        cudaError_t e = cudaFuncSetAttribute(qp2_kernel<KT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        attr_smem[dev] = smem;
+    }
+    // one persistent CTA per SM (never more: a CTA in its drain phase waits for the light phases of all others)
+    const int ctas = std::min((nl * A.n_scen + kLightW - 1) / kLightW, sm_count(dev));
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)ctas);
+    cfg.blockDim = dim3(kLightW * 32);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = s;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, qp2_kernel<KT>, A);
 }
 #endif
 

@@ -101,12 +101,16 @@ DMPC_HD unsigned qw_getb(unsigned m, int b) { return (m >> (8 * b)) & 0xffu; }
 DMPC_HD unsigned qw_setb(unsigned m, int b, unsigned v) { return (m & ~(0xffu << (8 * b))) | (v << (8 * b)); }
 
 // doubles / ints of shared memory the fast solver needs per agent
-DMPC_HD size_t qw_smem_doubles() { return (size_t)kQW * kMS + 16 * (size_t)kQW; }
+DMPC_HD size_t qw_smem_doubles(int QC = kQW) { return (size_t)QC * (QC + 2) + 16 * (size_t)kQW; }
 DMPC_HD size_t qw_smem_ints() { return 3 * (size_t)kQW; }
-DMPC_HD size_t qw_smem_bytes() { return qw_smem_doubles() * sizeof(double) + qw_smem_ints() * sizeof(int); }
+DMPC_HD size_t qw_smem_bytes(int QC = kQW) { return qw_smem_doubles(QC) * sizeof(double) + qw_smem_ints() * sizeof(int); }
 
-template <int KT>
+// QC: capacity of the active set = rows (and, + 2, the row stride) of M.  64 for the one-agent-per-sub-partition
+// layout; the throughput layout of K2 runs light agents with QC = 32 (a quarter of the shared memory, so that
+// twice as many agents are resident per SM) and sends the ones that outgrow it to a QC = 64 pass.
+template <int KT, int QC = kQW>
 struct QpW {
+    static constexpr int kMSq = QC + 2;  // row stride of M in doubles (conflict-free 128-bit row streaming)
     // ---- uniform problem data ---------------------------------------------------------------------
     int K, n3, nv, soft, kc_all, qcap;
     double alim, term, slb, qw, sw;
@@ -130,7 +134,7 @@ struct QpW {
 
     DMPC_D void carve(unsigned char* smem) {
         double* d = reinterpret_cast<double*>(smem);
-        M = d; d += (size_t)kQW * kMS;
+        M = d; d += (size_t)QC * kMSq;
         gs = d; d += kQW; rs = d; d += kQW; cb = d; cbp = d; d += kQW; cp = d; d += kQW; zs = d; d += kQW; Ls = d; d += kQW;
         rd0 = d; d += kQW; rd1 = d; d += kQW; rd2 = d; d += kQW; rdist = d; d += kQW; rrhs = d; d += kQW;
         rirn = d; d += kQW;
@@ -326,7 +330,7 @@ struct QpW {
             const Dbl2 g01 = ld2(gs + j), g23 = ld2(gs + j + 2);
             QW_FOR(h) {
                 if (h * kLanes < cnt) {  // uniform
-                    const double* Mr = M + (size_t)qw_item(h) * kMS + j;
+                    const double* Mr = M + (size_t)qw_item(h) * kMSq + j;
                     const Dbl2 m01 = ld2(Mr), m23 = ld2(Mr + 2);
                     acc[h][0] = fma(m01.x, g01.x, acc[h][0]);
                     acc[h][1] = fma(m01.y, g01.y, acc[h][1]);
@@ -364,7 +368,7 @@ struct QpW {
             const Dbl2 r01 = ld2(rs + j), r23 = ld2(rs + j + 2);
             QW_FOR(h) {
                 if (h * kLanes < cnt) {  // uniform
-                    double* Mr = M + (size_t)qw_item(h) * kMS + j;
+                    double* Mr = M + (size_t)qw_item(h) * kMSq + j;
                     Dbl2 m01 = ld2(Mr), m23 = ld2(Mr + 2);
                     m01.x = fma(ci[h], r01.x, m01.x);
                     m01.y = fma(ci[h], r01.y, m01.y);
@@ -379,8 +383,8 @@ struct QpW {
             if (h * kLanes <= cnt) {  // uniform: the half of the new slot included
                 const int s = qw_item(h);
                 const double v = (s == cnt) ? id : -ci[h];  // lanes beyond the set write (-)0
-                M[(size_t)s * kMS + cnt] = v;
-                M[(size_t)cnt * kMS + s] = v;
+                M[(size_t)s * kMSq + cnt] = v;
+                M[(size_t)cnt * kMSq + s] = v;
             }
         }
         wsync();
@@ -390,7 +394,7 @@ struct QpW {
     DMPC_D void append_isolated(int code, double uval, double mdiag) {
         const PInfo p = decode(code);
         if (lane_id() == 0) {
-            M[(size_t)q * kMS + q] = mdiag;  // the unused part of M is kept zero
+            M[(size_t)q * kMSq + q] = mdiag;  // the unused part of M is kept zero
             act[q] = code;
             put_record(q, p);
         }
@@ -406,12 +410,12 @@ struct QpW {
     DMPC_D void drop_slot(int l, double* vec, double vl, double* other) {
         const int last = q - 1;
         const int q4 = (q + 3) & ~3;
-        const double inv = qw_rcp(M[(size_t)l * kMS + l]);
+        const double inv = qw_rcp(M[(size_t)l * kMSq + l]);
         // column l (= row l, M is symmetric) as broadcast vector; zero beyond the set (invariant of M)
         QW_FOR(h) {
             if (h * kLanes < q4) {
                 const int s = qw_item(h);
-                gs[s] = M[(size_t)l * kMS + s];
+                gs[s] = M[(size_t)l * kMSq + s];
             }
         }
         wsync();
@@ -426,7 +430,7 @@ struct QpW {
             const Dbl2 g01 = ld2(gs + j), g23 = ld2(gs + j + 2);
             QW_FOR(h) {
                 if (h * kLanes < q) {  // uniform
-                    double* Mr = M + (size_t)qw_item(h) * kMS + j;
+                    double* Mr = M + (size_t)qw_item(h) * kMSq + j;
                     Dbl2 m01 = ld2(Mr), m23 = ld2(Mr + 2);
                     m01.x = fma(-ci[h], g01.x, m01.x);
                     m01.y = fma(-ci[h], g01.y, m01.y);
@@ -449,15 +453,15 @@ struct QpW {
             QW_FOR(h) {
                 const int s = qw_item(h);
                 if (s < last && s != l) {
-                    const double v = M[(size_t)s * kMS + last];
-                    M[(size_t)s * kMS + l] = v;
-                    M[(size_t)l * kMS + s] = v;
+                    const double v = M[(size_t)s * kMSq + last];
+                    M[(size_t)s * kMSq + l] = v;
+                    M[(size_t)l * kMSq + s] = v;
                 }
                 vec[h] = (s == l) ? vec_last : vec[h];
                 if (other) other[h] = (s == l) ? oth_last : other[h];
             }
             if (lane_id() == 0) {
-                M[(size_t)l * kMS + l] = M[(size_t)last * kMS + last];
+                M[(size_t)l * kMSq + l] = M[(size_t)last * kMSq + last];
                 act[l] = clast;
                 sv0[l] = sv0[last];
                 sv1[l] = sv1[last];
@@ -472,8 +476,8 @@ struct QpW {
         QW_FOR(h) {
             const int s = qw_item(h);
             if (s <= last) {
-                M[(size_t)s * kMS + last] = 0.0;
-                M[(size_t)last * kMS + s] = 0.0;
+                M[(size_t)s * kMSq + last] = 0.0;
+                M[(size_t)last * kMSq + s] = 0.0;
             }
             vec[h] = (s == last) ? 0.0 : vec[h];
             if (other) other[h] = (s == last) ? 0.0 : other[h];
@@ -694,8 +698,8 @@ struct QpW {
             QW_FOR(h) {
                 const int i = qw_item(h);
                 if (i <= s) {
-                    M[(size_t)i * kMS + s] = 0.0;
-                    M[(size_t)s * kMS + i] = 0.0;
+                    M[(size_t)i * kMSq + s] = 0.0;
+                    M[(size_t)s * kMSq + i] = 0.0;
                 }
             }
             wsync();
@@ -926,7 +930,7 @@ struct QpW {
             }
         }
         // the unused part of M is zero at all times
-        for (int e = lane_id(); e < kQW * kMS; e += kLanes) M[e] = 0.0;
+        for (int e = lane_id(); e < QC * kMSq; e += kLanes) M[e] = 0.0;
         wsync();
         rows_refresh();
     }
@@ -986,7 +990,7 @@ struct QpW {
         q = m;
         nmat = 0;
         nra = 0;
-        for (int e = lane_id(); e < kQW * kMS; e += kLanes) M[e] = 0.0;
+        for (int e = lane_id(); e < QC * kMSq; e += kLanes) M[e] = 0.0;
         QW_FOR(h) {
             const int i = qw_item(h);
             if (i < n3) {
@@ -1173,7 +1177,7 @@ struct QpW {
                     if (delta < ill_tol * p.nph) { dirty = true; rough = true; }
                     PROF(11);
                 } else {
-                    const double rl = rs[ldrop], mll = M[(size_t)ldrop * kMS + ldrop];
+                    const double rl = rs[ldrop], mll = M[(size_t)ldrop * kMSq + ldrop];
                     wsync();
                     drop_slot(ldrop, r, rl, u);
                     rough = true;
@@ -1226,7 +1230,7 @@ struct QpW {
 // tab: the whole table blob in shared memory; smem: qw_smem_bytes() of per-agent workspace.
 // Same contract as agent_solve() (agent_solve.cuh); returns the status word (ST_OVERFLOW: the active set
 // outgrew qcap -- the caller re-solves with the generic solver).
-template <int KT>
+template <int KT, int QC = kQW>
 DMPC_D int agent_solve_fast(const DevParams& Pm, const double* __restrict__ tab, unsigned char* smem, int qcap,
                             const AgentIO& io, AgentDiag* diag_out) {
     const int K = KT ? KT : Pm.K, n3 = 3 * K;
@@ -1237,7 +1241,7 @@ DMPC_D int agent_solve_fast(const DevParams& Pm, const double* __restrict__ tab,
     dg.nact = 0;
     int status = 0;
 
-    QpW<KT> qp;
+    QpW<KT, QC> qp;
     qp.carve(smem);
     const bool soft = (Pm.variant == VAR_SOFT_BOUND || Pm.variant == VAR_SOFT_BOUND2);
     const bool any_violation = io.kstar > 0;
@@ -1267,7 +1271,7 @@ DMPC_D int agent_solve_fast(const DevParams& Pm, const double* __restrict__ tab,
     qp.K = K; qp.n3 = n3; qp.nv = io.nv; qp.soft = soft ? 1 : 0;
     qp.kc_all = io.kstar > 0 ? io.kstar - 1 - (Pm.variant == VAR_SOFT_BOUND2 ? 1 : 0) : 0;
     qp.alim = Pm.alim; qp.qw = qw; qp.sw = sw;
-    qp.qcap = qcap < kQW ? qcap : kQW;
+    qp.qcap = qcap < QC ? qcap : QC;
     qp.ilnorm = tab + K * K + 2 * K; qp.T4 = t_T4;
 
     // ---- rows: global SoA (scan output) -> shared ---------------------------------------------------

@@ -585,6 +585,62 @@ def test_scenario_batch_equals_single_runs(dmpc):
     assert rb["reached"].sum() >= 3
 
 
+def test_throughput_layout_vs_classic_layout(dmpc, orc, monkeypatch):
+    """More than one wave of agents runs the two-role QP kernel (light agents with a 32-capacity active set,
+    eight agents per SM; heavy agents routed to the 64-capacity workspaces by the scan kernel's prediction or
+    on overflow).  The route an agent takes must not matter: (a) the layout is deterministic (two runs, same
+    bits, although the queues are served in a timing-dependent order), (b) it agrees with the classic layout
+    to rounding (the two kernels carry separately optimised copies of the solver) -- teacher-forced, so that
+    rounding cannot be amplified by the closed loop --, status words equal, and (c) with the oracle.  A large
+    dense swarm (N = 900: many heavy agents) and a batch of scenarios (8 x 100)."""
+    from multiagent_planning_b200 import scenarios
+    monkeypatch.setenv("DMPCB200_LAYOUT", "throughput")      # opt-in layout (the classic kernel is the default)
+    N = 900
+    pmin, pmax = scenarios.density_arena(N, density=1.5)
+    po, pf = scenarios.random_test(N, pmin, pmax, 0.35, 2.0, seed=99)
+    P = dmpc.default_params(0)
+    a, c = scenarios.density_arena(100)
+    scen = [scenarios.random_test(100, a, c, 0.35, 2.0, seed=700 + s) for s in range(8)]
+
+    def batch():
+        with dmpc.Solver(100, P, n_scenarios=8) as b:
+            for i, (o, f) in enumerate(scen):
+                b.set_scenario(i, o, f, a, c)
+            return b.run_batch(40, stop_on_fail=False, record=True)
+
+    with dmpc.Solver(N, P, pmin=pmin, pmax=pmax, pf=pf) as s:
+        s.init_horizons(po)
+        r1 = s.run(15, record=True, status_hist=True)
+        states = []                                  # the inputs of every step of this run
+        l, pk, vk, ak = s.init_horizons(po)
+        for k in range(15):
+            states.append((l, pk, vk, ak))
+            g = s.step(pk, vk, ak, l)
+            l, pk, vk, ak = g["l_new"], g["p1"], g["v1"], g["a1"]
+            states[-1] += (g,)
+        assert np.array_equal(r1["pk"][:, 15, :], pk)                    # (a) resident == host-stepped, odd step count
+        s.init_horizons(po)
+        r1b = s.run(15, record=True, status_hist=True)
+        assert np.array_equal(r1["pk"], r1b["pk"]) and np.array_equal(r1["status_hist"], r1b["status_hist"])
+        heavy = int((s.get_state()["diag"]["nact"] > 32).sum())
+    b1, b1b = batch(), batch()
+    for i in range(8):
+        assert np.array_equal(b1["pk"][i], b1b["pk"][i])
+    assert heavy >= 3                                                    # the 64-capacity route was really taken
+    monkeypatch.setenv("DMPCB200_LAYOUT", "classic")
+    with dmpc.Solver(N, P, pmin=pmin, pmax=pmax, pf=pf) as s:
+        for k in (0, 3, 8, 14):
+            l, pk, vk, ak, g = states[k]
+            gc = s.step(pk, vk, ak, l)
+            assert np.array_equal(gc["status"], g["status"])
+            assert np.abs(gc["l_new"] - g["l_new"]).max() < 1e-9
+        o = orc.step(oracle_params(orc, P), pk, vk, ak, pf, l, pmin, pmax)
+        assert np.array_equal(g["status"] & 0xFFFF, o["status"] & 0xFFFF) and np.abs(g["l_new"] - o["l_new"]).max() < TOL
+    b2 = batch()
+    for i in range(8):
+        assert b1["steps"][i] == b2["steps"][i] and np.abs(b1["pk"][i][:, :20] - b2["pk"][i][:, :20]).max() < 1e-9
+
+
 def _nccl_worker(rank, world, port, q):
     import torch
     import torch.distributed as dist
