@@ -96,6 +96,16 @@ int dmpcb200_device_count(void);
 /* defaults = the reference scripts' values for the given variant */
 void dmpcb200_default_params(dmpcb200_params* p, int variant);
 
+/* The semantics of the C++ port (solveQPv2, dmpc/cpp/dmpc.cpp:803-1287) as a parameter preset: k_ctr = k +
+ * k_factor (0 -> SOFT_BOUND, -1 -> SOFT_BOUND2 incl. the `k == 0` skip, :516,:890), neighbour threshold
+ * rmin (1 + k/k_hor) (:418), slack bound lim = 0.01 doubled together with the penalty for at most 20 retries
+ * (:1077-1109: max_tries = 21 solves), penalty `int term = -1e6` (:846), hard-coded collision weights 1000 /
+ * 100 (:940-945), struct Params defaults (dmpc.h:65-67: h 0.2, k_hor 12, c 1.5, rmin 0.5, alim 2, goal_tol
+ * 0.05).  Acceleration limits as rows instead of bounds (:993-996) describe the same feasible set.  NOT
+ * mirrored: the overflow of the 32-bit `term` after 11 doublings (undefined behaviour in the reference).
+ * Un-commanded agents as static obstacles (:1633-1649): dmpcb200_set_static_obstacles below. */
+void dmpcb200_default_params_cpp(dmpcb200_params* p, int k_factor);
+
 /* getPosMat.m:1-23, getDeltaMat.m:1-9, precompute dmpc_soft_bound.m:81-108
  * (C++: get_lambda_A_v_mat dmpc.cpp:83-108, get_delta_mat :110-134, get_A0_mat :136-155).
  * Host computation (runs once per scenario in the reference too). Any output may be NULL.
@@ -117,6 +127,12 @@ void dmpcb200_destroy(dmpcb200_t* h);
 /* workspace box (set_boundaries dmpc.h:126) and goals (set_final_pts dmpc.h:130); pf is 3 x N */
 int dmpcb200_set_bounds(dmpcb200_t* h, const double* pmin, const double* pmax);
 int dmpcb200_set_goals(dmpcb200_t* h, const double* pf);
+
+/* Agents [n_cmd, N) are STATIC OBSTACLES (the C++ port's N_cmd < N, dmpc.cpp:1633-1649: set_final_pts with fewer
+ * columns than set_initial_pts): they are never solved, their horizon is constant at their start point, the goal
+ * test and the failure scan cover agents [0, n_cmd) only.  Single-scenario handle with n0 = 0, n1 = N; call
+ * before dmpcb200_init_horizons.  set_goals still takes 3 x N (the obstacles' columns are ignored). */
+int dmpcb200_set_static_obstacles(dmpcb200_t* h, int n_cmd);
 
 /* initDMPC.m:1-13 for all N agents on the device: l (3 x K x N), p1,v1,a1 (3 x N) host outputs
  * (any may be NULL); also seeds the device-resident state for dmpcb200_run. po is 3 x N. */
@@ -257,6 +273,23 @@ typedef struct dmpcb200_post {
 int dmpcb200_postprocess(dmpcb200_t* h, int S, double* pk, double* vk, double* ak, double vmax, double amax,
                          double Ts, double goal_radius, double* p, double* v, double* a, int nt_cap,
                          int32_t* time_index, dmpcb200_post* res);
+
+/* ---- the reference's on-disk trajectory format (host code) ------------------------------------------
+ * DMPC::trajectories2file (dmpc/cpp/dmpc.cpp:2088-2126), read back by dmpc/cpp_results/read_result.m:1-42:
+ *   line 1: N N_cmd h_scaled pmin(3) pmax(3); po (3 lines of N); pf (3 lines of N_cmd); then per commanded
+ *   agent 3 lines of T positions, then all velocities, then all accelerations -- every matrix in Eigen's default
+ *   stream format (6 significant digits, columns right-aligned to the widest coefficient of that matrix).
+ * po 3 x N, pf 3 x N_cmd, pos / vel / acc 3 x T x N_cmd, column-major like everything else here.
+ * read: first call with the array pointers NULL returns the sizes (*N, *N_cmd, *T), second call fills them. */
+int dmpcb200_write_trajectories(const char* path, int N, int N_cmd, int T, double h_scaled, const double* pmin,
+                                const double* pmax, const double* po, const double* pf, const double* pos,
+                                const double* vel, const double* acc);
+int dmpcb200_read_trajectories(const char* path, int32_t* N, int32_t* N_cmd, int32_t* T, double* h_scaled,
+                               double* pmin, double* pmax, double* po, double* pf, double* pos, double* vel,
+                               double* acc);
+/* one rows x cols column-major matrix in that stream format into buf (NUL-terminated, truncated to cap);
+ * returns the full length */
+int dmpcb200_format_matrix(int rows, int cols, const double* col_major, char* buf, int cap);
 
 /* timing of the last dmpcb200_step / dmpcb200_run, CUDA events on the launch stream:
  * ms[0] = neighbour-scan kernel, ms[1] = QP kernel, ms[2] = whole step (device), averaged over

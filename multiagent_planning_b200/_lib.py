@@ -16,7 +16,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 _CSRC = os.path.join(_HERE, "csrc")
 LIB_PATH = os.path.join(_HERE, "libdmpc_b200.so")
 SOURCES = ["dmpc_b200.cu", "k_qp15.cu", "k_qp20.cu", "k_qpgen.cu", "k_scan.cu",
-           "model_tables.cpp"]
+           "model_tables.cpp", "traj_io.cpp"]
 HEADERS = ["dmpc_kernels.cuh", "small_kernels.cuh", "launch.cuh", "scan_core.cuh", "agent_solve.cuh", "qp_core.cuh",
            "qp_warp.cuh", "postprocess.cuh", "model_tables.h", os.path.join("..", "..", "include", "dmpc_b200.h")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
@@ -136,6 +136,8 @@ def lib():
         "dmpcb200_last_error": ([], C.c_char_p),
         "dmpcb200_device_count": ([], I),
         "dmpcb200_default_params": ([PP, I], None),
+        "dmpcb200_default_params_cpp": ([PP, I], None),
+        "dmpcb200_set_static_obstacles": ([vp, I], I),
         "dmpcb200_model_mats": ([D, I, dp, dp, dp, dp], I),
         "dmpcb200_create": ([PP, I, I, I, I, I, I, C.POINTER(vp)], I),
         "dmpcb200_set_scenario": ([vp, I, dp, dp, dp, dp], I),
@@ -161,6 +163,9 @@ def lib():
         "dmpcb200_prop_state": ([vp, I, dp, dp, dp, dp, dp], I),
         "dmpcb200_postprocess": ([vp, I, dp, dp, dp, D, D, D, D, dp, dp, dp, I, ip, C.POINTER(Post)], I),
         "dmpcb200_last_timing": ([vp, dp, C.POINTER(C.c_int64)], I),
+        "dmpcb200_write_trajectories": ([C.c_char_p, I, I, I, D, dp, dp, dp, dp, dp, dp, dp], I),
+        "dmpcb200_read_trajectories": ([C.c_char_p, ip, ip, ip, dp, dp, dp, dp, dp, dp, dp, dp], I),
+        "dmpcb200_format_matrix": ([I, I, dp, C.c_char_p, I], I),
         "dmpcb200_last_host_timing": ([vp, dp], I),
         "dmpcb200_device_ptr": ([vp, I], vp),
         "dmpcb200_swap_horizons": ([vp], I),
@@ -177,6 +182,7 @@ def lib():
 
 EXPORTS = [
     "dmpcb200_abi_version", "dmpcb200_last_error", "dmpcb200_device_count", "dmpcb200_default_params",
+    "dmpcb200_default_params_cpp", "dmpcb200_set_static_obstacles",
     "dmpcb200_model_mats", "dmpcb200_create", "dmpcb200_set_scenario", "dmpcb200_run_batch", "dmpcb200_get_scenario",
     "dmpcb200_last_batch_timing", "dmpcb200_destroy", "dmpcb200_set_bounds", "dmpcb200_set_goals",
     "dmpcb200_init_horizons", "dmpcb200_step", "dmpcb200_bind_step", "dmpcb200_step_bound", "dmpcb200_step_dev", "dmpcb200_goal_dev", "dmpcb200_reached_goal", "dmpcb200_run",
@@ -184,6 +190,7 @@ EXPORTS = [
     "dmpcb200_coll_constr", "dmpcb200_prop_state", "dmpcb200_postprocess", "dmpcb200_last_timing", "dmpcb200_last_host_timing",
     "dmpcb200_device_ptr",
     "dmpcb200_swap_horizons", "dmpcb200_config",
+    "dmpcb200_write_trajectories", "dmpcb200_read_trajectories", "dmpcb200_format_matrix",
 ]
 
 

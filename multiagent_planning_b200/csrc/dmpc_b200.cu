@@ -58,6 +58,7 @@ struct dmpcb200_handle {
     dmpcb200_params prm;
     DevParams dp;
     int N = 0, n0 = 0, n1 = 0, NL = 0, Npad = 0, K = 0, device = 0;
+    int n_static = 0;            // agents [N - n_static, N) are static obstacles (dmpcb200_set_static_obstacles)
     int S = 1;                   // scenarios batched in this handle (independent swarms of N agents)
     double* d_bounds = nullptr;  // S x 6: pmin, pmax of every scenario (dmpcb200_set_scenario)
     bool per_scen_bounds = false;
@@ -242,7 +243,7 @@ cudaError_t launch_qp(dmpcb200_t* h, const StepArgs& A, cudaStream_t s) {
 TailArgs make_tail(dmpcb200_t* h, const double* p, int ld, const int* status, const double* p1, const double* v1,
                    const double* a1, bool record, Ctrl* ctrl) {
     TailArgs T;
-    T.N = h->N;
+    T.N = h->N - h->n_static;  // goal test, failure scan and records cover the commanded agents
     T.n0 = h->n0;
     T.n1 = h->n1;
     T.ld = ld;
@@ -400,6 +401,19 @@ void dmpcb200_default_params(dmpcb200_params* p, int variant) {
     p->hard_radius = 1.0;
     p->init_div = 10.0;
     p->goal_tol = 0.01;
+}
+
+void dmpcb200_default_params_cpp(dmpcb200_params* p, int k_factor) {
+    // the semantics of the C++ port, solveQPv2 (dmpc/cpp/dmpc.cpp:803-1287), on top of the MATLAB defaults:
+    dmpcb200_default_params(p, k_factor == -1 ? DMPCB200_SOFT_BOUND2 : DMPCB200_SOFT_BOUND);  // k_ctr = k + k_factor (:516,:890)
+    p->neigh_mode = 1;    // neighbour threshold rmin (1 + k / k_hor) (:418)
+    p->slack_lb = -0.01;  // slack as rows  eps <= 0, -eps <= lim  with lim = 0.01 (:907-914, :1077)
+    p->max_tries = 21;    // one solve + `while (status && tries < 20)` with lim and term doubled (:1079-1109)
+    p->term = -1e6;       // `int term = -1000000` (:846)
+    p->Q1 = 1000.0;       // collision weights are hard-coded (:940-945)
+    p->S1 = 100.0;
+    // struct Params defaults (dmpc.h:65-67)
+    p->h = 0.2; p->K = 12; p->c = 1.5; p->rmin = 0.5; p->alim = 2.0; p->goal_tol = 0.05; p->coll_tol = 0.05;
 }
 
 int dmpcb200_model_mats(double h, int K, double* A_p, double* A_v, double* A_initp, double* Delta) {
@@ -609,6 +623,19 @@ int dmpcb200_set_goals(dmpcb200_t* h, const double* pf) {
     return 0;
 }
 
+int dmpcb200_set_static_obstacles(dmpcb200_t* h, int n_cmd) {
+    if (!h) return fail(DMPCB200_ERR_ARG, "set_static_obstacles: null handle");
+    if (h->S != 1 || h->n0 != 0 || h->n1 + h->n_static != h->N)
+        return fail(DMPCB200_ERR_STATE, "set_static_obstacles: needs a single-scenario handle that owns all agents");
+    if (n_cmd < 1 || n_cmd > h->N) return fail(DMPCB200_ERR_ARG, "set_static_obstacles: need 1 <= n_cmd <= N");
+    h->n_static = h->N - n_cmd;
+    h->n1 = n_cmd;
+    h->NL = n_cmd;
+    h->have_init = false;
+    drop_graph(h);
+    return 0;
+}
+
 int dmpcb200_init_horizons(dmpcb200_t* h, const double* po, double* l, double* p1, double* v1, double* a1) {
     if (!h || !po) return fail(DMPCB200_ERR_ARG, "init_horizons: null argument");
     if (h->S != 1) return fail(DMPCB200_ERR_STATE, "init_horizons: single-scenario entry point on a batched handle (use set_scenario / run_batch / get_scenario)");
@@ -619,9 +646,23 @@ int dmpcb200_init_horizons(dmpcb200_t* h, const double* po, double* l, double* p
     h->cur = 0;
     double* d_po = h->d_st[1][0];  // staging: the other state buffer
     CK(cudaMemcpyAsync(d_po, po, 3 * (size_t)N * sizeof(double), cudaMemcpyHostToDevice, s));
+    if (h->n_static) {
+        // un-commanded agents (dmpc.cpp:1633-1649) stay where they are: their goal is their start point, so
+        // initDMPC.m gives them a constant horizon
+        const size_t o = 3 * (size_t)h->n1;
+        CK(cudaMemcpyAsync(h->d_pf + o, po + o, 3 * (size_t)h->n_static * sizeof(double), cudaMemcpyHostToDevice, s));
+    }
     init_kernel<<<(N + 127) / 128, 128, 0, s>>>(N, K, h->prm.h, h->prm.init_div, d_po, h->d_pf, h->d_l[0],
                                                 h->d_st[0][0], h->d_st[0][1], h->d_st[0][2]);
     CK(cudaGetLastError());
+    if (h->n_static) {
+        // ... in BOTH buffers of the ping-pong (no kernel ever writes their rows)
+        const size_t oL = (size_t)h->n1 * 3 * K, bL = (size_t)h->n_static * 3 * K * sizeof(double);
+        const size_t o3 = 3 * (size_t)h->n1, b3 = 3 * (size_t)h->n_static * sizeof(double);
+        CK(cudaMemcpyAsync(h->d_l[1] + oL, h->d_l[0] + oL, bL, cudaMemcpyDeviceToDevice, s));
+        for (int q = 1; q < 3; ++q) CK(cudaMemsetAsync(h->d_st[1][q] + o3, 0, b3, s));
+        // (d_st[1][0] is the staging copy of po: already the obstacles' positions)
+    }
     if (l) CK(cudaMemcpyAsync(l, h->d_l[0], (size_t)N * 3 * K * sizeof(double), cudaMemcpyDeviceToHost, s));
     if (p1) CK(cudaMemcpyAsync(p1, h->d_st[0][0], 3 * (size_t)N * sizeof(double), cudaMemcpyDeviceToHost, s));
     if (v1) CK(cudaMemcpyAsync(v1, h->d_st[0][1], 3 * (size_t)N * sizeof(double), cudaMemcpyDeviceToHost, s));
@@ -856,7 +897,8 @@ int dmpcb200_run(dmpcb200_t* h, int max_steps, int stop_on_fail, int mode, doubl
                  int32_t* first_fail_step, int32_t* first_fail_agent) {
     if (!h || max_steps < 1) return fail(DMPCB200_ERR_ARG, "run: bad argument");
     if (h->S != 1) return fail(DMPCB200_ERR_STATE, "run: single-scenario entry point on a batched handle (use set_scenario / run_batch / get_scenario)");
-    if (h->n0 != 0 || h->n1 != h->N) return fail(DMPCB200_ERR_STATE, "run: needs a handle that owns all agents");
+    if (h->n0 != 0 || h->n1 + h->n_static != h->N)
+        return fail(DMPCB200_ERR_STATE, "run: needs a handle that owns all agents");
     if (!h->have_init || !h->have_bounds) return fail(DMPCB200_ERR_STATE, "run: set_bounds and init_horizons first");
     if (int rc = ensure_device(h)) return rc;
     const int N = h->N;

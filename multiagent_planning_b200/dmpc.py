@@ -109,6 +109,11 @@ class Solver:
         pf = _f(pf, (3, self.N))
         _lib.check(self.L.dmpcb200_set_goals(self.h, _p(pf)), "set_goals")
 
+    def set_static_obstacles(self, n_cmd):
+        """agents [n_cmd, N) are static obstacles (the C++ port's N_cmd < N, dmpc.cpp:1633-1649)"""
+        _lib.check(self.L.dmpcb200_set_static_obstacles(self.h, int(n_cmd)), "set_static_obstacles")
+        self.n1 = int(n_cmd)
+
     def init_horizons(self, po):
         """initDMPC.m for all agents.  Returns l (3,K,N), p1, v1, a1 (3,N)."""
         po = _f(po, (3, self.N))

@@ -203,6 +203,45 @@ def test_drop_ins_do_not_touch_the_resident_state(dmpc, golden):
         assert np.array_equal(s.get_state()["pk"], ref["pk"][:, 12, :])
 
 
+def test_cpp_semantics_preset_and_static_obstacles_vs_oracle(dmpc, orc):
+    """The C++ port's semantics as flags (dmpcb200_default_params_cpp: neighbour threshold rmin (1 + k/K),
+    slack bound 0.01 doubled for <= 20 retries, term -1e6, k_ctr = k + k_factor) and its un-commanded agents
+    (N_cmd < N: static obstacles, dmpc.cpp:1633-1649), teacher-forced against the oracle run with the same
+    parameters on agents [0, N_cmd)."""
+    import ctypes as C
+    from multiagent_planning_b200 import _lib, scenarios
+    N, n_cmd = 60, 45
+    pmin, pmax = scenarios.density_arena(N, density=2.5)
+    po, pf = scenarios.random_test(N, pmin, pmax, 0.5, 1.5, seed=31)
+    pf[:, n_cmd:] = po[:, n_cmd:]
+    for k_factor in (0, -1):
+        P = _lib.Params()
+        _lib.lib().dmpcb200_default_params_cpp(C.byref(P), k_factor)
+        P.K = 15
+        assert P.variant == (1 if k_factor else 0) and P.neigh_mode == 1 and P.max_tries == 21
+        O = oracle_params(orc, P)
+        with dmpc.Solver(N, P, pmin=pmin, pmax=pmax, pf=pf) as s:
+            s.set_static_obstacles(n_cmd)
+            l, pk, vk, ak = s.init_horizons(po)
+            assert np.array_equal(l[:, :, n_cmd:], np.repeat(po[:, None, n_cmd:], 15, axis=1))   # constant horizons
+            retried = 0
+            for _ in range(14):
+                g = s.step(pk, vk, ak, l)
+                o = orc.step(O, pk, vk, ak, pf, l, pmin, pmax, n1=n_cmd)
+                assert np.array_equal(g["status"][:n_cmd] & 0xFFFF, o["status"][:n_cmd] & 0xFFFF)
+                assert np.abs(g["l_new"] - o["l_new"]).max() <= TOL and np.abs(g["a1"] - o["a1"]).max() <= TOL
+                assert np.array_equal(g["l_new"][:, :, n_cmd:], l[:, :, n_cmd:])                   # obstacles untouched
+                retried += int((((o["status"][:n_cmd] >> 8) & 0xFF) > 0).sum())
+                l, pk, vk, ak = g["l_new"], g["p1"], g["v1"], g["a1"]
+            # the resident loop: obstacles stay, the goal test covers the commanded agents only
+            s.init_horizons(po)
+            r = s.run(120, record=True)
+            st = s.get_state()
+            assert np.array_equal(st["pk"][:, n_cmd:], po[:, n_cmd:]) and np.array_equal(st["l"][:, 0, n_cmd:], po[:, n_cmd:])
+            if r["reached"]:
+                assert np.sqrt(((st["pk"][:, :n_cmd] - pf[:, :n_cmd]) ** 2).sum(0)).max() < P.goal_tol
+
+
 def test_cpp_facade_solve_parallel(dmpc):
     """the Python mirror of class DMPC (dmpc/cpp/dmpc.h:70-182): solveParallelDMPCv2 == Solver.run"""
     from multiagent_planning_b200 import scenarios
