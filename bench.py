@@ -594,6 +594,29 @@ def run_batch(args):
             "outcomes": batch_outcomes(cfg, allr, S_all),
         }
         if not multi:
+            # the reference's whole experiment (test/failure_rate.m: N = 20:20:200, 50 trials each) through the
+            # Monte-Carlo harness: scenarios generated on the device, batched loops, post-processing per trial
+            try:
+                from multiagent_planning_b200 import montecarlo
+                montecarlo.failure_rate(N_vector=(20, 40), trials=10, seed=1)          # warm-up
+                t0 = time.perf_counter()
+                mc = montecarlo.failure_rate(seed=1)
+                t_mc = time.perf_counter() - t0
+                pub = montecarlo.published()
+                line["failure_rate_sweep"] = {
+                    "what": "test/failure_rate.m end to end: N = 20:20:200, 50 random trials each (10 batched handles), "
+                            "device scenario generation + MPC loops + 100 Hz post-check of every finished trial",
+                    "wall_s": t_mc, "N_vector": [int(x) for x in mc["N_vector"]],
+                    "prob_dmpc": [float(x) for x in mc["prob_dmpc"]],
+                    "failures": {k: [int(x) for x in v] for k, v in mc["taxonomy"].items()},
+                    "steps_to_goal_mean": [float(np.nanmean(np.where(mc["success_dmpc"][q] > 0, mc["steps"][q], np.nan)))
+                                           if (mc["success_dmpc"][q] > 0).any() else None for q in range(len(mc["N_vector"]))],
+                    "reference_published": {"prob_dmpc": [float(x) for x in pub["prob_dmpc"]],
+                                            "t_dmpc_mean_s_per_trial": [float(x) for x in pub["t_dmpc_mean_s"]],
+                                            "source": "data/failure_rate/failure_rate3.mat (MATLAB quadprog, unknown CPU)"}}
+            except Exception as ex:
+                line["failure_rate_sweep"] = {"error": repr(ex)[:300]}
+        if not multi:
             threads = os.cpu_count() or 1
             v, done, secs = cpu_port_run(cfg, 4, 20, threads, budget_s=12.0)
             line["cpu_baseline"] = {"value": v, "unit": "agent-steps/s", "cores": threads, "kind": "port",

@@ -183,8 +183,10 @@ int dmpcb200_reached_goal(dmpcb200_t* h, const double* p, const double* pf, doub
  * `while ~reached_goal && k < max_K` loop of test/failure_rate.m:99-127 after
  * dmpcb200_init_horizons (or dmpcb200_set_state).  Runs at most max_steps further MPC steps with
  * no host synchronisation inside the loop (CUDA graph + device control word); stops at the goal
- * (ReachedGoal.m) and, if stop_on_fail, at the first step in which an agent fails; otherwise
- * agents that fail keep their state.
+ * (ReachedGoal.m) and, if stop_on_fail = 1, at the first step in which an agent fails (any failure status);
+ * stop_on_fail = 2 stops only when an agent's QP is infeasible -- the reference's driver (test/failure_rate.m:
+ * 112-124 breaks the trial on ~feasible; `coll` / `outbound` leave feasible = 1 in solveSoftDMPCbound.m:29-30,
+ * 125-128 and the trial goes on); otherwise agents that fail keep their state.
  * mode: 0 = CUDA graph; bit 0 = per-kernel CUDA-event timing (plain launches);
  *       bit 1 = plain launches without per-kernel events.
  * traj_p/v/a: optional host outputs 3 x (max_steps+1) x N (column 0 = initial state).
@@ -199,6 +201,19 @@ int dmpcb200_run(dmpcb200_t* h, int max_steps, int stop_on_fail, int mode, doubl
  * set_bounds + set_goals + init_horizons in one call. */
 int dmpcb200_set_scenario(dmpcb200_t* h, int s, const double* po, const double* pf, const double* pmin,
                           const double* pmax);
+/* Scenario generation ON THE DEVICE for all n_scenarios of the handle at once (one CTA per scenario):
+ * mode 0 = randomTest.m:1-57 (start and goal sets drawn independently, pairwise ellipsoidal distance
+ * ||E1 (p - q)|| > rmin_init, a point that cannot be placed in 200000 tries restarts its set, :9-27; C++:
+ * gen_rand_pts dmpc.cpp:188-227), mode 1 = randomExchange.m:1-56 (Euclidean distance, goals = a random
+ * permutation of the starts in which every agent moves; C++: gen_rand_perm :229-265).  All scenarios share the
+ * arena pmin / pmax (test/failure_rate.m:63-64).  The random stream is counter based (splitmix64 of seed,
+ * scenario, set, draw index): reproducible, and restated bit for bit by the CPU oracle -- MATLAB's own stream is
+ * never seeded by the reference and cannot be.  Also sets the bounds and goals and runs initDMPC.m: the handle
+ * is ready for dmpcb200_run_batch (or dmpcb200_run when n_scenarios = 1).
+ * po_out, pf_out: optional host copies, 3 x N x n_scenarios.  At most 4096 agents per scenario. */
+int dmpcb200_gen_scenarios(dmpcb200_t* h, uint64_t seed, int mode, double rmin_init, const double* pmin,
+                           const double* pmax, double* po_out, double* pf_out);
+
 /* The closed loop of EVERY scenario, test/failure_rate.m:99-133 per trial: at most max_steps MPC steps; a
  * scenario stops at its goal (ReachedGoal.m) and, if stop_on_fail, at its first failing agent (the reference
  * `break`s the trial, failure_rate.m:112-123); the others go on.  Three launches per step for the whole batch
@@ -290,6 +305,11 @@ int dmpcb200_read_trajectories(const char* path, int32_t* N, int32_t* N_cmd, int
 /* one rows x cols column-major matrix in that stream format into buf (NUL-terminated, truncated to cap);
  * returns the full length */
 int dmpcb200_format_matrix(int rows, int cols, const double* col_major, char* buf, int cap);
+
+/* the same for scenario `scen` of a batched handle (goals of that scenario) */
+int dmpcb200_postprocess_scenario(dmpcb200_t* h, int scen, int S, double* pk, double* vk, double* ak, double vmax,
+                                  double amax, double Ts, double goal_radius, double* p, double* v, double* a,
+                                  int nt_cap, int32_t* time_index, dmpcb200_post* res);
 
 /* timing of the last dmpcb200_step / dmpcb200_run, CUDA events on the launch stream:
  * ms[0] = neighbour-scan kernel, ms[1] = QP kernel, ms[2] = whole step (device), averaged over

@@ -141,6 +141,7 @@ def lib():
         "dmpcb200_model_mats": ([D, I, dp, dp, dp, dp], I),
         "dmpcb200_create": ([PP, I, I, I, I, I, I, C.POINTER(vp)], I),
         "dmpcb200_set_scenario": ([vp, I, dp, dp, dp, dp], I),
+        "dmpcb200_gen_scenarios": ([vp, C.c_uint64, I, D, dp, dp, dp, dp], I),
         "dmpcb200_run_batch": ([vp, I, I, I, dp, dp, dp, ip, ip, ip, ip, dp], I),
         "dmpcb200_get_scenario": ([vp, I, dp, dp, dp, dp, ip, DP], I),
         "dmpcb200_last_batch_timing": ([vp, dp, C.POINTER(C.c_int64)], I),
@@ -162,6 +163,7 @@ def lib():
         "dmpcb200_coll_constr": ([vp, dp, dp, dp, I, I, dp, u8p, I, dp, dp, dp, ip], I),
         "dmpcb200_prop_state": ([vp, I, dp, dp, dp, dp, dp], I),
         "dmpcb200_postprocess": ([vp, I, dp, dp, dp, D, D, D, D, dp, dp, dp, I, ip, C.POINTER(Post)], I),
+        "dmpcb200_postprocess_scenario": ([vp, I, I, dp, dp, dp, D, D, D, D, dp, dp, dp, I, ip, C.POINTER(Post)], I),
         "dmpcb200_last_timing": ([vp, dp, C.POINTER(C.c_int64)], I),
         "dmpcb200_write_trajectories": ([C.c_char_p, I, I, I, D, dp, dp, dp, dp, dp, dp, dp], I),
         "dmpcb200_read_trajectories": ([C.c_char_p, ip, ip, ip, dp, dp, dp, dp, dp, dp, dp, dp], I),
@@ -183,11 +185,11 @@ def lib():
 EXPORTS = [
     "dmpcb200_abi_version", "dmpcb200_last_error", "dmpcb200_device_count", "dmpcb200_default_params",
     "dmpcb200_default_params_cpp", "dmpcb200_set_static_obstacles",
-    "dmpcb200_model_mats", "dmpcb200_create", "dmpcb200_set_scenario", "dmpcb200_run_batch", "dmpcb200_get_scenario",
+    "dmpcb200_model_mats", "dmpcb200_create", "dmpcb200_set_scenario", "dmpcb200_gen_scenarios", "dmpcb200_run_batch", "dmpcb200_get_scenario",
     "dmpcb200_last_batch_timing", "dmpcb200_destroy", "dmpcb200_set_bounds", "dmpcb200_set_goals",
     "dmpcb200_init_horizons", "dmpcb200_step", "dmpcb200_bind_step", "dmpcb200_step_bound", "dmpcb200_step_dev", "dmpcb200_goal_dev", "dmpcb200_reached_goal", "dmpcb200_run",
     "dmpcb200_get_state", "dmpcb200_set_state", "dmpcb200_solve_agent", "dmpcb200_check_coll",
-    "dmpcb200_coll_constr", "dmpcb200_prop_state", "dmpcb200_postprocess", "dmpcb200_last_timing", "dmpcb200_last_host_timing",
+    "dmpcb200_coll_constr", "dmpcb200_prop_state", "dmpcb200_postprocess", "dmpcb200_postprocess_scenario", "dmpcb200_last_timing", "dmpcb200_last_host_timing",
     "dmpcb200_device_ptr",
     "dmpcb200_swap_horizons", "dmpcb200_config",
     "dmpcb200_write_trajectories", "dmpcb200_read_trajectories", "dmpcb200_format_matrix",

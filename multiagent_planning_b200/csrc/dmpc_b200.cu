@@ -1062,6 +1062,53 @@ int dmpcb200_set_scenario(dmpcb200_t* h, int s, const double* po, const double* 
     return 0;
 }
 
+int dmpcb200_gen_scenarios(dmpcb200_t* h, uint64_t seed, int mode, double rmin_init, const double* pmin,
+                           const double* pmax, double* po_out, double* pf_out) {
+    if (!h || !pmin || !pmax) return fail(DMPCB200_ERR_ARG, "gen_scenarios: null argument");
+    if (mode != 0 && mode != 1) return fail(DMPCB200_ERR_ARG, "gen_scenarios: mode 0 (randomTest) or 1 (randomExchange)");
+    if (!(rmin_init > 0)) return fail(DMPCB200_ERR_ARG, "gen_scenarios: rmin_init must be positive");
+    if (h->n0 != 0 || h->n1 + h->n_static != h->N || h->n_static)
+        return fail(DMPCB200_ERR_STATE, "gen_scenarios: needs a handle that owns all agents");
+    for (int x = 0; x < 3; ++x)
+        if (!(pmin[x] < pmax[x])) return fail(DMPCB200_ERR_ARG, "gen_scenarios: need pmin < pmax");
+    const int N = h->N, K = h->K, S = h->S;
+    if (N > kGenMaxN) return fail(DMPCB200_ERR_ARG, "gen_scenarios: at most 4096 agents per scenario");
+    if (int rc = ensure_device(h)) return rc;
+    cudaStream_t st = h->stream;
+    double* d_po = h->d_st[1][0];  // staging: the other side's position block
+    const size_t smem = 3 * (size_t)N * sizeof(double);
+    static bool attr_set[64] = {false};
+    const int dev = current_device();
+    if (smem > 48 * 1024 && !attr_set[dev]) {
+        CK(cudaFuncSetAttribute(gen_scenarios_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 3 * kGenMaxN * (int)sizeof(double)));
+        attr_set[dev] = true;
+    }
+    gen_scenarios_kernel<<<S, 256, smem, st>>>(N, mode, (unsigned long long)seed, rmin_init, 1.0 / h->prm.c, pmin[0], pmin[1],
+                                              pmin[2], pmax[0], pmax[1], pmax[2], 200000, d_po, h->d_pf);
+    CK(cudaGetLastError());
+    std::vector<double> bb(6 * (size_t)S);
+    for (int s = 0; s < S; ++s)
+        for (int x = 0; x < 3; ++x) { bb[6 * s + x] = pmin[x]; bb[6 * s + 3 + x] = pmax[x]; }
+    CK(cudaMemcpyAsync(h->d_bounds, bb.data(), bb.size() * sizeof(double), cudaMemcpyHostToDevice, st));
+    for (int s = 0; s < S; ++s) {
+        const size_t o3 = 3 * (size_t)s * N;
+        init_kernel<<<(N + 127) / 128, 128, 0, st>>>(N, K, h->prm.h, h->prm.init_div, d_po + o3, h->d_pf + o3,
+                                                     h->d_l[0] + (size_t)s * h->Npad * 3 * K, h->d_st[0][0] + o3,
+                                                     h->d_st[0][1] + o3, h->d_st[0][2] + o3);
+    }
+    CK(cudaGetLastError());
+    if (po_out) CK(cudaMemcpyAsync(po_out, d_po, 3 * (size_t)N * S * sizeof(double), cudaMemcpyDeviceToHost, st));
+    if (pf_out) CK(cudaMemcpyAsync(pf_out, h->d_pf, 3 * (size_t)N * S * sizeof(double), cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    for (int x = 0; x < 3; ++x) { h->dp.pmin[x] = pmin[x]; h->dp.pmax[x] = pmax[x]; }
+    h->have_bounds = h->have_goals = h->have_init = true;
+    h->per_scen_bounds = true;
+    std::fill(h->scen_set.begin(), h->scen_set.end(), 1);
+    h->cur = 0;
+    drop_graph(h);
+    return 0;
+}
+
 int dmpcb200_run_batch(dmpcb200_t* h, int max_steps, int stop_on_fail, int mode, double* traj_p, double* traj_v,
                        double* traj_a, int32_t* steps_done, int32_t* reached, int32_t* first_fail_step,
                        int32_t* first_fail_agent, double* goal_dist) {
@@ -1403,13 +1450,16 @@ int dmpcb200_prop_state(dmpcb200_t* h, int B, const double* po, const double* vo
     return 0;
 }
 
-int dmpcb200_postprocess(dmpcb200_t* h, int S, double* pk, double* vk, double* ak, double vmax, double amax,
-                         double Ts, double goal_radius, double* p, double* v, double* a, int nt_cap,
-                         int32_t* time_index, dmpcb200_post* res) {
+}  // extern "C"
+
+namespace {
+int postprocess_impl(dmpcb200_t* h, const double* d_goals, int S, double* pk, double* vk, double* ak, double vmax,
+                     double amax, double Ts, double goal_radius, double* p, double* v, double* a, int nt_cap,
+                     int32_t* time_index, dmpcb200_post* res) {
     if (!h || !pk || !vk || !ak || !res) return fail(DMPCB200_ERR_ARG, "postprocess: null argument");
     if (S < 4) return fail(DMPCB200_ERR_ARG, "postprocess: needs at least 4 trajectory columns (not-a-knot spline)");
     if (!(vmax > 0) || !(amax > 0) || !(Ts > 0)) return fail(DMPCB200_ERR_ARG, "postprocess: vmax, amax, Ts must be positive");
-    if (!h->have_goals) return fail(DMPCB200_ERR_STATE, "postprocess: set_goals first");
+    if (!h->have_goals && !h->per_scen_bounds) return fail(DMPCB200_ERR_STATE, "postprocess: set_goals first");
     if (int rc = ensure_device(h)) return rc;
     const int N = h->N;
     cudaStream_t s = h->stream;
@@ -1479,7 +1529,7 @@ int dmpcb200_postprocess(dmpcb200_t* h, int S, double* pk, double* vk, double* a
         else
             pp_pairs_kernel<false><<<dim3(tiles, tiles), dim3(kPairTile, kPairTile), 0, s>>>(N, nt, h->prm.c, 1.0 / h->prm.c,
                                                                                              d_p, d_bits + 1);
-        pp_stats_kernel<<<(N + 3) / 4, 128, 0, s>>>(N, nt, goal_radius, d_p, h->d_pf, d_dist, d_tidx);
+        pp_stats_kernel<<<(N + 3) / 4, 128, 0, s>>>(N, nt, goal_radius, d_p, d_goals, d_dist, d_tidx);
     }
     cudaEventRecord(h->ev[1], s);
     if ((e = cudaGetLastError()) != cudaSuccess) return bail(e, "launch");
@@ -1521,6 +1571,25 @@ int dmpcb200_postprocess(dmpcb200_t* h, int S, double* pk, double* vk, double* a
     h->launches = 6;
     cleanup();
     return 0;
+}
+}  // namespace
+
+extern "C" {
+
+int dmpcb200_postprocess(dmpcb200_t* h, int S, double* pk, double* vk, double* ak, double vmax, double amax,
+                         double Ts, double goal_radius, double* p, double* v, double* a, int nt_cap,
+                         int32_t* time_index, dmpcb200_post* res) {
+    if (!h) return fail(DMPCB200_ERR_ARG, "postprocess: null handle");
+    return postprocess_impl(h, h->d_pf, S, pk, vk, ak, vmax, amax, Ts, goal_radius, p, v, a, nt_cap, time_index, res);
+}
+
+int dmpcb200_postprocess_scenario(dmpcb200_t* h, int scen, int S, double* pk, double* vk, double* ak, double vmax,
+                                  double amax, double Ts, double goal_radius, double* p, double* v, double* a,
+                                  int nt_cap, int32_t* time_index, dmpcb200_post* res) {
+    if (!h) return fail(DMPCB200_ERR_ARG, "postprocess_scenario: null handle");
+    if (scen < 0 || scen >= h->S) return fail(DMPCB200_ERR_ARG, "postprocess_scenario: scenario index out of range");
+    return postprocess_impl(h, h->d_pf + 3 * (size_t)scen * h->N, S, pk, vk, ak, vmax, amax, Ts, goal_radius, p, v, a,
+                            nt_cap, time_index, res);
 }
 
 /* host-side phases of the last dmpcb200_step in microseconds: pack, submit, wait, unpack */

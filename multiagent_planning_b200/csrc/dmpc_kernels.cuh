@@ -45,6 +45,8 @@ struct Ctrl {
     int max_steps;
     int rescue_used;  // global rescue slots handed out (monotone, diagnostics)
     double goal_dist;
+    int infeasible;   // stop_on_fail = 2: the loop ended on an infeasible QP
+    int pad;
 };
 
 struct TailArgs {
@@ -357,11 +359,11 @@ __global__ void __launch_bounds__(W * S * 32) scan_kernel(const __grid_constant_
 template <int NT>
 __device__ __forceinline__ void tail_body(const TailArgs& T) {
     __shared__ double s_md[16];
-    __shared__ int s_ff[16];
+    __shared__ int s_ff[16], s_fi[16];
     const int tid = threadIdx.x;
     const int step = T.ctrl ? T.ctrl->step : 0;
     double md = 0.0;
-    int ff = 0x7fffffff;
+    int ff = 0x7fffffff, fi = 0x7fffffff;  // lowest failing agent / lowest agent whose QP was infeasible
     // four agents per thread and pass: all loads of a pass are issued before anything is stored, so their
     // L2 round trips overlap (the last CTA is alone on the chip here: this is pure latency)
     constexpr int U = 4;
@@ -401,6 +403,7 @@ __device__ __forceinline__ void tail_body(const TailArgs& T) {
             if (T.status && n >= T.n0 && n < T.n1) {
                 const int st = stv[u];
                 if ((!(st & ST_SOLVED) || (st & ST_OUTBOUND)) && n < ff) ff = n;
+                if ((st & (ST_INFEASIBLE | ST_QPFAIL)) && n < fi) fi = n;
                 if (T.status_hist && step < T.S) T.status_hist[(size_t)step * T.N + n] = st;
             }
             if (rec) {
@@ -417,16 +420,19 @@ __device__ __forceinline__ void tail_body(const TailArgs& T) {
     for (int o = 16; o; o >>= 1) {
         md = fmax(md, __shfl_xor_sync(0xffffffffu, md, o));
         ff = min(ff, __shfl_xor_sync(0xffffffffu, ff, o));
+        fi = min(fi, __shfl_xor_sync(0xffffffffu, fi, o));
     }
     if ((tid & 31) == 0) {
         s_md[tid >> 5] = md;
         s_ff[tid >> 5] = ff;
+        s_fi[tid >> 5] = fi;
     }
     __syncthreads();
     if (tid == 0) {
         for (int w = 1; w < NT / 32; ++w) {
             md = fmax(md, s_md[w]);
             ff = min(ff, s_ff[w]);
+            fi = min(fi, s_fi[w]);
         }
         const int reached = (T.p && md < T.goal_tol) ? 1 : 0;
         if (T.goal_out) {
@@ -447,7 +453,14 @@ __device__ __forceinline__ void tail_body(const TailArgs& T) {
                 c->reached = 1;
                 c->done = 1;
             }
-            if (ff != 0x7fffffff && c->stop_on_fail) c->done = 1;
+            // stop_on_fail 1: any failing agent ends the loop; 2: only an infeasible QP does -- what the reference's
+            // driver does (test/failure_rate.m:112-124 breaks the trial on ~feasible; `coll` and `outbound` leave
+            // feasible = 1 in solveSoftDMPCbound.m and the trial goes on)
+            if (c->stop_on_fail == 1 && ff != 0x7fffffff) c->done = 1;
+            if (c->stop_on_fail == 2 && fi != 0x7fffffff) {
+                c->done = 1;
+                c->infeasible = 1;
+            }
             if (step + 1 >= c->max_steps) c->done = 1;
         }
     }

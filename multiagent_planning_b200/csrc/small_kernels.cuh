@@ -58,6 +58,121 @@ __global__ void init_kernel(int N, int K, double h, double init_div, const doubl
     }
 }
 
+// ---- randomTest.m:1-57 / randomExchange.m:1-56 on the device: one CTA per scenario ---------------------------
+// Rejection sampling of N start points (and N goals) with pairwise distance > rmin inside the arena; a point
+// that cannot be placed in max_iter tries restarts its whole set like the reference does (:9-27).  The random
+// stream is counter based (splitmix64 of (seed, scenario, set, draw index)), so the CPU oracle generates the
+// same scenarios bit for bit; MATLAB's own stream cannot be reproduced (the scripts never seed it).
+//   mode 0 (randomTest): start and goal sets independent, ellipsoidal distance ||E1 (p - q)||, E1 = diag(1,1,1/c)
+//   mode 1 (randomExchange): Euclidean distance; goals = a random permutation of the starts in which every
+//                            agent moves (:32-49)
+DMPC_HD unsigned long long splitmix64(unsigned long long x) {
+    x += 0x9E3779B97F4A7C15ull;
+    x = (x ^ (x >> 30)) * 0xBF58476D1CE4E5B9ull;
+    x = (x ^ (x >> 27)) * 0x94D049BB133111EBull;
+    return x ^ (x >> 31);
+}
+DMPC_HD unsigned long long gen_key(unsigned long long seed, int scen, int set) {
+    return splitmix64(seed + 0x632BE59BD9B4E019ull * (unsigned long long)(2 * scen + set + 1));
+}
+DMPC_HD double gen_u01(unsigned long long key, unsigned long long idx) {
+    return (double)(splitmix64(key + idx) >> 11) * (1.0 / 9007199254740992.0);  // [0, 1), 53 bits
+}
+
+constexpr int kGenMaxN = 4096;  // points of a scenario held in shared memory (3 x 8 B each)
+__global__ void __launch_bounds__(256) gen_scenarios_kernel(int N, int mode, unsigned long long seed, double rmin,
+                                                            double inv_c, double pmin0, double pmin1, double pmin2,
+                                                            double pmax0, double pmax1, double pmax2, int max_iter,
+                                                            double* po, double* pf) {
+    extern __shared__ double g_pts[];  // x[N], y[N], z[N]
+    const int scen = blockIdx.x, tid = threadIdx.x;
+    double* px = g_pts;
+    double* py = g_pts + N;
+    double* pz = g_pts + 2 * N;
+    const double lo[3] = {pmin0, pmin1, pmin2};
+    const double rg[3] = {__dsub_rn(pmax0, pmin0), __dsub_rn(pmax1, pmin1), __dsub_rn(pmax2, pmin2)};
+    const double ic = (mode == 0) ? inv_c : 1.0;
+    const int nsets = (mode == 0) ? 2 : 1;
+    for (int set = 0; set < nsets; ++set) {
+        const unsigned long long key = gen_key(seed, scen, set);
+        unsigned long long t = 0;  // candidates drawn so far (every thread keeps the same count)
+        int n = 0, tries = 0;
+        while (n < N) {
+            const double cx = __dadd_rn(lo[0], __dmul_rn(rg[0], gen_u01(key, 3 * t)));
+            const double cy = __dadd_rn(lo[1], __dmul_rn(rg[1], gen_u01(key, 3 * t + 1)));
+            const double cz = __dadd_rn(lo[2], __dmul_rn(rg[2], gen_u01(key, 3 * t + 2)));
+            ++t;
+            int ok = 1;
+            for (int j = tid; j < n; j += 256) {
+                const double dx = __dsub_rn(px[j], cx), dy = __dsub_rn(py[j], cy), ez = __dmul_rn(ic, __dsub_rn(pz[j], cz));
+                const double dist = __dsqrt_rn(__dadd_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)), __dmul_rn(ez, ez)));
+                ok &= dist > rmin;
+            }
+            ok = __syncthreads_and(ok);  // (also orders the reads above before the store below)
+            if (ok) {
+                if (tid == 0) { px[n] = cx; py[n] = cy; pz[n] = cz; }
+                ++n;
+                tries = 0;
+            } else if (++tries > max_iter) {  // randomTest.m:23-25: give up on this set and start it again
+                n = 0;
+                tries = 0;
+            }
+            __syncthreads();
+        }
+        double* out = (set == 0 ? po : pf) + 3 * (size_t)N * scen;
+        for (int j = tid; j < N; j += 256) {
+            out[3 * j] = px[j];
+            out[3 * j + 1] = py[j];
+            out[3 * j + 2] = pz[j];
+        }
+        __syncthreads();
+    }
+    if (mode == 1) {
+        // randomExchange.m:32-49: perm(i) drawn from what is left without i; the last two steps make sure that the
+        // last agent does not keep its own place.  Sequential (N steps of O(N)), one thread; `array` lives in the
+        // x coordinates' shared memory after they have been written out.
+        if (tid == 0) {
+            int* array = reinterpret_cast<int*>(g_pts);          // remaining indices, ascending
+            int* perm = array + N;
+            const unsigned long long key = gen_key(seed, scen, 1);
+            int left = N;
+            for (int i = 0; i < N; ++i) array[i] = i;
+            for (int i = 0; i < N; ++i) {
+                // array_aux = array without i
+                int pick;
+                if (i == N - 1) {
+                    pick = array[0];
+                } else {
+                    int last_aux = array[left - 1];
+                    if (last_aux == i) last_aux = array[left - 2];
+                    if (i == N - 2 && last_aux == N - 1) {
+                        pick = N - 1;
+                    } else {
+                        int j = (int)(gen_u01(key, (unsigned long long)i) * (double)(N - i - 1));  // randi([1 N-i]) - 1
+                        // j-th element of array_aux
+                        int cnt = -1, e = 0;
+                        for (; e < left; ++e) {
+                            if (array[e] == i) continue;
+                            if (++cnt == j) break;
+                        }
+                        pick = array[e];
+                    }
+                }
+                perm[i] = pick;
+                int w = 0;
+                for (int e = 0; e < left; ++e)
+                    if (array[e] != pick) array[w++] = array[e];
+                left = w;
+            }
+            const double* src = po + 3 * (size_t)N * scen;
+            double* dst = pf + 3 * (size_t)N * scen;
+            for (int i = 0; i < N; ++i)
+                for (int x = 0; x < 3; ++x) dst[3 * i + x] = src[3 * perm[i] + x];
+        }
+        __syncthreads();
+    }
+}
+
 // ---- CheckCollSoftDMPC.m:1-17 for one agent and one horizon step (helper drop-in) ---------------
 // out_d[0] = min distance, out_i[0] = any(violation)
 __global__ void __launch_bounds__(256) check_coll_kernel(DevParams P, double px, double py, double pz, const double* l,

@@ -129,6 +129,21 @@ class Solver:
         pmin, pmax = _f(pmin).ravel(), _f(pmax).ravel()
         _lib.check(self.L.dmpcb200_set_scenario(self.h, int(s), _p(po), _p(pf), _p(pmin), _p(pmax)), "set_scenario")
 
+    def gen_scenarios(self, seed, pmin, pmax, rmin_init=None, mode=0, want_points=True):
+        """randomTest.m (mode 0) / randomExchange.m (mode 1) for every scenario of the handle, on the device;
+        sets bounds and goals and runs initDMPC.m.  Returns po, pf of shape (S, 3, N) when want_points."""
+        pmin, pmax = _f(pmin).ravel(), _f(pmax).ravel()
+        po = pf = None
+        if want_points:
+            po, pf = np.zeros(3 * self.N * self.S), np.zeros(3 * self.N * self.S)
+        _lib.check(self.L.dmpcb200_gen_scenarios(self.h, int(seed), int(mode),
+                                                 float(self.P.rmin if rmin_init is None else rmin_init), _p(pmin),
+                                                 _p(pmax), _p(po), _p(pf)), "gen_scenarios")
+        if want_points:
+            shp = lambda a: np.stack([np.asfortranarray(a[3 * self.N * s:3 * self.N * (s + 1)].reshape((3, self.N), order="F"))
+                                      for s in range(self.S)])
+            return shp(po), shp(pf)
+
     def run_batch(self, max_steps, stop_on_fail=True, mode=0, record=False):
         """the closed loop of every scenario (failure_rate.m:99-133 per trial).  Returns per-scenario arrays
         steps, reached, first_fail_step, first_fail_agent, goal_dist (+ pk, vk, ak of shape (S, 3, T, N) in
@@ -139,7 +154,7 @@ class Solver:
         tp = tv = ta = None
         if record:
             tp, tv, ta = (np.zeros(3 * (max_steps + 1) * N * S) for _ in range(3))
-        _lib.check(self.L.dmpcb200_run_batch(self.h, int(max_steps), int(bool(stop_on_fail)), int(mode), _p(tp), _p(tv),
+        _lib.check(self.L.dmpcb200_run_batch(self.h, int(max_steps), int(stop_on_fail), int(mode), _p(tp), _p(tv),
                                              _p(ta), steps.ctypes.data_as(_ip), reached.ctypes.data_as(_ip),
                                              fs.ctypes.data_as(_ip), fa.ctypes.data_as(_ip), _p(gd)), "run_batch")
         ms, ast = C.c_double(0), C.c_int64(0)
@@ -242,7 +257,7 @@ class Solver:
             if not record:
                 tp, tv, ta = (np.zeros((3, max_steps + 1, N), order="F") for _ in range(3))
         steps, reached, fs, fa = (C.c_int32(0) for _ in range(4))
-        _lib.check(self.L.dmpcb200_run(self.h, int(max_steps), int(bool(stop_on_fail)), int(mode), _p(tp), _p(tv),
+        _lib.check(self.L.dmpcb200_run(self.h, int(max_steps), int(stop_on_fail), int(mode), _p(tp), _p(tv),
                                        _p(ta), None if hist is None else hist.ctypes.data_as(_ip),
                                        C.byref(steps), C.byref(reached), C.byref(fs), C.byref(fa)), "run")
         s = int(steps.value)
@@ -260,7 +275,7 @@ class Solver:
         _lib.check(self.L.dmpcb200_last_host_timing(self.h, us), "last_host_timing")
         return dict(pack_us=us[0], submit_us=us[1], wait_us=us[2], unpack_us=us[3])
 
-    def postprocess(self, pk, vk, ak, vmax=2.0, amax=1.0, Ts=0.01, goal_radius=0.05, want_interp=True):
+    def postprocess(self, pk, vk, ak, vmax=2.0, amax=1.0, Ts=0.01, goal_radius=0.05, want_interp=True, scenario=None):
         """The rest of the reference's t_dmpc (test/failure_rate.m:134-195) for a finished transition: time
         scaling to the limits, 100 Hz spline interpolation, pairwise collision check, distance and trajectory
         time.  pk, vk, ak: (3, S, N) as `run(record=True)` returns them.  Returns a dict with the scaled
@@ -279,9 +294,15 @@ class Solver:
                          (vmax / np.sqrt((vk[0] ** 2 + vk[1] ** 2) + vk[2] ** 2)).min())
             cap = int(np.floor((S - 1) * self.P.h / np.sqrt(rf) / Ts + 1e-9)) + 2
             p, v, a = (np.zeros((3, cap, N), order="F") for _ in range(3))
-        _lib.check(self.L.dmpcb200_postprocess(self.h, S, _p(pk), _p(vk), _p(ak), float(vmax), float(amax), float(Ts),
-                                               float(goal_radius), _p(p), _p(v), _p(a), cap,
-                                               tidx.ctypes.data_as(_ip), C.byref(res)), "postprocess")
+        if scenario is None:
+            _lib.check(self.L.dmpcb200_postprocess(self.h, S, _p(pk), _p(vk), _p(ak), float(vmax), float(amax), float(Ts),
+                                                   float(goal_radius), _p(p), _p(v), _p(a), cap,
+                                                   tidx.ctypes.data_as(_ip), C.byref(res)), "postprocess")
+        else:  # goals of one scenario of a batched handle
+            _lib.check(self.L.dmpcb200_postprocess_scenario(self.h, int(scenario), S, _p(pk), _p(vk), _p(ak), float(vmax),
+                                                            float(amax), float(Ts), float(goal_radius), _p(p), _p(v),
+                                                            _p(a), cap, tidx.ctypes.data_as(_ip), C.byref(res)),
+                       "postprocess_scenario")
         out = dict(pk=pk, vk=vk, ak=ak, time_index=tidx, **{k: getattr(res, k) for k, _ in Post._fields_})
         if want_interp:
             nt = res.nt

@@ -886,3 +886,85 @@ int orc_step(const orc_params* P, int N, int n0, int n1, const double* pk, const
     model_free(&X.M);
     return first_fail;
 }
+
+/* ------------------------------------------------------------------------- */
+/* scenario generation: randomTest.m:1-57 / randomExchange.m:1-56             */
+/* (C++: gen_rand_pts dmpc.cpp:188-227, gen_rand_perm :229-265)               */
+/* ------------------------------------------------------------------------- */
+/* The reference draws from MATLAB's unseeded `rand`; its streams cannot be reproduced.  The random stream here
+ * is the counter-based one the library documents (include/dmpc_b200.h, dmpcb200_gen_scenarios): splitmix64 of
+ * (seed, scenario, set, draw index).  Everything else follows the reference line by line. */
+static uint64_t splitmix64(uint64_t x) {
+    x += 0x9E3779B97F4A7C15ull;
+    x = (x ^ (x >> 30)) * 0xBF58476D1CE4E5B9ull;
+    x = (x ^ (x >> 27)) * 0x94D049BB133111EBull;
+    return x ^ (x >> 31);
+}
+static uint64_t gen_key(uint64_t seed, int scen, int set) {
+    return splitmix64(seed + 0x632BE59BD9B4E019ull * (uint64_t)(2 * scen + set + 1));
+}
+static double gen_u01(uint64_t key, uint64_t idx) {
+    return (double)(splitmix64(key + idx) >> 11) * (1.0 / 9007199254740992.0);
+}
+
+/* one set of N points: randomTest.m:7-29 (mode 0: ellipsoidal distance) / randomExchange.m:7-29 (mode 1) */
+static void gen_set(uint64_t key, int N, const double* pmin, const double* pmax, double rmin, double inv_c,
+                    int max_iter, double* pts /*3 x N*/) {
+    uint64_t t = 0;
+    int n = 0, tries = 0;
+    while (n < N) {
+        double c[3];
+        for (int x = 0; x < 3; ++x) c[x] = pmin[x] + (pmax[x] - pmin[x]) * gen_u01(key, 3 * t + (uint64_t)x);
+        ++t;
+        int ok = 1;
+        for (int j = 0; j < n && ok; ++j) {
+            double dx = pts[3 * j] - c[0], dy = pts[3 * j + 1] - c[1], ez = inv_c * (pts[3 * j + 2] - c[2]);
+            double dist = sqrt(dx * dx + dy * dy + ez * ez);
+            ok = dist > rmin;
+        }
+        if (ok) {
+            pts[3 * n] = c[0]; pts[3 * n + 1] = c[1]; pts[3 * n + 2] = c[2];
+            ++n;
+            tries = 0;
+        } else if (++tries > max_iter) { /* :23-25: start the set again */
+            n = 0;
+            tries = 0;
+        }
+    }
+}
+
+void orc_gen_scenario(uint64_t seed, int scen, int mode, int N, const double* pmin, const double* pmax,
+                      double rmin, double c, double* po, double* pf) {
+    const int max_iter = 200000;
+    gen_set(gen_key(seed, scen, 0), N, pmin, pmax, rmin, mode == 0 ? 1.0 / c : 1.0, max_iter, po);
+    if (mode == 0) {
+        gen_set(gen_key(seed, scen, 1), N, pmin, pmax, rmin, 1.0 / c, max_iter, pf);
+        return;
+    }
+    /* randomExchange.m:32-49 */
+    int* array = (int*)malloc(sizeof(int) * (size_t)N);
+    int* aux = (int*)malloc(sizeof(int) * (size_t)N);
+    int* perm = (int*)malloc(sizeof(int) * (size_t)N);
+    int left = N;
+    uint64_t key = gen_key(seed, scen, 1);
+    for (int i = 0; i < N; ++i) array[i] = i;
+    for (int i = 0; i < N; ++i) {
+        int na = 0;
+        for (int e = 0; e < left; ++e)
+            if (array[e] != i) aux[na++] = array[e]; /* array_aux(array_aux == i) = [] */
+        int pick;
+        if (i == N - 1) pick = array[0];
+        else if (i == N - 2 && aux[na - 1] == N - 1) pick = N - 1;
+        else pick = aux[(int)(gen_u01(key, (uint64_t)i) * (double)(N - i - 1))]; /* randi([1 N-i]) */
+        perm[i] = pick;
+        int w = 0;
+        for (int e = 0; e < left; ++e)
+            if (array[e] != pick) array[w++] = array[e];
+        left = w;
+    }
+    for (int i = 0; i < N; ++i)
+        for (int x = 0; x < 3; ++x) pf[3 * i + x] = po[3 * perm[i] + x];
+    free(array);
+    free(aux);
+    free(perm);
+}

@@ -140,6 +140,11 @@ int orc_qp_gi(int n, const double* H, const double* f, int m, const double* A, i
               const double* b, const double* lb, const double* ub, double* x, double* lam,
               int32_t* iters, orc_diag* kkt);
 
+/* randomTest.m:1-57 (mode 0) / randomExchange.m:1-56 (mode 1) for scenario `scen` of a batch: po, pf 3 x N.
+ * Counter-based random stream (splitmix64 of seed, scenario, set, draw index) -- see dmpc_oracle.c. */
+void orc_gen_scenario(uint64_t seed, int scen, int mode, int N, const double* pmin, const double* pmax,
+                      double rmin, double c, double* po, double* pf);
+
 #ifdef __cplusplus
 }
 #endif

@@ -448,6 +448,18 @@ def spline_not_a_knot(x, y, xq):
     return y0 + t * (s0 + t * (c2 + t * c3))
 
 
+def gen_scenario(seed, scen, mode, N, pmin, pmax, rmin, c):
+    """randomTest.m (mode 0) / randomExchange.m (mode 1), scenario `scen` of a batch -> po, pf (3, N)"""
+    po, pf = np.zeros((3, N), order="F"), np.zeros((3, N), order="F")
+    f = lib().orc_gen_scenario
+    f.argtypes = [C.c_uint64, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_double), C.c_double,
+                  C.c_double, C.POINTER(C.c_double), C.POINTER(C.c_double)]
+    f.restype = None
+    f(int(seed), int(scen), int(mode), int(N), _dp(_f(pmin).ravel()), _dp(_f(pmax).ravel()), float(rmin), float(c),
+      _dp(po), _dp(pf))
+    return po, pf
+
+
 def postprocess(pk, vk, ak, pf, h, c=2.0, rmin=0.35, vmax=2.0, amax=1.0, Ts=0.01, coll_tol=0.05,
                 goal_radius=0.05, want_interp=True):
     """failure_rate.m:134-195 for one finished transition.  pk, vk, ak: (3, S, N) as the loop left them

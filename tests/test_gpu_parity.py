@@ -680,6 +680,43 @@ def test_throughput_layout_vs_classic_layout(dmpc, orc, monkeypatch):
         assert b1["steps"][i] == b2["steps"][i] and np.abs(b1["pk"][i][:, :20] - b2["pk"][i][:, :20]).max() < 1e-9
 
 
+def test_device_scenario_generation_and_monte_carlo_harness(dmpc, orc):
+    """randomTest.m / randomExchange.m on the device (one CTA per scenario) == the oracle's restatement bit for
+    bit; the failure_rate.m-shaped harness classifies a small batch consistently with single-scenario runs."""
+    from multiagent_planning_b200 import montecarlo, scenarios
+    N, S = 60, 7
+    pmin, pmax = scenarios.density_arena(N)
+    P = dmpc.default_params(0)
+    for mode in (0, 1):
+        with dmpc.Solver(N, P, n_scenarios=S) as b:
+            po, pf = b.gen_scenarios(123, pmin, pmax, rmin_init=0.35, mode=mode)
+            for s in range(S):
+                opo, opf = orc.gen_scenario(123, s, mode, N, pmin, pmax, 0.35, P.c)
+                assert np.array_equal(po[s], opo) and np.array_equal(pf[s], opf), (mode, s)
+            st = b.get_scenario(2)
+            assert np.array_equal(st["pk"], po[2]) and np.array_equal(st["l"][:, 0, :], po[2])    # initDMPC ran
+        E = np.array([1.0, 1.0, 1.0 / P.c if mode == 0 else 1.0])[:, None, None]
+        d = np.sqrt((((po[0][:, :, None] - po[0][:, None, :]) * E) ** 2).sum(0)) + 9 * np.eye(N)
+        assert d.min() > 0.35 and (po[0] >= pmin[:, None]).all() and (po[0] <= pmax[:, None]).all()
+        if mode == 1:
+            assert sorted(map(tuple, po[1].T)) == sorted(map(tuple, pf[1].T)) and not (po[1] == pf[1]).all(0).any()
+    r = montecarlo.failure_rate(N_vector=(12, 24), trials=6, seed=5)
+    assert r["prob_dmpc"].shape == (2,) and ((r["success_dmpc"] <= r["feasible"]).all())
+    assert (r["success_dmpc"] + r["failed_goal"] <= 1).all()
+    ok = r["success_dmpc"][0] > 0
+    assert ok.any() and np.isfinite(r["traj_time"][0][ok]).all() and (r["min_dist"][0][ok] >= 0.35 - 0.05).all()
+    # trial 1 of the first size on its own: same steps, same post-processing figures
+    pmin, pmax = scenarios.density_arena(12)
+    po, pf = orc.gen_scenario(5, 1, 0, 12, pmin, pmax, 0.35, P.c)
+    with dmpc.Solver(12, P, pmin=pmin, pmax=pmax, pf=pf) as s:
+        s.init_horizons(po)
+        one = s.run(149, stop_on_fail=2, record=True)
+        assert one["steps"] == int(r["steps"][0, 1]) and bool(one["reached"]) == bool(r["feasible"][0, 1] and not r["failed_goal"][0, 1])
+        if one["reached"]:
+            pp = s.postprocess(one["pk"], one["vk"], one["ak"], want_interp=False)
+            assert pp["traj_time"] == r["traj_time"][0, 1] and pp["violation"] == r["violation"][0, 1]
+
+
 def _nccl_worker(rank, world, port, q):
     import torch
     import torch.distributed as dist
