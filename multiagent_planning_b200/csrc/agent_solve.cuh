@@ -60,7 +60,11 @@ struct AgentIO {
     double *p1, *v1, *a1;  // 3 each
     const double* l_prev_n;  // previous horizon of this agent (copied to out_p when unsolved)
     const double* bounds = nullptr;  // workspace box of the agent's scenario: pmin[3], pmax[3]; null = P.pmin / P.pmax
+    // cross-step warm start of the fast path (qp_warp.cuh warm_start / warm_store); both optional
+    const int* gidx = nullptr;  // global rows: neighbour's agent index of each row [RMAX]
+    int* warm = nullptr;        // per agent kWarmStride ints: [0] = count, [1..] = the stored active set
 };
+constexpr int kWarmStride = 68;
 
 // All lanes of the warp call this with identical arguments.  Returns the status word.
 // tab: the whole table blob (model_tables.h layout), normally resident in shared memory.

@@ -50,6 +50,12 @@
 #endif
 #endif
 
+#if defined(DMPC_WARM_STATS)
+#define DMPC_WARM_STAT(x) x
+#else
+#define DMPC_WARM_STAT(x)
+#endif
+
 namespace dmpc {
 
 constexpr int kQW = 64;             // capacity: entries, rows, slots
@@ -94,6 +100,12 @@ struct Dbl2 { double x, y; };
 inline Dbl2 ld2(const double* p) { Dbl2 v; v.x = p[0]; v.y = p[1]; return v; }
 inline void st2(double* p, Dbl2 v) { p[0] = v.x; p[1] = v.y; }
 inline double qw_rcp(double x) { return 1.0 / x; }
+#endif
+
+#if defined(__CUDA_ARCH__)
+DMPC_D int wmaxi(int v) { return __reduce_max_sync(0xffffffffu, v); }
+#else
+inline int wmaxi(int v) { return v; }
 #endif
 
 DMPC_HD int qw_item(int h) { return lane_id() + h * kLanes; }
@@ -1025,10 +1037,212 @@ struct QpW {
         return true;
     }
 
+#if defined(DMPC_WARM_START)
+    // ---- cross-step warm start (EXPERIMENT, not compiled into the product: measured NOT to pay) -----------
+    // Result of the experiment (scripts/warm_probe.py, profiles/r2c_warm_start_probe.txt): the final sets of
+    // consecutive steps overlap by 85-95 %, but the part that differs is the collision rows (the first
+    // violating step moves, its rows belong to other neighbours), and the saturated acceleration bounds are
+    // active BECAUSE of those rows: with stale or missing rows the equality-constrained multipliers of the
+    // guessed bounds are negative and the dual method has to drop most of the guess again (C3: 22 of 35), so the
+    // slowest agent of a step needs as many iterations as from the cold start plus the assembly.
+    // The heavy agents of a dense step end with almost the same active set as one MPC step earlier (shifted
+    // by one horizon index); a cold start re-discovers it one constraint per iteration.  The final set of a
+    // solved step is therefore kept per agent (warm_store: bounds shifted by one index, rows keyed by the
+    // NEIGHBOUR's agent index) and the next step starts from it (warm_start): M is assembled for the guessed
+    // set by bordering (no primal step, no ratio test: ~0.4 of an iteration per constraint; constraints that are
+    // (nearly) dependent on the set so far are left out), the multipliers of the equality-constrained problem
+    // on the set are u = -M (N'x_unc - b), constraints with a negative multiplier are dropped until u >= 0 and
+    // x is synthesised from u: a valid Goldfarb-Idnani starting pair for solve(), which ends at the same
+    // unique optimum as from the cold start.
+    // List entry: type << 16 | index (T_BOX*/T_WS*: entry index of the NEW horizon; T_ROW: neighbour's agent
+    // index, bit 24: slack upper bound active, bit 25: slack lower bound active).
+    static constexpr int kWarmSub = 1 << 24, kWarmSlb = 1 << 25;
+    static constexpr double kWarmDepTol = 1e-5;  // = ill_tol of solve(): no ill-conditioned bordering step
+
+    // add `code` to the set being assembled; false (nothing changed) when it is dependent on the set so far
+    DMPC_COLD bool warm_add(int code) {
+        if (q + 1 > qcap) return false;
+        const PInfo p = decode(code);
+        gvec(p, q);
+        const double gr = mat_vec<true>(q, nullptr);
+        const double delta = p.nph - gr;
+        if (!(delta > kWarmDepTol * p.nph)) return false;
+        border(q, delta);
+        if (lane_id() == 0) {
+            act[q] = code;
+            put_record(q, p);
+        }
+        set_active(code, (unsigned)q);
+        count_active(code, +1);
+        wsync();
+        ++q;
+        return true;
+    }
+
+    // rid: per-lane neighbour index of the lane's rows (-1 beyond nv).  list: nw entries (any memory).
+    // Expects the state of cold_start().  Returns false when the list gave nothing usable (state = cold start).
+    DMPC_COLD bool warm_start(const int* list, int nw, const int* rid) {
+        int* wl = reinterpret_cast<int*>(cp);  // (the coefficient / direction vectors are not in use yet)
+        int* seq = reinterpret_cast<int*>(zs);  // the constraints to assemble, in order (<= 2 kQW ints)
+        nw = nw < kQW ? nw : kQW;
+        for (int e = lane_id(); e < nw; e += kLanes) wl[e] = list[e];
+        wsync();
+        // bounds first (their S entries are pure table lookups), then the rows, each followed by its slack
+        // lower bound; the neighbour of a stored row is looked up among this step's rows
+        int n2 = 0;
+        for (int e = 0; e < nw; ++e) {
+            const int c = wl[e];
+            if (c < 0 || code_type(c & 0xffffff) > T_WSU || code_idx(c) >= n3) continue;
+            if (lane_id() == 0) seq[n2] = c & 0xffffff;
+            ++n2;
+        }
+        for (int e = 0; e < nw; ++e) {
+            const int c = wl[e];
+            if (c < 0 || code_type(c & 0xffffff) != T_ROW) continue;
+#ifdef DMPC_WARM_NOROWS
+            continue;
+#endif
+            const int nid = code_idx(c);
+            int j = -1;
+            QW_FOR(h) j = (rid[h] == nid) ? qw_item(h) : j;
+            j = wmaxi(j);
+            if (j < 0 || j >= nv) continue;  // that neighbour has no row in this step
+            if (lane_id() == 0) {
+                seq[n2] = mk_code(T_ROW, j) | (c & (kWarmSub | kWarmSlb));
+                if (soft && (c & kWarmSlb) && !(c & kWarmSub)) seq[n2 + 1] = mk_code(T_SLB, j);
+            }
+            n2 += (soft && (c & kWarmSlb) && !(c & kWarmSub)) ? 2 : 1;
+        }
+        wsync();
+        int jskip = -1;
+        for (int e = 0; e < n2; ++e) {
+            const int c = seq[e], code = c & 0xffffff, t = code_type(code), j = code_idx(code);
+            bool sub = false;
+            if (t == T_SLB && j == jskip) continue;
+            if (t == T_ROW && soft) {
+                if (q + 2 > qcap) { jskip = j; continue; }
+                QW_FOR(h) if (j == qw_item(h)) rmap[h] = qw_setb(rmap[h], 3, 1u);
+                ++nmat;
+                if (c & kWarmSub) {
+                    append_isolated(mk_code(T_SUB, j), 0.0, 2.0);
+                    sub = true;
+                }
+            }
+            const bool ok = warm_add(code);
+            if (!ok && t == T_ROW) {
+                // dependent: leave the row as the cold start has it (not materialised)
+                jskip = j;
+                if (sub) {
+                    --q;
+                    if (lane_id() == 0) M[(size_t)q * kMSq + q] = 0.0;
+                    set_active(mk_code(T_SUB, j), kNone);
+                    count_active(mk_code(T_SUB, j), -1);
+                    wsync();
+                }
+                if (soft) {
+                    QW_FOR(h) if (j == qw_item(h)) rmap[h] = qw_setb(rmap[h], 3, 0u);
+                    --nmat;
+                }
+            }
+        }
+        if (q == 0) return false;
+        // x_unc on the free variables: materialised slacks sit at -term / 2
+        QW_FOR(h) {
+            const int i = qw_item(h);
+            if (i < n3) {
+                zs[i] = aunc[h];
+                Ls[i] = Punc[h];
+            }
+            eps[h] = (soft && i < nv && qw_getb(rmap[h], 3)) ? -0.5 * term : 0.0;
+        }
+        wsync();
+        rows_refresh();
+        const int q4 = (q + 3) & ~3;
+        QW_FOR(h) {
+            const int s = qw_item(h);
+            if (s < q) gs[s] = -resid_shared(act[s]);
+            else if (s < q4) gs[s] = 0.0;
+        }
+        wsync();
+        mat_vec<false>(q, nullptr);
+        double bad = 0.0;
+        QW_FOR(h) {
+            u[h] = r[h];
+            if (!(fabs(r[h]) < 1e300)) bad = 1.0;
+        }
+        if (wmax(bad) > 0.0) {
+            cold_start();
+            return false;
+        }
+        DMPC_WARM_STAT(stat_built = q);
+        // refine u until the active residuals vanish (M comes from up to q bordering steps); refinement can
+        // push a small multiplier below zero again
+        for (int pass = 0; pass < 4; ++pass) {
+            const int nd = drop_negative();
+            if (pass && !nd) break;
+            polish();
+        }
+        if (q == 0) {
+            cold_start();
+            return false;
+        }
+        return true;
+    }
+    DMPC_WARM_STAT(int stat_built = 0;)
+
+    // final active set of a solved step -> list for the next step (at most kQW entries); returns the count.
+    // rid as in warm_start.  One ordered pass per constraint family, compacted with ballots.
+    DMPC_COLD int warm_store(int* list, const int* rid) const {
+        int n = 0;
+#if defined(__CUDA_ARCH__)
+#define QW_PUSH(cond, val)                                                        \
+    do {                                                                          \
+        const unsigned bal_ = wballot(cond);                                      \
+        if ((cond) && n + popc_below(bal_) < kQW) list[n + popc_below(bal_)] = (val); \
+        n += popc_all(bal_);                                                      \
+    } while (0)
+#else
+#define QW_PUSH(cond, val)                  \
+    do {                                    \
+        if (cond) {                         \
+            if (n < kQW) list[n] = (val);   \
+            ++n;                            \
+        }                                   \
+    } while (0)
+#endif
+        QW_FOR(h) {
+            const int i = qw_item(h);
+            const unsigned m = emap[h];
+#pragma unroll
+            for (int t = 0; t < 4; ++t) {
+                // the horizon moves on by one step: index k of this solution is index k - 1 of the next
+#ifndef DMPC_WARM_SHIFT
+#define DMPC_WARM_SHIFT 3
+#endif
+                const bool on = i < n3 && i >= DMPC_WARM_SHIFT && qw_getb(m, t) != kNone;
+                QW_PUSH(on, mk_code(t, i - DMPC_WARM_SHIFT));
+            }
+        }
+        QW_FOR(h) {
+            const int j = qw_item(h);
+            const unsigned m = rmap[h];
+            const bool on = j < nv && qw_getb(m, 0) != kNone;
+            const int v = mk_code(T_ROW, rid[h] & 0xffff) | ((soft && qw_getb(m, 1) != kNone) ? kWarmSub : 0) |
+                          ((soft && qw_getb(m, 2) != kNone) ? kWarmSlb : 0);
+            QW_PUSH(on, v);
+        }
+#undef QW_PUSH
+        return n < kQW ? n : kQW;
+    }
+#endif  // DMPC_WARM_START
+
     // ---- the solver -----------------------------------------------------------------------------
     // expects a valid GI state: x minimises the objective on the active set, u >= 0
     DMPC_D QpResult solve(int max_iter, bool* m_valid_out) {
-        const double feas_tol = 1e-10;
+#ifndef DMPC_FEAS_TOL
+#define DMPC_FEAS_TOL 1e-10
+#endif
+        const double feas_tol = DMPC_FEAS_TOL;
         const double dep_tol = 1e-9;   // on delta = z'Hz relative to n_p'H^{-1}n_p
         const double ill_tol = 1e-5;   // adds below this mark M for an exact rebuild
         int iters = 0, npolish = 0;
@@ -1354,6 +1568,8 @@ DMPC_D int agent_solve_fast(const DevParams& Pm, const double* __restrict__ tab,
         }
     }
     bool give_up = false;
+    bool use_list = io.warm && io.gidx && io.warm[0] > 0;  // (DMPC_WARM_START experiment only)
+    (void)use_list;
     for (;;) {
         // skip the tries that the 3-D necessary condition proves infeasible (with a 1e-6 margin on slb)
         while (relax && qp.relaxed_infeasible(slb * (1.0 + 1e-6), ylo, yhi)) {
@@ -1364,10 +1580,29 @@ DMPC_D int agent_solve_fast(const DevParams& Pm, const double* __restrict__ tab,
         if (give_up) break;
         qp.term = term;
         qp.slb = slb;
-        if (!(warm && qp.warm_restart())) qp.cold_start();
-        const QpResult r = qp.solve(max_iter, &m_valid);
+        bool guessed = false;
+        if (!(warm && qp.warm_restart())) {
+            qp.cold_start();
+#if defined(DMPC_WARM_START)
+            if (use_list) {
+                // first solve of this step: start from the previous step's final active set
+                use_list = false;
+                int rid[kEPL];
+                QW_FOR(h) rid[h] = (qw_item(h) < nv) ? io.gidx[qw_item(h) & (kQW - 1)] : -1;
+                guessed = qp.warm_start(io.warm + 1, io.warm[0], rid);
+                DMPC_WARM_STAT(dg.nact += (qp.q << 8) | (qp.stat_built << 16) | (io.warm[0] << 24));
+            }
+#endif
+        }
+        QpResult r = qp.solve(max_iter, &m_valid);
         dg.iters += r.iters;
-        dg.nact = r.q;
+        if (guessed && r.rc != QP_OK) {
+            // any verdict other than "solved" is taken from the cold start only
+            qp.cold_start();
+            r = qp.solve(max_iter, &m_valid);
+            dg.iters += r.iters;
+        }
+        dg.nact = (dg.nact & ~0xff) | r.q;
         if (r.rc == QP_OK) { solved = true; break; }
         if (r.rc == QP_ITERCAP) { status |= ST_QPFAIL; break; }
         if (r.rc == QP_OVERFLOW) { status |= ST_QPFAIL | ST_OVERFLOW; break; }
@@ -1415,7 +1650,18 @@ DMPC_D int agent_solve_fast(const DevParams& Pm, const double* __restrict__ tab,
             inb = inb && (p1x < qp.bnd6[3 + x] + Pm.inb_tol) && (p1x > qp.bnd6[x] - Pm.inb_tol);
         }
         if (!inb) status |= ST_OUTBOUND;
+#if defined(DMPC_WARM_START)
+        if (io.warm && io.gidx) {
+            int rid[kEPL];
+            QW_FOR(h) rid[h] = (qw_item(h) < nv) ? io.gidx[qw_item(h) & (kQW - 1)] : -1;
+            const int nw = qp.warm_store(io.warm + 1, rid);
+            if (lane_id() == 0) io.warm[0] = nw;
+        }
+#endif
     } else {
+#if defined(DMPC_WARM_START)
+        if (io.warm && lane_id() == 0) io.warm[0] = 0;
+#endif
         if (!(status & ST_QPFAIL)) status |= ST_INFEASIBLE;
         // the reference returns empty p,v,a: the caller keeps the old horizon and state
         for (int i = lane_id(); i < n3; i += kLanes) io.out_p[i] = io.l_prev_n[i];

@@ -115,13 +115,16 @@ struct ScanAcc {
 // the estimate is good to a few ulp) the pair goes through the reference's exact rounding sequence.  The
 // fp64 pipe sees 7 operations per (neighbour, step); everything else is 32-bit integer work.
 // KT: compile-time horizon (own[] then lives in registers after unrolling); 0 = run-time P.K.
+// idx != null: the tile comes from a spatially SORTED copy of the buffer; idx[ibase + m] is the neighbour's own
+// agent index (what the near masks and the rows are keyed by).
 template <int KT>
 DMPC_D void scan_tile_hw(const DevParams& P, const ScanThr* __restrict__ thr, const double* __restrict__ own, int n,
-                         const double* __restrict__ tile, int ibase, int cnt, unsigned* nearmask, ScanAcc& acc) {
+                         const double* __restrict__ tile, int ibase, int cnt, unsigned* nearmask, ScanAcc& acc,
+                         const int* __restrict__ idx = nullptr) {
     const int K = KT ? KT : P.K;
     const int m = lane_id();
-    const int i = ibase + m;
     if (m >= cnt) return;
+    const int i = idx ? idx[ibase + m] : ibase + m;
     unsigned nm = 0;
     if (i != n) {
         const double* pj = tile + (size_t)m * 3 * K;

@@ -32,7 +32,8 @@ extern "C" int emul_step(const dmpcb200_params* p, int N, int n0, int n1, const 
                          const double* vk, const double* ak, const double* pf, const double* l_prev,
                          const double* pmin, const double* pmax, int QMAX, int RCAP, int RMAX,
                          double* l_new, double* p1, double* v1, double* a1, double* v_hor,
-                         double* a_hor, int32_t* status, int32_t* diag /*4 per agent*/) {
+                         double* a_hor, int32_t* status, int32_t* diag /*4 per agent*/,
+                         int32_t* warm /*optional: kWarmStride per agent, kept by the caller across steps*/) {
     const int K = p->K;
     DevParams D = to_dev(p, N, pmin, pmax);
     std::vector<double> tab;
@@ -65,6 +66,8 @@ extern "C" int emul_step(const dmpcb200_params* p, int N, int n0, int n1, const 
         io.out_a = a_hor ? a_hor + (size_t)3 * K * n : nullptr;
         io.p1 = p1 + 3 * n; io.v1 = v1 + 3 * n; io.a1 = a1 + 3 * n;
         io.l_prev_n = own;
+        io.gidx = gidx.data();
+        io.warm = warm ? warm + (size_t)kWarmStride * n : nullptr;
         AgentDiag dg;
         if (fast && 3 * K <= kQW && so.nv <= kQW && D.variant != VAR_HARD && !so.flag)
             status[n] = agent_solve_fast<0>(D, tab.data() + tables_fast_offset(K), smem.data(), QMAX, io, &dg);

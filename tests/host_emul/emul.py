@@ -30,7 +30,7 @@ def build(force=False):
     deps = srcs + [os.path.join(_ROOT, "multiagent_planning_b200/csrc", f)
                    for f in ("qp_core.cuh", "qp_warp.cuh", "agent_solve.cuh", "scan_core.cuh", "model_tables.h")]
     if force or not os.path.exists(so) or any(os.path.getmtime(d) > os.path.getmtime(so) for d in deps):
-        subprocess.check_call(["g++", "-O2", "-fPIC", "-std=c++17", "-ffp-contract=off", "-shared",
+        subprocess.check_call(["g++", "-O2", "-fPIC", "-std=c++17", "-ffp-contract=off", "-shared"] + os.environ.get("EMUL_FLAGS", "").split() + [
                                "-o", so] + srcs)
     return so
 
@@ -53,7 +53,7 @@ def params_from(obj) -> Params:
     return P
 
 
-def step(P, pk, vk, ak, pf, l_prev, pmin, pmax, n0=0, n1=None, QMAX=64, RCAP=64, RMAX=None):
+def step(P, pk, vk, ak, pf, l_prev, pmin, pmax, n0=0, n1=None, QMAX=64, RCAP=64, RMAX=None, warm=None):
     f = lambda a: np.asfortranarray(np.asarray(a, np.float64))
     dp = lambda a: a.ctypes.data_as(C.POINTER(C.c_double))
     l_prev = f(l_prev)
@@ -70,5 +70,6 @@ def step(P, pk, vk, ak, pf, l_prev, pmin, pmax, n0=0, n1=None, QMAX=64, RCAP=64,
     pmin, pmax = f(pmin).ravel(), f(pmax).ravel()
     lib().emul_step(C.byref(P), N, n0, n1, dp(pk), dp(vk), dp(ak), dp(pf), dp(l_prev), dp(pmin), dp(pmax),
                     QMAX, RCAP, RMAX, dp(l_new), dp(p1), dp(v1), dp(a1), dp(v_hor), dp(a_hor),
-                    status.ctypes.data_as(C.POINTER(C.c_int32)), diag.ctypes.data_as(C.POINTER(C.c_int32)))
+                    status.ctypes.data_as(C.POINTER(C.c_int32)), diag.ctypes.data_as(C.POINTER(C.c_int32)),
+                    warm.ctypes.data_as(C.POINTER(C.c_int32)) if warm is not None else None)
     return dict(l_new=l_new, p1=p1, v1=v1, a1=a1, v_hor=v_hor, a_hor=a_hor, status=status, diag=diag)
