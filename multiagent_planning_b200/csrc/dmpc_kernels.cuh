@@ -754,10 +754,11 @@ DMPC_D bool qp_agent(const StepArgs& A, int li, const double* tab_s, unsigned ch
     AgentDiag dg;
     int st = 0, it0 = 0;
     // fast path: the register-resident warp solver (qp_warp.cuh) -- every agent of the soft variants whose
-    // rows fit.  The generic solver (qp_core.cuh) takes the rest: solveHardDMPC (rows on many horizon
-    // steps), more than 64 rows, and -- in a global-memory rescue slot of capacity QBIG -- agents whose
-    // active set outgrew the on-chip capacity.  One call site, so the generic solver exists once.
-    const bool fast_ok = (n3 <= kQW) && (sr.nv <= kQW) && (A.P.variant != VAR_HARD) && !sr.flag;
+    // rows fit (more than 64 rows: a working set of 64 with exact row exchange, qp_warp.cuh).  The generic
+    // solver (qp_core.cuh) takes the rest: solveHardDMPC (rows on many horizon steps) and -- in a
+    // global-memory rescue slot of capacity QBIG -- agents whose active set outgrew the on-chip capacity or
+    // whose working set has no free slot left.  One call site, so the generic solver exists once.
+    const bool fast_ok = (n3 <= kQW) && (sr.nv <= kRowsFastMax) && (A.P.variant != VAR_HARD) && !sr.flag;
     if (MODE == 1) {
         if (sr.flag) {
             // the scan already decided (predicted collision at the next step / row overflow): the reference

@@ -56,6 +56,10 @@
 #define DMPC_WARM_STAT(x)
 #endif
 
+#ifndef DMPC_FEAS_TOL
+#define DMPC_FEAS_TOL 1e-10  // a constraint counts as violated beyond this (normalised residual)
+#endif
+
 namespace dmpc {
 
 constexpr int kQW = 64;             // capacity: entries, rows, slots
@@ -114,7 +118,8 @@ DMPC_HD unsigned qw_setb(unsigned m, int b, unsigned v) { return (m & ~(0xffu <<
 
 // doubles / ints of shared memory the fast solver needs per agent
 DMPC_HD size_t qw_smem_doubles(int QC = kQW) { return (size_t)QC * (QC + 2) + 16 * (size_t)kQW; }
-DMPC_HD size_t qw_smem_ints() { return 3 * (size_t)kQW; }
+DMPC_HD size_t qw_smem_ints() { return 5 * (size_t)kQW; }
+constexpr int kRowsFastMax = 512;  // rows of the scan the fast path accepts (kQW of them in the working set at a time)
 DMPC_HD size_t qw_smem_bytes(int QC = kQW) { return qw_smem_doubles(QC) * sizeof(double) + qw_smem_ints() * sizeof(int); }
 
 // QC: capacity of the active set = rows (and, + 2, the row stride) of M.  64 for the one-agent-per-sub-partition
@@ -132,6 +137,7 @@ struct QpW {
     double *rd0, *rd1, *rd2, *rdist, *rrhs, *rirn;  // static row data
     double *sv0, *sv1, *sv2, *se;                   // slot records (normal of the constraint in the slot)
     int *rkc, *sinfo, *act;
+    int *rsrc, *kept;  // row working set (more than kQW rows): scan row of slot j; bitmap of the scan rows in the set
     // ---- per-lane state ---------------------------------------------------------------------------
     double a[kEPL], P[kEPL], z[kEPL], L[kEPL], aunc[kEPL], Punc[kEPL];
     double elo[kEPL], ehi[kEPL], eiln[kEPL];  // workspace box and 1/||lam[k,:]|| of the entry
@@ -153,6 +159,7 @@ struct QpW {
         sv0 = d; d += kQW; sv1 = d; d += kQW; sv2 = d; d += kQW; se = d; d += kQW;
         int* ip = reinterpret_cast<int*>(d);
         rkc = ip; ip += kQW; sinfo = ip; ip += kQW; act = ip; ip += kQW;
+        rsrc = ip; ip += kQW; kept = ip; ip += kQW;
     }
 
     // ---- value of item idx of a per-lane array, on every lane -----------------------------------
@@ -1236,18 +1243,133 @@ struct QpW {
     }
 #endif  // DMPC_WARM_START
 
+    // ---- row working set ------------------------------------------------------------------------------------
+    // A dense swarm gives an agent more rows than the kQW the per-lane state holds, but only a handful are ever
+    // active.  The solver then works on kQW of them (the most violated at the unconstrained optimum first);
+    // after it has converged the rows left out are checked at the solution: a row that holds with its slack at
+    // the upper bound 0 does not change the optimum, so if all hold the result is the full problem's.  Rows
+    // that are violated are exchanged for rows of the set that were never touched (inactive, slack not
+    // materialised -- the state of the method does not depend on them) and the iteration continues from the
+    // same valid state.  Exact in every case; the generic solver remains the fallback when no slot is free.
+
+    // static data of scan row r -> slot j (one lane)
+    DMPC_D void load_row(int j, int r, const AgentIO& io, const double* t_lnorm) {
+        const double d0 = io.grow[r], d1 = io.grow[(size_t)io.RMAX + r], d2 = io.grow[2 * (size_t)io.RMAX + r];
+        const double dist = io.grow[3 * (size_t)io.RMAX + r];
+        const int kc = io.gkc[r];
+        rd0[j] = d0; rd1[j] = d1; rd2[j] = d2; rdist[j] = dist;
+        rrhs[j] = io.grow[4 * (size_t)io.RMAX + r];
+        rkc[j] = kc;
+        const double dd = d0 * d0 + d1 * d1 + d2 * d2;
+        const double ln = t_lnorm[kc];
+        rirn[j] = 1.0 / sqrt(dd * ln * ln + (soft ? dist * dist : 0.0));
+    }
+
+    // choose the first working set: the kQW rows with the smallest normalised residual at y = P_unc[kc_all]
+    // (ties: lower row first), kept in the scan's order.  M is used as scratch (before cold_start clears it).
+    DMPC_COLD void select_rows(int NT, const AgentIO& io, const double* t_lnorm) {
+        double* key = M;
+        int* rank = reinterpret_cast<int*>(M + kRowsFastMax);
+        const double y0 = item_d(Punc, 3 * kc_all), y1 = item_d(Punc, 3 * kc_all + 1), y2 = item_d(Punc, 3 * kc_all + 2);
+        for (int r = lane_id(); r < NT; r += kLanes) {
+            const double d0 = io.grow[r], d1 = io.grow[(size_t)io.RMAX + r], d2 = io.grow[2 * (size_t)io.RMAX + r];
+            const double dist = io.grow[3 * (size_t)io.RMAX + r], ln = t_lnorm[io.gkc[r]];
+            const double dd = d0 * d0 + d1 * d1 + d2 * d2;
+            key[r] = (d0 * y0 + d1 * y1 + d2 * y2 - io.grow[4 * (size_t)io.RMAX + r]) /
+                     sqrt(dd * ln * ln + (soft ? dist * dist : 0.0));
+        }
+        for (int w = lane_id(); w < kQW; w += kLanes) kept[w] = 0;
+        wsync();
+        for (int r = lane_id(); r < NT; r += kLanes) {
+            const double kr = key[r];
+            int rk = 0;
+            for (int t = 0; t < NT; ++t) {
+                const double kt = key[t];
+                rk += (kt < kr || (kt == kr && t < r)) ? 1 : 0;
+            }
+            rank[r] = rk;
+        }
+        wsync();
+        int cnt = 0;
+        for (int base = 0; base < NT; base += kLanes) {
+            const int r = base + lane_id();
+            const bool keep = r < NT && rank[r] < kQW;
+            const unsigned bal = wballot(keep);
+            if (keep) rsrc[cnt + popc_below(bal)] = r;
+            if (lane_id() == 0) kept[base >> 5] |= (int)(bal << (base & 31));
+            cnt += popc_all(bal);
+        }
+        wsync();
+    }
+
+    // after a converged solve: exchange violated rows outside the set for untouched rows of the set.
+    // Returns the number of rows brought in (0: the solution is the full problem's), -1: violated rows remain
+    // and no slot is free (the caller falls back to the generic solver).
+    DMPC_COLD int exchange_rows(int NT, const AgentIO& io, const double* t_lnorm, double tol) {
+        int* vio = reinterpret_cast<int*>(cp);  // (the shared copies of eps / residuals are not needed here)
+        const double y0 = item_d(P, 3 * kc_all), y1 = item_d(P, 3 * kc_all + 1), y2 = item_d(P, 3 * kc_all + 2);
+        int nvio = 0;
+        for (int base = 0; base < NT; base += kLanes) {
+            const int r = base + lane_id();
+            bool v = false;
+            if (r < NT && !((kept[r >> 5] >> (r & 31)) & 1)) {
+                const double d0 = io.grow[r], d1 = io.grow[(size_t)io.RMAX + r], d2 = io.grow[2 * (size_t)io.RMAX + r];
+                const double dist = io.grow[3 * (size_t)io.RMAX + r], ln = t_lnorm[io.gkc[r]];
+                const double dd = d0 * d0 + d1 * d1 + d2 * d2;
+                const double res = d0 * y0 + d1 * y1 + d2 * y2 - io.grow[4 * (size_t)io.RMAX + r];
+                // the test of most_violated: residual / norm of the row < -tol
+                v = res < -tol * sqrt(dd * ln * ln + (soft ? dist * dist : 0.0));
+            }
+            const unsigned bal = wballot(v);
+            const int pos = nvio + popc_below(bal);
+            if (v && pos < 2 * kQW) vio[pos] = r;
+            nvio += popc_all(bal);
+        }
+        if (nvio == 0) return 0;
+        if (nvio > 2 * kQW) nvio = 2 * kQW;  // (the rest is found by the next pass)
+        wsync();
+        int nfree = 0;
+        QW_FOR(h) {
+            const int j = qw_item(h);
+            const unsigned m = rmap[h];
+            const bool fr = j < nv && qw_getb(m, 0) == kNone && !qw_getb(m, 3);
+            const unsigned bal = wballot(fr);
+            const int pos = nfree + popc_below(bal);
+            if (fr && pos < nvio) {
+                const int rn = vio[pos], ro = rsrc[j];
+                load_row(j, rn, io, t_lnorm);
+                rsrc[j] = rn;
+#if defined(__CUDA_ARCH__)
+                atomicAnd(&kept[ro >> 5], ~(1 << (ro & 31)));
+                atomicOr(&kept[rn >> 5], 1 << (rn & 31));
+#else
+                kept[ro >> 5] &= ~(1 << (ro & 31));
+                kept[rn >> 5] |= 1 << (rn & 31);
+#endif
+            }
+            nfree += popc_all(bal);
+        }
+        const int nsw = nfree < nvio ? nfree : nvio;
+        if (nsw == 0) return -1;
+        QW_FOR(h) {
+            const int i = qw_item(h);
+            if (i < n3) Ls[i] = P[h];
+        }
+        wsync();
+        rows_refresh();
+        return nsw;
+    }
+
     // ---- the solver -----------------------------------------------------------------------------
     // expects a valid GI state: x minimises the objective on the active set, u >= 0
-    DMPC_D QpResult solve(int max_iter, bool* m_valid_out) {
-#ifndef DMPC_FEAS_TOL
-#define DMPC_FEAS_TOL 1e-10
-#endif
+    // rough0: x has not been synthesised from the multipliers since an earlier solve() -- end with a polish
+    DMPC_D QpResult solve(int max_iter, bool* m_valid_out, bool rough0 = false) {
         const double feas_tol = DMPC_FEAS_TOL;
         const double dep_tol = 1e-9;   // on delta = z'Hz relative to n_p'H^{-1}n_p
         const double ill_tol = 1e-5;   // adds below this mark M for an exact rebuild
         int iters = 0, npolish = 0;
         int nsteps = 0;          // primal steps since x was last synthesised from the multipliers
-        bool rough = false;      // a drop, a rebuild or an ill-conditioned add happened since then
+        bool rough = rough0;     // a drop, a rebuild or an ill-conditioned add happened since then
         bool polished = false, dirty = false, m_valid = true;
         QpResult res;
         res.rc = QP_OK;
@@ -1482,32 +1604,17 @@ DMPC_D int agent_solve_fast(const DevParams& Pm, const double* __restrict__ tab,
     const double* t_lnorm = tab + K * K + K;
     // tab: the shared-memory blob of model_tables.h (header padded to 4 doubles, then T4 per weight set)
     const double* t_T4 = tab + tab_fast_header(K) + (size_t)wset * 4 * K * K;
-    qp.K = K; qp.n3 = n3; qp.nv = io.nv; qp.soft = soft ? 1 : 0;
+    qp.K = K; qp.n3 = n3; qp.soft = soft ? 1 : 0;
     qp.kc_all = io.kstar > 0 ? io.kstar - 1 - (Pm.variant == VAR_SOFT_BOUND2 ? 1 : 0) : 0;
     qp.alim = Pm.alim; qp.qw = qw; qp.sw = sw;
     qp.qcap = qcap < QC ? qcap : QC;
     qp.ilnorm = tab + K * K + 2 * K; qp.T4 = t_T4;
 
-    // ---- rows: global SoA (scan output) -> shared ---------------------------------------------------
-    const int nv = io.nv;
-    QW_FOR(h) {
-        const int j = qw_item(h);
-        if (j < nv) {
-            const double d0 = io.grow[j], d1 = io.grow[(size_t)io.RMAX + j], d2 = io.grow[2 * (size_t)io.RMAX + j];
-            const double dist = io.grow[3 * (size_t)io.RMAX + j];
-            const int kc = io.gkc[j];
-            qp.rd0[j] = d0; qp.rd1[j] = d1; qp.rd2[j] = d2; qp.rdist[j] = dist;
-            qp.rrhs[j] = io.grow[4 * (size_t)io.RMAX + j];
-            qp.rkc[j] = kc;
-            const double dd = d0 * d0 + d1 * d1 + d2 * d2;
-            const double ln = t_lnorm[kc];
-            qp.rirn[j] = 1.0 / sqrt(dd * ln * ln + (soft ? dist * dist : 0.0));
-        } else if (j < kQW) {
-            // rows beyond nv are read (and discarded) by the branch-free loops: keep them finite
-            qp.rd0[j] = 0.0; qp.rd1[j] = 0.0; qp.rd2[j] = 0.0; qp.rdist[j] = 0.0; qp.rrhs[j] = 0.0; qp.rirn[j] = 0.0;
-            qp.rkc[j] = 0;
-        }
-    }
+    // ---- rows: at most kQW of the scan's rows are in the working set at a time (see select_rows) ----------
+    const int NT = io.nv;
+    const int nv = NT < kQW ? NT : kQW;
+    const bool subset = NT > kQW;
+    qp.nv = nv;
     // ---- a_unc = -G f,  P_unc = A_initp [po;vo] + Lam a_unc  (solveSoftDMPCbound.m:82-88) ------------
     QW_FOR(h) {
         const int i = qw_item(h);
@@ -1543,6 +1650,20 @@ DMPC_D int agent_solve_fast(const DevParams& Pm, const double* __restrict__ tab,
             pu = s + (pox + t_tt[k] * vox);
         }
         qp.Punc[h] = pu;
+    }
+    wsync();
+
+    // ---- rows: global SoA (scan output) -> shared ---------------------------------------------------
+    if (subset) qp.select_rows(NT, io, t_lnorm);
+    QW_FOR(h) {
+        const int j = qw_item(h);
+        if (j < nv) {
+            qp.load_row(j, subset ? qp.rsrc[j] : j, io, t_lnorm);
+        } else if (j < kQW) {
+            // rows beyond nv are read (and discarded) by the branch-free loops: keep them finite
+            qp.rd0[j] = 0.0; qp.rd1[j] = 0.0; qp.rd2[j] = 0.0; qp.rdist[j] = 0.0; qp.rrhs[j] = 0.0; qp.rirn[j] = 0.0;
+            qp.rkc[j] = 0;
+        }
     }
     wsync();
 
@@ -1602,7 +1723,17 @@ DMPC_D int agent_solve_fast(const DevParams& Pm, const double* __restrict__ tab,
             r = qp.solve(max_iter, &m_valid);
             dg.iters += r.iters;
         }
+        // more rows than the working set holds: bring in the ones the solution violates and go on
+        bool no_slot = false;
+        while (subset && r.rc == QP_OK) {
+            const int nsw = qp.exchange_rows(NT, io, t_lnorm, DMPC_FEAS_TOL);
+            if (nsw == 0) break;
+            if (nsw < 0) { no_slot = true; break; }
+            r = qp.solve(max_iter, &m_valid, true);
+            dg.iters += r.iters;
+        }
         dg.nact = (dg.nact & ~0xff) | r.q;
+        if (no_slot) { status |= ST_QPFAIL | ST_OVERFLOW; break; }
         if (r.rc == QP_OK) { solved = true; break; }
         if (r.rc == QP_ITERCAP) { status |= ST_QPFAIL; break; }
         if (r.rc == QP_OVERFLOW) { status |= ST_QPFAIL | ST_OVERFLOW; break; }

@@ -69,7 +69,7 @@ extern "C" int emul_step(const dmpcb200_params* p, int N, int n0, int n1, const 
         io.gidx = gidx.data();
         io.warm = warm ? warm + (size_t)kWarmStride * n : nullptr;
         AgentDiag dg;
-        if (fast && 3 * K <= kQW && so.nv <= kQW && D.variant != VAR_HARD && !so.flag)
+        if (fast && 3 * K <= kQW && so.nv <= kRowsFastMax && D.variant != VAR_HARD && !so.flag)
             status[n] = agent_solve_fast<0>(D, tab.data() + tables_fast_offset(K), smem.data(), QMAX, io, &dg);
         else
             status[n] = agent_solve<0>(D, tab.data(), smem.data(), QMAX, RCAP, io, &dg);

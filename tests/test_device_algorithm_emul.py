@@ -171,3 +171,35 @@ def test_fast_path_k20(orc, emul):
     for k in range(8):
         o, e = _cmp(orc, emul, P, pk, vk, ak, pf, l, pmin, pmax, QMAX=-64)
         l, pk, vk, ak = e["l_new"], e["p1"], e["v1"], e["a1"]
+
+
+def test_fast_path_row_working_set(orc, emul):
+    """dense swarm (C4: N = 2000, K = 20): some agents get more than the 64 rows the register-resident solver
+    holds.  It then works on 64 of them and exchanges rows the converged solution violates (exact: a row that
+    holds with zero slack does not change the optimum) -- status, retry count and result must be the oracle's,
+    and nothing may fall back to the overflow path."""
+    from multiagent_planning_b200 import scenarios
+    cfg = scenarios.config("C4")
+    N = cfg["N"]
+    P = orc.default_params(cfg["variant"])
+    for k, v in cfg["params"].items():
+        setattr(P, k, v)
+    K = P.K
+    l = np.zeros((3, K, N), order="F")
+    for n in range(N):
+        l[:, :, n] = orc.init_dmpc(cfg["po"][:, n], cfg["pf"][:, n], P.h, K, P.init_div)[0]
+    pk, vk, ak = l[:, 0, :].copy(), np.zeros((3, N)), np.zeros((3, N))
+    nbig = 0
+    for k in range(7):
+        o = orc.step(P, pk, vk, ak, cfg["pf"], l, cfg["pmin"], cfg["pmax"], nthreads=4)
+        e = emul.step(emul.params_from(P), pk, vk, ak, cfg["pf"], l, cfg["pmin"], cfg["pmax"], QMAX=-64, RMAX=256)
+        big = e["diag"][:, 1] > 64
+        nbig += int(big.sum())
+        assert np.array_equal(o["status"], e["status"])          # flags AND retry counts
+        assert not (e["status"] & 32).any()
+        assert np.abs(o["l_new"] - e["l_new"]).max() <= 1e-8
+        if big.any():
+            assert np.abs(o["l_new"][:, :, big] - e["l_new"][:, :, big]).max() <= 1e-9
+            assert e["diag"][big, 2].max() < 80                  # (the generic solver needs up to 200 iterations here)
+        l, pk, vk, ak = o["l_new"], o["p1"], o["v1"], o["a1"]
+    assert nbig >= 10
