@@ -104,11 +104,6 @@ struct dmpcb200_handle {
     // throughput layout of the QP kernel (launches of more than one wave of agents)
     RouteQ* d_rq = nullptr;
     int *d_qlight = nullptr, *d_qheavy = nullptr;
-    // spatially pruned scan of large single swarms: sorted copy of the horizons, boxes, sort keys
-    double *d_ls = nullptr, *d_abox = nullptr, *d_sbox = nullptr, *d_tbox = nullptr;
-    int* d_sidx = nullptr;
-    unsigned* d_keys = nullptr;
-    int prune_min_n = 0;  // swarm size from which the pruned scan is used (DMPCB200_SCAN_PRUNE=<n>; 0 = never: the default until it beats the brute-force kernel)
     int layout = 1;  // 1 classic persistent kernel (default), 0 two-role throughput kernel (DMPCB200_LAYOUT=throughput)
     Ctrl* d_ctrl = nullptr;
     double* d_goal = nullptr;  // 2 doubles
@@ -212,35 +207,9 @@ bool use_throughput_layout(const dmpcb200_t* h, const StepArgs& A) {
 // (15, 20) are compiled with the horizon as a constant (the own horizon then lives in registers)
 cudaError_t launch_scan(dmpcb200_t* h, const StepArgs& A, cudaStream_t s) {
     const int nl = A.n1 - A.n0, K = h->K, N = h->N;  // (per scenario)
-    if (h->d_ls && h->prune_min_n > 0 && N >= h->prune_min_n && A.n_scen == 1 && A.n0 == 0 && nl == N && !A.rq &&
-        h->have_bounds) {
-        // large single swarm: sort by space, skip the tiles out of reach (exact: decisions unchanged)
-        PruneArgs G;
-        G.N = N;
-        G.K = K;
-        G.Ntiles = (N + kTile - 1) / kTile;
-        G.inv_c = 1.0 / h->dp.c;
-        double thr = h->dp.rmin;
-        for (int k = 1; k <= K; ++k) thr = std::max(thr, neigh_thr(h->dp, k));
-        G.thr_max = thr * (1.0 + 1e-9) + 1e-12;
-        double ext = 0.0;
-        for (int x = 0; x < 3; ++x) {
-            G.lo[x] = h->dp.pmin[x] - 1.0;
-            ext = std::max(ext, h->dp.pmax[x] - h->dp.pmin[x] + 2.0);
-        }
-        G.cell = ext / 16.0;
-        G.l = A.l_prev;
-        G.ls = h->d_ls;
-        G.sidx = h->d_sidx;
-        G.abox = h->d_abox;
-        G.sbox = h->d_sbox;
-        G.tbox = h->d_tbox;
-        G.keys = h->d_keys;
-        return launch_scan_pruned(A, G, K, s);
-    }
     if (const char* e = getenv("DMPCB200_SCAN_LAYOUT")) {  // experiment hook
-        const int id = atoi(e);
-        if (id >= 0 && id <= 6) return launch_scan_layout((ScanLayout)id, A, nl, K, s);
+        const int id = *e ? atoi(e) : -1;
+        if (id >= 0 && id < SCAN_LAYOUTS) return launch_scan_layout((ScanLayout)id, A, nl, K, s);
     }
     // throughput mode (batched scenarios / more than one wave of agents) with every tile of a scenario resident:
     // 8 agents x 2 warps per CTA with the own horizon in shared memory (occupancy beats the register-resident
@@ -581,16 +550,6 @@ int dmpcb200_create(const dmpcb200_params* p, int N, int n0, int n1, int n_scena
     if ((e = dalloc(&h->d_rescue, h->rescue_bytes * h->n_rescue)) != cudaSuccess) return bail(e, "rescue");
     if ((e = dalloc(&h->d_rescue_next, 1)) != cudaSuccess) return bail(e, "rescue counter");
     if ((e = dalloc(&h->d_done, 2)) != cudaSuccess) return bail(e, "done / work counters");
-    if (const char* pe = getenv("DMPCB200_SCAN_PRUNE")) h->prune_min_n = atoi(pe);
-    if (h->prune_min_n > 0 && N >= h->prune_min_n && h->S == 1 && n0 == 0 && n1 == N) {
-        const size_t np = (size_t)h->Npad;
-        if ((e = dalloc(&h->d_ls, np * n3)) != cudaSuccess) return bail(e, "sorted horizons");
-        if ((e = dalloc(&h->d_abox, 6 * np)) != cudaSuccess) return bail(e, "boxes");
-        if ((e = dalloc(&h->d_sbox, 6 * np)) != cudaSuccess) return bail(e, "boxes");
-        if ((e = dalloc(&h->d_tbox, 6 * (np / kTile))) != cudaSuccess) return bail(e, "boxes");
-        if ((e = dalloc(&h->d_sidx, np)) != cudaSuccess) return bail(e, "sort index");
-        if ((e = dalloc(&h->d_keys, np)) != cudaSuccess) return bail(e, "sort keys");
-    }
     {
         const char* lay = getenv("DMPCB200_LAYOUT");
         // The two-role kernel (8 agents per SM, light agents with a 32-capacity active set) is an OPT-IN experiment:
@@ -629,8 +588,6 @@ void dmpcb200_destroy(dmpcb200_t* h) {
     cudaFree(h->d_pf); cudaFree(h->d_bounds); cudaFree(h->d_vhor); cudaFree(h->d_ahor);
     cudaFree(h->d_scan); cudaFree(h->d_grow); cudaFree(h->d_gkc); cudaFree(h->d_gidx);
     cudaFree(h->d_gscr_d); cudaFree(h->d_gscr_i); cudaFree(h->d_rescue); cudaFree(h->d_rescue_next);
-    cudaFree(h->d_ls); cudaFree(h->d_abox); cudaFree(h->d_sbox); cudaFree(h->d_tbox); cudaFree(h->d_sidx);
-    cudaFree(h->d_keys);
     cudaFree(h->d_rq); cudaFree(h->d_qlight); cudaFree(h->d_qheavy);
     cudaFree(h->d_done); cudaFree(h->d_ctrl); cudaFree(h->d_goal); cudaFree(h->d_u8); cudaFree(h->d_small);
     cudaFree(h->d_ismall);

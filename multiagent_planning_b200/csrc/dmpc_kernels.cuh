@@ -191,7 +191,9 @@ DMPC_HD size_t scan_smem_bytes(int K, int W, int stages, int Npad, int RMAX) {
 #define SCAN_PROF(i)
 #endif
 
-template <int W, int S, int KT>
+// OWNREG: the agent's own horizon lives in registers (needs KT > 0 and ~2 x 3KT registers: layouts of up to 8
+// warps); false: it is read from shared memory (broadcast reads) -- the 16-warp layouts, where occupancy beats it
+template <int W, int S, int KT, bool OWNREG = (KT > 0)>
 __global__ void __launch_bounds__(W * S * 32) scan_kernel(const __grid_constant__ StepArgs A, int stages) {
     // programmatic dependent launch: the QP kernel of this step may start its prologue (barrier, table
     // TMA) while this grid is still running; it waits (griddepcontrol.wait) before it reads our output
@@ -249,12 +251,12 @@ __global__ void __launch_bounds__(W * S * 32) scan_kernel(const __grid_constant_
     __syncthreads();  // barrier init + own horizons visible
     SCAN_PROF(0);
 
-    double ow[KT ? 3 * KT : 1];
-    if (KT) {
+    double ow[OWNREG ? 3 * KT : 1];
+    if (OWNREG) {
 #pragma unroll
-        for (int i = 0; i < 3 * KT; ++i) ow[i] = own[i];
+        for (int i = 0; i < (OWNREG ? 3 * KT : 1); ++i) ow[i] = own[i];
     }
-    const double* ownp = KT ? ow : own;
+    const double* ownp = OWNREG ? ow : own;
 
     unsigned* nm = nm_all + (size_t)ag * Npad;
     ScanAcc acc;
@@ -351,217 +353,6 @@ __global__ void __launch_bounds__(W * S * 32) scan_kernel(const __grid_constant_
         }
     }
     SCAN_PROF(3);
-}
-
-// ---- K1 for large swarms: spatially pruned scan ---------------------------------------------------------------
-// The brute-force scan evaluates every pair at every horizon step: O(N^2 K).  An agent only interacts with
-// neighbours whose horizon comes within the largest threshold (3 rmin) of its own, so for a large swarm almost
-// all of that work decides "far" K times over.  Pruning that cannot change a decision: sort the agents by the
-// Morton code of their horizon's centroid cell, gather a sorted copy of the horizon buffer (so that a 32-agent
-// tile is spatially compact) with the axis-aligned bounding box of every horizon and of every tile; a tile (or a
-// single agent against a tile) is skipped when the distance between the boxes in the ellipsoid metric exceeds
-// the largest threshold -- every per-step distance of such a pair is at least the distance of the boxes, so all
-// its mask bits are zero, which is what a skipped tile leaves behind (the masks are cleared first).  Near masks
-// and rows stay keyed by the agents' own indices, so the rows come out in the reference's order.
-struct PruneArgs {
-    int N, K, Ntiles;
-    double inv_c, thr_max;   // skip when the box distance exceeds thr_max (the largest threshold, padded)
-    double lo[3], cell;      // cell grid of the Morton code
-    const double* l;         // horizon buffer (N x K x 3)
-    double* ls;              // sorted copy (Ntiles * 32 x K x 3)
-    int* sidx;               // sorted position -> agent index (Ntiles * 32; -1 beyond N)
-    double* abox;            // per agent (by agent index) lo[3], hi[3]
-    double* sbox;            // per sorted position lo[3], hi[3]
-    double* tbox;            // per tile lo[3], hi[3]
-    unsigned* keys;          // per agent Morton key
-};
-constexpr int kPruneBins = 4096;  // 4 bits per axis
-
-// (1) boxes + keys + counting sort, ONE CTA (N <= a few thousand: the sort is a histogram in shared memory)
-static __global__ void __launch_bounds__(1024) prune_sort_kernel(const PruneArgs G) {
-    __shared__ unsigned s_cnt[kPruneBins];
-    const int tid = threadIdx.x, n3 = 3 * G.K;
-    for (int b = tid; b < kPruneBins; b += 1024) s_cnt[b] = 0;
-    __syncthreads();
-    for (int n = tid; n < G.N; n += 1024) {
-        const double* p = G.l + (size_t)n * n3;
-        double lo[3] = {p[0], p[1], p[2]}, hi[3] = {p[0], p[1], p[2]};
-        for (int k = 1; k < G.K; ++k)
-            for (int x = 0; x < 3; ++x) {
-                lo[x] = fmin(lo[x], p[3 * k + x]);
-                hi[x] = fmax(hi[x], p[3 * k + x]);
-            }
-        unsigned key = 0;
-        for (int x = 0; x < 3; ++x) {
-            G.abox[6 * n + x] = lo[x];
-            G.abox[6 * n + 3 + x] = hi[x];
-            int c = (int)floor((0.5 * (lo[x] + hi[x]) - G.lo[x]) / G.cell);
-            c = c < 0 ? 0 : (c > 15 ? 15 : c);
-            for (int b = 0; b < 4; ++b) key |= ((unsigned)(c >> b) & 1u) << (3 * b + x);  // Morton interleave
-        }
-        G.keys[n] = key;
-        atomicAdd(&s_cnt[key], 1u);
-    }
-    __syncthreads();
-    // exclusive prefix over the 4096 bins: 4 bins per thread + a block scan of the partial sums
-    __shared__ unsigned s_part[1024];
-    unsigned c4[4], sum = 0;
-    for (int b = 0; b < 4; ++b) { c4[b] = s_cnt[4 * tid + b]; sum += c4[b]; }
-    s_part[tid] = sum;
-    __syncthreads();
-    for (int o = 1; o < 1024; o <<= 1) {
-        const unsigned v = tid >= o ? s_part[tid - o] : 0u;
-        __syncthreads();
-        s_part[tid] += v;
-        __syncthreads();
-    }
-    unsigned base = s_part[tid] - sum;
-    for (int b = 0; b < 4; ++b) { s_cnt[4 * tid + b] = base; base += c4[b]; }
-    __syncthreads();
-    for (int n = tid; n < G.N; n += 1024) G.sidx[atomicAdd(&s_cnt[G.keys[n]], 1u)] = n;
-    for (int p = G.N + tid; p < G.Ntiles * 32; p += 1024) G.sidx[p] = -1;
-}
-
-// (2) gather the sorted copy, the sorted boxes and the tile boxes: one warp per tile
-static __global__ void __launch_bounds__(128) prune_gather_kernel(const PruneArgs G) {
-    const int tile = blockIdx.x * 4 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
-    if (tile >= G.Ntiles) return;
-    const int n3 = 3 * G.K;
-    const int pos = tile * 32 + lane;
-    const int n = G.sidx[pos];
-    double lo[3] = {1e300, 1e300, 1e300}, hi[3] = {-1e300, -1e300, -1e300};
-    if (n >= 0)
-        for (int x = 0; x < 3; ++x) { lo[x] = G.abox[6 * n + x]; hi[x] = G.abox[6 * n + 3 + x]; }
-    for (int x = 0; x < 3; ++x) { G.sbox[6 * (size_t)pos + x] = lo[x]; G.sbox[6 * (size_t)pos + 3 + x] = hi[x]; }
-    for (int o = 16; o; o >>= 1)
-        for (int x = 0; x < 3; ++x) {
-            lo[x] = fmin(lo[x], __shfl_xor_sync(0xffffffffu, lo[x], o));
-            hi[x] = fmax(hi[x], __shfl_xor_sync(0xffffffffu, hi[x], o));
-        }
-    if (lane < 3) { G.tbox[6 * tile + lane] = lo[lane]; G.tbox[6 * tile + 3 + lane] = hi[lane]; }
-    // horizons: the warp copies its 32 agents' rows (coalesced per row)
-    for (int m = 0; m < 32; ++m) {
-        const int src = __shfl_sync(0xffffffffu, n, m);
-        double* dst = G.ls + ((size_t)tile * 32 + m) * n3;
-        for (int i = lane; i < n3; i += 32) dst[i] = src >= 0 ? G.l[(size_t)src * n3 + i] : 1e9;  // padding: far away
-    }
-}
-
-// distance of two boxes in the ellipsoid metric (lower bound of every point-to-point distance)
-DMPC_D double box_gap(const double* a, const double* b, double inv_c) {
-    const double gx = fmax(0.0, fmax(a[0] - b[3], b[0] - a[3]));
-    const double gy = fmax(0.0, fmax(a[1] - b[4], b[1] - a[4]));
-    const double gz = fmax(0.0, fmax(a[2] - b[5], b[2] - a[5])) * inv_c;
-    return sqrt(gx * gx + gy * gy + gz * gz);
-}
-
-DMPC_HD size_t scan_pruned_smem_bytes(int K, int W, int stages, int Npad, int RMAX, int Ntiles) {
-    return (size_t)stages * kTile * 3 * K * sizeof(double) + scan_fixed_bytes(K, W, Npad, RMAX) +
-           (size_t)round_up(Ntiles, 2) * sizeof(int) + 6 * sizeof(double) * (size_t)(W + 1);
-}
-
-// (3) the scan over the kept tiles.  One warp per agent, W agents (consecutive in SORTED order: neighbours in
-// space) per CTA; single swarm, all agents on this handle.
-template <int W, int KT>
-__global__ void __launch_bounds__(W * 32) scan_pruned_kernel(const __grid_constant__ StepArgs A, const PruneArgs G,
-                                                             int stages) {
-    asm volatile("griddepcontrol.launch_dependents;");
-    if (A.ctrl && A.ctrl->done) return;
-    extern __shared__ __align__(128) unsigned char smem_raw[];
-    const int K = KT ? KT : A.P.K, n3 = 3 * K, n3p = round_up(n3, 2), N = A.P.N;
-    const int tile_d = kTile * n3;
-    const uint32_t tile_bytes = (uint32_t)(tile_d * sizeof(double));
-    double* tiles = reinterpret_cast<double*>(smem_raw);
-    double* own_all = tiles + (size_t)stages * tile_d;
-    uint64_t* bars = reinterpret_cast<uint64_t*>(own_all + W * n3p);
-    unsigned* s_acc = reinterpret_cast<unsigned*>(bars + kScanMaxStages);
-    unsigned* nm_all = s_acc + 64 * 2;
-    const int Npad = round_up(N, kTile);
-    int* list_all = reinterpret_cast<int*>(nm_all + (size_t)W * Npad);
-    int* s_tiles = list_all + (size_t)W * A.RMAX;
-    double* s_box = reinterpret_cast<double*>(s_tiles + round_up(G.Ntiles, 2));  // W agent boxes + the CTA's union
-    __shared__ int s_nt;
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int pos = blockIdx.x * W + warp;        // sorted position of this warp's agent
-    const int n = pos < G.Ntiles * 32 ? G.sidx[pos] : -1;
-    const bool valid = n >= 0;
-    const int li = n;                              // (n0 = 0: scratch index = agent index)
-    double* own = own_all + warp * n3p;
-    unsigned* nm = nm_all + (size_t)warp * Npad;
-    if (threadIdx.x == 0)
-        for (int b = 0; b < stages; ++b) mbar_init(&bars[b], 1);
-    if (valid)
-        for (int i = lane; i < n3; i += 32) own[i] = G.ls[(size_t)pos * n3 + i];
-    for (int i = lane; i < Npad; i += 32) nm[i] = 0u;  // skipped tiles leave "far at every step"
-    if (lane < 6) s_box[6 * warp + lane] = valid ? G.sbox[6 * (size_t)pos + lane] : (lane < 3 ? 1e300 : -1e300);
-    __syncthreads();
-    // the CTA's box and the tiles within reach of it (warp 0; ascending tile order)
-    if (warp == 0) {
-        if (lane < 6) {
-            double v = s_box[lane];
-            for (int w = 1; w < W; ++w) v = lane < 3 ? fmin(v, s_box[6 * w + lane]) : fmax(v, s_box[6 * w + lane]);
-            s_box[6 * W + lane] = v;
-        }
-        __syncwarp();
-        int nt = 0;
-        for (int base = 0; base < G.Ntiles; base += 32) {
-            const int t = base + lane;
-            const bool keep = t < G.Ntiles && box_gap(s_box + 6 * W, G.tbox + 6 * t, G.inv_c) <= G.thr_max;
-            const unsigned bal = __ballot_sync(0xffffffffu, keep);
-            if (keep) s_tiles[nt + __popc(bal & ((1u << lane) - 1u))] = t;
-            nt += __popc(bal);
-        }
-        if (lane == 0) {
-            s_nt = nt;
-            mbar_fence_init();
-        }
-        __syncwarp();
-        if (lane == 0)
-            for (int i = 0; i < stages && i < nt; ++i) {
-                mbar_expect_tx(&bars[i], tile_bytes);
-                tma_bulk_g2s(tiles + (size_t)i * tile_d, G.ls + (size_t)s_tiles[i] * tile_d, tile_bytes, &bars[i]);
-            }
-    }
-    __syncthreads();
-    const int nt = s_nt;
-    double ow[KT ? 3 * KT : 1];
-    if (KT) {
-#pragma unroll
-        for (int i = 0; i < 3 * KT; ++i) ow[i] = own[i];
-    }
-    const double* ownp = KT ? ow : own;
-    ScanAcc acc;
-    acc.vmask = 0;
-    acc.coll0 = 0;
-    for (int i = 0; i < nt; ++i) {
-        const int b = i % stages, t = s_tiles[i];
-        mbar_wait(&bars[b], (uint32_t)((i / stages) & 1));
-        // this agent against this tile: the same box test once more, per warp
-        if (valid && box_gap(s_box + 6 * warp, G.tbox + 6 * t, G.inv_c) <= G.thr_max) {
-            const int base = t * kTile;
-            const int cnt = (N - base < kTile) ? (N - base) : kTile;  // (sorted positions >= N are padding)
-            scan_tile_hw<KT>(A.P, &A.thr, ownp, n, tiles + (size_t)b * tile_d, base, cnt, nm, acc, G.sidx);
-        }
-        __syncthreads();  // every warp is done with this stage
-        if (threadIdx.x == 0 && i + stages < nt) {
-            mbar_expect_tx(&bars[b], tile_bytes);
-            tma_bulk_g2s(tiles + (size_t)b * tile_d, G.ls + (size_t)s_tiles[i + stages] * tile_d, tile_bytes, &bars[b]);
-        }
-    }
-    if (!valid) return;
-    acc.vmask = wor(acc.vmask);
-    acc.coll0 = wor(acc.coll0);
-    const ScanOut so = scan_finish(A.P, own, n, A.l_prev, nm, acc, A.RMAX, A.grow + (size_t)li * 5 * A.RMAX,
-                                   A.gkc + (size_t)li * A.RMAX, A.gidx ? A.gidx + (size_t)li * A.RMAX : nullptr,
-                                   list_all + (size_t)warp * A.RMAX);
-    if (lane == 0) {
-        ScanRec r;
-        r.kstar = so.kstar;
-        r.nv = so.nv;
-        r.flag = so.flag;
-        r.pad = 0;
-        A.scan[li] = r;
-    }
 }
 
 // ---- K3 (defined first: K2 runs it in its last CTA) --------------------------------------------

@@ -14,9 +14,4 @@ cudaError_t launch_scan_layout(ScanLayout id, const StepArgs& A, int nl, int K, 
         default: return launch_scan_w<8, 2, 0>(A, nl, K, s);
     }
 }
-cudaError_t launch_scan_pruned(const StepArgs& A, const PruneArgs& G, int K, cudaStream_t s) {
-    if (K == 15) return launch_scan_pruned_w<8, 15>(A, G, K, s);
-    if (K == 20) return launch_scan_pruned_w<8, 20>(A, G, K, s);
-    return launch_scan_pruned_w<8, 0>(A, G, K, s);
-}
 }  // namespace dmpc

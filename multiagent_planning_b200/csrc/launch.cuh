@@ -33,15 +33,12 @@ cudaError_t launch_qp_3_0(const StepArgs& A, int nl, size_t smem, cudaStream_t s
 cudaError_t launch_qp2_15(const StepArgs& A, int nl, cudaStream_t s);
 cudaError_t launch_qp2_20(const StepArgs& A, int nl, cudaStream_t s);
 // scan layouts: W agents per CTA x S warps per agent, horizon KT (0: run time)
-enum ScanLayout { SCAN_1_2_0, SCAN_4_2_15, SCAN_4_2_20, SCAN_4_4_0, SCAN_8_1_15, SCAN_8_1_20, SCAN_8_2_0 };
+enum ScanLayout { SCAN_1_2_0, SCAN_4_2_15, SCAN_4_2_20, SCAN_4_4_0, SCAN_8_1_15, SCAN_8_1_20, SCAN_8_2_0, SCAN_LAYOUTS };
 cudaError_t launch_scan_layout(ScanLayout id, const StepArgs& A, int nl, int K, cudaStream_t s);
-
-// spatially pruned scan for large single swarms (prune_sort_kernel + prune_gather_kernel + scan_pruned_kernel)
-cudaError_t launch_scan_pruned(const StepArgs& A, const PruneArgs& G, int K, cudaStream_t s);
 
 // ---- templates (instantiated by the k_*.cu files only) ---------------------------------------------
 #if defined(DMPC_LAUNCH_IMPL)
-template <int W, int S, int KT>
+template <int W, int S, int KT, bool OWNREG = (KT > 0)>
 cudaError_t launch_scan_w(const StepArgs& A, int nl, int K, cudaStream_t s) {
     const int Npad = round_up(A.P.N, kTile);
     int stages = scan_stages(K, A.P.N, W, A.RMAX);
@@ -52,33 +49,11 @@ cudaError_t launch_scan_w(const StepArgs& A, int nl, int K, cudaStream_t s) {
     static size_t attr_smem[kMaxDevices] = {0};
     const int dev = current_device();
     if (attr_smem[dev] < smem) {
-        cudaError_t e = cudaFuncSetAttribute(scan_kernel<W, S, KT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaError_t e = cudaFuncSetAttribute(scan_kernel<W, S, KT, OWNREG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
         attr_smem[dev] = smem;
     }
-    scan_kernel<W, S, KT><<<(nl + W - 1) / W * A.n_scen, W * S * 32, smem, s>>>(A, stages);
-    return cudaGetLastError();
-}
-template <int W, int KT>
-cudaError_t launch_scan_pruned_w(const StepArgs& A, const PruneArgs& G, int K, cudaStream_t s) {
-    const int N = A.P.N, Npad = round_up(N, kTile);
-    const size_t tile_bytes = (size_t)kTile * 3 * K * sizeof(double);
-    const size_t fixed = scan_pruned_smem_bytes(K, W, 0, Npad, A.RMAX, G.Ntiles);
-    const size_t budget = 200u * 1024u;
-    if (fixed + 2 * tile_bytes > budget) return cudaErrorInvalidConfiguration;
-    int stages = (int)((budget - fixed) / tile_bytes);
-    stages = stages > 8 ? 8 : stages;
-    const size_t smem = scan_pruned_smem_bytes(K, W, stages, Npad, A.RMAX, G.Ntiles);
-    static size_t attr_smem[kMaxDevices] = {0};
-    const int dev = current_device();
-    if (attr_smem[dev] < smem) {
-        cudaError_t e = cudaFuncSetAttribute(scan_pruned_kernel<W, KT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return e;
-        attr_smem[dev] = smem;
-    }
-    prune_sort_kernel<<<1, 1024, 0, s>>>(G);
-    prune_gather_kernel<<<(G.Ntiles + 3) / 4, 128, 0, s>>>(G);
-    scan_pruned_kernel<W, KT><<<(N + W - 1) / W, W * 32, smem, s>>>(A, G, stages);
+    scan_kernel<W, S, KT, OWNREG><<<(nl + W - 1) / W * A.n_scen, W * S * 32, smem, s>>>(A, stages);
     return cudaGetLastError();
 }
 template <int W, int KT>

@@ -107,27 +107,20 @@ struct ScanAcc {
     unsigned coll0;  // per lane: some neighbour is closer than rmin - coll_tol at step 1
 };
 
-// Accumulate ONE neighbour per lane (cnt <= kLanes) starting at global index ibase whose horizons lie at
-// `tile` (cnt x K x 3 doubles, same layout as l).  own = this agent's previous horizon (3K doubles).
-// nearmask[i] (i global) receives the K-bit near mask.  Decisions are taken on the HIGH WORD
+// One (agent, neighbour) pair on this lane: pj = the neighbour's horizon (3K doubles), i = its agent index, own =
+// this agent's previous horizon (3K doubles).  Accumulates the violation bits into acc and stores the K-bit near
+// mask at nearmask[i].  Decisions are taken on the HIGH WORD
 // of the FMA estimate of s with integer compares: for positive doubles  s < T  <=>  hi(s) < hi(T)  unless
 // the high words are within 1 of each other -- only then (relative distance to a threshold < 2^-19, and
 // the estimate is good to a few ulp) the pair goes through the reference's exact rounding sequence.  The
 // fp64 pipe sees 7 operations per (neighbour, step); everything else is 32-bit integer work.
 // KT: compile-time horizon (own[] then lives in registers after unrolling); 0 = run-time P.K.
-// idx != null: the tile comes from a spatially SORTED copy of the buffer; idx[ibase + m] is the neighbour's own
-// agent index (what the near masks and the rows are keyed by).
 template <int KT>
-DMPC_D void scan_tile_hw(const DevParams& P, const ScanThr* __restrict__ thr, const double* __restrict__ own, int n,
-                         const double* __restrict__ tile, int ibase, int cnt, unsigned* nearmask, ScanAcc& acc,
-                         const int* __restrict__ idx = nullptr) {
+DMPC_D void scan_pair_hw(const DevParams& P, const ScanThr* __restrict__ thr, const double* __restrict__ own,
+                         const double* __restrict__ pj, int i, unsigned* nearmask, ScanAcc& acc) {
     const int K = KT ? KT : P.K;
-    const int m = lane_id();
-    if (m >= cnt) return;
-    const int i = idx ? idx[ibase + m] : ibase + m;
     unsigned nm = 0;
-    if (i != n) {
-        const double* pj = tile + (size_t)m * 3 * K;
+    {
         const double inv_c = thr->inv_c;
         const unsigned hv_m = thr->hv_m;
         unsigned vm = 0, amb = 0, c0 = 0;
@@ -164,6 +157,19 @@ DMPC_D void scan_tile_hw(const DevParams& P, const ScanThr* __restrict__ thr, co
         acc.coll0 |= c0;
     }
     nearmask[i] = nm;
+}
+
+// ONE neighbour per lane (cnt <= kLanes) starting at global index ibase whose horizons lie at `tile`
+// (cnt x K x 3 doubles, same layout as l)
+template <int KT>
+DMPC_D void scan_tile_hw(const DevParams& P, const ScanThr* __restrict__ thr, const double* __restrict__ own, int n,
+                         const double* __restrict__ tile, int ibase, int cnt, unsigned* nearmask, ScanAcc& acc) {
+    const int K = KT ? KT : P.K;
+    const int m = lane_id();
+    if (m >= cnt) return;
+    const int i = ibase + m;
+    if (i != n) scan_pair_hw<KT>(P, thr, own, tile + (size_t)m * 3 * K, i, nearmask, acc);
+    else nearmask[i] = 0u;
 }
 
 struct ScanOut {

@@ -717,30 +717,6 @@ def test_device_scenario_generation_and_monte_carlo_harness(dmpc, orc):
             assert pp["traj_time"] == r["traj_time"][0, 1] and pp["violation"] == r["violation"][0, 1]
 
 
-@pytest.mark.parametrize("name", ["N2000", "C4"])
-def test_pruned_scan_equals_brute_force(dmpc, monkeypatch, name):
-    """Large single swarms: the spatially pruned scan (sorted tiles, bounding-box rejection) must leave every
-    decision unchanged -- first violating step, neighbour sets, rows (hence the whole step) bit-identical to the
-    brute-force O(N^2 K) kernel, over closed-loop steps in which the swarm mixes."""
-    from multiagent_planning_b200 import scenarios
-    cfg = scenarios.config(name)
-    P = dmpc.default_params(cfg["variant"], **cfg["params"])
-    res = {}
-    for mode in ("pruned", "brute"):
-        monkeypatch.setenv("DMPCB200_SCAN_PRUNE", "0" if mode == "brute" else "1024")   # (opt-in: 0 is the default)
-        with dmpc.Solver(cfg["N"], P, pmin=cfg["pmin"], pmax=cfg["pmax"], pf=cfg["pf"]) as s:
-            s.init_horizons(cfg["po"])
-            r = s.run(12, record=True, status_hist=True)
-            st = s.get_state()
-            res[mode] = (r, st, s.last_timing())
-    (r1, s1, _), (r2, s2, _) = res["pruned"], res["brute"]
-    assert np.array_equal(s1["diag"]["kstar"], s2["diag"]["kstar"]) and np.array_equal(s1["diag"]["nv"], s2["diag"]["nv"])
-    assert (s1["diag"]["nv"] > 0).sum() > 200
-    for k in ("pk", "vk", "ak", "status_hist"):
-        assert np.array_equal(r1[k], r2[k]), k
-    assert np.array_equal(s1["l"], s2["l"])
-
-
 def _nccl_worker(rank, world, port, q):
     import torch
     import torch.distributed as dist
