@@ -15,7 +15,8 @@ import subprocess
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _CSRC = os.path.join(_HERE, "csrc")
 LIB_PATH = os.path.join(_HERE, "libdmpc_b200.so")
-SOURCES = ["dmpc_b200.cu", "k_qp15.cu", "k_qp20.cu", "k_qpgen.cu", "k_scan.cu",
+_ALT = os.environ.get("DMPCB200_LIB")  # experiment hook: an alternative build of the library (A/B runs, profiling builds)
+SOURCES = ["dmpc_b200.cu", "k_qp15.cu", "k_qp20.cu", "k_qpgen.cu", "k_qphard.cu", "k_scan.cu",
            "model_tables.cpp", "traj_io.cpp"]
 HEADERS = ["dmpc_kernels.cuh", "small_kernels.cuh", "launch.cuh", "scan_core.cuh", "agent_solve.cuh", "qp_core.cuh",
            "qp_warp.cuh", "postprocess.cuh", "model_tables.h", os.path.join("..", "..", "include", "dmpc_b200.h")]
@@ -124,10 +125,14 @@ def lib():
     global _LIB
     if _LIB is not None:
         return _LIB
-    if not os.path.exists(LIB_PATH):
+    if _ALT:
+        path = _ALT
+    else:
+        path = LIB_PATH
+    if not os.path.exists(path):
         raise DmpcError(f"{LIB_PATH} is missing: run `python -c 'import __graft_entry__ as g; g.build()'` "
                         "(there is no CPU fallback)")
-    L = C.CDLL(LIB_PATH)
+    L = C.CDLL(path)
     dp, ip, u8p, vp = C.POINTER(C.c_double), C.POINTER(C.c_int32), C.POINTER(C.c_uint8), C.c_void_p
     PP, DP = C.POINTER(Params), C.POINTER(Diag)
     I, D = C.c_int, C.c_double

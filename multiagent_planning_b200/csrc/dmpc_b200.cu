@@ -18,6 +18,7 @@
 #include "k_qp15.cu"
 #include "k_qp20.cu"
 #include "k_qpgen.cu"
+#include "k_qphard.cu"
 #include "k_scan.cu"
 #endif
 #include "launch.cuh"
@@ -233,6 +234,10 @@ cudaError_t launch_qp(dmpcb200_t* h, const StepArgs& A, cudaStream_t s) {
     const int nl = A.n1 - A.n0;
     if (A.rq) return h->K == 15 ? launch_qp2_15(A, nl, s) : launch_qp2_20(A, nl, s);
     const size_t smem = qp_smem_bytes(h->K, h->W, h->QMAX, h->RCAP);
+    if (h->dp.variant == VAR_HARD) {
+        if (h->K == 15 && h->W == 4) return launch_qp_hard_4_15(A, nl, smem, s);
+        return h->W == 4 ? launch_qp_hard_4_0(A, nl, smem, s) : launch_qp_hard_3_0(A, nl, smem, s);
+    }
     if (h->K == 15 && h->W == 4) return launch_qp_4_15(A, nl, smem, s);
     if (h->K == 20 && h->W == 4) return launch_qp_4_20(A, nl, smem, s);
     // W = 4 for every horizon up to 21, 3 beyond (the tables grow with K^2)

@@ -496,7 +496,9 @@ constexpr int kLightQ = 32;
 // call site per MODE, so within a kernel an agent's bits do not depend on how it was scheduled.  Two kernels
 // (classic / throughput layout) carry separately optimised copies whose FMA contraction may differ: across
 // layouts results agree to rounding (~1e-14), not bit for bit.
-template <int KT, int MODE>
+// HARD: the kernel serves solveHardDMPC (its own instantiation of the register-resident solver, rows on several
+// horizon indices); the other kernels keep exactly the code of the on-demand variants.
+template <int KT, int MODE, bool HARD = false>
 DMPC_D bool qp_agent(const StepArgs& A, int li, const double* tab_s, unsigned char* scratch) {
     const int K = KT ? KT : A.P.K, n3 = 3 * K;
     const int lane = threadIdx.x & 31;
@@ -545,11 +547,11 @@ DMPC_D bool qp_agent(const StepArgs& A, int li, const double* tab_s, unsigned ch
     AgentDiag dg;
     int st = 0, it0 = 0;
     // fast path: the register-resident warp solver (qp_warp.cuh) -- every agent of the soft variants whose
-    // rows fit (more than 64 rows: a working set of 64 with exact row exchange, qp_warp.cuh).  The generic
-    // solver (qp_core.cuh) takes the rest: solveHardDMPC (rows on many horizon steps) and -- in a
-    // global-memory rescue slot of capacity QBIG -- agents whose active set outgrew the on-chip capacity or
+    // rows fit (more than 64 rows: a working set of 64 with exact row exchange, qp_warp.cuh; solveHardDMPC
+    // with its rows on many horizon steps: the MK instantiation).  The generic solver (qp_core.cuh) takes
+    // the rest: horizons beyond 21 steps and -- in a global-memory rescue slot of capacity QBIG -- agents whose active set outgrew the on-chip capacity or
     // whose working set has no free slot left.  One call site, so the generic solver exists once.
-    const bool fast_ok = (n3 <= kQW) && (sr.nv <= kRowsFastMax) && (A.P.variant != VAR_HARD) && !sr.flag;
+    const bool fast_ok = (n3 <= kQW) && (sr.nv <= kRowsFastMax) && !sr.flag && (HARD || A.P.variant != VAR_HARD);
     if (MODE == 1) {
         if (sr.flag) {
             // the scan already decided (predicted collision at the next step / row overflow): the reference
@@ -564,14 +566,15 @@ DMPC_D bool qp_agent(const StepArgs& A, int li, const double* tab_s, unsigned ch
             }
         } else {
             if (!fast_ok) return false;
-            st = agent_solve_fast<KT, kLightQ>(A.P, tab_s, scratch, A.QMAX, io, &dg);
+            if (sr.nv > kQW) return false;  // (row working set: full path only)
+            st = agent_solve_fast<KT, kLightQ, false, false>(A.P, tab_s, scratch, A.QMAX, io, &dg);
             if (st & ST_OVERFLOW) return false;  // the active set outgrew the light capacity: full path
         }
     } else {
         bool generic = !fast_ok, rescue = false;
         int cap = A.QMAX;
         if (fast_ok) {
-            st = agent_solve_fast<KT>(A.P, tab_s, scratch, A.QMAX, io, &dg);
+            st = agent_solve_fast<KT, kQW, HARD>(A.P, tab_s, scratch, A.QMAX, io, &dg);
             if ((st & ST_OVERFLOW) && A.rescue) {
                 generic = true;
                 rescue = true;
@@ -605,7 +608,7 @@ DMPC_D bool qp_agent(const StepArgs& A, int li, const double* tab_s, unsigned ch
     return true;
 }
 
-template <int W, int KT>
+template <int W, int KT, bool HARD = false>
 __global__ void __launch_bounds__(W * 32, 1) qp_kernel(const __grid_constant__ StepArgs A) {
     if (A.ctrl && A.n_scen == 1 && A.ctrl->done) return;
     extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -635,7 +638,7 @@ __global__ void __launch_bounds__(W * 32, 1) qp_kernel(const __grid_constant__ S
     unsigned char* const scratch = smem_raw + tab_bytes + (size_t)warp * per_warp;
     while (li < nl) {
         mbar_wait(bar, 0);  // tables have landed
-        qp_agent<KT, 0>(A, li, tab_s, scratch);
+        qp_agent<KT, 0, HARD>(A, li, tab_s, scratch);
         if (!queued) break;
         if (lane == 0) li = (int)gridDim.x * W + (int)atomicAdd(A.work_cnt, 1u);
         li = __shfl_sync(0xffffffffu, li, 0);

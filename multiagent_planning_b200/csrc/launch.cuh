@@ -29,6 +29,10 @@ cudaError_t launch_qp_4_15(const StepArgs& A, int nl, size_t smem, cudaStream_t 
 cudaError_t launch_qp_4_20(const StepArgs& A, int nl, size_t smem, cudaStream_t s);
 cudaError_t launch_qp_4_0(const StepArgs& A, int nl, size_t smem, cudaStream_t s);
 cudaError_t launch_qp_3_0(const StepArgs& A, int nl, size_t smem, cudaStream_t s);
+// solveHardDMPC (k_qphard.cu): K = 15 compiled in, any other horizon generic
+cudaError_t launch_qp_hard_4_15(const StepArgs& A, int nl, size_t smem, cudaStream_t s);
+cudaError_t launch_qp_hard_4_0(const StepArgs& A, int nl, size_t smem, cudaStream_t s);
+cudaError_t launch_qp_hard_3_0(const StepArgs& A, int nl, size_t smem, cudaStream_t s);
 // throughput layout (two-role persistent kernel, 8 light / 4 heavy agents per SM), horizons 15 and 20
 cudaError_t launch_qp2_15(const StepArgs& A, int nl, cudaStream_t s);
 cudaError_t launch_qp2_20(const StepArgs& A, int nl, cudaStream_t s);
@@ -56,13 +60,13 @@ cudaError_t launch_scan_w(const StepArgs& A, int nl, int K, cudaStream_t s) {
     scan_kernel<W, S, KT, OWNREG><<<(nl + W - 1) / W * A.n_scen, W * S * 32, smem, s>>>(A, stages);
     return cudaGetLastError();
 }
-template <int W, int KT>
+template <int W, int KT, bool HARD = false>
 cudaError_t launch_qp_w(const StepArgs& A, int nl, size_t smem, cudaStream_t s) {
     static size_t attr_smem[kMaxDevices] = {0};  // per device, like the SM count below
     const int dev = current_device();
     if (attr_smem[dev] < smem) {  // (the kernel also has a few hundred bytes of static shared memory)
         cudaError_t e =
-            cudaFuncSetAttribute(qp_kernel<W, KT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            cudaFuncSetAttribute(qp_kernel<W, KT, HARD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
         attr_smem[dev] = smem;
     }
@@ -80,7 +84,7 @@ cudaError_t launch_qp_w(const StepArgs& A, int nl, size_t smem, cudaStream_t s) 
     at[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = at;
     cfg.numAttrs = 1;
-    return cudaLaunchKernelEx(&cfg, qp_kernel<W, KT>, A);
+    return cudaLaunchKernelEx(&cfg, qp_kernel<W, KT, HARD>, A);
 }
 template <int KT>
 cudaError_t launch_qp2_w(const StepArgs& A, int nl, cudaStream_t s) {

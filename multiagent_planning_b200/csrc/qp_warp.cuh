@@ -22,8 +22,9 @@
 //     iterations; tries that are certainly infeasible are skipped without running the 45-variable
 //     solver on them (it would need ~100 iterations to find out).  A try that passes the test is
 //     solved normally, so the outcome is the reference's in every case.
-// Capacity: 3K <= 64 entries, <= 64 rows that all act on one horizon index (every variant except
-// solveHardDMPC), <= 64 active constraints.  Anything else is solved by the generic solver.
+// Capacity: 3K <= 64 entries, 64 rows in the working set at a time (more rows: exact row exchange), <= 64 active
+// constraints.  solveHardDMPC (rows on several horizon indices) runs on the MK instantiation.  Anything else is
+// solved by the generic solver.
 //
 // The file compiles for the host with one "lane" that owns all 64 items (a test-only build): that
 // build is a debugging aid of the test-suite and is never part of the product library.
@@ -119,13 +120,17 @@ DMPC_HD unsigned qw_setb(unsigned m, int b, unsigned v) { return (m & ~(0xffu <<
 // doubles / ints of shared memory the fast solver needs per agent
 DMPC_HD size_t qw_smem_doubles(int QC = kQW) { return (size_t)QC * (QC + 2) + 16 * (size_t)kQW; }
 DMPC_HD size_t qw_smem_ints() { return 5 * (size_t)kQW; }
-constexpr int kRowsFastMax = 512;  // rows of the scan the fast path accepts (kQW of them in the working set at a time)
+constexpr int kRowsFastMax = 512;  // rows of the scan the fast path accepts (kQW of them in the working set at a time;
+                                  // the bitmap of the set has 48 words = 1536 bits)
 DMPC_HD size_t qw_smem_bytes(int QC = kQW) { return qw_smem_doubles(QC) * sizeof(double) + qw_smem_ints() * sizeof(int); }
 
 // QC: capacity of the active set = rows (and, + 2, the row stride) of M.  64 for the one-agent-per-sub-partition
 // layout; the throughput layout of K2 runs light agents with QC = 32 (a quarter of the shared memory, so that
 // twice as many agents are resident per SM) and sends the ones that outgrow it to a QC = 64 pass.
-template <int KT, int QC = kQW>
+// MK: the rows act on several horizon indices (solveHardDMPC: rows for every step at which a neighbour is
+// within hard_radius, solveHardDMPC.m:18-22) -- false: all rows act on kc_all (the on-demand variants; the hot
+// loop then reads one position for all rows and adds one 3-vector to one horizon index).
+template <int KT, int QC = kQW, bool MK = false>
 struct QpW {
     static constexpr int kMSq = QC + 2;  // row stride of M in doubles (conflict-free 128-bit row streaming)
     // ---- uniform problem data ---------------------------------------------------------------------
@@ -510,7 +515,7 @@ struct QpW {
     //   cp: coefficients on rows of Lam (workspace constraints and collision rows at kc_all)
     DMPC_D void coefs() {
         double D0 = 0.0, D1 = 0.0, D2 = 0.0;
-        if (nra) {
+        if (!MK && nra) {
             QW_FOR(h) {
                 if (h * kLanes < nv) {  // uniform
                     const int j = qw_item(h) & (kQW - 1);
@@ -534,10 +539,35 @@ struct QpW {
             cc.x = ((sl != kNone) ? c0 : 0.0) - ((su != kNone) ? c1 : 0.0);
             cc.y = ((wl != kNone) ? c2 : 0.0) - ((wu != kNone) ? c3 : 0.0);
             const double dx = (ex[h] == 0) ? D0 : ((ex[h] == 1) ? D1 : D2);
-            cc.y += (nra && ek[h] == kc_all) ? dx : 0.0;
+            if (!MK) cc.y += (nra && ek[h] == kc_all) ? dx : 0.0;
             if (i < n3) st2(cbp + 2 * (ex[h] * Kk + ek[h]), cc);
         }
         wsync();
+        if (MK && nra) {
+            // rows on several horizon indices: every active row adds c_j d_j to the three entries of ITS index
+            // (shared-memory atomics: two active rows may share an index)
+            QW_FOR(h) {
+                if (h * kLanes < nv) {  // uniform
+                    const int j = qw_item(h) & (kQW - 1);
+                    const unsigned sr = qw_getb(rmap[h], 0);
+                    if (sr != kNone) {
+                        const double c = rs[sr & (kQW - 1)];
+                        const int k = rkc[j];
+                        shared_add(cbp + 2 * k + 1, c * rd0[j]);
+                        shared_add(cbp + 2 * (Kk + k) + 1, c * rd1[j]);
+                        shared_add(cbp + 2 * (2 * Kk + k) + 1, c * rd2[j]);
+                    }
+                }
+            }
+            wsync();
+        }
+    }
+    DMPC_D static void shared_add(double* p, double v) {
+#if defined(__CUDA_ARCH__)
+        atomicAdd(p, v);
+#else
+        *p += v;
+#endif
     }
 
     // ---- ONE pass over the interleaved table:  oa_i = ba_i + sgn (G cb + B cp)_i,
@@ -667,7 +697,9 @@ struct QpW {
         QW_FOR(h) {
             const int j = qw_item(h);
             if (j < nv) {
-                double s = rd0[j] * l0 + rd1[j] * l1 + rd2[j] * l2 - rrhs[j];
+                const int kj = 3 * rkc[j];
+                double s = MK ? rd0[j] * Ls[kj] + rd1[j] * Ls[kj + 1] + rd2[j] * Ls[kj + 2] - rrhs[j]
+                              : rd0[j] * l0 + rd1[j] * l1 + rd2[j] * l2 - rrhs[j];
                 if (soft) s -= rdist[j] * eps[h];
                 rres[h] = s;
                 cb[j] = eps[h];
@@ -1252,8 +1284,32 @@ struct QpW {
     // materialised -- the state of the method does not depend on them) and the iteration continues from the
     // same valid state.  Exact in every case; the generic solver remains the fallback when no slot is free.
 
+    // where the scan's rows live (global memory, SoA with stride RMAX) and how many there are
+    struct RowSrc {
+        const double* grow;
+        const int* gkc;
+        int RMAX, NT;
+    };
+    // parked in the spare words of the bitmap array while the solver runs (see agent_solve_fast)
+    DMPC_D void park(const RowSrc& io) {
+        if (lane_id() == 0) {
+            *reinterpret_cast<const double**>(kept + 48) = io.grow;
+            *reinterpret_cast<const int**>(kept + 50) = io.gkc;
+            kept[52] = io.RMAX;
+            kept[53] = io.NT;
+        }
+    }
+    DMPC_D RowSrc unpark() const {
+        RowSrc io;
+        io.grow = *reinterpret_cast<const double* const*>(kept + 48);
+        io.gkc = *reinterpret_cast<const int* const*>(kept + 50);
+        io.RMAX = kept[52];
+        io.NT = kept[53];
+        return io;
+    }
+
     // static data of scan row r -> slot j (one lane)
-    DMPC_D void load_row(int j, int r, const AgentIO& io, const double* t_lnorm) {
+    DMPC_D void load_row(int j, int r, const RowSrc& io, const double* t_lnorm) {
         const double d0 = io.grow[r], d1 = io.grow[(size_t)io.RMAX + r], d2 = io.grow[2 * (size_t)io.RMAX + r];
         const double dist = io.grow[3 * (size_t)io.RMAX + r];
         const int kc = io.gkc[r];
@@ -1267,18 +1323,25 @@ struct QpW {
 
     // choose the first working set: the kQW rows with the smallest normalised residual at y = P_unc[kc_all]
     // (ties: lower row first), kept in the scan's order.  M is used as scratch (before cold_start clears it).
-    DMPC_COLD void select_rows(int NT, const AgentIO& io, const double* t_lnorm) {
+    DMPC_COLD void select_rows(const RowSrc& io, const double* t_lnorm) {
+        const int NT = io.NT;
         double* key = M;
         int* rank = reinterpret_cast<int*>(M + kRowsFastMax);
-        const double y0 = item_d(Punc, 3 * kc_all), y1 = item_d(Punc, 3 * kc_all + 1), y2 = item_d(Punc, 3 * kc_all + 2);
+        QW_FOR(h) {
+            const int i = qw_item(h);
+            if (i < n3) Ls[i] = Punc[h];
+        }
+        wsync();
         for (int r = lane_id(); r < NT; r += kLanes) {
             const double d0 = io.grow[r], d1 = io.grow[(size_t)io.RMAX + r], d2 = io.grow[2 * (size_t)io.RMAX + r];
+            const int kr = 3 * io.gkc[r];
             const double dist = io.grow[3 * (size_t)io.RMAX + r], ln = t_lnorm[io.gkc[r]];
             const double dd = d0 * d0 + d1 * d1 + d2 * d2;
+            const double y0 = Ls[kr], y1 = Ls[kr + 1], y2 = Ls[kr + 2];
             key[r] = (d0 * y0 + d1 * y1 + d2 * y2 - io.grow[4 * (size_t)io.RMAX + r]) /
                      sqrt(dd * ln * ln + (soft ? dist * dist : 0.0));
         }
-        for (int w = lane_id(); w < kQW; w += kLanes) kept[w] = 0;
+        for (int w = lane_id(); w < 48; w += kLanes) kept[w] = 0;  // (words 48.. hold the parked row source)
         wsync();
         for (int r = lane_id(); r < NT; r += kLanes) {
             const double kr = key[r];
@@ -1305,18 +1368,24 @@ struct QpW {
     // after a converged solve: exchange violated rows outside the set for untouched rows of the set.
     // Returns the number of rows brought in (0: the solution is the full problem's), -1: violated rows remain
     // and no slot is free (the caller falls back to the generic solver).
-    DMPC_COLD int exchange_rows(int NT, const AgentIO& io, const double* t_lnorm, double tol) {
+    DMPC_COLD int exchange_rows(const RowSrc& io, const double* t_lnorm, double tol) {
+        const int NT = io.NT;
         int* vio = reinterpret_cast<int*>(cp);  // (the shared copies of eps / residuals are not needed here)
-        const double y0 = item_d(P, 3 * kc_all), y1 = item_d(P, 3 * kc_all + 1), y2 = item_d(P, 3 * kc_all + 2);
+        QW_FOR(h) {
+            const int i = qw_item(h);
+            if (i < n3) Ls[i] = P[h];
+        }
+        wsync();
         int nvio = 0;
         for (int base = 0; base < NT; base += kLanes) {
             const int r = base + lane_id();
             bool v = false;
             if (r < NT && !((kept[r >> 5] >> (r & 31)) & 1)) {
                 const double d0 = io.grow[r], d1 = io.grow[(size_t)io.RMAX + r], d2 = io.grow[2 * (size_t)io.RMAX + r];
+                const int kr = 3 * io.gkc[r];
                 const double dist = io.grow[3 * (size_t)io.RMAX + r], ln = t_lnorm[io.gkc[r]];
                 const double dd = d0 * d0 + d1 * d1 + d2 * d2;
-                const double res = d0 * y0 + d1 * y1 + d2 * y2 - io.grow[4 * (size_t)io.RMAX + r];
+                const double res = d0 * Ls[kr] + d1 * Ls[kr + 1] + d2 * Ls[kr + 2] - io.grow[4 * (size_t)io.RMAX + r];
                 // the test of most_violated: residual / norm of the row < -tol
                 v = res < -tol * sqrt(dd * ln * ln + (soft ? dist * dist : 0.0));
             }
@@ -1351,12 +1420,8 @@ struct QpW {
         }
         const int nsw = nfree < nvio ? nfree : nvio;
         if (nsw == 0) return -1;
-        QW_FOR(h) {
-            const int i = qw_item(h);
-            if (i < n3) Ls[i] = P[h];
-        }
         wsync();
-        rows_refresh();
+        rows_refresh();  // (Ls holds P)
         return nsw;
     }
 
@@ -1483,7 +1548,9 @@ struct QpW {
                         QW_FOR(h) {
                             if (h * kLanes >= nv) continue;  // uniform
                             const int j = qw_item(h) & (kQW - 1);
-                            double nz = rd0[j] * l0 + rd1[j] * l1 + rd2[j] * l2;
+                            const int kj = 3 * rkc[j];
+                            double nz = MK ? rd0[j] * Ls[kj] + rd1[j] * Ls[kj + 1] + rd2[j] * Ls[kj + 2]
+                                           : rd0[j] * l0 + rd1[j] * l1 + rd2[j] * l2;
                             const double ze = zeps[h];  // 0 unless soft and materialised
                             eps[h] = fma(t, ze, eps[h]);
                             nz = fma(-rdist[j], ze, nz);
@@ -1566,7 +1633,13 @@ struct QpW {
 // tab: the whole table blob in shared memory; smem: qw_smem_bytes() of per-agent workspace.
 // Same contract as agent_solve() (agent_solve.cuh); returns the status word (ST_OVERFLOW: the active set
 // outgrew qcap -- the caller re-solves with the generic solver).
-template <int KT, int QC = kQW>
+// ROWSET: can hold a working set of the scan's rows (io.nv > kQW).  What the exchange needs after a solve (row
+// arrays, counts) is parked in shared memory meanwhile: kept alive in registers across the solver it cost every
+// agent 2.6 % (C3, A/B on one box), and a second inlined copy of the solver for these agents cost 16 %.
+#ifndef DMPC_ROWSET_DEFAULT
+#define DMPC_ROWSET_DEFAULT true  // (false: A/B build without the row working set)
+#endif
+template <int KT, int QC = kQW, bool MK = false, bool ROWSET = DMPC_ROWSET_DEFAULT>
 DMPC_D int agent_solve_fast(const DevParams& Pm, const double* __restrict__ tab, unsigned char* smem, int qcap,
                             const AgentIO& io, AgentDiag* diag_out) {
     const int K = KT ? KT : Pm.K, n3 = 3 * K;
@@ -1577,10 +1650,11 @@ DMPC_D int agent_solve_fast(const DevParams& Pm, const double* __restrict__ tab,
     dg.nact = 0;
     int status = 0;
 
-    QpW<KT, QC> qp;
+    QpW<KT, QC, MK> qp;
     qp.carve(smem);
     const bool soft = (Pm.variant == VAR_SOFT_BOUND || Pm.variant == VAR_SOFT_BOUND2);
-    const bool any_violation = io.kstar > 0;
+    // solveHardDMPC quirk: Ain_coll is never empty for N >= 2 -> collision weights always
+    const bool any_violation = (Pm.variant == VAR_HARD) ? (Pm.N >= 2) : (io.kstar > 0);
     double x_po[3], x_pf[3], x_vo[3], x_ao[3];
 #pragma unroll
     for (int x = 0; x < 3; ++x) {
@@ -1605,15 +1679,13 @@ DMPC_D int agent_solve_fast(const DevParams& Pm, const double* __restrict__ tab,
     // tab: the shared-memory blob of model_tables.h (header padded to 4 doubles, then T4 per weight set)
     const double* t_T4 = tab + tab_fast_header(K) + (size_t)wset * 4 * K * K;
     qp.K = K; qp.n3 = n3; qp.soft = soft ? 1 : 0;
-    qp.kc_all = io.kstar > 0 ? io.kstar - 1 - (Pm.variant == VAR_SOFT_BOUND2 ? 1 : 0) : 0;
+    qp.kc_all = (!MK && io.kstar > 0) ? io.kstar - 1 - (Pm.variant == VAR_SOFT_BOUND2 ? 1 : 0) : 0;
     qp.alim = Pm.alim; qp.qw = qw; qp.sw = sw;
     qp.qcap = qcap < QC ? qcap : QC;
     qp.ilnorm = tab + K * K + 2 * K; qp.T4 = t_T4;
 
     // ---- rows: at most kQW of the scan's rows are in the working set at a time (see select_rows) ----------
-    const int NT = io.nv;
-    const int nv = NT < kQW ? NT : kQW;
-    const bool subset = NT > kQW;
+    const int nv = io.nv < kQW ? io.nv : kQW;
     qp.nv = nv;
     // ---- a_unc = -G f,  P_unc = A_initp [po;vo] + Lam a_unc  (solveSoftDMPCbound.m:82-88) ------------
     QW_FOR(h) {
@@ -1654,12 +1726,23 @@ DMPC_D int agent_solve_fast(const DevParams& Pm, const double* __restrict__ tab,
     wsync();
 
     // ---- rows: global SoA (scan output) -> shared ---------------------------------------------------
-    if (subset) qp.select_rows(NT, io, t_lnorm);
+    {
+        typename QpW<KT, QC, MK>::RowSrc src;
+        src.grow = io.grow;
+        src.gkc = io.gkc;
+        src.RMAX = io.RMAX;
+        src.NT = io.nv;
+        const bool subset = ROWSET && io.nv > kQW;
+        if (ROWSET) qp.park(src);
+        if (subset) qp.select_rows(src, t_lnorm);
+        QW_FOR(h) {
+            const int j = qw_item(h);
+            if (j < nv) qp.load_row(j, subset ? qp.rsrc[j] : j, src, t_lnorm);
+        }
+    }
     QW_FOR(h) {
         const int j = qw_item(h);
-        if (j < nv) {
-            qp.load_row(j, subset ? qp.rsrc[j] : j, io, t_lnorm);
-        } else if (j < kQW) {
+        if (j >= nv && j < kQW) {
             // rows beyond nv are read (and discarded) by the branch-free loops: keep them finite
             qp.rd0[j] = 0.0; qp.rd1[j] = 0.0; qp.rd2[j] = 0.0; qp.rdist[j] = 0.0; qp.rrhs[j] = 0.0; qp.rirn[j] = 0.0;
             qp.rkc[j] = 0;
@@ -1691,49 +1774,44 @@ DMPC_D int agent_solve_fast(const DevParams& Pm, const double* __restrict__ tab,
     bool give_up = false;
     bool use_list = io.warm && io.gidx && io.warm[0] > 0;  // (DMPC_WARM_START experiment only)
     (void)use_list;
+    bool resume = false;  // go on from the current state (rows were exchanged); solve() has ONE call site
     for (;;) {
-        // skip the tries that the 3-D necessary condition proves infeasible (with a 1e-6 margin on slb)
-        while (relax && qp.relaxed_infeasible(slb * (1.0 + 1e-6), ylo, yhi)) {
-            slb *= 2.0;
-            term *= 2.0;
-            if (++tries >= Pm.max_tries) { give_up = true; break; }
-        }
-        if (give_up) break;
-        qp.term = term;
-        qp.slb = slb;
         bool guessed = false;
-        if (!(warm && qp.warm_restart())) {
-            qp.cold_start();
-#if defined(DMPC_WARM_START)
-            if (use_list) {
-                // first solve of this step: start from the previous step's final active set
-                use_list = false;
-                int rid[kEPL];
-                QW_FOR(h) rid[h] = (qw_item(h) < nv) ? io.gidx[qw_item(h) & (kQW - 1)] : -1;
-                guessed = qp.warm_start(io.warm + 1, io.warm[0], rid);
-                DMPC_WARM_STAT(dg.nact += (qp.q << 8) | (qp.stat_built << 16) | (io.warm[0] << 24));
+        if (!resume) {
+            // skip the tries that the 3-D necessary condition proves infeasible (with a 1e-6 margin on slb)
+            while (relax && qp.relaxed_infeasible(slb * (1.0 + 1e-6), ylo, yhi)) {
+                slb *= 2.0;
+                term *= 2.0;
+                if (++tries >= Pm.max_tries) { give_up = true; break; }
             }
+            if (give_up) break;
+            qp.term = term;
+            qp.slb = slb;
+            if (!(warm && qp.warm_restart())) {
+                qp.cold_start();
+#if defined(DMPC_WARM_START)
+                if (use_list) {
+                    // first solve of this step: start from the previous step's final active set
+                    use_list = false;
+                    int rid[kEPL];
+                    QW_FOR(h) rid[h] = (qw_item(h) < nv) ? io.gidx[qw_item(h) & (kQW - 1)] : -1;
+                    guessed = qp.warm_start(io.warm + 1, io.warm[0], rid);
+                    DMPC_WARM_STAT(dg.nact += (qp.q << 8) | (qp.stat_built << 16) | (io.warm[0] << 24));
+                }
 #endif
+            }
         }
-        QpResult r = qp.solve(max_iter, &m_valid);
+        const QpResult r = qp.solve(max_iter, &m_valid, resume);
+        resume = false;
         dg.iters += r.iters;
-        if (guessed && r.rc != QP_OK) {
-            // any verdict other than "solved" is taken from the cold start only
-            qp.cold_start();
-            r = qp.solve(max_iter, &m_valid);
-            dg.iters += r.iters;
-        }
-        // more rows than the working set holds: bring in the ones the solution violates and go on
-        bool no_slot = false;
-        while (subset && r.rc == QP_OK) {
-            const int nsw = qp.exchange_rows(NT, io, t_lnorm, DMPC_FEAS_TOL);
-            if (nsw == 0) break;
-            if (nsw < 0) { no_slot = true; break; }
-            r = qp.solve(max_iter, &m_valid, true);
-            dg.iters += r.iters;
-        }
         dg.nact = (dg.nact & ~0xff) | r.q;
-        if (no_slot) { status |= ST_QPFAIL | ST_OVERFLOW; break; }
+        if (guessed && r.rc != QP_OK) continue;  // any verdict other than "solved" is taken from the cold start only
+        if (ROWSET && r.rc == QP_OK && qp.kept[53] > kQW) {
+            // more rows than the working set holds: bring in the ones the solution violates and go on
+            const int nsw = qp.exchange_rows(qp.unpark(), tab + K * K + K, DMPC_FEAS_TOL);
+            if (nsw > 0) { resume = true; continue; }
+            if (nsw < 0) { status |= ST_QPFAIL | ST_OVERFLOW; break; }
+        }
         if (r.rc == QP_OK) { solved = true; break; }
         if (r.rc == QP_ITERCAP) { status |= ST_QPFAIL; break; }
         if (r.rc == QP_OVERFLOW) { status |= ST_QPFAIL | ST_OVERFLOW; break; }

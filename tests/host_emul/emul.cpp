@@ -69,8 +69,10 @@ extern "C" int emul_step(const dmpcb200_params* p, int N, int n0, int n1, const 
         io.gidx = gidx.data();
         io.warm = warm ? warm + (size_t)kWarmStride * n : nullptr;
         AgentDiag dg;
-        if (fast && 3 * K <= kQW && so.nv <= kRowsFastMax && D.variant != VAR_HARD && !so.flag)
-            status[n] = agent_solve_fast<0>(D, tab.data() + tables_fast_offset(K), smem.data(), QMAX, io, &dg);
+        if (fast && 3 * K <= kQW && so.nv <= kRowsFastMax && !so.flag)
+            status[n] = (D.variant == VAR_HARD)
+                            ? agent_solve_fast<0, kQW, true>(D, tab.data() + tables_fast_offset(K), smem.data(), QMAX, io, &dg)
+                            : agent_solve_fast<0>(D, tab.data() + tables_fast_offset(K), smem.data(), QMAX, io, &dg);
         else
             status[n] = agent_solve<0>(D, tab.data(), smem.data(), QMAX, RCAP, io, &dg);
         if (diag) { diag[4 * n] = dg.kstar; diag[4 * n + 1] = dg.nv; diag[4 * n + 2] = dg.iters; diag[4 * n + 3] = dg.nact; }

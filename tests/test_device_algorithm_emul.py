@@ -203,3 +203,35 @@ def test_fast_path_row_working_set(orc, emul):
             assert e["diag"][big, 2].max() < 80                  # (the generic solver needs up to 200 iterations here)
         l, pk, vk, ak = o["l_new"], o["p1"], o["v1"], o["a1"]
     assert nbig >= 10
+
+
+def test_fast_path_hard_variant(orc, emul, golden):
+    """solveHardDMPC on the register-resident solver (rows on several horizon indices, more rows than the working
+    set holds): one step on the N = 100 known-answer inputs and a closed-loop stretch of C2 against the oracle"""
+    g = golden["kat_soft_bound2"]
+    P = orc.default_params(orc.VARIANT_HARD)
+    o = orc.step(P, g["pk_prev"], g["vk_prev"], g["ak_prev"], g["pf"], g["l"], g["pmin"], g["pmax"], nthreads=4)
+    e = emul.step(emul.params_from(P), g["pk_prev"], g["vk_prev"], g["ak_prev"], g["pf"], g["l"], g["pmin"],
+                  g["pmax"], QMAX=-64, RMAX=1024)
+    assert np.array_equal(o["status"], e["status"]) and not (e["status"] & 32).any()
+    assert np.abs(o["l_new"] - e["l_new"]).max() <= 1e-9
+    from multiagent_planning_b200 import scenarios
+    cfg = scenarios.config("C2")
+    N = cfg["N"]
+    P = orc.default_params(cfg["variant"])
+    for k, v in cfg["params"].items():
+        setattr(P, k, v)
+    K = P.K
+    l = np.zeros((3, K, N), order="F")
+    for n in range(N):
+        l[:, :, n] = orc.init_dmpc(cfg["po"][:, n], cfg["pf"][:, n], P.h, K, P.init_div)[0]
+    pk, vk, ak = l[:, 0, :].copy(), np.zeros((3, N)), np.zeros((3, N))
+    big = 0
+    for k in range(10):
+        o = orc.step(P, pk, vk, ak, cfg["pf"], l, cfg["pmin"], cfg["pmax"], nthreads=4)
+        e = emul.step(emul.params_from(P), pk, vk, ak, cfg["pf"], l, cfg["pmin"], cfg["pmax"], QMAX=-64, RMAX=1024)
+        assert np.array_equal(o["status"], e["status"]) and not (e["status"] & 32).any()
+        assert np.abs(o["l_new"] - e["l_new"]).max() <= 1e-8
+        big += int((e["diag"][:, 1] > 64).sum())
+        l, pk, vk, ak = o["l_new"], o["p1"], o["v1"], o["a1"]
+    assert big >= 20      # agents with more rows than the working set
