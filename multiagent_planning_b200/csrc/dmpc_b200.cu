@@ -218,14 +218,22 @@ cudaError_t launch_scan(dmpcb200_t* h, const StepArgs& A, cudaStream_t s) {
     if ((A.rq || A.n_scen > 1 || (long long)nl * A.n_scen > 4LL * sm_count(current_device())) &&
         scan_stages(K, N, 8, A.RMAX) >= (N + kTile - 1) / kTile)
         return launch_scan_layout(SCAN_8_2_0, A, nl, K, s);
-    if (nl <= 4 * 148 || scan_stages(K, N, 8, A.RMAX) < 2) {
+    // single swarms with a compiled-in horizon: the register-tile layout (a warp per tile, the CTA's agents looped
+    // over: 2.5x fewer shared-memory wavefronts per pair).  Measured (scan per step, N = 500 / 2000 / C4): 16.7 ->
+    // 15.4 us, 120 -> 75 us (14 agents per CTA: one wave of 143 CTAs), 200 -> 126 us; bit-identical rows.
+    const int n_sm = sm_count(current_device());
+    if (nl <= 4 * n_sm || scan_stages(K, N, 8, A.RMAX) < 2) {
         if (scan_stages(K, N, 4, A.RMAX) < 1) return launch_scan_layout(SCAN_1_2_0, A, nl, K, s);
-        if (K == 15) return launch_scan_layout(SCAN_4_2_15, A, nl, K, s);
-        if (K == 20) return launch_scan_layout(SCAN_4_2_20, A, nl, K, s);
+        if (K == 15) return launch_scan_layout(SCAN_RT_4_8_15, A, nl, K, s);
+        if (K == 20) return launch_scan_layout(SCAN_RT_4_8_20, A, nl, K, s);
         return launch_scan_layout(SCAN_4_4_0, A, nl, K, s);
     }
-    if (K == 15) return launch_scan_layout(SCAN_8_1_15, A, nl, K, s);  // measured at N=2000: 123 us vs 151 (<8,2,0>) / 145 (<4,2,15>)
-    if (K == 20) return launch_scan_layout(SCAN_8_1_20, A, nl, K, s);
+    if (K == 15) {
+        // one wave of CTAs when 14 agents per CTA cover the swarm and 8 tiles still fit beside their masks
+        if ((nl + 13) / 14 <= n_sm && scan_stages(K, N, 14, A.RMAX) >= 8) return launch_scan_layout(SCAN_RT_14_8_15, A, nl, K, s);
+        return launch_scan_layout(SCAN_RT_8_8_15, A, nl, K, s);
+    }
+    if (K == 20) return launch_scan_layout(SCAN_RT_8_8_20, A, nl, K, s);
     return launch_scan_layout(SCAN_8_2_0, A, nl, K, s);
 }
 // horizon lengths 15 and 20 (the reference's configurations) are compiled with the horizon as a

@@ -355,6 +355,196 @@ __global__ void __launch_bounds__(W * S * 32) scan_kernel(const __grid_constant_
     SCAN_PROF(3);
 }
 
+// ---- K1, register-tile layout -----------------------------------------------------------------------------
+// The tile loop of scan_kernel is bound by shared-memory wavefronts: every warp (one agent) re-reads the whole
+// tile, 2 wavefronts per 64-bit read and lane (profiles/r2f_scan_experiments.txt: the SM runs at ~1.65 warp
+// instructions per cycle whatever the occupancy, whatever the number of pair evaluations).  Here the roles are
+// swapped: a warp takes a TILE, every lane holds one neighbour's whole horizon in REGISTERS (3 KT doubles) and
+// the warp loops over the CTA's W agents, whose horizons are read from shared memory as 128-bit BROADCASTS
+// (one wavefront per two doubles): ~2.5x fewer wavefronts per pair.  Tiles are drawn from a shared counter (NW
+// warps, any number of ring slots: the warp that has finished a tile re-arms its slot itself with the tile
+// `stages` further on -- no CTA-wide barrier in the loop).  Same per-pair arithmetic and decisions as
+// scan_pair_hw (high-word compares, exact redo next to a threshold): bit-identical masks.
+// Needs a compile-time horizon (KT = 15, 20).  smem: like scan_kernel (+ own horizons padded to 128-bit rows).
+template <int KT>
+DMPC_D void scan_pair_rt(const DevParams& P, const ScanThr* __restrict__ thr, const double* __restrict__ own_s,
+                         const double (&pj)[3 * KT], const double* __restrict__ pj_mem, unsigned& vm_out, unsigned& nm_out,
+                         unsigned& c0_out) {
+    const double inv_c = thr->inv_c;
+    const unsigned hv_m = thr->hv_m;
+    unsigned vm = 0, nm = 0, amb = 0, c0 = 0;
+    constexpr int n3 = 3 * KT;
+    double ow[n3 + 1];
+#pragma unroll
+    for (int w = 0; w < n3; w += 2) {  // rows of own_all are padded to an even length, 16-byte aligned
+        const double2 v = *reinterpret_cast<const double2*>(own_s + w);
+        ow[w] = v.x;
+        ow[w + 1] = v.y;  // (w + 1 == n3: the padding, never used)
+    }
+#pragma unroll
+    for (int k = 0; k < KT; ++k) {
+        const double dx = ow[3 * k] - pj[3 * k];
+        const double dy = ow[3 * k + 1] - pj[3 * k + 1];
+        const double ez = (ow[3 * k + 2] - pj[3 * k + 2]) * inv_c;
+        const unsigned he = hi_word(fma(ez, ez, fma(dy, dy, dx * dx)));
+        const unsigned xv = he - hv_m, xn = he - thr->hn_m[k];
+        vm |= ((int)xv < 0 ? 1u : 0u) << k;
+        nm |= ((int)xn < 0 ? 1u : 0u) << k;
+        amb |= (xv <= 2u || xn <= 2u) ? 1u : 0u;
+        if (k == 0) {
+            const unsigned xc = he - thr->hc_m;
+            c0 = ((int)xc < 0) ? 1u : 0u;
+            amb |= (xc <= 2u) ? 1u : 0u;
+        }
+    }
+    if (amb) {
+        // some estimate sits next to a threshold: redo this pair exactly (operands from shared memory)
+        vm = 0;
+        nm = 0;
+        c0 = 0;
+        for (int k = 0; k < KT; ++k) {
+            const double s = ell_sq(own_s[3 * k] - pj_mem[3 * k], own_s[3 * k + 1] - pj_mem[3 * k + 1],
+                                    own_s[3 * k + 2] - pj_mem[3 * k + 2], P.c);
+            if (s < thr->T_viol) vm |= 1u << k;
+            if (s < thr->T_near[k]) nm |= 1u << k;
+            if (k == 0 && s < thr->T_coll) c0 = 1u;
+        }
+    }
+    vm_out = vm;
+    nm_out = nm;
+    c0_out = c0;
+}
+
+template <int W, int NW, int KT>
+__global__ void __launch_bounds__(NW * 32) scan_rt_kernel(const __grid_constant__ StepArgs A, int stages) {
+    static_assert(KT > 0, "register-tile scan: compile-time horizon");
+    asm volatile("griddepcontrol.launch_dependents;");
+    const int nl_s = A.n1 - A.n0;
+    const int cps = (nl_s + W - 1) / W;
+    const int scen = (A.n_scen > 1) ? (int)blockIdx.x / cps : 0;
+    const int blk = (int)blockIdx.x - scen * cps;
+    const double* const l_prev = A.l_prev + (size_t)scen * A.lstride;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    constexpr int K = KT, n3 = 3 * K, n3p = (n3 + 1) / 2 * 2;
+    const int N = A.P.N;
+    constexpr int tile_d = kTile * n3;
+    constexpr uint32_t tile_bytes = (uint32_t)(tile_d * sizeof(double));
+    double* tiles = reinterpret_cast<double*>(smem_raw);
+    double* own_all = tiles + (size_t)stages * tile_d;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(own_all + W * n3p);
+    unsigned* s_acc = reinterpret_cast<unsigned*>(bars + kScanMaxStages);  // [2a] violation mask, [2a+1] coll0; [127] tile counter
+    unsigned* nm_all = s_acc + 64 * 2;
+    const int Npad = round_up(N, kTile);
+    int* list_all = reinterpret_cast<int*>(nm_all + (size_t)W * Npad);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int a0 = A.n0 + blk * W;  // first agent of this CTA
+    const int na = (A.n1 - a0 < W) ? (A.n1 - a0) : W;
+    if (A.ctrl && A.ctrl[scen].done) {
+        if (A.rq && A.n_scen > 1 && lane == 0)
+            for (int a = warp; a < na; a += NW) A.q_light[atomicAdd(&A.rq->n_light, 1u)] = scen * nl_s + blk * W + a;
+        return;
+    }
+    const int ntma = A.tile_padded ? (N + kTile - 1) / kTile : N / kTile;
+    const int rot = ntma ? (int)((unsigned)blk % (unsigned)ntma) : 0;
+    if (threadIdx.x == 0) {
+        for (int b = 0; b < stages; ++b) mbar_init(&bars[b], 1);
+        mbar_fence_init();
+        for (int t = 0; t < stages && t < ntma; ++t) {
+            int tau = t + rot;
+            tau -= (tau >= ntma) ? ntma : 0;
+            mbar_expect_tx(&bars[t], tile_bytes);
+            tma_bulk_g2s(tiles + (size_t)t * tile_d, l_prev + (size_t)tau * tile_d, tile_bytes, &bars[t]);
+        }
+        s_acc[127] = 0u;
+    }
+    for (int i = threadIdx.x; i < 2 * W; i += NW * 32) s_acc[i] = 0u;
+    for (int i = threadIdx.x; i < W * n3p; i += NW * 32) {
+        const int a = i / n3p, c = i - a * n3p;
+        own_all[i] = (a < na && c < n3) ? l_prev[(size_t)(a0 + a) * n3 + c] : 0.0;
+    }
+    __syncthreads();
+    for (;;) {
+        int t = 0;
+        if (lane == 0) t = (int)atomicAdd(&s_acc[127], 1u);
+        t = __shfl_sync(0xffffffffu, t, 0);
+        if (t >= ntma) break;
+        const int b = t % stages;
+        mbar_wait(&bars[b], (uint32_t)((t / stages) & 1));
+        int tau = t + rot;
+        tau -= (tau >= ntma) ? ntma : 0;
+        const int i = tau * kTile + lane;  // this lane's neighbour
+        const double* pjm = tiles + (size_t)b * tile_d + (size_t)lane * n3;
+        double pj[n3];
+#pragma unroll
+        for (int w = 0; w < n3; ++w) pj[w] = pjm[w];
+        for (int a = 0; a < na; ++a) {
+            unsigned vm, nm, c0;
+            scan_pair_rt<KT>(A.P, &A.thr, own_all + a * n3p, pj, pjm, vm, nm, c0);
+            const bool on = i < N && i != a0 + a;
+            nm_all[(size_t)a * Npad + i] = on ? nm : 0u;
+            vm = __reduce_or_sync(0xffffffffu, on ? vm : 0u);
+            c0 = __reduce_or_sync(0xffffffffu, on ? c0 : 0u);
+            if (lane == 0 && (vm | c0)) {
+                atomicOr(&s_acc[2 * a], vm);
+                atomicOr(&s_acc[2 * a + 1], c0);
+            }
+        }
+        __syncwarp();  // every lane has its copy of the tile: the slot can take the tile `stages` further on
+        if (lane == 0 && t + stages < ntma) {
+            int tn = t + stages + rot;
+            tn -= (tn >= ntma) ? ntma : 0;
+            mbar_expect_tx(&bars[b], tile_bytes);
+            tma_bulk_g2s(tiles + (size_t)b * tile_d, l_prev + (size_t)tn * tile_d, tile_bytes, &bars[b]);
+        }
+    }
+    const int rem_base = ntma * kTile;
+    if (rem_base < N) {
+        // caller-owned buffer without tile padding: the ragged last tile goes through the per-agent function
+        const int cnt = N - rem_base;
+        __syncthreads();
+        for (int i = threadIdx.x; i < cnt * n3; i += NW * 32) tiles[i] = l_prev[(size_t)rem_base * n3 + i];
+        __syncthreads();
+        for (int a = warp; a < na; a += NW) {
+            ScanAcc acc;
+            acc.vmask = 0;
+            acc.coll0 = 0;
+            scan_tile_hw<KT>(A.P, &A.thr, own_all + a * n3p, a0 + a, tiles, rem_base, cnt, nm_all + (size_t)a * Npad, acc);
+            const unsigned vm = wor(acc.vmask), c0 = wor(acc.coll0);
+            if (lane == 0) {
+                atomicOr(&s_acc[2 * a], vm);
+                atomicOr(&s_acc[2 * a + 1], c0);
+            }
+        }
+    }
+    __syncthreads();  // masks and violation bits of all tiles are in place
+    for (int a = warp; a < na; a += NW) {
+    const int n = a0 + a, li = scen * nl_s + blk * W + a;
+    ScanAcc acc;
+    acc.vmask = s_acc[2 * a];
+    acc.coll0 = s_acc[2 * a + 1];
+    const bool resident = stages >= ntma && rem_base >= N;
+    const ScanOut so = scan_finish(A.P, own_all + a * n3p, n, l_prev, nm_all + (size_t)a * Npad, acc, A.RMAX,
+                                   A.grow + (size_t)li * 5 * A.RMAX, A.gkc + (size_t)li * A.RMAX,
+                                   A.gidx ? A.gidx + (size_t)li * A.RMAX : nullptr, list_all + (size_t)a * A.RMAX,
+                                   resident ? tiles : nullptr, rot, ntma);
+    if (lane == 0) {
+        ScanRec r;
+        r.kstar = so.kstar;
+        r.nv = so.nv;
+        r.flag = so.flag;
+        r.pad = 0;
+        A.scan[li] = r;
+        if (A.rq) {
+            const int ng = scen * N + n;
+            const bool heavy = !so.flag && (A.P.variant == VAR_HARD || so.nv > kQW ||
+                                            (A.diag && A.diag[ng].nact >= kRouteNact));
+            if (heavy) A.q_heavy[atomicAdd(&A.rq->n_heavy, 1u)] = li;
+            else A.q_light[atomicAdd(&A.rq->n_light, 1u)] = li;
+        }
+    }
+    }
+}
+
 // ---- K3 (defined first: K2 runs it in its last CTA) --------------------------------------------
 // body of K3 for a CTA of NT threads (NT <= 512).  The inputs may have been written by other CTAs of the
 // SAME kernel (fused tail): they are read with ld.global.cg (L2), never from a stale L1 line.

@@ -11,6 +11,11 @@ cudaError_t launch_scan_layout(ScanLayout id, const StepArgs& A, int nl, int K, 
         case SCAN_4_4_0: return launch_scan_w<4, 4, 0>(A, nl, K, s);
         case SCAN_8_1_15: return launch_scan_w<8, 1, 15>(A, nl, K, s);
         case SCAN_8_1_20: return launch_scan_w<8, 1, 20>(A, nl, K, s);
+        case SCAN_RT_4_8_15: return launch_scan_rt_w<4, 8, 15>(A, nl, K, s);
+        case SCAN_RT_4_8_20: return launch_scan_rt_w<4, 8, 20>(A, nl, K, s);
+        case SCAN_RT_8_8_15: return launch_scan_rt_w<8, 8, 15>(A, nl, K, s);
+        case SCAN_RT_8_8_20: return launch_scan_rt_w<8, 8, 20>(A, nl, K, s);
+        case SCAN_RT_14_8_15: return launch_scan_rt_w<14, 8, 15>(A, nl, K, s);
         default: return launch_scan_w<8, 2, 0>(A, nl, K, s);
     }
 }

@@ -37,7 +37,9 @@ cudaError_t launch_qp_hard_3_0(const StepArgs& A, int nl, size_t smem, cudaStrea
 cudaError_t launch_qp2_15(const StepArgs& A, int nl, cudaStream_t s);
 cudaError_t launch_qp2_20(const StepArgs& A, int nl, cudaStream_t s);
 // scan layouts: W agents per CTA x S warps per agent, horizon KT (0: run time)
-enum ScanLayout { SCAN_1_2_0, SCAN_4_2_15, SCAN_4_2_20, SCAN_4_4_0, SCAN_8_1_15, SCAN_8_1_20, SCAN_8_2_0, SCAN_LAYOUTS };
+enum ScanLayout { SCAN_1_2_0, SCAN_4_2_15, SCAN_4_2_20, SCAN_4_4_0, SCAN_8_1_15, SCAN_8_1_20, SCAN_8_2_0,
+                  SCAN_RT_4_8_15, SCAN_RT_4_8_20, SCAN_RT_8_8_15, SCAN_RT_8_8_20, SCAN_RT_14_8_15,  // register-tile layout (scan_rt_kernel)
+                  SCAN_LAYOUTS };
 cudaError_t launch_scan_layout(ScanLayout id, const StepArgs& A, int nl, int K, cudaStream_t s);
 
 // ---- templates (instantiated by the k_*.cu files only) ---------------------------------------------
@@ -58,6 +60,22 @@ cudaError_t launch_scan_w(const StepArgs& A, int nl, int K, cudaStream_t s) {
         attr_smem[dev] = smem;
     }
     scan_kernel<W, S, KT, OWNREG><<<(nl + W - 1) / W * A.n_scen, W * S * 32, smem, s>>>(A, stages);
+    return cudaGetLastError();
+}
+template <int W, int NW, int KT>
+cudaError_t launch_scan_rt_w(const StepArgs& A, int nl, int K, cudaStream_t s) {
+    const int Npad = round_up(A.P.N, kTile);
+    const int stages = scan_stages(K, A.P.N, W, A.RMAX);
+    if (stages < 1) return cudaErrorInvalidConfiguration;
+    const size_t smem = scan_smem_bytes(K, W, stages, Npad, A.RMAX);
+    static size_t attr_smem[kMaxDevices] = {0};
+    const int dev = current_device();
+    if (attr_smem[dev] < smem) {
+        cudaError_t e = cudaFuncSetAttribute(scan_rt_kernel<W, NW, KT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        attr_smem[dev] = smem;
+    }
+    scan_rt_kernel<W, NW, KT><<<(nl + W - 1) / W * A.n_scen, NW * 32, smem, s>>>(A, stages);
     return cudaGetLastError();
 }
 template <int W, int KT, bool HARD = false>

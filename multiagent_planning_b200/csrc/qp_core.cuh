@@ -720,19 +720,34 @@ struct Qp {
         mat_vec<false>(q, nullptr);
         for (int i = lane_id(); i < q; i += kLanes) w.u[i] = w.r[i];
         wsync();
+        drop_negative(0.0);
+        synth_from_u();
+    }
+
+    // drop the active constraints whose multiplier is below -rel_tol max|u|, most negative first (rank-1 updates
+    // of u and M); returns the number of drops
+    DMPC_COLD int drop_negative(double rel_tol) {
+        double thr = 0.0;
+        if (rel_tol > 0.0) {
+            double um = 0.0;
+            for (int i = lane_id(); i < q; i += kLanes) um = fmax(um, fabs(w.u[i]));
+            thr = rel_tol * wmax(um);
+        }
+        int nd = 0;
         for (;;) {
             double neg = 0.0;
             int l = -1;
             for (int i = lane_id(); i < q; i += kLanes) {
                 const double ui = w.u[i];
-                if (ui < 0.0 && (l < 0 || -ui > neg)) { neg = -ui; l = i; }
+                if (ui < -thr && (l < 0 || -ui > neg)) { neg = -ui; l = i; }
             }
             const int src = warg_max_nonneg(neg, l >= 0);
             if (src < 0) break;
             l = wbcast(l, src);
             drop_slot(l, w.u);
+            ++nd;
         }
-        synth_from_u();
+        return nd;
     }
 
     // start state: nothing active
@@ -770,6 +785,12 @@ struct Qp {
                     if (!(polish() > 1e-9)) break;
                 }
                 polished = true;
+                // a constraint that ended with a negative multiplier (see qp_warp.cuh) is dropped and the
+                // iteration goes on from the valid pair of the smaller set
+                if (drop_negative(1e-9) > 0) {
+                    synth_from_u();
+                    polished = false;
+                }
                 PROF(2);
                 if (++npolish > 8) { res.rc = QP_ITERCAP; break; }
                 continue;

@@ -988,14 +988,20 @@ struct QpW {
 
     // ---- drop the active constraints with a negative multiplier, most negative first (rank-1 updates of u
     //      and M), until u >= 0.  Returns the number of drops. ----------------------------------------------
-    DMPC_COLD int drop_negative() {
+    DMPC_COLD int drop_negative(double rel_tol = 0.0) {
         int nd = 0;
+        double thr = 0.0;
+        if (rel_tol > 0.0) {  // "negative" relative to the largest multiplier
+            double um = 0.0;
+            QW_FOR(h) if (qw_item(h) < q) um = fmax(um, fabs(u[h]));
+            thr = rel_tol * wmax(um);
+        }
         for (;;) {
             double neg = 0.0;
             int l = -1;
             QW_FOR(h) {
                 const int s = qw_item(h);
-                if (s < q && u[h] < 0.0 && (l < 0 || -u[h] > neg)) { neg = -u[h]; l = s; }
+                if (s < q && u[h] < -thr && (l < 0 || -u[h] > neg)) { neg = -u[h]; l = s; }
             }
             const int src = warg_max_nonneg(neg, l >= 0);
             if (src < 0) break;
@@ -1457,6 +1463,24 @@ struct QpW {
                 polished = true;
                 nsteps = 0;
                 rough = false;
+                // The refined multipliers are those of the equality-constrained problem on the active set.  An add
+                // next to linear dependence (delta ~ 1e-7 n_p'H^-1 n_p) amplifies the rounding of the running
+                // multipliers by 1/delta, and a constraint can end up active with a NEGATIVE multiplier: the
+                // point is then not the optimum.  Such constraints are dropped (rank-1 updates of u and M), x is
+                // synthesised for the smaller set -- a valid pair again -- and the iteration goes on.
+                if (drop_negative(1e-9) > 0) {
+                    synth_from_u();
+                    polished = false;
+                    rough = true;
+                }
+#if defined(DMPC_DEBUG) && !defined(__CUDA_ARCH__)
+                {
+                    double umin = 0.0;
+                    int smin = -1;
+                    QW_FOR(h) if (qw_item(h) < q && u[h] < umin) { umin = u[h]; smin = qw_item(h); }
+                    fprintf(stderr, "[polish] q %d iters %d min u %.3e (slot %d code %#x)\n", q, iters, umin, smin, smin >= 0 ? act[smin] : 0);
+                }
+#endif
                 PROF(2);
                 if (++npolish > 8) { res.rc = QP_ITERCAP; break; }
                 continue;

@@ -235,3 +235,30 @@ def test_fast_path_hard_variant(orc, emul, golden):
         big += int((e["diag"][:, 1] > 64).sum())
         l, pk, vk, ak = o["l_new"], o["p1"], o["v1"], o["a1"]
     assert big >= 20      # agents with more rows than the working set
+
+
+def test_negative_multiplier_after_polish_is_dropped(orc, emul):
+    """N = 2000, K = 15, third closed-loop step: one agent's active set passes next to linear dependence (an add
+    with delta ~ 1e-7 n'H^-1 n), the running multipliers lose their accuracy and a constraint ends up active with
+    a negative multiplier.  Both device solvers must drop it after the polish and reach the oracle's optimum
+    (they used to stop 2.9e-5 m away, flags equal)."""
+    from multiagent_planning_b200 import scenarios
+    cfg = scenarios.config("N2000")
+    N = cfg["N"]
+    P = orc.default_params(cfg["variant"])
+    for k, v in cfg["params"].items():
+        setattr(P, k, v)
+    K = P.K
+    l = np.zeros((3, K, N), order="F")
+    for n in range(N):
+        l[:, :, n] = orc.init_dmpc(cfg["po"][:, n], cfg["pf"][:, n], P.h, K, P.init_div)[0]
+    pk, vk, ak = l[:, 0, :].copy(), np.zeros((3, N)), np.zeros((3, N))
+    for k in range(3):
+        o = orc.step(P, pk, vk, ak, cfg["pf"], l, cfg["pmin"], cfg["pmax"], nthreads=4)
+        if k == 2:
+            for qmax in (-64, 160):
+                e = emul.step(emul.params_from(P), pk, vk, ak, cfg["pf"], l, cfg["pmin"], cfg["pmax"], QMAX=qmax,
+                              RCAP=256, RMAX=256)
+                assert np.array_equal(o["status"], e["status"])
+                assert np.abs(o["l_new"] - e["l_new"]).max() <= 1e-8
+        l, pk, vk, ak = o["l_new"], o["p1"], o["v1"], o["a1"]

@@ -479,6 +479,20 @@ def test_c4_n2000_k20_dense_vs_oracle(dmpc, orc):
         assert (g["diag"]["kstar"] > 0).sum() > 500      # it is the dense case
 
 
+def test_n2000_k15_vs_oracle(dmpc, orc):
+    """N = 2000, K = 15 (north_star's largest swarm): six dense steps teacher-forced against the oracle.  Step 3 holds
+    an agent whose active set passes next to linear dependence (delta ~ 1e-7): without the multiplier check after the
+    polish the solver stopped 2.9e-5 m from the optimum with a constraint active at a negative multiplier."""
+    from multiagent_planning_b200 import scenarios
+    cfg = scenarios.config("N2000")
+    P = dmpc.default_params(cfg["variant"], **cfg["params"])
+    with dmpc.Solver(cfg["N"], P, pmin=cfg["pmin"], pmax=cfg["pmax"], pf=cfg["pf"]) as s:
+        l, pk, vk, ak = s.init_horizons(cfg["po"])
+        for _ in range(6):
+            g, o = _cmp_step(orc, P, s, pk, vk, ak, cfg["pf"], l, cfg["pmin"], cfg["pmax"])
+            l, pk, vk, ak = o["l_new"], o["p1"], o["v1"], o["a1"]
+
+
 def test_k20_small_swarm_vs_oracle(dmpc, orc):
     """K = 20 on a swarm that fits one wave (scan_kernel<4,2,20>, one agent per warp), 12 closed-loop steps"""
     from multiagent_planning_b200 import scenarios
@@ -715,6 +729,29 @@ def test_device_scenario_generation_and_monte_carlo_harness(dmpc, orc):
         if one["reached"]:
             pp = s.postprocess(one["pk"], one["vk"], one["ak"], want_interp=False)
             assert pp["traj_time"] == r["traj_time"][0, 1] and pp["violation"] == r["violation"][0, 1]
+
+
+@pytest.mark.parametrize("name,layouts", [("C3", ("1", "7")), ("N2000", ("4", "9")), ("N2000", ("4", "11")), ("C4", ("5", "10"))])
+def test_register_tile_scan_equals_per_agent_scan(dmpc, monkeypatch, name, layouts):
+    """the two organisations of the neighbour scan (a warp per agent re-reading the tiles / a warp per tile with the
+    neighbour's horizon in registers, looping over the CTA's agents) evaluate every pair with the same arithmetic:
+    first violating step, neighbour sets and rows -- hence whole closed-loop steps -- must be bit-identical"""
+    from multiagent_planning_b200 import scenarios
+    cfg = scenarios.config(name)
+    P = dmpc.default_params(cfg["variant"], **cfg["params"])
+    res = []
+    for lay in layouts:
+        monkeypatch.setenv("DMPCB200_SCAN_LAYOUT", lay)
+        with dmpc.Solver(cfg["N"], P, pmin=cfg["pmin"], pmax=cfg["pmax"], pf=cfg["pf"]) as s:
+            s.init_horizons(cfg["po"])
+            r = s.run(10, record=True, status_hist=True)
+            res.append((r, s.get_state()))
+    (r1, s1), (r2, s2) = res
+    assert np.array_equal(s1["diag"]["kstar"], s2["diag"]["kstar"]) and np.array_equal(s1["diag"]["nv"], s2["diag"]["nv"])
+    assert (s1["diag"]["nv"] > 0).sum() > 50
+    for k in ("pk", "vk", "ak", "status_hist"):
+        assert np.array_equal(r1[k], r2[k]), k
+    assert np.array_equal(s1["l"], s2["l"])
 
 
 def _nccl_worker(rank, world, port, q):
