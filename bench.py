@@ -358,7 +358,9 @@ def run_single(args):
     ach_step = b_alg(N, K) * N / (ms_per_step * 1e-3) / 1e9
     qp_name = f"qp_kernel<{conf['agents_per_qp_block']}, {K if K in (15, 20) else 0}>"
     prof_qp, prof_qp_path = ncu_profile("qp_kernel")
-    prof_sc, prof_sc_path = ncu_profile("scan_kernel")
+    prof_sc, prof_sc_path = ncu_profile("scan_rt_kernel")
+    if prof_sc is None:
+        prof_sc, prof_sc_path = ncu_profile("scan_kernel")
     sm_mhz = (clocks or {}).get("sm_mhz") or 1965.0
     slow_it = float(np.mean(it_max)) if it_max else None
     compulsory = 24 * K * N + (24 * K + 168) * N  # every horizon once from DRAM + per-agent state and outputs
@@ -402,8 +404,9 @@ def run_single(args):
                                  "warps_active_pct": prof_qp.get("warps_active_pct") if prof_qp else None,
                                  "note": "launch time = iterations of the slowest agent x time per iteration (+ "
                                          "set-up); one warp per SM sub-partition; see DESIGN.md section 4"}},
-        "roofline_scan": {"bound": "shared-memory bandwidth / fp64 issue", "contract_bound": "hbm",
-                          "kernel": "scan_kernel (neighbour scan + constraint rows)",
+        "roofline_scan": {"bound": "instruction issue / shared-memory wavefronts", "contract_bound": "hbm",
+                          "kernel": "scan_rt_kernel (neighbour scan + constraint rows; register-tile layout)"
+                          if K in (15, 20) else "scan_kernel (neighbour scan + constraint rows)",
                           "achieved": ach_scan, "peak": peak, "unit": "GB/s", "frac": ach_scan / peak,
                           "traffic": prof_sc["traffic"] if prof_sc else None,
                           "traffic_source": prof_sc_path, "avg_launch_us": scan_us,
@@ -416,8 +419,9 @@ def run_single(args):
                           "fp64_pipe_pct": prof_sc.get("fp64_pipe_pct") if prof_sc else None,
                           "note": "every CTA streams the whole neighbour buffer through shared memory by TMA: the "
                                   "buffer is L2 resident, so the contract's byte model (algorithmic bytes >> DRAM "
-                                  "bytes) may exceed the DRAM peak; the kernel's own limit is the shared-memory / "
-                                  "fp64 work of the distance loop"},
+                                  "bytes) may exceed the DRAM peak; the kernel's own limit is the issue rate of the "
+                                  "distance loop (7 fp64 + ~12 integer instructions per pair and horizon step) and "
+                                  "the shared-memory wavefronts of its operands"},
         "roofline_step": {"bound": "hbm (contract accounting)", "achieved": ach_step, "peak": peak, "unit": "GB/s",
                           "frac": ach_step / peak, "note": "B_alg*N over the whole step (scan + QP incl. tail)"},
         "kernel_us": {"scan_kernel": scan_us, "qp_kernel": qp_us,

@@ -67,7 +67,10 @@ constexpr int kQW = 64;             // capacity: entries, rows, slots
 constexpr int kMS = 66;             // row stride of M in doubles
 constexpr int kEPL = kQW / kLanes;  // items per lane: 2 on the device, 64 in the host build
 constexpr unsigned kNone = 0xffu;
-constexpr double kBoundWeight = 0.125;  // see most_violated
+#ifndef DMPC_BOUND_WEIGHT
+#define DMPC_BOUND_WEIGHT 0.125
+#endif
+constexpr double kBoundWeight = DMPC_BOUND_WEIGHT;  // see most_violated
 constexpr int kPolishSkip = 64;  // plain adds after which the final re-synthesis of x is skipped
 
 #if defined(__CUDA_ARCH__)

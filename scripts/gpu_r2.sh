@@ -17,7 +17,7 @@ fi
 if [ "${NCU:-0}" = "1" ]; then
   timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/${TAG}_launches_bench.csv \
     python bench.py --steps 20 --warmup 5 > gpurun_out/${TAG}_bench_under_ncu.log 2>&1; echo launches rc=$?
-  timeout 900 ncu --set full --clock-control none --import-source on -k regex:'qp_kernel|scan_kernel' -s 8 -c 6 -f -o gpurun_out/${TAG}_full \
+  timeout 900 ncu --set full --clock-control none --import-source on -k regex:'qp_kernel|scan_rt_kernel|scan_kernel' -s 8 -c 6 -f -o gpurun_out/${TAG}_full \
     python scripts/prof_run.py C3 12 > gpurun_out/${TAG}_ncu_full.log 2>&1; echo full rc=$?
 fi
 python - <<PY

@@ -21,8 +21,13 @@ def main():
     top = int(sys.argv[5]) if len(sys.argv) > 5 else 40
     tmp = tempfile.mkdtemp()
     subprocess.run(["cuobjdump", "-xelf", "all", os.path.abspath(so)], cwd=tmp, check=True, capture_output=True)
-    cub = max((os.path.join(tmp, f) for f in os.listdir(tmp)), key=os.path.getsize)
-    dis = subprocess.run(["nvdisasm", "--print-line-info", "-c", cub], capture_output=True, text=True).stdout
+    # one cubin per translation unit: take the one that defines the kernel
+    dis = ""
+    for f in sorted(os.listdir(tmp)):
+        d = subprocess.run(["nvdisasm", "--print-line-info", "-c", os.path.join(tmp, f)], capture_output=True, text=True).stdout
+        if any(ln.startswith(".text.") and kern in ln for ln in d.splitlines()):
+            dis = d
+            break
     lines, cur, on = [], ("?", 0), False
     for ln in dis.splitlines():
         if ln.startswith(".text."):
