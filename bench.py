@@ -387,12 +387,14 @@ def run_single(args):
         # an agent-step (B_alg = 24 K N + 24 K + 168 bytes, dominated by the neighbour horizons that
         # scan_kernel streams) -- but that is not what bounds it: its DRAM traffic is < 1 MB per launch and the
         # launch lasts as long as its SLOWEST agent's dependent chain of dual active-set iterations.
-        "roofline": {"bound": "latency", "contract_bound": "hbm",
+        "roofline": {"bound": "latency" if N <= 592 else "latency (persistent grid: one warp per SM sub-partition, agents queued)",
+                     "contract_bound": "hbm",
                      "kernel": f"{qp_name} (batched per-agent QP, tail fused)",
                      "achieved": ach_qp, "peak": peak, "unit": "GB/s", "frac": ach_qp / peak,
-                     "traffic": prof_qp["traffic"] if prof_qp else None,
+                     # (the tracked capture is of the C3 workload: no DRAM figure is claimed for the others)
+                     "traffic": prof_qp["traffic"] if prof_qp and args.workload == "C3" else None,
                      "traffic_source": (f"ncu --set full, {prof_qp_path} (dram__bytes_read.sum + dram__bytes_write.sum, "
-                                        f"mean of {prof_qp['launches_averaged']} launches)") if prof_qp else
+                                        f"mean of {prof_qp['launches_averaged']} launches of the C3 workload)") if prof_qp else
                      "no tracked ncu summary lists this kernel",
                      "peak_source": peak_src, "avg_launch_us": qp_us,
                      "algorithmic_bytes_per_launch": b_alg(N, K) * N,
@@ -408,13 +410,13 @@ def run_single(args):
                           "kernel": "scan_rt_kernel (neighbour scan + constraint rows; register-tile layout)"
                           if K in (15, 20) else "scan_kernel (neighbour scan + constraint rows)",
                           "achieved": ach_scan, "peak": peak, "unit": "GB/s", "frac": ach_scan / peak,
-                          "traffic": prof_sc["traffic"] if prof_sc else None,
+                          "traffic": prof_sc["traffic"] if prof_sc and args.workload == "C3" else None,
                           "traffic_source": prof_sc_path, "avg_launch_us": scan_us,
                           "algorithmic_bytes_per_launch": b_alg(N, K) * N,
                           "compulsory_dram_bytes_per_launch": compulsory,
                           "compulsory_dram_frac_of_peak": compulsory / (scan_us * 1e-6) / 1e9 / peak,
                           "smem_bytes_per_launch": (prof_sc["lsu_shared_wavefronts"] * 128) if prof_sc and
-                          "lsu_shared_wavefronts" in prof_sc else None,
+                          "lsu_shared_wavefronts" in prof_sc and args.workload == "C3" else None,
                           "issue_active_pct": prof_sc.get("issue_active_pct") if prof_sc else None,
                           "fp64_pipe_pct": prof_sc.get("fp64_pipe_pct") if prof_sc else None,
                           "note": "every CTA streams the whole neighbour buffer through shared memory by TMA: the "
@@ -762,7 +764,8 @@ def run_multi(args):
             "gpu_launches": 2 * S,
             "resident_graph": {"ms_per_step": graph_ms, "value": (N / (graph_ms * 1e-3)) if graph_ms else None,
                                "note": "torch CUDA graph of two steps incl. NCCL all-gather"},
-            "roofline": {"bound": "latency", "contract_bound": "hbm",
+            "roofline": {"bound": "latency" if N <= 592 else "latency (persistent grid: one warp per SM sub-partition, agents queued)",
+                     "contract_bound": "hbm",
                          "kernel": "whole step (scan + QP + all-gather), max over ranks",
                          "achieved": ach, "peak": peak * world, "unit": "GB/s", "frac": ach / (peak * world),
                          "traffic": None, "peak_source": peak_src,
