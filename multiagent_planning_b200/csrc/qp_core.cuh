@@ -779,11 +779,15 @@ struct Qp {
             if (pcode < 0) {
                 if (polished || q == 0) break;  // optimal
                 // x is re-synthesised from the multipliers; a poor residual triggers one exact rebuild
+                bool consistent = false;
                 for (int pass = 0; pass < 2; ++pass) {
                     if (dirty || pass) refresh();
                     dirty = false;
-                    if (!(polish() > 1e-9)) break;
+                    if (!(polish() > 1e-9)) { consistent = true; break; }
                 }
+                // an active set whose constraints cannot be met together even with M rebuilt exactly is a solver
+                // failure (reported as such), never a solution
+                if (!consistent) { res.rc = QP_ITERCAP; break; }
                 polished = true;
                 // a constraint that ended with a negative multiplier (see qp_warp.cuh) is dropped and the
                 // iteration goes on from the valid pair of the smaller set

@@ -1458,10 +1458,20 @@ struct QpW {
                 // a short run of plain adds carries no drift worth removing (each step is one fused
                 // multiply-add per entry on top of a synthesised x): accept it as it is
                 if (nsteps <= kPolishSkip && !rough && !dirty) break;
+                bool consistent = false;
                 for (int pass = 0; pass < 2; ++pass) {
                     if (dirty || pass) refresh();
                     dirty = false;
-                    if (!(polish() > 1e-9)) break;
+                    if (!(polish() > 1e-9)) { consistent = true; break; }
+                }
+                if (!consistent) {
+                    // Even with M rebuilt exactly the active constraints cannot be met together: the set has
+                    // become numerically dependent (an add with a tiny but accepted delta).  The point is NOT a
+                    // solution -- reporting it as one returned an infeasible try as solved (N = 2000, step 13,
+                    // agent 826: slack bound violated by 0.075 with 0 retries).  Hand the problem to the generic
+                    // solver (the caller's overflow path), whose pivoting order avoids the dependent set.
+                    res.rc = QP_OVERFLOW;
+                    break;
                 }
                 polished = true;
                 nsteps = 0;
@@ -1636,6 +1646,20 @@ struct QpW {
             }
             if (failed) break;
         }
+#if defined(DMPC_DEBUG) && !defined(__CUDA_ARCH__)
+        fprintf(stderr, "[solve exit] rc %d q %d iters %d slb %.4g term %.4g nv %d nmat %d\n", res.rc, q, iters, slb, term, nv, nmat);
+        for (int j = 0; j < nv; ++j)
+            fprintf(stderr, "   row %d: rres %.3e eps %.5f (eps - slb %.3e) flags row %u sub %u slb %u mat %u kc %d\n", j, rres[j], eps[j],
+                    eps[j] - slb, qw_getb(rmap[j], 0), qw_getb(rmap[j], 1), qw_getb(rmap[j], 2), qw_getb(rmap[j], 3), rkc[j]);
+        {
+            double wa = 0, wp = 0;
+            for (int i = 0; i < n3; ++i) {
+                wa = fmax(wa, fabs(a[i]) - alim);
+                wp = fmax(wp, fmax(elo[i] - P[i], P[i] - ehi[i]));
+            }
+            fprintf(stderr, "   worst box violation %.3e, workspace %.3e\n", wa, wp);
+        }
+#endif
         res.iters = iters;
         res.q = q;
         if (m_valid_out) *m_valid_out = m_valid;

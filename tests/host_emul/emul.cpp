@@ -75,6 +75,14 @@ extern "C" int emul_step(const dmpcb200_params* p, int N, int n0, int n1, const 
                             : agent_solve_fast<0>(D, tab.data() + tables_fast_offset(K), smem.data(), QMAX, io, &dg);
         else
             status[n] = agent_solve<0>(D, tab.data(), smem.data(), QMAX, RCAP, io, &dg);
+        if (fast && QMAX == kQW && (status[n] & ST_OVERFLOW) && !so.flag) {
+            // the kernel's rescue path: the generic solver with a large capacity decides (active set beyond the
+            // on-chip capacity, no free slot in the row working set, numerically inconsistent active set)
+            const int it0 = dg.iters;
+            std::vector<unsigned char> big(agent_smem_bytes(K, 3 * kQW, RMAX) + 64);
+            status[n] = agent_solve<0>(D, tab.data(), big.data(), 3 * kQW, RMAX, io, &dg);
+            dg.iters += it0;
+        }
         if (diag) { diag[4 * n] = dg.kstar; diag[4 * n + 1] = dg.nv; diag[4 * n + 2] = dg.iters; diag[4 * n + 3] = dg.nact; }
     }
     return 0;

@@ -237,7 +237,7 @@ def test_fast_path_hard_variant(orc, emul, golden):
     assert big >= 20      # agents with more rows than the working set
 
 
-def test_negative_multiplier_after_polish_is_dropped(orc, emul):
+def test_negative_multiplier_and_inconsistent_active_set(orc, emul):
     """N = 2000, K = 15, third closed-loop step: one agent's active set passes next to linear dependence (an add
     with delta ~ 1e-7 n'H^-1 n), the running multipliers lose their accuracy and a constraint ends up active with
     a negative multiplier.  Both device solvers must drop it after the polish and reach the oracle's optimum
@@ -253,12 +253,16 @@ def test_negative_multiplier_after_polish_is_dropped(orc, emul):
     for n in range(N):
         l[:, :, n] = orc.init_dmpc(cfg["po"][:, n], cfg["pf"][:, n], P.h, K, P.init_div)[0]
     pk, vk, ak = l[:, 0, :].copy(), np.zeros((3, N)), np.zeros((3, N))
-    for k in range(3):
+    for k in range(13):
         o = orc.step(P, pk, vk, ak, cfg["pf"], l, cfg["pmin"], cfg["pmax"], nthreads=4)
-        if k == 2:
+        if k in (2, 12):
+            # k = 12: one agent's first try is infeasible, and the register-resident solver's pivoting order leads it
+            # into a numerically dependent active set whose constraints cannot be met together; it used to report
+            # that point as the solution (0 retries, slack bound violated by 0.075).  It must hand the problem to
+            # the generic solver, which finds the try infeasible like the oracle (1 retry).
             for qmax in (-64, 160):
                 e = emul.step(emul.params_from(P), pk, vk, ak, cfg["pf"], l, cfg["pmin"], cfg["pmax"], QMAX=qmax,
                               RCAP=256, RMAX=256)
-                assert np.array_equal(o["status"], e["status"])
+                assert np.array_equal(o["status"], e["status"]), (k, qmax)
                 assert np.abs(o["l_new"] - e["l_new"]).max() <= 1e-8
         l, pk, vk, ak = o["l_new"], o["p1"], o["v1"], o["a1"]

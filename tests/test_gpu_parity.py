@@ -480,15 +480,18 @@ def test_c4_n2000_k20_dense_vs_oracle(dmpc, orc):
 
 
 def test_n2000_k15_vs_oracle(dmpc, orc):
-    """N = 2000, K = 15 (north_star's largest swarm): six dense steps teacher-forced against the oracle.  Step 3 holds
+    """N = 2000, K = 15 (north_star's largest swarm): 14 dense steps teacher-forced against the oracle.  Step 3 holds
     an agent whose active set passes next to linear dependence (delta ~ 1e-7): without the multiplier check after the
-    polish the solver stopped 2.9e-5 m from the optimum with a constraint active at a negative multiplier."""
+    polish the solver stopped 2.9e-5 m from the optimum with a constraint active at a negative multiplier.  Step 13
+    holds an agent whose first try is infeasible and whose active set becomes numerically dependent on the
+    register-resident solver: it must go to the generic solver (rescue path) and come back with the oracle's retry
+    count instead of reporting the inconsistent point as solved."""
     from multiagent_planning_b200 import scenarios
     cfg = scenarios.config("N2000")
     P = dmpc.default_params(cfg["variant"], **cfg["params"])
     with dmpc.Solver(cfg["N"], P, pmin=cfg["pmin"], pmax=cfg["pmax"], pf=cfg["pf"]) as s:
         l, pk, vk, ak = s.init_horizons(cfg["po"])
-        for _ in range(6):
+        for _ in range(14):
             g, o = _cmp_step(orc, P, s, pk, vk, ak, cfg["pf"], l, cfg["pmin"], cfg["pmax"])
             l, pk, vk, ak = o["l_new"], o["p1"], o["v1"], o["a1"]
 
