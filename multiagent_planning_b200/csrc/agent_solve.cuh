@@ -63,6 +63,7 @@ struct AgentIO {
     // cross-step warm start of the fast path (qp_warp.cuh warm_start / warm_store); both optional
     const int* gidx = nullptr;  // global rows: neighbour's agent index of each row [RMAX]
     int* warm = nullptr;        // per agent kWarmStride ints: [0] = count, [1..] = the stored active set
+    int dbg_n = -1;             // agent index (debug traces only)
 };
 constexpr int kWarmStride = 68;
 

@@ -733,6 +733,7 @@ DMPC_D bool qp_agent(const StepArgs& A, int li, const double* tab_s, unsigned ch
     io.v1 = A.v1 + 3 * ng;
     io.a1 = A.a1 + 3 * ng;
     io.l_prev_n = l_prev + (size_t)n * n3;
+    io.dbg_n = n;
 
     AgentDiag dg;
     int st = 0, it0 = 0;

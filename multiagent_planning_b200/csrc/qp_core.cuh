@@ -36,7 +36,7 @@
 
 #include <math.h>
 #include <stdint.h>
-#ifdef DMPC_DEBUG
+#if defined(DMPC_DEBUG) || defined(DMPC_GPU_TRACE)
 #include <stdio.h>
 #endif
 
@@ -570,8 +570,9 @@ struct Qp {
 
     // r = M[0:cnt,0:cnt] g.  Returns g'r (NEED_GR, one reduction) or 0; *rmax_out (optional) gets
     // max |r_i| to 2^-20 relative (one redux) for the ratio-test threshold.
+    // acc_r: r += M g instead (one step of iterative refinement of r, see solve())
     template <bool NEED_GR>
-    DMPC_D double mat_vec(int cnt, double* rmax_out) {
+    DMPC_D double mat_vec(int cnt, double* rmax_out, bool acc_r = false) {
         const int Q = w.QMAX;
         double gr = 0.0, rm = 0.0;
         for (int i = lane_id(); i < cnt; i += kLanes) {
@@ -584,7 +585,8 @@ struct Qp {
                 s3 = fma(w.M[i + Q * (j + 3)], w.g[j + 3], s3);
             }
             for (; j < cnt; ++j) s0 = fma(w.M[i + Q * j], w.g[j], s0);
-            const double ri = (s0 + s1) + (s2 + s3);
+            const double rn = (s0 + s1) + (s2 + s3);
+            const double ri = acc_r ? w.r[i] + rn : rn;
             w.r[i] = ri;
             if (NEED_GR) gr = fma(w.g[i], ri, gr);
             rm = fmax(rm, fabs(ri));
@@ -593,6 +595,19 @@ struct Qp {
         if (rmax_out) *rmax_out = wmax_approx_nonneg(rm);
         wsync();
         return gr;
+    }
+
+    // g[s] = n_{act[s]}'z for s < cnt: the residual g - S r of the system the direction rests on
+    DMPC_COLD void ndotz(int cnt) {
+        for (int s = lane_id(); s < cnt; s += kLanes) {
+            const int info = w.sinfo[s];
+            const int sp = info & 1, ks = (info >> 1) & 0xff, js = (info >> 9) - 1;
+            const double* base = sp ? w.Lz : w.z;
+            double v = w.sv0[s] * base[3 * ks] + w.sv1[s] * base[3 * ks + 1] + w.sv2[s] * base[3 * ks + 2];
+            if (js >= 0) v = fma(w.se[s], w.zeps[js], v);
+            w.g[s] = v;
+        }
+        wsync();
     }
 
     // bordering update: M <- inverse of [[S, g],[g', nph]] given r = M g and delta = nph - g'r
@@ -819,13 +834,16 @@ struct Qp {
             bool need_r = true;   // r = M g must be (re)computed from scratch
             bool have_z = false;  // z / Lz / zeps / delta describe the current active set
             bool failed = false, added = false, rebuilt = false;
+            bool refine = false, refined = false;
             while (!added) {
                 if (need_r) {
                     if (dirty) { refresh(); dirty = false; }
-                    gvec(p, q);
+                    if (refine) ndotz(q);
+                    else gvec(p, q);
                     PROF(4);
-                    mat_vec<false>(q, &rmax);
+                    mat_vec<false>(q, &rmax, refine);
                     PROF(5);
+                    refine = false;
                     need_r = false;
                     have_z = false;
                 }
@@ -874,7 +892,14 @@ struct Qp {
                 printf("it %d p type %d idx %d sp %.3e nph %.3e delta %.3e q %d\n", iters, p.type, p.idx, sp, p.nph,
                        delta, q);
 #endif
-                const bool dependent = !(delta > dep_tol * p.nph) || (q >= w.n3 + nmat);
+                // an ambiguous delta is recomputed from a refined r and judged at 1e-11 (see qp_warp.cuh)
+                if (!refined && q > 0 && delta < 1e-8 * p.nph && fabs(delta) >= 1e-12 * p.nph) {
+                    refined = true;
+                    refine = true;
+                    need_r = true;
+                    continue;
+                }
+                const bool dependent = !(delta > (refined ? 1e-11 : dep_tol) * p.nph) || (q >= w.n3 + nmat);
                 // dual ratio test: smallest u_i / r_i over r_i > 0
                 const double rthr = 1e-12 * rmax;
                 double t1 = INFINITY;
@@ -935,6 +960,7 @@ struct Qp {
                     const double rl = w.r[ldrop], mll = w.M[ldrop + Q * ldrop];
                     wsync();
                     drop_slot(ldrop, w.r);
+                    refined = false;
                     if (dirty) {
                         need_r = true;  // rebuild M, then r from scratch
                     } else if (dependent && (q < w.n3 + nmat)) {

@@ -51,12 +51,24 @@
 #endif
 #endif
 
+#if defined(DMPC_DEBUG) && !defined(__CUDA_ARCH__)
+#define DMPC_ILL_STAT(ill) fprintf(stderr, "[verdict] infeasible, ill_seen %d iters %d q %d\n", (int)(ill), iters, q)
+#else
+#define DMPC_ILL_STAT(ill)
+#endif
 #if defined(DMPC_WARM_STATS)
 #define DMPC_WARM_STAT(x) x
 #else
 #define DMPC_WARM_STAT(x)
 #endif
 
+#ifndef DMPC_REFINE
+// Refinement of ambiguous directions in the register-resident solver: compiled into the MK (solveHardDMPC)
+// instantiation only.  In the kernels of the on-demand variants its mere presence costs 2.8 % (A/B on one box, code
+// layout: it is executed ~3 times per step); there an infeasibility verdict that rests on an ill-conditioned active
+// set goes to the generic solver instead, which always refines.
+#define DMPC_REFINE MK
+#endif
 #ifndef DMPC_FEAS_TOL
 #define DMPC_FEAS_TOL 1e-10  // a constraint counts as violated beyond this (normalised residual)
 #endif
@@ -155,6 +167,9 @@ struct QpW {
     unsigned rmap[kEPL];  // bytes: slot of ROW, SUB, SLB of the row (0xff: inactive), materialised flag
     int ek[kEPL], ex[kEPL];
     int q, nmat, nra, nbox, npos;
+#if defined(DMPC_GPU_TRACE)
+    bool trace = false;
+#endif
 
     DMPC_D int KK() const { return KT ? KT : K; }
 
@@ -347,8 +362,9 @@ struct QpW {
 
     // ---- r = M gs into the registers and into rs.  Rows of M beyond the active set are zero (invariant)
     //      and gs is zero there, so no lane needs a bound check.  Returns g'r (NEED_GR) ------------------
+    // acc: r += M gs instead (one step of iterative refinement of r, see solve())
     template <bool NEED_GR>
-    DMPC_D double mat_vec(int cnt, double* rmax_out) {
+    DMPC_D double mat_vec(int cnt, double* rmax_out, bool acc_r = false) {
         const int cnt4 = (cnt + 3) & ~3;
         double acc[kEPL][4];
         QW_FOR(h) { acc[h][0] = 0.0; acc[h][1] = 0.0; acc[h][2] = 0.0; acc[h][3] = 0.0; }
@@ -369,7 +385,8 @@ struct QpW {
         double gr = 0.0, rm = 0.0;
         QW_FOR(h) {
             const int s = qw_item(h);
-            const double ri = (acc[h][0] + acc[h][1]) + (acc[h][2] + acc[h][3]);
+            const double rn = (acc[h][0] + acc[h][1]) + (acc[h][2] + acc[h][3]);
+            const double ri = acc_r ? r[h] + rn : rn;
             r[h] = ri;
             if (h * kLanes < cnt4) {  // uniform
                 rs[s] = ri;
@@ -381,6 +398,29 @@ struct QpW {
         if (rmax_out) *rmax_out = wmax_approx_nonneg(rm);
         wsync();
         return gr;
+    }
+
+    // ---- gs[s] = n_{act[s]}'z for s < cnt (z, Lz as published by direction_finish; zeps from the registers):
+    //      the residual g - S r of the system the direction rests on (zero in exact arithmetic) ------------
+    DMPC_COLD void ndotz(int cnt) {
+        QW_FOR(h) {
+            const int j = qw_item(h);
+            if (j < nv) cb[j & (kQW - 1)] = zeps[h];  // (the coefficient pairs are not needed any more)
+        }
+        wsync();
+        const int cnt4 = (cnt + 3) & ~3;
+        QW_FOR(h) {
+            const int s = qw_item(h);
+            if (s < cnt4) {
+                const int info = sinfo[s];
+                const int sp = info & 1, ks = (info >> 1) & 0xff, js = (info >> 9) - 1;
+                const double* base = sp ? Ls : zs;
+                double v = sv0[s] * base[3 * ks] + sv1[s] * base[3 * ks + 1] + sv2[s] * base[3 * ks + 2];
+                if (js >= 0) v = fma(se[s], cb[js & (kQW - 1)], v);
+                gs[s] = (s < cnt) ? v : 0.0;
+            }
+        }
+        wsync();
     }
 
     // ---- bordering update: M <- inverse of [[S, g],[g', nph]] given r (registers + rs), delta.
@@ -406,6 +446,7 @@ struct QpW {
                 }
             }
         }
+        wsync();  // row cnt was streamed (zeros) by its owner above; its entries are written by the other lanes below
         QW_FOR(h) {
             if (h * kLanes <= cnt) {  // uniform: the half of the new slot included
                 const int s = qw_item(h);
@@ -910,6 +951,10 @@ struct QpW {
                             cert -= r3[i] * bA[i];
                             if (r3[i] > 0.0) ok = false;  // (0, 1e-12]: not a clean certificate
                         }
+#if defined(DMPC_DEBUG) && !defined(__CUDA_ARCH__)
+                    fprintf(stderr, "[relaxed] sl %.6g it %d qa %d ok %d cert %.6e thr %.6e delta %.3e det %.3e\n", sl, it, qa, (int)ok, cert,
+                            sqrt(delta) * rad + 1e-9 * (fabs(bp) + 1.0), delta, det);
+#endif
                     return ok && (cert > sqrt(delta) * rad + 1e-9 * (fabs(bp) + 1.0));
                 }
                 const double t = (t1 < t2) ? t1 : t2;
@@ -1445,6 +1490,7 @@ struct QpW {
         int nsteps = 0;          // primal steps since x was last synthesised from the multipliers
         bool rough = rough0;     // a drop, a rebuild or an ill-conditioned add happened since then
         bool polished = false, dirty = false, m_valid = true;
+        bool ill_seen = false;   // an add next to linear dependence happened in this solve: verdicts are not trusted
         QpResult res;
         res.rc = QP_OK;
         PROF_BEGIN();
@@ -1513,13 +1559,16 @@ struct QpW {
             PROF(3);
             double up = 0.0, rmax = 0.0, delta = 0.0;
             bool need_r = true, have_z = false, failed = false, added = false, rebuilt = false;
+            bool refine = false, refined = false;
             while (!added) {
                 if (need_r) {
                     if (__builtin_expect(dirty, 0)) { refresh(); dirty = false; }
-                    gvec(p, q);
+                    if (__builtin_expect(refine, 0)) ndotz(q);
+                    else gvec(p, q);
                     PROF(4);
-                    mat_vec<false>(q, &rmax);
+                    mat_vec<false>(q, &rmax, refine);
                     PROF(5);
+                    refine = false;
                     need_r = false;
                     have_z = false;
                 }
@@ -1565,11 +1614,41 @@ struct QpW {
                         continue;
                     }
                 }
-                const bool dependent = !(delta > dep_tol * p.nph) || (q >= n3 + nmat);
+                // Next to linear dependence delta = n_p'z is what is left of a cancellation and carries the error of
+                // r = M g (M explicit, entries up to 1/delta of earlier adds): deciding "dependent" on it at 1e-9
+                // declared tries infeasible whose feasible set is merely thin (solveSoftDMPCbound2 soaks: three retry
+                // counts off in 2500 retried agent-steps).  An ambiguous delta is therefore recomputed from a
+                // REFINED r (one step of iterative refinement: r += M (g - S r), g - S r = N'z) and judged at 1e-11.
+                // (Measured on C3: unrefined values >= 2e-8 n'H^-1 n do not move under refinement, exact dependences
+                // come out below 1e-12 in magnitude, noise of true dependences reaches 2e-9: the band in between.)
+                if (__builtin_expect(DMPC_REFINE && !refined && q > 0 && delta < 1e-8 * p.nph && fabs(delta) >= 1e-12 * p.nph, 0)) {
+                    refined = true;
+                    refine = true;
+                    need_r = true;
+#if defined(DMPC_DEBUG) && !defined(__CUDA_ARCH__)
+                    fprintf(stderr, "[refine] q %d delta/nph %.3e\n", q, delta / p.nph);
+#endif
+                    continue;
+                }
+#if defined(DMPC_DEBUG) && !defined(__CUDA_ARCH__)
+                if (refined) fprintf(stderr, "[refined] q %d delta/nph %.3e\n", q, delta / p.nph);
+#endif
+                const bool dependent = !(delta > (refined ? 1e-11 : dep_tol) * p.nph) || (q >= n3 + nmat);
                 const double t2 = dependent ? INFINITY : (-sp * qw_rcp(delta));
                 const double t = (t1 < t2) ? t1 : t2;
+#if defined(DMPC_GPU_TRACE)
+                if (trace && lane_id() == 0)
+                    printf("[trace] it %d q %d p type %d idx %d k %d sp %.6e nph %.6e delta %.6e dep %d t1 %.6e (drop %d) t2 %.6e slb %.4g nmat %d\n",
+                           iters, q, p.type, p.idx, p.k, sp, p.nph, delta, (int)dependent, t1, ldrop, t2, slb, nmat);
+#endif
                 if (__builtin_expect(!(t < INFINITY), 0)) {  // also catches NaN
-                    res.rc = QP_INFEASIBLE;
+                    // An infeasibility verdict is exact only as far as M is: after an add next to linear dependence
+                    // (delta < ill_tol n'H^-1 n: entries of M ~ 1/delta) the sign pattern of r it rests on is
+                    // rounding.  C3 / seed 11 / solveSoftDMPCbound2, step 1, agent 160: a try whose feasible set is
+                    // 5e-4 wide was declared infeasible on the GPU (one retry too many; the host build of the same
+                    // code, rounding differently, solved it).  Such verdicts go to the generic solver.
+                    res.rc = ill_seen ? QP_OVERFLOW : QP_INFEASIBLE;
+                    DMPC_ILL_STAT(ill_seen);
                     failed = true;
                     if (!(t == t) || !(delta == delta)) m_valid = false;
                     break;
@@ -1614,13 +1693,14 @@ struct QpW {
                     ++q;
                     added = true;
                     ++nsteps;
-                    if (delta < ill_tol * p.nph) { dirty = true; rough = true; }
+                    if (delta < ill_tol * p.nph) { dirty = true; rough = true; ill_seen = true; }
                     PROF(11);
                 } else {
                     const double rl = rs[ldrop], mll = M[(size_t)ldrop * kMSq + ldrop];
                     wsync();
                     drop_slot(ldrop, r, rl, u);
                     rough = true;
+                    refined = false;  // (r follows by the rank-1 formula: an ambiguous delta is refined again)
                     if (dirty) {
                         need_r = true;  // rebuild M, then r from scratch
                     } else {
@@ -1822,6 +1902,10 @@ DMPC_D int agent_solve_fast(const DevParams& Pm, const double* __restrict__ tab,
             yhi[x] = fmin(c0 + l1 + pad, qp.bnd6[3 + x]);
         }
     }
+#if defined(DMPC_GPU_TRACE)
+    qp.trace = (io.dbg_n == DMPC_GPU_TRACE);
+    if (qp.trace && lane_id() == 0) printf("[trace] agent %d kstar %d nv %d kc_all %d\n", io.dbg_n, io.kstar, io.nv, qp.kc_all);
+#endif
     bool give_up = false;
     bool use_list = io.warm && io.gidx && io.warm[0] > 0;  // (DMPC_WARM_START experiment only)
     (void)use_list;
@@ -1853,6 +1937,9 @@ DMPC_D int agent_solve_fast(const DevParams& Pm, const double* __restrict__ tab,
             }
         }
         const QpResult r = qp.solve(max_iter, &m_valid, resume);
+#if defined(DMPC_GPU_TRACE)
+        if (qp.trace && lane_id() == 0) printf("[trace] solve rc %d iters %d q %d tries %d slb %.4g\n", r.rc, r.iters, r.q, tries, slb);
+#endif
         resume = false;
         dg.iters += r.iters;
         dg.nact = (dg.nact & ~0xff) | r.q;

@@ -114,8 +114,10 @@ def test_longer_horizon_k20(orc, emul):
 def test_fast_path_single_step_matches_oracle(orc, emul, golden, name, variant):
     g = golden[name]
     P = orc.default_params(variant)
+    # (1e-8: a constraint that is independent only at the 1e-10 level is now taken into the active set like the
+    # oracle does instead of being called dependent; the polished point then carries ~3e-9 m)
     o, e = _cmp(orc, emul, P, g["pk_prev"], g["vk_prev"], g["ak_prev"], g["pf"], g["l"], g["pmin"], g["pmax"],
-                QMAX=-64)
+                tol=1e-8, QMAX=-64)
     # the retry count (slack bound / penalty doublings) is the reference's: skipped tries are counted
     assert np.array_equal((o["status"] >> 8) & 0xFF, (e["status"] >> 8) & 0xFF)
 
