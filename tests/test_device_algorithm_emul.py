@@ -268,3 +268,29 @@ def test_negative_multiplier_and_inconsistent_active_set(orc, emul):
                 assert np.array_equal(o["status"], e["status"]), (k, qmax)
                 assert np.abs(o["l_new"] - e["l_new"]).max() <= 1e-8
         l, pk, vk, ak = o["l_new"], o["p1"], o["v1"], o["a1"]
+
+
+def test_bound2_thin_feasible_set_is_not_called_infeasible(orc, emul):
+    """solveSoftDMPCbound2, N = 500, seed 21, step 14, agent 288: the slack lower bound enters with
+    delta = 4e-10 n'H^-1 n.  Judged at 1e-9 the constraint was called dependent and the (feasible) try infeasible:
+    one retry too many.  With the direction recomputed from a refined r both device solvers agree with the oracle."""
+    from multiagent_planning_b200 import scenarios
+    cfg = scenarios.config("C3")
+    N = cfg["N"]
+    po, pf = scenarios.random_test(N, cfg["pmin"], cfg["pmax"], 0.35, 2.0, 21)
+    P = orc.default_params(1)
+    K = P.K
+    l = np.zeros((3, K, N), order="F")
+    for n in range(N):
+        l[:, :, n] = orc.init_dmpc(po[:, n], pf[:, n], P.h, K, P.init_div)[0]
+    pk, vk, ak = l[:, 0, :].copy(), np.zeros((3, N)), np.zeros((3, N))
+    for k in range(14):
+        o = orc.step(P, pk, vk, ak, pf, l, cfg["pmin"], cfg["pmax"], nthreads=4)
+        if k == 13:
+            n = 288
+            for qmax in (-64, 160):
+                e = emul.step(emul.params_from(P), pk, vk, ak, pf, l, cfg["pmin"], cfg["pmax"], n0=n, n1=n + 1,
+                              QMAX=qmax, RCAP=256, RMAX=256)
+                assert e["status"][n] == o["status"][n] == 0x1
+                assert np.abs(e["l_new"][:, :, n] - o["l_new"][:, :, n]).max() <= 1e-8
+        l, pk, vk, ak = o["l_new"], o["p1"], o["v1"], o["a1"]

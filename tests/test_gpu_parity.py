@@ -496,6 +496,26 @@ def test_n2000_k15_vs_oracle(dmpc, orc):
             l, pk, vk, ak = o["l_new"], o["p1"], o["v1"], o["a1"]
 
 
+@pytest.mark.parametrize("name,seed,steps", [("C3", 11, 16), ("C3", 21, 16), ("N2000", 24, 17)])
+def test_bound2_thin_feasible_sets_vs_oracle(dmpc, orc, name, seed, steps):
+    """solveSoftDMPCbound2 (rows one horizon index earlier: many retries, feasible sets that are merely thin).  The
+    three cases the wide soak found: a try declared infeasible on the GPU although its feasible set is 5e-4 wide
+    (C3 / seed 11, step 1: verdict after an ill-conditioned add), constraints called dependent at delta = 4e-10
+    (seed 21, step 14; N = 2000 / seed 24, steps 3 and 16).  Flags AND retry counts must be the oracle's."""
+    from multiagent_planning_b200 import scenarios
+    cfg = scenarios.config(name)
+    po, pf = scenarios.random_test(cfg["N"], cfg["pmin"], cfg["pmax"], 0.35, 2.0, seed)
+    P = dmpc.default_params(dmpc.SOFT_BOUND2)
+    with dmpc.Solver(cfg["N"], P, pmin=cfg["pmin"], pmax=cfg["pmax"], pf=pf) as s:
+        l, pk, vk, ak = s.init_horizons(po)
+        retried = 0
+        for _ in range(steps):
+            g, o = _cmp_step(orc, P, s, pk, vk, ak, pf, l, cfg["pmin"], cfg["pmax"])
+            retried += int((((o["status"] >> 8) & 0xFF) > 0).sum())
+            l, pk, vk, ak = o["l_new"], o["p1"], o["v1"], o["a1"]
+        assert retried > 50
+
+
 def test_k20_small_swarm_vs_oracle(dmpc, orc):
     """K = 20 on a swarm that fits one wave (scan_kernel<4,2,20>, one agent per warp), 12 closed-loop steps"""
     from multiagent_planning_b200 import scenarios
