@@ -16,6 +16,7 @@ enum { VAR_SOFT_BOUND = 0, VAR_SOFT_BOUND2 = 1, VAR_HARD = 2, VAR_HARD_ONDEMAND 
 // kernel-side copy of the parameters (plain data, passed by value)
 struct DevParams {
     int K, variant, max_tries, neigh_mode, N;
+    int ill_fallback = 1;  // infeasibility verdicts after an ill-conditioned add go to the generic solver (qp_warp.cuh)
     double h, rmin, c, alim, Q1, S1, term, Q_far, Q_near, S_free, near_radius, slack_lb,
         neigh_factor, coll_tol, inb_tol, hard_radius;
     double pmin[3], pmax[3];
@@ -64,6 +65,7 @@ struct AgentIO {
     const int* gidx = nullptr;  // global rows: neighbour's agent index of each row [RMAX]
     int* warm = nullptr;        // per agent kWarmStride ints: [0] = count, [1..] = the stored active set
     int dbg_n = -1;             // agent index (debug traces only)
+    int start_tries = 0;        // generic solver: first try of the retry loop (slack bound and penalty doubled that often)
 };
 constexpr int kWarmStride = 68;
 
@@ -221,6 +223,12 @@ DMPC_D int agent_solve(const DevParams& P, const double* __restrict__ tab, unsig
         // ---- retry loop (solveSoftDMPCbound.m:102-155) -------------------------------------------
         double term = P.term, slb = P.slack_lb;
         int tries = 0;
+        // re-solve on behalf of the register-resident solver: the tries it has already found infeasible (exact 3-D
+        // certificate or an unambiguous verdict) are not repeated
+        for (; tries < io.start_tries && tries < P.max_tries; ++tries) {
+            slb *= 2.0;
+            term *= 2.0;
+        }
         bool solved = false;
         const int max_iter = 40 * (n3 + nv) + 200;
         bool warm = false;

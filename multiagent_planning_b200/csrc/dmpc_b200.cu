@@ -475,6 +475,7 @@ int dmpcb200_create(const dmpcb200_params* p, int N, int n0, int n1, int n_scena
     D.Q_far = p->Q_far; D.Q_near = p->Q_near; D.S_free = p->S_free; D.near_radius = p->near_radius;
     D.slack_lb = p->slack_lb; D.neigh_factor = p->neigh_factor; D.coll_tol = p->coll_tol;
     D.inb_tol = p->inb_tol; D.hard_radius = p->hard_radius;
+    if (const char* e = getenv("DMPCB200_ILL_FALLBACK")) D.ill_fallback = atoi(e);  // experiment hook (default 1)
     for (int x = 0; x < 3; ++x) { D.pmin[x] = -1e30; D.pmax[x] = 1e30; }
 
     const int K = p->K, n3 = 3 * K;

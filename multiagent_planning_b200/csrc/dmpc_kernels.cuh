@@ -770,6 +770,7 @@ DMPC_D bool qp_agent(const StepArgs& A, int li, const double* tab_s, unsigned ch
                 generic = true;
                 rescue = true;
                 it0 = dg.iters;
+                io.start_tries = (st >> 8) & 0xff;  // (the tries already found infeasible are not repeated)
             }
         }
         while (generic) {

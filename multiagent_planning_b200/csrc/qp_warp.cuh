@@ -149,7 +149,7 @@ template <int KT, int QC = kQW, bool MK = false>
 struct QpW {
     static constexpr int kMSq = QC + 2;  // row stride of M in doubles (conflict-free 128-bit row streaming)
     // ---- uniform problem data ---------------------------------------------------------------------
-    int K, n3, nv, soft, kc_all, qcap;
+    int K, n3, nv, soft, kc_all, qcap, ill_fb;
     double alim, term, slb, qw, sw;
     const double *ilnorm, *T4;  // shared memory: 1/||lam[k,:]||, interleaved {G,B,B',C}[k][j] of the weight set in use
     // ---- shared-memory workspace ---------------------------------------------------------------------
@@ -1490,7 +1490,6 @@ struct QpW {
         int nsteps = 0;          // primal steps since x was last synthesised from the multipliers
         bool rough = rough0;     // a drop, a rebuild or an ill-conditioned add happened since then
         bool polished = false, dirty = false, m_valid = true;
-        bool ill_seen = false;   // an add next to linear dependence happened in this solve: verdicts are not trusted
         QpResult res;
         res.rc = QP_OK;
         PROF_BEGIN();
@@ -1642,13 +1641,16 @@ struct QpW {
                            iters, q, p.type, p.idx, p.k, sp, p.nph, delta, (int)dependent, t1, ldrop, t2, slb, nmat);
 #endif
                 if (__builtin_expect(!(t < INFINITY), 0)) {  // also catches NaN
-                    // An infeasibility verdict is exact only as far as M is: after an add next to linear dependence
-                    // (delta < ill_tol n'H^-1 n: entries of M ~ 1/delta) the sign pattern of r it rests on is
-                    // rounding.  C3 / seed 11 / solveSoftDMPCbound2, step 1, agent 160: a try whose feasible set is
-                    // 5e-4 wide was declared infeasible on the GPU (one retry too many; the host build of the same
-                    // code, rounding differently, solved it).  Such verdicts go to the generic solver.
-                    res.rc = ill_seen ? QP_OVERFLOW : QP_INFEASIBLE;
-                    DMPC_ILL_STAT(ill_seen);
+                    // An infeasibility verdict rests on "dependent": delta = n_p'z below 1e-9 n_p'H^-1 n_p.  Where |delta|
+                    // is not clearly zero (>= 1e-12: exact dependences come out smaller, the noise of the explicit
+                    // inverse reaches 2e-9) the constraint may be independent at the 1e-10 level and the try
+                    // feasible -- its feasible set is merely thin (solveSoftDMPCbound2 soaks: agent 160 of C3 / seed 11
+                    // on the GPU, agent 288 of seed 21).  Those verdicts go to the generic solver, which recomputes
+                    // the direction from a refined r.  (Sending every verdict that followed an ill-conditioned add
+                    // cost the batched C5 workload 15 %; this test fires a few times per transition.)
+                    const bool amb = dependent && !refined && fabs(delta) >= 1e-12 * p.nph;  // (refined: already decided on the refined value)
+                    res.rc = (amb && ill_fb) ? QP_OVERFLOW : QP_INFEASIBLE;
+                    DMPC_ILL_STAT(amb);
                     failed = true;
                     if (!(t == t) || !(delta == delta)) m_valid = false;
                     break;
@@ -1693,7 +1695,7 @@ struct QpW {
                     ++q;
                     added = true;
                     ++nsteps;
-                    if (delta < ill_tol * p.nph) { dirty = true; rough = true; ill_seen = true; }
+                    if (delta < ill_tol * p.nph) { dirty = true; rough = true; }
                     PROF(11);
                 } else {
                     const double rl = rs[ldrop], mll = M[(size_t)ldrop * kMSq + ldrop];
@@ -1813,6 +1815,7 @@ DMPC_D int agent_solve_fast(const DevParams& Pm, const double* __restrict__ tab,
     qp.kc_all = (!MK && io.kstar > 0) ? io.kstar - 1 - (Pm.variant == VAR_SOFT_BOUND2 ? 1 : 0) : 0;
     qp.alim = Pm.alim; qp.qw = qw; qp.sw = sw;
     qp.qcap = qcap < QC ? qcap : QC;
+    qp.ill_fb = Pm.ill_fallback;
     qp.ilnorm = tab + K * K + 2 * K; qp.T4 = t_T4;
 
     // ---- rows: at most kQW of the scan's rows are in the working set at a time (see select_rows) ----------

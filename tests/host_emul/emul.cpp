@@ -79,6 +79,7 @@ extern "C" int emul_step(const dmpcb200_params* p, int N, int n0, int n1, const 
             // the kernel's rescue path: the generic solver with a large capacity decides (active set beyond the
             // on-chip capacity, no free slot in the row working set, numerically inconsistent active set)
             const int it0 = dg.iters;
+            io.start_tries = (status[n] >> 8) & 0xff;
             std::vector<unsigned char> big(agent_smem_bytes(K, 3 * kQW, RMAX) + 64);
             status[n] = agent_solve<0>(D, tab.data(), big.data(), 3 * kQW, RMAX, io, &dg);
             dg.iters += it0;
