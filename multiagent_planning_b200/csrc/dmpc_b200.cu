@@ -795,16 +795,6 @@ int step_impl(dmpcb200_t* h, const dmpcb200_handle::Bound& B, int32_t* first_fai
         std::memcpy(hs_in + off_st[2], ak, sN);
     }
     const auto tp1 = std::chrono::steady_clock::now();
-    if (in_pinned) {
-        // pinned caller arrays: DMA straight from them (the horizons first: the scan kernel needs only those)
-        CK(cudaMemcpyAsync(h->d_l[c], l_prev, lB, cudaMemcpyHostToDevice, s));
-        CK(cudaMemcpyAsync(h->d_st[c][0], pk, sN, cudaMemcpyHostToDevice, h->stream2));
-        CK(cudaMemcpyAsync(h->d_st[c][1], vk, sN, cudaMemcpyHostToDevice, h->stream2));
-        CK(cudaMemcpyAsync(h->d_st[c][2], ak, sN, cudaMemcpyHostToDevice, h->stream2));
-        CK(cudaEventRecord(h->ev_in, h->stream2));
-    } else {
-        CK(cudaMemcpyAsync(h->d_l[c], hs_in, h->side_bytes, cudaMemcpyHostToDevice, s));
-    }
     if (int rc = ensure_events(h, 4)) return rc;
     // outputs: the QP kernel writes the new horizons and states STRAIGHT into the mapped pinned block (posted
     // writes over PCIe as each agent finishes, overlapped with the rest of the kernel); the last CTA adds
@@ -813,6 +803,9 @@ int step_impl(dmpcb200_t* h, const dmpcb200_handle::Bound& B, int32_t* first_fai
     // caller arrays that are pinned are written by the kernel directly (no staging, nothing to hand over)
     double *w_l = B.w_l, *w_p = B.w_p, *w_v = B.w_v, *w_a = B.w_a;
     const bool direct = w_l && w_p && w_v && w_a;
+    // (all host-side preparation happens BEFORE the first device call: once the horizons are on their way the
+    // scan kernel must already be in the queue -- the GPU used to idle ~10 us behind the copy while the host was
+    // still enqueueing the small state copies and building the arguments)
     StepArgs A = make_args(h, h->n0, h->n1, h->d_st[c][0], h->d_st[c][1], h->d_st[c][2], h->d_l[c],
                            direct ? w_l : reinterpret_cast<double*>(ds_out),
                            direct ? w_p : reinterpret_cast<double*>(ds_out + off_st[0]),
@@ -825,9 +818,22 @@ int step_impl(dmpcb200_t* h, const dmpcb200_handle::Bound& B, int32_t* first_fai
     A.T.copy_dst = ds_out + h->side_bytes;
     A.T.copy_bytes = h->tailblk_bytes;
     A.fuse_tail = 1;  // first failing agent + rescue-slot reset in the last CTA of the QP kernel
-    CK(cudaEventRecord(h->ev[0], s));
     if (use_throughput_layout(h, A)) A.rq = h->d_rq;
-    CK(launch_scan(h, A, s));
+    if (in_pinned) {
+        // pinned caller arrays: DMA straight from them -- the horizons first (the scan kernel needs only those),
+        // the scan right behind them, the states on a second stream beside the scan
+        CK(cudaMemcpyAsync(h->d_l[c], l_prev, lB, cudaMemcpyHostToDevice, s));
+        CK(cudaEventRecord(h->ev[0], s));
+        CK(launch_scan(h, A, s));
+        CK(cudaMemcpyAsync(h->d_st[c][0], pk, sN, cudaMemcpyHostToDevice, h->stream2));
+        CK(cudaMemcpyAsync(h->d_st[c][1], vk, sN, cudaMemcpyHostToDevice, h->stream2));
+        CK(cudaMemcpyAsync(h->d_st[c][2], ak, sN, cudaMemcpyHostToDevice, h->stream2));
+        CK(cudaEventRecord(h->ev_in, h->stream2));
+    } else {
+        CK(cudaMemcpyAsync(h->d_l[c], hs_in, h->side_bytes, cudaMemcpyHostToDevice, s));
+        CK(cudaEventRecord(h->ev[0], s));
+        CK(launch_scan(h, A, s));
+    }
     CK(cudaEventRecord(h->ev[1], s));
     if (in_pinned) CK(cudaStreamWaitEvent(s, h->ev_in, 0));  // the states have arrived
     CK(launch_qp(h, A, s));
