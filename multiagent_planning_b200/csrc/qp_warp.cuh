@@ -69,6 +69,9 @@
 // set goes to the generic solver instead, which always refines.
 #define DMPC_REFINE MK
 #endif
+#ifndef DMPC_NEGDROP
+#define DMPC_NEGDROP true  // (false: A/B build without the multiplier check after the polish)
+#endif
 #ifndef DMPC_FEAS_TOL
 #define DMPC_FEAS_TOL 1e-10  // a constraint counts as violated beyond this (normalised residual)
 #endif
@@ -1526,7 +1529,7 @@ struct QpW {
                 // multipliers by 1/delta, and a constraint can end up active with a NEGATIVE multiplier: the
                 // point is then not the optimum.  Such constraints are dropped (rank-1 updates of u and M), x is
                 // synthesised for the smaller set -- a valid pair again -- and the iteration goes on.
-                if (drop_negative(1e-9) > 0) {
+                if (DMPC_NEGDROP && drop_negative(1e-9) > 0) {
                     synth_from_u();
                     polished = false;
                     rough = true;
