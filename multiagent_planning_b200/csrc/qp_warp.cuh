@@ -69,6 +69,22 @@
 // set goes to the generic solver instead, which always refines.
 #define DMPC_REFINE MK
 #endif
+#ifndef DMPC_UNROLL_MV
+#define DMPC_UNROLL_MV 2  // unroll factors of the hot loops (tuned by A/B runs: scripts/scan_probe.py with DMPCB200_LIB)
+#endif
+#ifndef DMPC_UNROLL_BD
+#define DMPC_UNROLL_BD 2
+#endif
+#ifndef DMPC_UNROLL_AP
+#define DMPC_UNROLL_AP 5
+#endif
+#define DMPC_PRAGMA_(x) _Pragma(#x)
+#define DMPC_PRAGMA(x) DMPC_PRAGMA_(x)
+#if defined(__CUDACC__)
+#define DMPC_UNROLL(n) DMPC_PRAGMA(unroll n)
+#else
+#define DMPC_UNROLL(n)
+#endif
 #ifndef DMPC_NEGDROP
 #define DMPC_NEGDROP true  // (false: A/B build without the multiplier check after the polish)
 #endif
@@ -371,7 +387,7 @@ struct QpW {
         const int cnt4 = (cnt + 3) & ~3;
         double acc[kEPL][4];
         QW_FOR(h) { acc[h][0] = 0.0; acc[h][1] = 0.0; acc[h][2] = 0.0; acc[h][3] = 0.0; }
-#pragma unroll 2
+DMPC_UNROLL(DMPC_UNROLL_MV)
         for (int j = 0; j < cnt4; j += 4) {
             const Dbl2 g01 = ld2(gs + j), g23 = ld2(gs + j + 2);
             QW_FOR(h) {
@@ -433,7 +449,7 @@ struct QpW {
         const double id = qw_rcp(delta);
         double ci[kEPL];
         QW_FOR(h) ci[h] = r[h] * id;
-#pragma unroll 2
+DMPC_UNROLL(DMPC_UNROLL_BD)
         for (int j = 0; j < cnt4; j += 4) {
             const Dbl2 r01 = ld2(rs + j), r23 = ld2(rs + j + 2);
             QW_FOR(h) {
@@ -631,7 +647,7 @@ struct QpW {
             cq[h] = cbp + 2 * (ex[h] * Kk);
             sa[h][0] = sa[h][1] = sP[h][0] = sP[h][1] = 0.0;
         }
-#pragma unroll 5
+DMPC_UNROLL(DMPC_UNROLL_AP)
         for (int j = 0; j < (q > 0 ? Kk : 0); ++j) {  // empty active set: the coefficient vectors are zero
             QW_FOR(h) {
                 if (h * kLanes < n3) {  // uniform
