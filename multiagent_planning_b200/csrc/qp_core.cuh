@@ -673,7 +673,7 @@ struct Qp {
             for (int s = lane_id(); s < q; s += kLanes) {
                 const double rs = resid(w.act[s]);
                 w.g[s] = rs;
-                mx = fmax(mx, fabs(rs));
+                mx = (fabs(rs) < 1e300) ? fmax(mx, fabs(rs)) : INFINITY;  // (fmax drops a NaN)
             }
             mx = wmax(mx);
             wsync();
@@ -919,7 +919,18 @@ struct Qp {
                 PROF(9);
                 const double t2 = dependent ? INFINITY : (-sp * frcp(delta));
                 const double t = (t1 < t2) ? t1 : t2;
-                if (!(t < INFINITY)) { res.rc = QP_INFEASIBLE; failed = true; break; }  // also catches NaN
+                if (!(t < INFINITY)) {  // also catches NaN
+                    // a verdict is only final on a refined r (see qp_warp.cuh): refine now and decide again
+                    if (!refined && q > 0 && t == t && delta == delta) {
+                        refined = true;
+                        refine = true;
+                        need_r = true;
+                        continue;
+                    }
+                    res.rc = QP_INFEASIBLE;
+                    failed = true;
+                    break;
+                }
                 if (!dependent) {
                     for (int i = lane_id(); i < N3(); i += kLanes) {
                         w.a[i] = fma(t, w.z[i], w.a[i]);

@@ -837,7 +837,8 @@ DMPC_UNROLL(DMPC_UNROLL_AP)
                 if (s < q) {
                     const double v = resid_shared(act[s]);
                     gs[s] = v;
-                    mx = fmax(mx, fabs(v));
+                    // (fmax drops a NaN: a non-finite residual must not pass for a converged one)
+                    mx = (fabs(v) < 1e300) ? fmax(mx, fabs(v)) : INFINITY;
                 } else if (s < q4) {
                     gs[s] = 0.0;
                 }
@@ -1509,6 +1510,7 @@ DMPC_UNROLL(DMPC_UNROLL_AP)
         int nsteps = 0;          // primal steps since x was last synthesised from the multipliers
         bool rough = rough0;     // a drop, a rebuild or an ill-conditioned add happened since then
         bool polished = false, dirty = false, m_valid = true;
+        bool ill_m = false;  // an add next to linear dependence happened: M stays ill-conditioned for the rest of this solve
         QpResult res;
         res.rc = QP_OK;
         PROF_BEGIN();
@@ -1521,7 +1523,10 @@ DMPC_UNROLL(DMPC_UNROLL_AP)
                 if (polished || q == 0) break;  // optimal
                 // a short run of plain adds carries no drift worth removing (each step is one fused
                 // multiply-add per entry on top of a synthesised x): accept it as it is
-                if (nsteps <= kPolishSkip && !rough && !dirty) break;
+                // (`rough` is sticky: the polish repairs x and u, not M -- after a drop or a rebuild the direction of a
+                // LATER add is inexact too and leaves the active constraints by ~1e-6: host-build soak, bound2 / N = 500 /
+                // seed 1009, step 11, agent 85 was accepted 3.5e-3 m off the optimum after an add that followed a polish)
+                if (nsteps <= kPolishSkip && !rough && !dirty && !ill_m) break;
                 bool consistent = false;
                 for (int pass = 0; pass < 2; ++pass) {
                     if (dirty || pass) refresh();
@@ -1539,7 +1544,6 @@ DMPC_UNROLL(DMPC_UNROLL_AP)
                 }
                 polished = true;
                 nsteps = 0;
-                rough = false;
                 // The refined multipliers are those of the equality-constrained problem on the active set.  An add
                 // next to linear dependence (delta ~ 1e-7 n_p'H^-1 n_p) amplifies the rounding of the running
                 // multipliers by 1/delta, and a constraint can end up active with a NEGATIVE multiplier: the
@@ -1660,14 +1664,27 @@ DMPC_UNROLL(DMPC_UNROLL_AP)
                            iters, q, p.type, p.idx, p.k, sp, p.nph, delta, (int)dependent, t1, ldrop, t2, slb, nmat);
 #endif
                 if (__builtin_expect(!(t < INFINITY), 0)) {  // also catches NaN
-                    // An infeasibility verdict rests on "dependent": delta = n_p'z below 1e-9 n_p'H^-1 n_p.  Where |delta|
-                    // is not clearly zero (>= 1e-12: exact dependences come out smaller, the noise of the explicit
-                    // inverse reaches 2e-9) the constraint may be independent at the 1e-10 level and the try
-                    // feasible -- its feasible set is merely thin (solveSoftDMPCbound2 soaks: agent 160 of C3 / seed 11
-                    // on the GPU, agent 288 of seed 21).  Those verdicts go to the generic solver, which recomputes
-                    // the direction from a refined r.  (Sending every verdict that followed an ill-conditioned add
-                    // cost the batched C5 workload 15 %; this test fires a few times per transition.)
-                    const bool amb = dependent && !refined && fabs(delta) >= 1e-12 * p.nph;  // (refined: already decided on the refined value)
+                    // An infeasibility verdict rests on "dependent" (delta = n_p'z below 1e-9 n_p'H^-1 n_p) and on the sign
+                    // pattern of r = M g (no r_i > 0 to drop): both are what is left of cancellations and carry the error of
+                    // the explicit inverse.  Soaks of solveSoftDMPCbound2 found tries declared infeasible whose feasible
+                    // set is merely thin, with |delta| in the noise band and below it (GPU: C3 / seed 11 agent 160; host
+                    // build: N = 500 / seed 1002 agent 20).  A verdict is therefore only final on a REFINED r: the
+                    // instantiation that refines does so now and decides again; the others hand the try to the generic
+                    // solver (rescue path), which refines.  NaNs go the same way.
+                    const bool nan = !(t == t) || !(delta == delta);
+                    if (DMPC_REFINE && !refined && !nan && q > 0) {
+                        refined = true;
+                        refine = true;
+                        need_r = true;
+                        continue;
+                    }
+                    // Which verdicts are confirmed (ill_fb): for solveSoftDMPCbound2, whose rows sit one horizon index
+                    // earlier and whose tries are routinely on the edge of feasibility, ALL of them (2); for the other
+                    // variants those whose delta lies in the noise band (1) -- no wrong verdict outside it was seen in 4 M
+                    // soaked agent-steps of solveSoftDMPCbound, confirming all of them costs the batched C5 workload 16 %,
+                    // and without slacks (solveHardDMPCOnDemand) infeasible agents are the rule and would exhaust the
+                    // rescue slots.
+                    const bool amb = nan || (!refined && (ill_fb > 1 || fabs(delta) >= 1e-12 * p.nph));
                     res.rc = (amb && ill_fb) ? QP_OVERFLOW : QP_INFEASIBLE;
                     DMPC_ILL_STAT(amb);
                     failed = true;
@@ -1714,7 +1731,7 @@ DMPC_UNROLL(DMPC_UNROLL_AP)
                     ++q;
                     added = true;
                     ++nsteps;
-                    if (delta < ill_tol * p.nph) { dirty = true; rough = true; }
+                    if (delta < ill_tol * p.nph) { dirty = true; rough = true; ill_m = true; }
                     PROF(11);
                 } else {
                     const double rl = rs[ldrop], mll = M[(size_t)ldrop * kMSq + ldrop];
@@ -1834,7 +1851,7 @@ DMPC_D int agent_solve_fast(const DevParams& Pm, const double* __restrict__ tab,
     qp.kc_all = (!MK && io.kstar > 0) ? io.kstar - 1 - (Pm.variant == VAR_SOFT_BOUND2 ? 1 : 0) : 0;
     qp.alim = Pm.alim; qp.qw = qw; qp.sw = sw;
     qp.qcap = qcap < QC ? qcap : QC;
-    qp.ill_fb = Pm.ill_fallback;
+    qp.ill_fb = Pm.ill_fallback ? (Pm.variant == VAR_SOFT_BOUND2 ? 2 : 1) : 0;
     qp.ilnorm = tab + K * K + 2 * K; qp.T4 = t_T4;
 
     // ---- rows: at most kQW of the scan's rows are in the working set at a time (see select_rows) ----------

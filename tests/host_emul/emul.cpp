@@ -67,6 +67,7 @@ extern "C" int emul_step(const dmpcb200_params* p, int N, int n0, int n1, const 
         io.p1 = p1 + 3 * n; io.v1 = v1 + 3 * n; io.a1 = a1 + 3 * n;
         io.l_prev_n = own;
         io.gidx = gidx.data();
+        io.dbg_n = n;
         io.warm = warm ? warm + (size_t)kWarmStride * n : nullptr;
         AgentDiag dg;
         if (fast && 3 * K <= kQW && so.nv <= kRowsFastMax && !so.flag)
