@@ -782,7 +782,8 @@ struct Qp {
         const double dep_tol = 1e-9;    // on delta = z'Hz relative to n_p'H^{-1}n_p
         const double ill_tol = 1e-5;    // adds below this mark M for an exact rebuild
         int iters = 0, npolish = 0;
-        bool polished = false, dirty = false;
+        bool polished = false, dirty = false, redo = false;
+        int drift_code = -1;  // candidate after which x was re-synthesised instead of declaring the try infeasible
         QpResult res;
         res.rc = QP_OK;
         PROF_BEGIN();
@@ -927,6 +928,16 @@ struct Qp {
                         need_r = true;
                         continue;
                     }
+                    // A dependent candidate that is violated by a hair (|sp| tiny) is drift of x, not infeasibility:
+                    // re-synthesise x from the multipliers once and look again (CPU soak, bound2 / N = 300 / seed
+                    // 6023: a bound "violated" by 4e-9 after an ill-conditioned add ended a feasible try).
+                    if (-sp < 1e-6 && drift_code != pcode && q > 0) {
+                        drift_code = pcode;
+                        refresh();
+                        polish();
+                        redo = true;
+                        break;
+                    }
                     res.rc = QP_INFEASIBLE;
                     failed = true;
                     break;
@@ -986,6 +997,7 @@ struct Qp {
                     PROF(12);
                 }
             }
+            if (redo) { redo = false; polished = false; continue; }
             if (failed) break;
         }
         res.iters = iters;

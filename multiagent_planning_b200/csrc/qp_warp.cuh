@@ -1990,7 +1990,10 @@ DMPC_D int agent_solve_fast(const DevParams& Pm, const double* __restrict__ tab,
             if (nsw < 0) { status |= ST_QPFAIL | ST_OVERFLOW; break; }
         }
         if (r.rc == QP_OK) { solved = true; break; }
-        if (r.rc == QP_ITERCAP) { status |= ST_QPFAIL; break; }
+        // (an iteration cap is a cycle between two borderline-dependent constraints -- CPU soak, bound2 / N = 300 /
+        // seed 9116: ROW and SUB of one row, delta = 8.8e-10 -- which the refining generic solver resolves: same route
+        // as an overflow)
+        if (r.rc == QP_ITERCAP) { status |= ST_QPFAIL | ST_OVERFLOW; break; }
         if (r.rc == QP_OVERFLOW) { status |= ST_QPFAIL | ST_OVERFLOW; break; }
         // infeasible: soft variants with slack double the slack bound and the penalty and retry;
         // otherwise the reference only loosens quadprog's tolerance or gives up.
