@@ -294,3 +294,34 @@ def test_bound2_thin_feasible_set_is_not_called_infeasible(orc, emul):
                 assert e["status"][n] == o["status"][n] == 0x1
                 assert np.abs(e["l_new"][:, :, n] - o["l_new"][:, :, n]).max() <= 1e-8
         l, pk, vk, ak = o["l_new"], o["p1"], o["v1"], o["a1"]
+
+
+@pytest.mark.parametrize("N,variant,seed,step,agent,density,what", [
+    (150, 2, 5001, 1, 117, 1.0, "a non-finite residual passed for a converged polish: NaN returned as solved"),
+    (500, 1, 1009, 10, 85, 1.0, "an add after a polish rode an inexact direction: accepted 3.5e-3 m off the optimum"),
+    (500, 1, 1002, 18, 20, 1.0, "infeasibility verdict with |delta| below the noise band on a thin feasible set"),
+    (300, 1, 6023, 16, 181, 1.5, "a bound violated by 4e-9 (drift) ended a feasible try in the generic solver"),
+    (300, 1, 9116, 3, 198, 2.5, "cycle between ROW and SUB of one row (delta = 8.8e-10) ended in the iteration cap"),
+])
+def test_cases_found_by_the_host_build_soak(orc, emul, N, variant, seed, step, agent, density, what):
+    """scripts/soak_host_build.py (host build of the device algorithm against the oracle over ~150 seeds) found
+    these; each must give the oracle's status word (flags and retry count) and solution on both device solvers'
+    routes (register-resident solver with the kernel's generic fallback, generic solver alone)."""
+    from multiagent_planning_b200 import scenarios
+    pmin, pmax = scenarios.density_arena(N, density)
+    po, pf = scenarios.random_test(N, pmin, pmax, 0.35, 2.0, seed)
+    P = orc.default_params(variant)
+    K = P.K
+    l = np.zeros((3, K, N), order="F")
+    for n in range(N):
+        l[:, :, n] = orc.init_dmpc(po[:, n], pf[:, n], P.h, K, P.init_div)[0]
+    pk, vk, ak = l[:, 0, :].copy(), np.zeros((3, N)), np.zeros((3, N))
+    RM = min(N - 1, 256) * (K if variant == 2 else 1)
+    for k in range(step + 1):
+        o = orc.step(P, pk, vk, ak, pf, l, pmin, pmax, nthreads=4)
+        if k == step:
+            for kw in (dict(QMAX=-64, RMAX=RM), dict(QMAX=192, RCAP=RM, RMAX=RM)):
+                e = emul.step(emul.params_from(P), pk, vk, ak, pf, l, pmin, pmax, n0=agent, n1=agent + 1, **kw)
+                assert e["status"][agent] == o["status"][agent], (what, kw)
+                assert np.abs(e["l_new"][:, :, agent] - o["l_new"][:, :, agent]).max() <= 1e-8, (what, kw)
+        l, pk, vk, ak = o["l_new"], o["p1"], o["v1"], o["a1"]
