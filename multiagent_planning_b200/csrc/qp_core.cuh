@@ -795,11 +795,15 @@ struct Qp {
             if (pcode < 0) {
                 if (polished || q == 0) break;  // optimal
                 // x is re-synthesised from the multipliers; a poor residual triggers one exact rebuild
+                // (a residual that stagnates at ~1e-9 is the noise of an ill-conditioned set and is accepted as before;
+                // a set that is INCONSISTENT leaves ~1e-2.  The line between them: 1e-6, NaN-safe.)
                 bool consistent = false;
                 for (int pass = 0; pass < 2; ++pass) {
                     if (dirty || pass) refresh();
                     dirty = false;
-                    if (!(polish() > 1e-9)) { consistent = true; break; }
+                    const double left = polish();
+                    if (left <= 1e-6) consistent = true;
+                    if (left <= 1e-9) break;
                 }
                 // an active set whose constraints cannot be met together even with M rebuilt exactly is a solver
                 // failure (reported as such), never a solution

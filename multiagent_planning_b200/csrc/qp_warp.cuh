@@ -1527,11 +1527,15 @@ DMPC_UNROLL(DMPC_UNROLL_AP)
                 // LATER add is inexact too and leaves the active constraints by ~1e-6: host-build soak, bound2 / N = 500 /
                 // seed 1009, step 11, agent 85 was accepted 3.5e-3 m off the optimum after an add that followed a polish)
                 if (nsteps <= kPolishSkip && !rough && !dirty && !ill_m) break;
+                // (a residual that stagnates at ~1e-9 is the noise of an ill-conditioned set and is accepted as before;
+                // a set that is INCONSISTENT leaves ~1e-2.  The line between them: 1e-6, NaN-safe.)
                 bool consistent = false;
                 for (int pass = 0; pass < 2; ++pass) {
                     if (dirty || pass) refresh();
                     dirty = false;
-                    if (!(polish() > 1e-9)) { consistent = true; break; }
+                    const double left = polish();
+                    if (left <= 1e-6) consistent = true;
+                    if (left <= 1e-9) break;
                 }
                 if (!consistent) {
                     // Even with M rebuilt exactly the active constraints cannot be met together: the set has

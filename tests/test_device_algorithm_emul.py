@@ -302,6 +302,12 @@ def test_bound2_thin_feasible_set_is_not_called_infeasible(orc, emul):
     (500, 1, 1002, 18, 20, 1.0, "infeasibility verdict with |delta| below the noise band on a thin feasible set"),
     (300, 1, 6023, 16, 181, 1.5, "a bound violated by 4e-9 (drift) ended a feasible try in the generic solver"),
     (300, 1, 9116, 3, 198, 2.5, "cycle between ROW and SUB of one row (delta = 8.8e-10) ended in the iteration cap"),
+    # a polish residual that stagnates at ~1e-9 (noise of an ill-conditioned set, not an inconsistent one: those leave
+    # ~1e-2) was reported as a solver failure (0x10) where the oracle solves the try
+    (300, 1, 12001, 8, 73, 2.0, "polish residual of ~1e-9 on an ill-conditioned set read as an inconsistent set"),
+    (300, 1, 12003, 10, 19, 2.0, "same, first retry"),
+    (300, 1, 12037, 12, 207, 2.0, "same, fourth retry"),
+    (200, 1, 13058, 2, 175, 3.0, "same, N = 200 at 3 agents/m^3"),
 ])
 def test_cases_found_by_the_host_build_soak(orc, emul, N, variant, seed, step, agent, density, what):
     """scripts/soak_host_build.py (host build of the device algorithm against the oracle over ~150 seeds) found

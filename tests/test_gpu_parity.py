@@ -516,6 +516,23 @@ def test_bound2_thin_feasible_sets_vs_oracle(dmpc, orc, name, seed, steps):
         assert retried > 50
 
 
+@pytest.mark.parametrize("N,density,seed,steps", [(300, 2.0, 12001, 10), (200, 3.0, 13058, 4)])
+def test_bound2_ill_conditioned_polish_vs_oracle(dmpc, orc, N, density, seed, steps):
+    """solveSoftDMPCbound2 on dense small swarms: the polish of an ill-conditioned (not inconsistent) active set
+    stagnates at a residual of ~1e-9; judged at 1e-9 it was a reported solver failure where the oracle solves the try
+    (host-build soak, seeds 12001 / step 8 / agent 73 and 13058 / step 2 / agent 175).  The line between noise and an
+    inconsistent set (which leaves ~1e-2) is 1e-6.  Flags AND retry counts must be the oracle's."""
+    from multiagent_planning_b200 import scenarios
+    pmin, pmax = scenarios.density_arena(N, density)
+    po, pf = scenarios.random_test(N, pmin, pmax, 0.35, 2.0, seed)
+    P = dmpc.default_params(dmpc.SOFT_BOUND2)
+    with dmpc.Solver(N, P, pmin=pmin, pmax=pmax, pf=pf) as s:
+        l, pk, vk, ak = s.init_horizons(po)
+        for _ in range(steps):
+            g, o = _cmp_step(orc, P, s, pk, vk, ak, pf, l, pmin, pmax)
+            l, pk, vk, ak = o["l_new"], o["p1"], o["v1"], o["a1"]
+
+
 def test_k20_small_swarm_vs_oracle(dmpc, orc):
     """K = 20 on a swarm that fits one wave (scan_kernel<4,2,20>, one agent per warp), 12 closed-loop steps"""
     from multiagent_planning_b200 import scenarios
